@@ -1,0 +1,156 @@
+/*
+ * irlosc.h - C ABI of the B200-native batched operational-space controller.
+ *
+ * The reference (ir-lab/irl_control) has no FFI layer: its per-timestep hot
+ * path is the Python method `OSC.generate` (irl_control/osc.py:120-210) fed by
+ * the state pulls of `Robot.get_all_states` (irl_control/robot.py:125-136) and
+ * `Device.get_all_states` (irl_control/device.py:183-197).  This header is the
+ * boundary a maintainer would bind from `OSC.generate` (ctypes stub shown in
+ * INTEGRATION.md): plain pointers and sizes, no torch / numpy types.
+ *
+ * One handle == one controller configuration (what the `Device`, `Robot` and
+ * `OSC` constructors resolve: index maps, DoF masks, gains) on the CUDA
+ * device that is current when `irlosc_create` is called.  A step evaluates the
+ * whole control law for B independent robot instances.  All arithmetic is
+ * IEEE float64, like the reference's numpy / MuJoCo mjtNum path.
+ *
+ * Threading: a handle is thread-compatible, not thread-safe (one caller at a
+ * time per handle), matching the reference ("one caller thread runs
+ * generate").  `irlosc_step` never synchronises with the host.
+ */
+#ifndef IRLOSC_H_
+#define IRLOSC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRLOSC_ABI_VERSION 1
+#define IRLOSC_MAX_DEVICES 4   /* target devices per controller (DualUR5: base + 2 arms) */
+#define IRLOSC_MAX_N 32        /* robot DoF, Robot.num_joints_total (robot.py:32); DualUR5: 25 */
+#define IRLOSC_MAX_K 24        /* stacked task rows, sum of ctrlr_dof over targets; DualUR5: <= 13 */
+
+/* return codes */
+#define IRLOSC_OK 0
+#define IRLOSC_ERR_INVALID 1   /* bad argument / parameter block          */
+#define IRLOSC_ERR_CUDA 2      /* CUDA runtime error, see irlosc_last_error */
+#define IRLOSC_ERR_NOMEM 3
+
+/* per-instance status byte written by a step (bit field) */
+#define IRLOSC_ST_PINV 0x01         /* |det(J M^-1 J^T)| < 1e-4: pinv(rcond=1e-5) branch (osc.py:52-55) */
+#define IRLOSC_ST_M_NOT_PD 0x02     /* M had a non-positive pivot: outputs are NaN                      */
+#define IRLOSC_ST_EIGEN 0x04        /* task-space inverse went through the Jacobi eigen-solver          */
+#define IRLOSC_ST_VEL_BRANCH 0x08   /* >=1 device took the non-zero target-velocity branch (osc.py:175-177) */
+#define IRLOSC_ST_DX_RANGE 0x10     /* that branch indexed dx out of range: the reference raises IndexError
+                                       (robot.py:52-55 vs osc.py:150,176); outputs are NaN               */
+
+/* layouts of the inertia / Jacobian inputs */
+#define IRLOSC_M_DENSE 0        /* [B][ldm rows used: n][ldm]  row-major n x n block, row stride ldm   */
+#define IRLOSC_M_PACKED 1       /* [B][n(n+1)/2] lower triangle, row-major: (i,j<=i) at i(i+1)/2+j     */
+#define IRLOSC_J_ROWS 0         /* [B][k][ldj]   only the controlled rows, target order (osc.py:136-138) */
+#define IRLOSC_J_FULL6 1        /* [B][D][6][ldj] full [jacp;jacr] per target device (device.py:125-130);
+                                   rows with ctrlr_dof == 0 are never read                              */
+
+/* One target device, in TARGET order (the order of the dict given to generate). */
+typedef struct irlosc_device_params {
+    int32_t ctrlr_dof[6];                 /* device.py:33-36: xyz then abg mask                        */
+    int32_t n_joints_all;                 /* len(Device.joint_ids_all)            (device.py:69)       */
+    int32_t joint_ids_all[IRLOSC_MAX_N];  /* robot-local joint positions          (robot.py:64)        */
+    int32_t n_ctrl;                       /* len(Device.actuator_trnids)          (device.py:73-74)    */
+    int32_t actuator_trnids[IRLOSC_MAX_N];/* robot-local joints whose force is returned (osc.py:207)   */
+    int32_t dx_idx[6];                    /* Robot J_idxs[name] (robot.py:54), first sum(ctrlr_dof) used;
+                                             may exceed k-1, see IRLOSC_ST_DX_RANGE                     */
+    int32_t has_max_vel;                  /* Device.max_vel is not None           (osc.py:163)         */
+    double max_vel[2];                    /* default when io.max_vel == NULL      (device.py:31)       */
+    double kp, kv, ko;                    /* controller_configs entry             (osc.py:36)          */
+    double k[3], d[3];                    /* stiffness / damping, xyz part        (osc.py:160-161)     */
+} irlosc_device_params;
+
+typedef struct irlosc_params {
+    int32_t abi_version;                  /* IRLOSC_ABI_VERSION                                        */
+    int32_t n;                            /* Robot.num_joints_total                                    */
+    int32_t n_devices;                    /* number of targets                                         */
+    int32_t use_g;                        /* OSC(use_g=...)                       (osc.py:190)         */
+    int32_t admittance;                   /* OSC(admittance=...)                  (osc.py:184)         */
+    int32_t has_nullspace;                /* nullspace_config is not None         (osc.py:195)         */
+    double nullspace_kv;                  /* nullspace_config['kv']               (osc.py:196)         */
+    irlosc_device_params dev[IRLOSC_MAX_DEVICES];
+} irlosc_params;
+
+/*
+ * Per-step arrays; every array has the instance index as its leading axis and
+ * is densely packed unless a stride is given.  D = n_devices, n = params.n,
+ * k = sum of ctrlr_dof.  For `irlosc_step` these are DEVICE pointers, for
+ * `irlosc_step_host` HOST pointers.  Optional pointers may be NULL.
+ */
+typedef struct irlosc_io {
+    const double *M;          /* RobotState.M (robot.py:68-72)                                        */
+    int32_t m_layout;         /* IRLOSC_M_DENSE | IRLOSC_M_PACKED                                      */
+    int32_t ldm;              /* dense: row stride in doubles (>= n; scene nv if the block is a view)  */
+    int64_t m_stride;         /* doubles between instances; 0 = tight (ldm*n dense, n(n+1)/2 packed)   */
+    const double *J;          /* RobotState.J stacked for the targets                                  */
+    int32_t j_layout;         /* IRLOSC_J_ROWS | IRLOSC_J_FULL6                                        */
+    int32_t ldj;              /* row stride in doubles (>= n)                                          */
+    int64_t j_stride;         /* doubles between instances; 0 = tight                                  */
+    const double *dq;         /* [B][n]    RobotState.DQ (robot.py:60-65)                              */
+    const double *bias;       /* [B][n]    sim.data.qfrc_bias[joint_ids_all] (osc.py:191); NULL iff !use_g */
+    const double *ee_xyz;     /* [B][D][3] DeviceState.EE_XYZ  (device.py:93)                          */
+    const double *ee_quat;    /* [B][D][4] DeviceState.EE_QUAT (device.py:95), w x y z                 */
+    const double *target_xyz; /* [B][D][3] Target.get_xyz()    (utils.py:17)                           */
+    const double *target_quat;/* [B][D][4] Target.get_quat()   (utils.py:23)                           */
+    const double *target_vel; /* [B][D][6] [xyz_vel, abg_vel] (osc.py:172); NULL = all zero            */
+    const double *max_vel;    /* [B][D][2] Device.max_vel per instance (insertion_task.py:294); NULL = params */
+    const double *ft_xmat;    /* [B][D][9] site_xmat of the F/T frame (device.py:135-143); NULL iff !admittance */
+    const double *ft_raw;     /* [B][D][6] sensor-frame force|torque (device.py:150-167); NULL iff !admittance  */
+    double *u_all;            /* [B][n]      out, optional: joint-space signal before packing (osc.py:152-200) */
+    double *ctrl;             /* [B][n_ctrl] out: u_all[actuator_trnids] per target, concatenated (osc.py:203-208) */
+    uint8_t *status;          /* [B]         out, optional: IRLOSC_ST_* bits                           */
+} irlosc_io;
+
+typedef struct irlosc_handle irlosc_handle;
+
+/* Thread-local, human-readable description of the last failure on this thread. */
+const char *irlosc_last_error(void);
+int32_t irlosc_abi_version(void);
+
+/* Replaces: Device.__init__ index maps (device.py:41-74), Robot.__init__ (robot.py:26-32),
+ * OSC.__init__ gain precompute (osc.py:26-39).  Validates and copies `params`. */
+int32_t irlosc_create(const irlosc_params *params, irlosc_handle **out);
+int32_t irlosc_destroy(irlosc_handle *h);
+
+/* Sizes derived from the parameter block. */
+int32_t irlosc_num_task_rows(const irlosc_handle *h);   /* k      */
+int32_t irlosc_num_ctrl(const irlosc_handle *h);        /* n_ctrl */
+
+/* Replaces: OSC.generate (osc.py:120-210) for B instances whose state already lives in
+ * device memory.  Asynchronous on `cuda_stream` (a cudaStream_t, NULL = default stream). */
+int32_t irlosc_step(irlosc_handle *h, int64_t B, const irlosc_io *io_device, void *cuda_stream);
+
+/* Same with HOST buffers: copies inputs host->device, runs the step, copies ctrl / u_all /
+ * status back and returns when they are valid.  Work is pipelined in chunks over internal
+ * streams; buffers from irlosc_host_alloc (pinned) make the copies asynchronous. */
+int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io *io_host);
+
+/* Replaces: OSC.calc_error (osc.py:101-118), also called by insertion_task.py:173-179.
+ * err[B][D][6] (unmasked), device pointers, asynchronous. */
+int32_t irlosc_calc_error(irlosc_handle *h, int64_t B, const double *ee_xyz, const double *ee_quat,
+                          const double *target_xyz, const double *target_quat, double *err,
+                          void *cuda_stream);
+
+/* Pinned host memory for irlosc_step_host callers. */
+int32_t irlosc_host_alloc(void **ptr, int64_t bytes);
+int32_t irlosc_host_free(void *ptr);
+
+/* Kernel selection: 0 = auto, 1 = generic (any n, k), 2 = register-tiled DualUR5 kernel. */
+int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which);
+/* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
+int64_t irlosc_kernel_launches(const irlosc_handle *h);
+/* Name of the kernel the last step dispatched to (static string). */
+const char *irlosc_last_kernel(const irlosc_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRLOSC_H_ */

@@ -1,0 +1,86 @@
+"""Built-in robot / controller configurations of the DualUR5 demos.
+
+The reference keeps these as YAML (`irl_control/robot_configs/*.yaml`); the
+same keys and values are expressed here as Python so they travel with the
+package (the GPU box has no reference tree).  `MujocoApp` also accepts the
+path of any YAML file with this schema, including the reference's own.
+
+`start_body` note: the shipped default YAMLs leave
+`start_body` commented out, which makes `Device.__init__` fail for the arms
+(7 chain joints vs 6 start angles).  The built-ins therefore come in two
+flavours: `<name>` exactly as shipped and `<name>+start_body`, which adds the
+`iros2022.yaml:13,22` setting so the DualUR5 can actually be constructed.
+"""
+import copy
+
+_K = [1, 2, 3]
+_D = [0.5, 1, 1]
+
+
+def _ctrl(name, kp, kv, ko):
+    return {"name": name, "kp": kp, "kv": kv, "ki": 1, "ko": ko, "k": list(_K), "d": list(_D)}
+
+
+def _devices(arm_abg, base_max_vel, arm_max_vel, base_start, right_start, left_start, start_body):
+    arm = lambda idx, name, start: dict(
+        id=idx, name=name, max_vel=list(arm_max_vel), EE="ur_EE_" + name,
+        ctrlr_dof_xyz=[True, True, True], ctrlr_dof_abg=[arm_abg] * 3,
+        start_angles=list(start), num_gripper_joints=6,
+        **({"start_body": "dual_ur_stand"} if start_body else {}))
+    return [
+        dict(id=0, name="base", max_vel=list(base_max_vel), EE="ur_stand_dummy",
+             ctrlr_dof_xyz=[False, False, False], ctrlr_dof_abg=[False, False, True],
+             start_angles=list(base_start), num_gripper_joints=0),
+        arm(1, "ur5right", right_start),
+        arm(2, "ur5left", left_start),
+    ]
+
+
+_ROBOTS = [{"id": 0, "name": "DualUR5", "device_ids": [0, 1, 2]}]
+_LEFT_DEFAULT = [0.126, -0.942, -1.88, -4.15, -4.78, 0.0]
+
+
+def _default(arm_abg, osc2_kv, start_body):
+    return {
+        "devices": _devices(arm_abg, [0, 20], [1, 5], [0.0], [0.0] * 6, _LEFT_DEFAULT, start_body),
+        "robots": copy.deepcopy(_ROBOTS),
+        "controller_configs": [
+            _ctrl("osc0", 2000, 20, 2000), _ctrl("osc1", 200, 50, 200), _ctrl("osc2", 200, osc2_kv, 200),
+            {"name": "nullspace", "kv": 10},
+        ],
+    }
+
+
+def _iros2022():
+    return {
+        "devices": _devices(
+            True, [0, 2], [2.0, 5], [-1.56],
+            [-0.03614821, -0.27430234, -0.47910152, -0.14136462, -0.01368577, -0.54591325],
+            [0.05044541, 0.18777629, 0.30305106, -3.10725317, 1.58646237, 2.71767586], True),
+        "robots": copy.deepcopy(_ROBOTS),
+        "controller_configs": [
+            _ctrl("osc0", 200, 20, 75), _ctrl("osc1", 200, 50, 200), _ctrl("osc2", 200, 20, 75),
+            {"name": "nullspace", "kv": 10},
+        ],
+    }
+
+
+def robot_config(name: str):
+    """Fresh (deep-copied) config dict for a built-in name; KeyError if unknown."""
+    start_body = name.endswith("+start_body")
+    base = name[:-len("+start_body")] if start_body else name
+    if base == "default_xyz.yaml":          # gain_test.py:180 (arms position-only, osc2 kv 20)
+        return _default(False, 20, start_body)
+    if base == "default_xyz_abg.yaml":      # admit_test.py:85, insertion_task.py:424 (osc2 kv 50)
+        return _default(True, 50, start_body)
+    if base == "iros2022.yaml":
+        return _iros2022()
+    raise KeyError(name)
+
+
+# free bodies each demo scene adds after the robot (scene nv = 25 + 6 * count)
+SCENE_FREE_OBJECTS = {
+    "gain_test_scene.xml": 0,        # gain_test_scene.xml:5-6
+    "admit_test_scene.xml": 2,       # admit_test_scene.xml:14-15
+    "insertion_task_scene.xml": 4,   # insertion_task_scene.xml:10-13
+}

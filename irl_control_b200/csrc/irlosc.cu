@@ -1,0 +1,360 @@
+// C ABI of the batched OSC (include/irlosc.h): parameter validation / flattening,
+// kernel dispatch, and the host-buffer pipeline.  No torch, no Python.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdarg>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+#include "../../include/irlosc.h"
+#include "irlosc_device.cuh"
+#include "osc_generic.cuh"
+#include "osc_tiled.cuh"
+
+using namespace irlosc;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+
+static int32_t fail(int32_t rc, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return rc;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t e_ = (expr);                                                              \
+        if (e_ != cudaSuccess)                                                                \
+            return fail(IRLOSC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                  \
+    } while (0)
+
+extern "C" const char *irlosc_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t irlosc_abi_version(void) { return IRLOSC_ABI_VERSION; }
+
+// ------------------------------------------------------------------ handle
+namespace {
+
+constexpr int kPipeDepth = 3;   // chunks in flight in irlosc_step_host
+
+struct FieldSpec {            // one per-instance array of irlosc_io
+    size_t in_elems;          // doubles per instance to copy host->device (0 = absent)
+    size_t out_elems;         // doubles (or bytes for status) per instance device->host
+};
+
+struct Staging {
+    cudaStream_t stream = nullptr;
+    void *buf[16] = {nullptr};
+    size_t cap[16] = {0};
+};
+
+}  // namespace
+
+struct irlosc_handle {
+    irlosc_params user;
+    KParams kp;
+    int device = 0;
+    int sm_count = 0;
+    int kernel_choice = 0;    // 0 auto, 1 generic, 2 tiled
+    int64_t launches = 0;
+    const char *last_kernel = "none";
+    Staging stage[kPipeDepth];
+    int64_t host_chunk = 8192;
+};
+
+static int32_t build_kparams(const irlosc_params &u, KParams &kp) {
+    memset(&kp, 0, sizeof kp);
+    if (u.abi_version != IRLOSC_ABI_VERSION)
+        return fail(IRLOSC_ERR_INVALID, "abi_version %d, library is %d", u.abi_version, IRLOSC_ABI_VERSION);
+    if (u.n < 1 || u.n > IRLOSC_MAX_N) return fail(IRLOSC_ERR_INVALID, "n=%d outside 1..%d", u.n, IRLOSC_MAX_N);
+    if (u.n_devices < 1 || u.n_devices > IRLOSC_MAX_DEVICES)
+        return fail(IRLOSC_ERR_INVALID, "n_devices=%d outside 1..%d", u.n_devices, IRLOSC_MAX_DEVICES);
+    kp.n = u.n;
+    kp.D = u.n_devices;
+    kp.use_g = u.use_g != 0;
+    kp.admittance = u.admittance != 0;
+    kp.has_nullspace = u.has_nullspace != 0;
+    kp.nullspace_kv = u.nullspace_kv;
+    int row = 0, ctrl = 0;
+    for (int d = 0; d < u.n_devices; ++d) {
+        const irlosc_device_params &s = u.dev[d];
+        KDevice &t = kp.dev[d];
+        t.row0 = row;
+        t.ctrl0 = ctrl;
+        int kd = 0;
+        for (int i = 0; i < 6; ++i) {
+            t.dof[i] = s.ctrlr_dof[i] != 0;
+            if (t.dof[i]) {
+                if (row >= IRLOSC_MAX_K) return fail(IRLOSC_ERR_INVALID, "more than %d task rows", IRLOSC_MAX_K);
+                kp.row_dev[row] = (int8_t)d;
+                kp.row_comp[row] = (int8_t)i;
+                t.dx_idx[kd] = s.dx_idx[kd];
+                if (s.dx_idx[kd] < 0) return fail(IRLOSC_ERR_INVALID, "device %d: negative dx_idx", d);
+                ++row;
+                ++kd;
+            }
+        }
+        t.kdev = kd;
+        t.any_xyz = (t.dof[0] + t.dof[1] + t.dof[2]) > 0;
+        t.any_abg = (t.dof[3] + t.dof[4] + t.dof[5]) > 0;
+        t.has_max_vel = s.has_max_vel != 0;
+        t.max_vel[0] = s.max_vel[0];
+        t.max_vel[1] = s.max_vel[1];
+        t.kp = s.kp; t.kv = s.kv; t.ko = s.ko;
+        if (!(s.kv != 0.0)) return fail(IRLOSC_ERR_INVALID, "device %d: kv must be non-zero", d);
+        for (int i = 0; i < 6; ++i) {
+            t.gain[i] = (i < 3) ? s.kp : s.ko;
+            t.lamb[i] = t.gain[i] / s.kv;
+            t.stiff[i] = (i < 3) ? s.k[i] : 1.0;
+            t.damp[i] = (i < 3) ? s.d[i] : 1.0;
+        }
+        if (s.n_joints_all < 0 || s.n_joints_all > u.n)
+            return fail(IRLOSC_ERR_INVALID, "device %d: n_joints_all=%d", d, s.n_joints_all);
+        t.n_joints_all = s.n_joints_all;
+        for (int i = 0; i < s.n_joints_all; ++i) {
+            const int j = s.joint_ids_all[i];
+            if (j < 0 || j >= u.n) return fail(IRLOSC_ERR_INVALID, "device %d: joint id %d outside 0..%d", d, j, u.n - 1);
+            t.joint_mask |= (1u << j);
+        }
+        if (s.n_ctrl < 0 || s.n_ctrl > u.n) return fail(IRLOSC_ERR_INVALID, "device %d: n_ctrl=%d", d, s.n_ctrl);
+        t.n_ctrl = s.n_ctrl;
+        for (int i = 0; i < s.n_ctrl; ++i) {
+            const int j = s.actuator_trnids[i];
+            if (j < 0 || j >= u.n) return fail(IRLOSC_ERR_INVALID, "device %d: actuator joint %d outside 0..%d", d, j, u.n - 1);
+            t.actuator[i] = (int8_t)j;
+        }
+        ctrl += s.n_ctrl;
+    }
+    if (row < 1) return fail(IRLOSC_ERR_INVALID, "no controlled task rows");
+    if (ctrl < 1 || ctrl > 32) return fail(IRLOSC_ERR_INVALID, "n_ctrl=%d outside 1..32", ctrl);
+    kp.k = row;
+    kp.n_ctrl = ctrl;
+    return IRLOSC_OK;
+}
+
+extern "C" int32_t irlosc_create(const irlosc_params *params, irlosc_handle **out) {
+    if (!params || !out) return fail(IRLOSC_ERR_INVALID, "null argument");
+    *out = nullptr;
+    irlosc_handle *h = new (std::nothrow) irlosc_handle();
+    if (!h) return fail(IRLOSC_ERR_NOMEM, "out of host memory");
+    h->user = *params;
+    int32_t rc = build_kparams(*params, h->kp);
+    if (rc != IRLOSC_OK) { delete h; return rc; }
+    cudaError_t e = cudaGetDevice(&h->device);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail(IRLOSC_ERR_CUDA, "cudaGetDevice failed: %s (is a CUDA device present?)", cudaGetErrorString(e));
+    }
+    e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, h->device);
+    if (e != cudaSuccess) { delete h; return fail(IRLOSC_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e)); }
+    e = cudaFuncSetAttribute(osc_step_generic, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(sizeof(GenericSmem) * kGenericWarps));
+    if (e != cudaSuccess) { delete h; return fail(IRLOSC_ERR_CUDA, "cudaFuncSetAttribute(generic): %s", cudaGetErrorString(e)); }
+    rc = tiled_prepare();
+    if (rc != IRLOSC_OK) { delete h; return fail(IRLOSC_ERR_CUDA, "tiled kernel setup failed"); }
+    *out = h;
+    return IRLOSC_OK;
+}
+
+extern "C" int32_t irlosc_destroy(irlosc_handle *h) {
+    if (!h) return IRLOSC_OK;
+    for (int s = 0; s < kPipeDepth; ++s) {
+        for (int i = 0; i < 16; ++i)
+            if (h->stage[s].buf[i]) cudaFree(h->stage[s].buf[i]);
+        if (h->stage[s].stream) cudaStreamDestroy(h->stage[s].stream);
+    }
+    delete h;
+    return IRLOSC_OK;
+}
+
+extern "C" int32_t irlosc_num_task_rows(const irlosc_handle *h) { return h ? h->kp.k : -1; }
+extern "C" int32_t irlosc_num_ctrl(const irlosc_handle *h) { return h ? h->kp.n_ctrl : -1; }
+extern "C" int64_t irlosc_kernel_launches(const irlosc_handle *h) { return h ? h->launches : -1; }
+extern "C" const char *irlosc_last_kernel(const irlosc_handle *h) { return h ? h->last_kernel : "none"; }
+
+extern "C" int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which) {
+    if (!h || which < 0 || which > 2) return fail(IRLOSC_ERR_INVALID, "kernel selector must be 0, 1 or 2");
+    h->kernel_choice = which;
+    return IRLOSC_OK;
+}
+
+// ------------------------------------------------------------------ step (device pointers)
+static int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k) {
+    const KParams &P = h->kp;
+    if (!io) return fail(IRLOSC_ERR_INVALID, "io is null");
+    if (!io->M || !io->J || !io->dq || !io->ee_xyz || !io->ee_quat || !io->target_xyz || !io->target_quat || !io->ctrl)
+        return fail(IRLOSC_ERR_INVALID, "a required array (M, J, dq, ee_xyz, ee_quat, target_xyz, target_quat, ctrl) is null");
+    if (P.use_g && !io->bias) return fail(IRLOSC_ERR_INVALID, "use_g is set but bias is null");
+    if (P.admittance && (!io->ft_xmat || !io->ft_raw))
+        return fail(IRLOSC_ERR_INVALID, "admittance is set but ft_xmat / ft_raw is null");
+    k.M = io->M; k.m_layout = io->m_layout;
+    if (io->m_layout == IRLOSC_M_DENSE) {
+        k.ldm = io->ldm ? io->ldm : P.n;
+        if (k.ldm < P.n) return fail(IRLOSC_ERR_INVALID, "ldm=%d < n=%d", k.ldm, P.n);
+        k.m_stride = io->m_stride ? io->m_stride : (int64_t)k.ldm * P.n;
+    } else if (io->m_layout == IRLOSC_M_PACKED) {
+        k.ldm = 0;
+        k.m_stride = io->m_stride ? io->m_stride : (int64_t)P.n * (P.n + 1) / 2;
+    } else {
+        return fail(IRLOSC_ERR_INVALID, "unknown m_layout %d", io->m_layout);
+    }
+    k.J = io->J; k.j_layout = io->j_layout;
+    k.ldj = io->ldj ? io->ldj : P.n;
+    if (k.ldj < P.n) return fail(IRLOSC_ERR_INVALID, "ldj=%d < n=%d", k.ldj, P.n);
+    if (io->j_layout == IRLOSC_J_ROWS) k.j_stride = io->j_stride ? io->j_stride : (int64_t)k.ldj * P.k;
+    else if (io->j_layout == IRLOSC_J_FULL6) k.j_stride = io->j_stride ? io->j_stride : (int64_t)k.ldj * 6 * P.D;
+    else return fail(IRLOSC_ERR_INVALID, "unknown j_layout %d", io->j_layout);
+    k.dq = io->dq; k.bias = io->bias; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    k.target_xyz = io->target_xyz; k.target_quat = io->target_quat; k.target_vel = io->target_vel;
+    k.max_vel = io->max_vel; k.ft_xmat = io->ft_xmat; k.ft_raw = io->ft_raw;
+    k.u_all = io->u_all; k.ctrl = io->ctrl; k.status = io->status;
+    return IRLOSC_OK;
+}
+
+static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st) {
+    if (B == 0) return IRLOSC_OK;
+    bool use_tiled = false;
+    if (h->kernel_choice != 1) use_tiled = tiled_supported(h->kp, k);
+    if (h->kernel_choice == 2 && !use_tiled)
+        return fail(IRLOSC_ERR_INVALID, "tiled kernel requested but this shape/layout is not supported (n=%d k=%d)", h->kp.n, h->kp.k);
+    if (use_tiled) {
+        cudaError_t e = tiled_launch(h->kp, k, B, h->sm_count, st, &h->last_kernel);
+        if (e != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "tiled kernel launch: %s", cudaGetErrorString(e));
+    } else {
+        const int64_t blocks_needed = (B + kGenericWarps - 1) / kGenericWarps;
+        const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)h->sm_count * 8);
+        osc_step_generic<<<grid, kGenericWarps * 32, sizeof(GenericSmem) * kGenericWarps, st>>>(h->kp, k, B);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "generic kernel launch: %s", cudaGetErrorString(e));
+        h->last_kernel = "osc_step_generic";
+    }
+    h->launches += 1;
+    return IRLOSC_OK;
+}
+
+extern "C" int32_t irlosc_step(irlosc_handle *h, int64_t B, const irlosc_io *io, void *cuda_stream) {
+    if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
+    if (B < 0) return fail(IRLOSC_ERR_INVALID, "B=%lld is negative", (long long)B);
+    KIo k;
+    int32_t rc = resolve_io(h, io, k);
+    if (rc != IRLOSC_OK) return rc;
+    return launch_step(h, B, k, (cudaStream_t)cuda_stream);
+}
+
+// ------------------------------------------------------------------ calc_error
+__global__ void calc_error_kernel(const KParams P, const double *ee_xyz, const double *ee_quat,
+                                  const double *t_xyz, const double *t_quat, double *err, int64_t total) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int d = (int)(i % P.D);
+    double ee[3], eq[4], tx[3], tq[4], u[6];
+    for (int c = 0; c < 3; ++c) { ee[c] = ee_xyz[i * 3 + c]; tx[c] = t_xyz[i * 3 + c]; }
+    for (int c = 0; c < 4; ++c) { eq[c] = ee_quat[i * 4 + c]; tq[c] = t_quat[i * 4 + c]; }
+    device_pose_error(P.dev[d], ee, eq, tx, tq, u);
+    for (int c = 0; c < 6; ++c) err[i * 6 + c] = u[c];
+}
+
+extern "C" int32_t irlosc_calc_error(irlosc_handle *h, int64_t B, const double *ee_xyz, const double *ee_quat,
+                                     const double *target_xyz, const double *target_quat, double *err,
+                                     void *cuda_stream) {
+    if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
+    if (B < 0) return fail(IRLOSC_ERR_INVALID, "B is negative");
+    if (!ee_xyz || !ee_quat || !target_xyz || !target_quat || !err) return fail(IRLOSC_ERR_INVALID, "null array");
+    if (B == 0) return IRLOSC_OK;
+    const int64_t total = B * h->kp.D;
+    const int threads = 128;
+    calc_error_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)cuda_stream>>>(
+        h->kp, ee_xyz, ee_quat, target_xyz, target_quat, err, total);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "calc_error launch: %s", cudaGetErrorString(e));
+    h->launches += 1;
+    h->last_kernel = "calc_error_kernel";
+    return IRLOSC_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer pipeline
+extern "C" int32_t irlosc_host_alloc(void **ptr, int64_t bytes) {
+    if (!ptr || bytes < 0) return fail(IRLOSC_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaHostAlloc(ptr, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault));
+    return IRLOSC_OK;
+}
+
+extern "C" int32_t irlosc_host_free(void *ptr) {
+    if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+    return IRLOSC_OK;
+}
+
+static int32_t ensure_cap(Staging &s, int slot, size_t bytes) {
+    if (bytes <= s.cap[slot]) return IRLOSC_OK;
+    if (s.buf[slot]) { CUDA_TRY(cudaFree(s.buf[slot])); s.buf[slot] = nullptr; s.cap[slot] = 0; }
+    CUDA_TRY(cudaMalloc(&s.buf[slot], bytes));
+    s.cap[slot] = bytes;
+    return IRLOSC_OK;
+}
+
+extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io *io) {
+    if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
+    if (B < 0) return fail(IRLOSC_ERR_INVALID, "B is negative");
+    KIo hk;   // host-pointer view with resolved strides
+    int32_t rc = resolve_io(h, io, hk);
+    if (rc != IRLOSC_OK) return rc;
+    if (B == 0) return IRLOSC_OK;
+    const KParams &P = h->kp;
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int s = 0; s < kPipeDepth; ++s)
+        if (!h->stage[s].stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->stage[s].stream, cudaStreamNonBlocking));
+
+    // per-instance element counts of every array, in the slot order used below
+    const size_t D = P.D, n = P.n;
+    struct In { const double *src; size_t per; } ins[12] = {
+        {hk.M, (size_t)hk.m_stride}, {hk.J, (size_t)hk.j_stride}, {hk.dq, n}, {hk.bias, n},
+        {hk.ee_xyz, 3 * D}, {hk.ee_quat, 4 * D}, {hk.target_xyz, 3 * D}, {hk.target_quat, 4 * D},
+        {hk.target_vel, 6 * D}, {hk.max_vel, 2 * D}, {hk.ft_xmat, 9 * D}, {hk.ft_raw, 6 * D}};
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->host_chunk, B));
+    int turn = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += chunk, ++turn) {
+        const int64_t nb = std::min<int64_t>(chunk, B - b0);
+        Staging &S = h->stage[turn % kPipeDepth];
+        const double *dptr[12];
+        for (int i = 0; i < 12; ++i) {
+            dptr[i] = nullptr;
+            if (!ins[i].src) continue;
+            const size_t bytes = ins[i].per * (size_t)nb * sizeof(double);
+            rc = ensure_cap(S, i, ins[i].per * (size_t)chunk * sizeof(double));
+            if (rc != IRLOSC_OK) return rc;
+            CUDA_TRY(cudaMemcpyAsync(S.buf[i], ins[i].src + ins[i].per * (size_t)b0, bytes,
+                                     cudaMemcpyHostToDevice, S.stream));
+            dptr[i] = (const double *)S.buf[i];
+        }
+        rc = ensure_cap(S, 12, (size_t)chunk * P.n_ctrl * sizeof(double));
+        if (rc == IRLOSC_OK && hk.u_all) rc = ensure_cap(S, 13, (size_t)chunk * n * sizeof(double));
+        if (rc == IRLOSC_OK && hk.status) rc = ensure_cap(S, 14, (size_t)chunk);
+        if (rc != IRLOSC_OK) return rc;
+        KIo dk = hk;
+        dk.M = dptr[0]; dk.J = dptr[1]; dk.dq = dptr[2]; dk.bias = dptr[3];
+        dk.ee_xyz = dptr[4]; dk.ee_quat = dptr[5]; dk.target_xyz = dptr[6]; dk.target_quat = dptr[7];
+        dk.target_vel = dptr[8]; dk.max_vel = dptr[9]; dk.ft_xmat = dptr[10]; dk.ft_raw = dptr[11];
+        dk.ctrl = (double *)S.buf[12];
+        dk.u_all = hk.u_all ? (double *)S.buf[13] : nullptr;
+        dk.status = hk.status ? (uint8_t *)S.buf[14] : nullptr;
+        rc = launch_step(h, nb, dk, S.stream);
+        if (rc != IRLOSC_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(hk.ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
+                                 cudaMemcpyDeviceToHost, S.stream));
+        if (hk.u_all)
+            CUDA_TRY(cudaMemcpyAsync(hk.u_all + (size_t)b0 * n, dk.u_all, (size_t)nb * n * sizeof(double),
+                                     cudaMemcpyDeviceToHost, S.stream));
+        if (hk.status)
+            CUDA_TRY(cudaMemcpyAsync(hk.status + b0, dk.status, (size_t)nb, cudaMemcpyDeviceToHost, S.stream));
+    }
+    for (int s = 0; s < kPipeDepth; ++s) CUDA_TRY(cudaStreamSynchronize(h->stage[s].stream));
+    return IRLOSC_OK;
+}

@@ -1,0 +1,232 @@
+"""`BatchedOSC` - Python face of one `irlosc_handle` (include/irlosc.h).
+
+Evaluates the reference's `OSC.generate` control law (osc.py:120-210) for B
+independent robot instances per call:
+
+    step(...)       state already in GPU memory (torch CUDA tensors, float64);
+                    asynchronous on the current torch stream, returns tensors
+    step_host(...)  state in host memory (numpy arrays); host->device copies,
+                    kernel and device->host copies are pipelined in chunks
+                    inside the library; returns numpy arrays
+
+Field names follow the reference's state enums: M, J, DQ (RobotState,
+robot.py:11-14), EE_XYZ, EE_QUAT (DeviceState, device.py:7-18), qfrc_bias
+(osc.py:191), plus the Target fields (utils.py:5-67).  Per-device arrays are
+indexed in TARGET order.
+
+torch is used for device memory and streams only; all arithmetic happens in
+the CUDA library.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _native
+from .layout import OscLayout
+
+_OPTIONAL = ("bias", "target_vel", "max_vel", "ft_xmat", "ft_raw")
+_FIELDS = ("M", "J", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat",
+           "target_vel", "max_vel", "ft_xmat", "ft_raw")
+
+
+class BatchedOSC:
+    def __init__(self, layout: OscLayout, device: Optional[int] = None):
+        self.layout = layout
+        self.lib = _native.load()
+        self._handle = C.c_void_p()
+        self._torch_device = None
+        if device is not None:
+            import torch
+            torch.cuda.set_device(device)
+            self._torch_device = torch.device("cuda", device)
+        params = layout.to_c_params()
+        _native.check(self.lib.irlosc_create(C.byref(params), C.byref(self._handle)))
+        self.n = layout.n
+        self.D = layout.D
+        self.k = self.lib.irlosc_num_task_rows(self._handle)
+        self.n_ctrl = self.lib.irlosc_num_ctrl(self._handle)
+        assert self.k == layout.k and self.n_ctrl == layout.n_ctrl
+
+    # ------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_handle", None) is not None and self._handle.value:
+            self.lib.irlosc_destroy(self._handle)
+            self._handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_kernel(self, which: int):
+        _native.check(self.lib.irlosc_set_kernel(self._handle, int(which)))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.irlosc_kernel_launches(self._handle))
+
+    @property
+    def last_kernel(self) -> str:
+        return self.lib.irlosc_last_kernel(self._handle).decode()
+
+    # ------------------------------------------------------------------
+    def _shapes(self, B: int, m_layout: int, j_layout: int) -> Dict[str, tuple]:
+        n, D, k = self.n, self.D, self.k
+        return {
+            "M": (B, n, n) if m_layout == _native.M_DENSE else (B, n * (n + 1) // 2),
+            "J": (B, k, n) if j_layout == _native.J_ROWS else (B, D, 6, n),
+            "dq": (B, n), "bias": (B, n),
+            "ee_xyz": (B, D, 3), "ee_quat": (B, D, 4),
+            "target_xyz": (B, D, 3), "target_quat": (B, D, 4),
+            "target_vel": (B, D, 6), "max_vel": (B, D, 2),
+            "ft_xmat": (B, D, 9), "ft_raw": (B, D, 6),
+        }
+
+    def _infer_layouts(self, state):
+        M, J = state["M"], state["J"]
+        m_layout = _native.M_DENSE if len(M.shape) == 3 else _native.M_PACKED
+        j_layout = _native.J_FULL6 if len(J.shape) == 4 else _native.J_ROWS
+        return m_layout, j_layout
+
+    def _check(self, state, B, shapes, is_ok):
+        for name in _FIELDS:
+            arr = state.get(name)
+            if arr is None:
+                if name in _OPTIONAL:
+                    continue
+                raise ValueError("state['%s'] is required" % name)
+            want = shapes[name]
+            got = tuple(arr.shape)
+            if name == "ft_xmat" and got == (B, self.D, 3, 3):
+                got = want
+            if got != want:
+                raise ValueError("state['%s'] has shape %s, expected %s" % (name, got, want))
+            is_ok(name, arr)
+        if self.layout.use_g and state.get("bias") is None:
+            raise ValueError("use_g is set: state['bias'] (qfrc_bias) is required")
+        if self.layout.admittance and (state.get("ft_xmat") is None or state.get("ft_raw") is None):
+            raise ValueError("admittance is set: state['ft_xmat'] and state['ft_raw'] are required")
+
+    # ------------------------------------------------------------------
+    def step(self, state: Dict, out: Optional[Dict] = None, want_u_all: bool = False,
+             want_status: bool = True) -> Dict:
+        """One control step for B instances resident on the GPU.
+
+        state : dict of CUDA float64 contiguous tensors (see module docstring)
+        out   : optional preallocated {"ctrl", "u_all", "status"} tensors
+        """
+        import torch
+        M = state["M"]
+        if not M.is_cuda:
+            raise ValueError("BatchedOSC.step expects CUDA tensors; use step_host for host arrays")
+        B = int(M.shape[0])
+        m_layout, j_layout = self._infer_layouts(state)
+        shapes = self._shapes(B, m_layout, j_layout)
+
+        def ok(name, t):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device == M.device):
+                raise ValueError("state['%s'] must be a contiguous float64 CUDA tensor on %s" % (name, M.device))
+        self._check(state, B, shapes, ok)
+        out = {} if out is None else out
+        if "ctrl" not in out:
+            out["ctrl"] = torch.empty(B, self.n_ctrl, dtype=torch.float64, device=M.device)
+        if want_u_all and "u_all" not in out:
+            out["u_all"] = torch.empty(B, self.n, dtype=torch.float64, device=M.device)
+        if want_status and "status" not in out:
+            out["status"] = torch.empty(B, dtype=torch.uint8, device=M.device)
+        io = _native.Io()
+        io.m_layout, io.j_layout = m_layout, j_layout
+        for name in _FIELDS:
+            t = state.get(name)
+            setattr(io, name, t.data_ptr() if t is not None else None)
+        io.ctrl = out["ctrl"].data_ptr()
+        io.u_all = out["u_all"].data_ptr() if "u_all" in out else None
+        io.status = out["status"].data_ptr() if "status" in out else None
+        stream = torch.cuda.current_stream(M.device).cuda_stream
+        with torch.cuda.device(M.device):
+            _native.check(self.lib.irlosc_step(self._handle, B, C.byref(io), C.c_void_p(stream)))
+        return out
+
+    def step_host(self, state: Dict, out: Optional[Dict] = None, want_u_all: bool = False,
+                  want_status: bool = True) -> Dict:
+        """Same step with HOST numpy arrays (float64, C-contiguous); blocks until results are valid."""
+        M = state["M"]
+        B = int(M.shape[0])
+        m_layout, j_layout = self._infer_layouts(state)
+        shapes = self._shapes(B, m_layout, j_layout)
+
+        def ok(name, a):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("state['%s'] must be a C-contiguous float64 numpy array" % name)
+        self._check(state, B, shapes, ok)
+        out = {} if out is None else out
+        if "ctrl" not in out:
+            out["ctrl"] = np.empty((B, self.n_ctrl), dtype=np.float64)
+        if want_u_all and "u_all" not in out:
+            out["u_all"] = np.empty((B, self.n), dtype=np.float64)
+        if want_status and "status" not in out:
+            out["status"] = np.empty((B,), dtype=np.uint8)
+        io = _native.Io()
+        io.m_layout, io.j_layout = m_layout, j_layout
+        for name in _FIELDS:
+            a = state.get(name)
+            setattr(io, name, a.ctypes.data if a is not None else None)
+        io.ctrl = out["ctrl"].ctypes.data
+        io.u_all = out["u_all"].ctypes.data if "u_all" in out else None
+        io.status = out["status"].ctypes.data if "status" in out else None
+        if self._torch_device is not None:
+            import torch
+            with torch.cuda.device(self._torch_device):
+                _native.check(self.lib.irlosc_step_host(self._handle, B, C.byref(io)))
+        else:
+            _native.check(self.lib.irlosc_step_host(self._handle, B, C.byref(io)))
+        return out
+
+    def calc_error(self, ee_xyz, ee_quat, target_xyz, target_quat):
+        """Batched `OSC.calc_error` (osc.py:101-118) on CUDA tensors -> (B, D, 6)."""
+        import torch
+        B = int(ee_xyz.shape[0])
+        err = torch.empty(B, self.D, 6, dtype=torch.float64, device=ee_xyz.device)
+        stream = torch.cuda.current_stream(ee_xyz.device).cuda_stream
+        with torch.cuda.device(ee_xyz.device):
+            _native.check(self.lib.irlosc_calc_error(
+                self._handle, B, ee_xyz.data_ptr(), ee_quat.data_ptr(), target_xyz.data_ptr(),
+                target_quat.data_ptr(), err.data_ptr(), C.c_void_p(stream)))
+        return err
+
+
+def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
+    """numpy array backed by pinned host memory from `irlosc_host_alloc` (kept alive by the array)."""
+    lib = _native.load()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    ptr = C.c_void_p()
+    _native.check(lib.irlosc_host_alloc(C.byref(ptr), nbytes))
+    buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
+
+    class _Owner:
+        def __init__(self, p):
+            self.p = p
+
+        def __del__(self):
+            try:
+                lib.irlosc_host_free(self.p)
+            except Exception:
+                pass
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    owner = _Owner(ptr)
+    # tie lifetime of the pinned block to the array
+    holder = np.ndarray.__new__(_PinnedArray, shape, dtype, buffer=buf)
+    holder._owner = owner
+    return holder
+
+
+class _PinnedArray(np.ndarray):
+    _owner = None
+
+    def __array_finalize__(self, obj):
+        if obj is not None and getattr(obj, "_owner", None) is not None:
+            self._owner = obj._owner

@@ -1,0 +1,147 @@
+"""Flattening of `Device` / `Robot` / `OSC` configuration into index tables.
+
+Everything the reference resolves in its constructors - joint chains and
+actuator maps (`device.py:41-74`), the robot joint set (`robot.py:26-32`), the
+gain vectors (`osc.py:35-39`) - plus the target order chosen by the caller of
+`generate` (`osc.py:136-138,156`) is reduced to one small, immutable
+description.  It is handed to the CUDA library as `irlosc_params`
+(include/irlosc.h) and, as a plain dict, to the test oracle.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _native
+
+
+@dataclass(frozen=True)
+class DeviceLayout:
+    name: str
+    ctrlr_dof: tuple            # 6 bools, xyz then abg (device.py:36)
+    joint_ids_all: tuple        # robot-local (robot.py:64 uses the global ids as local ones)
+    actuator_trnids: tuple      # robot-local joints returned by generate (osc.py:207)
+    ctrl_idxs: tuple            # sim.data.ctrl slots those forces go to (osc.py:208)
+    dx_idx: tuple               # Robot J_idxs[name] in SUB-DEVICE order (robot.py:52-55)
+    has_max_vel: bool
+    max_vel: tuple
+    kp: float
+    kv: float
+    ko: float
+    k: tuple
+    d: tuple
+
+    @property
+    def n_rows(self) -> int:
+        return int(sum(bool(x) for x in self.ctrlr_dof))
+
+
+@dataclass(frozen=True)
+class OscLayout:
+    n: int
+    devices: tuple              # DeviceLayout, TARGET order
+    use_g: bool = True
+    admittance: bool = False
+    nullspace_kv: Optional[float] = None
+
+    @property
+    def D(self) -> int:
+        return len(self.devices)
+
+    @property
+    def k(self) -> int:
+        return sum(d.n_rows for d in self.devices)
+
+    @property
+    def n_ctrl(self) -> int:
+        return sum(len(d.actuator_trnids) for d in self.devices)
+
+    @property
+    def ctrl_slices(self) -> List[slice]:
+        out, at = [], 0
+        for d in self.devices:
+            out.append(slice(at, at + len(d.actuator_trnids)))
+            at += len(d.actuator_trnids)
+        return out
+
+    def as_dict(self) -> Dict:
+        return {
+            "n": self.n, "use_g": self.use_g, "admittance": self.admittance,
+            "nullspace_kv": self.nullspace_kv,
+            "devices": [{
+                "name": d.name, "ctrlr_dof": list(d.ctrlr_dof), "joint_ids_all": list(d.joint_ids_all),
+                "actuator_trnids": list(d.actuator_trnids), "ctrl_idxs": list(d.ctrl_idxs),
+                "dx_idx": list(d.dx_idx), "has_max_vel": d.has_max_vel, "max_vel": list(d.max_vel),
+                "kp": d.kp, "kv": d.kv, "ko": d.ko, "k": list(d.k), "d": list(d.d),
+            } for d in self.devices],
+        }
+
+    def to_c_params(self) -> "_native.Params":
+        if self.D > _native.MAX_DEVICES:
+            raise ValueError("at most %d target devices are supported" % _native.MAX_DEVICES)
+        p = _native.Params()
+        p.abi_version = _native.ABI_VERSION
+        p.n = self.n
+        p.n_devices = self.D
+        p.use_g = int(self.use_g)
+        p.admittance = int(self.admittance)
+        p.has_nullspace = int(self.nullspace_kv is not None)
+        p.nullspace_kv = float(self.nullspace_kv or 0.0)
+        for i, d in enumerate(self.devices):
+            c = p.dev[i]
+            for j in range(6):
+                c.ctrlr_dof[j] = int(bool(d.ctrlr_dof[j]))
+            c.n_joints_all = len(d.joint_ids_all)
+            for j, v in enumerate(d.joint_ids_all):
+                c.joint_ids_all[j] = int(v)
+            c.n_ctrl = len(d.actuator_trnids)
+            for j, v in enumerate(d.actuator_trnids):
+                c.actuator_trnids[j] = int(v)
+            for j, v in enumerate(d.dx_idx):
+                c.dx_idx[j] = int(v)
+            c.has_max_vel = int(d.has_max_vel)
+            c.max_vel[0], c.max_vel[1] = (float(d.max_vel[0]), float(d.max_vel[1])) if d.has_max_vel else (0.0, 0.0)
+            c.kp, c.kv, c.ko = float(d.kp), float(d.kv), float(d.ko)
+            for j in range(3):
+                c.k[j] = float(d.k[j])
+                c.d[j] = float(d.d[j])
+        return p
+
+
+def compile_layout(robot, device_configs: Dict[str, Dict], target_names: Sequence[str],
+                   nullspace_config: Optional[Dict], use_g: bool, admittance: bool) -> OscLayout:
+    """Build the layout for one target order.
+
+    robot          : a `Robot` (ours or anything with sub_devices_dict / joint_ids_all)
+    device_configs : device name -> controller config dict with kp, kv, ko, k, d
+    """
+    local = {int(g): i for i, g in enumerate(robot.joint_ids_all)}
+    # J_idxs as Robot.jacobians numbers them: every sub-device, construction order
+    j_idxs, row = {}, 0
+    for name, dev in robot.sub_devices_dict.items():
+        rows = int(np.sum(dev.ctrlr_dof))
+        j_idxs[name] = tuple(range(row, row + rows))
+        row += rows
+    devs = []
+    for name in target_names:
+        dev = robot.sub_devices_dict[name]          # KeyError for unknown names, as the reference
+        cfg = device_configs[name]
+        mv = dev.max_vel
+        devs.append(DeviceLayout(
+            name=name,
+            ctrlr_dof=tuple(bool(x) for x in dev.ctrlr_dof),
+            joint_ids_all=tuple(local[int(g)] for g in dev.joint_ids_all),
+            actuator_trnids=tuple(local[int(g)] for g in dev.actuator_trnids),
+            ctrl_idxs=tuple(int(x) for x in dev.ctrl_idxs),
+            dx_idx=j_idxs[name],
+            has_max_vel=mv is not None,
+            max_vel=(float(mv[0]), float(mv[1])) if mv is not None else (0.0, 0.0),
+            kp=float(cfg['kp']), kv=float(cfg['kv']), ko=float(cfg['ko']),
+            k=tuple(float(x) for x in cfg['k']), d=tuple(float(x) for x in cfg['d']),
+        ))
+    return OscLayout(
+        n=int(robot.num_joints_total), devices=tuple(devs), use_g=bool(use_g),
+        admittance=bool(admittance),
+        nullspace_kv=None if nullspace_config is None else float(nullspace_config['kv']))

@@ -1,0 +1,77 @@
+"""`MujocoApp` - base class of the demo applications (reference: mujoco_app.py:10-63).
+
+Same constructor and helper methods.  The simulator behind `self.sim` is
+pluggable: the reference hard-wires `mujoco_py.MjSim`; here a `sim_factory`
+may be injected, and the default is `SyntheticSim` (no MuJoCo in this image).
+Scene XML files are not parsed - a scene name only selects how many free
+bodies follow the robot (`configs.SCENE_FREE_OBJECTS`).
+"""
+import os
+import time
+from typing import Callable, Dict, Optional
+
+import numpy as np
+import yaml
+
+from . import configs
+from .device import Device
+from .dual_ur5 import DualUR5Model
+from .robot import Robot
+from .sim import SyntheticSim
+
+
+class MujocoApp:
+    def __init__(self, robot_config_file: str = None, scene_file: str = None, use_sim: bool = True,
+                 sim_factory: Optional[Callable[[str], object]] = None):
+        self.config = self._load_config(robot_config_file)
+        if sim_factory is not None:
+            self.sim = sim_factory(scene_file)
+        else:
+            n_free = configs.SCENE_FREE_OBJECTS.get(os.path.basename(scene_file or ""), 0)
+            self.sim = SyntheticSim(DualUR5Model(n_free_objects=n_free))
+        self.model = self.sim.model
+        self.devices = np.array([Device(dev, self.model, self.sim, use_sim) for dev in self.config['devices']])
+        self.create_robot_devices(self.config['robots'], use_sim)
+        self.controller_configs = self.config['controller_configs']
+        self.timer_running = False
+
+    @staticmethod
+    def _load_config(robot_config_file: str) -> Dict:
+        if robot_config_file is not None and os.path.isfile(robot_config_file):
+            with open(robot_config_file, 'r') as fh:
+                return yaml.safe_load(fh)
+        return configs.robot_config(robot_config_file)
+
+    def create_robot_devices(self, robot_yml, use_sim: bool):
+        """Replace the devices listed under each robot entry by one `Robot` (mujoco_app.py:24-35)."""
+        robots, grouped = [], []
+        for entry in robot_yml:
+            ids = list(entry['device_ids'])
+            grouped += ids
+            robots.append(Robot(list(self.devices[ids]), entry['name'], self.sim, use_sim))
+        loose = [self.devices[i] for i in range(len(self.devices)) if i not in set(grouped)]
+        self.devices = np.array(loose + robots, dtype=object)
+
+    def sleep_for(self, sleep_time: float):
+        assert self.timer_running == False  # noqa: E712 (same contract as the reference)
+        self.timer_running = True
+        time.sleep(sleep_time)
+        self.timer_running = False
+
+    def get_robot(self, robot_name: str) -> Robot:
+        for item in self.devices:
+            if type(item) == Robot and item.name == robot_name:
+                return item
+
+    def get_controller_config(self, name: str) -> Dict:
+        for entry in self.config['controller_configs']:
+            if entry['name'] == name:
+                return entry
+
+    def set_free_joint_qpos(self, free_joint_name, quat=None, pos=None):
+        jnt_id = self.sim.model.joint_name2id(free_joint_name)
+        offset = self.sim.model.jnt_qposadr[jnt_id]
+        if quat is not None:
+            self.sim.data.qpos[offset + 3:offset + 7] = quat
+        if pos is not None:
+            self.sim.data.qpos[offset:offset + 3] = pos

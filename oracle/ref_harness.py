@@ -1,0 +1,264 @@
+"""TEST INFRASTRUCTURE ONLY - run the UNMODIFIED reference OSC against a fake sim.
+
+Imports `irl_control/{device,robot,osc,utils}.py` straight from
+/root/reference (read-only, never copied) after registering stub modules for
+the two third-party packages those files import and that do not exist in this
+image:
+
+    mujoco_py      (osc.py:3, robot.py:3)  -> only `cymj._mj_fullM` is called
+                                              (robot.py:69); `load_model_from_path`
+                                              / `MjSim` are import-time names
+                                              for mujoco_app.py:2
+    transforms3d   (osc.py:4-7, utils.py:3) -> oracle/t3d.py
+
+`FakeSim` serves one robot instance's state from arrays, exposing exactly the
+`sim.model` / `sim.data` accessors the reference touches.
+This module only works where /root/reference exists (this container); it is
+used by tests/golden/make_golden.py and by tests that are skipped elsewhere.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import yaml
+
+REFERENCE_ROOT = os.environ.get("IRL_REFERENCE_ROOT", "/root/reference")
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "irl_control", "osc.py"))
+
+
+def _install_stubs():
+    from . import t3d
+    if "mujoco_py" not in sys.modules:
+        mjp = types.ModuleType("mujoco_py")
+        cymj = types.ModuleType("mujoco_py.cymj")
+
+        def _mj_fullM(model, dst, qM):
+            dst[:] = np.asarray(qM).reshape(-1)
+
+        cymj._mj_fullM = _mj_fullM
+        mjp.cymj = cymj
+        mjp.load_model_from_path = lambda *a, **k: (_ for _ in ()).throw(
+            RuntimeError("mujoco_py stub: no simulator in this image"))
+        mjp.MjSim = object
+        sys.modules["mujoco_py"] = mjp
+        sys.modules["mujoco_py.cymj"] = cymj
+    if "transforms3d" not in sys.modules:
+        pkg = types.ModuleType("transforms3d")
+        der = types.ModuleType("transforms3d.derivations")
+        derq = types.ModuleType("transforms3d.derivations.quaternions")
+        derq.qmult = t3d.qmult
+        qs = types.ModuleType("transforms3d.quaternions")
+        qs.qconjugate = t3d.qconjugate
+        qs.qmult = lambda a, b: np.array(t3d.qmult(a, b))
+        qs.quat2mat = t3d.quat2mat
+        eu = types.ModuleType("transforms3d.euler")
+        eu.quat2euler = t3d.quat2euler
+        eu.euler2quat = t3d.euler2quat
+        eu.mat2euler = t3d.mat2euler
+        eu.euler2mat = t3d.euler2mat
+        eu.quat2mat = t3d.quat2mat
+        ut = types.ModuleType("transforms3d.utils")
+        ut.normalized_vector = t3d.normalized_vector
+        pkg.derivations, pkg.quaternions, pkg.euler, pkg.utils = der, qs, eu, ut
+        der.quaternions = derq
+        for name, mod in [("transforms3d", pkg), ("transforms3d.derivations", der),
+                          ("transforms3d.derivations.quaternions", derq),
+                          ("transforms3d.quaternions", qs), ("transforms3d.euler", eu),
+                          ("transforms3d.utils", ut)]:
+            sys.modules[name] = mod
+
+
+def import_reference():
+    """Returns the reference's (Device, Robot, OSC, Target, DeviceState, RobotState) classes."""
+    if not reference_available():
+        raise RuntimeError("reference sources not found under %s" % REFERENCE_ROOT)
+    _install_stubs()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    import irl_control  # noqa: F401  (pulls device, robot, osc, mujoco_app)
+    from irl_control.device import Device, DeviceState
+    from irl_control.robot import Robot, RobotState
+    from irl_control.osc import OSC
+    from irl_control.utils import Target
+    return Device, Robot, OSC, Target, DeviceState, RobotState
+
+
+def load_reference_yaml(name: str, inject_start_body: bool = True) -> Dict:
+    """Reads robot_configs/<name> from the reference.  SURVEY.md N1: the default
+    YAMLs comment out `start_body`, which makes `Device.__init__` fail for the
+    arms (7 joints vs 6 start angles); `inject_start_body` restores the
+    `iros2022.yaml:13,22` setting so the DualUR5 can be constructed."""
+    path = os.path.join(REFERENCE_ROOT, "irl_control", "robot_configs", name)
+    with open(path, "r") as fh:
+        cfg = yaml.safe_load(fh)
+    if inject_start_body:
+        for dev in cfg["devices"]:
+            if dev["name"] in ("ur5right", "ur5left"):
+                dev.setdefault("start_body", "dual_ur_stand")
+    return cfg
+
+
+class _FakeData:
+    def __init__(self, model):
+        self._model = model
+        self.qpos = np.zeros(model.nq)
+        self.qvel = np.zeros(model.nv)
+        self.qacc = np.zeros(model.nv)
+        self.qM = np.eye(model.nv).reshape(-1)
+        self.qfrc_bias = np.zeros(model.nv)
+        self.sensordata = np.zeros(model.nsensordata)
+        self.ctrl = np.zeros(model.nu)
+        self.xpos: Dict[str, np.ndarray] = {}
+        self.xquat: Dict[str, np.ndarray] = {}
+        self.xvelp: Dict[str, np.ndarray] = {}
+        self.jacp: Dict[str, np.ndarray] = {}
+        self.jacr: Dict[str, np.ndarray] = {}
+        self.site_xmat: Dict[str, np.ndarray] = {}
+
+    def get_body_xpos(self, name):
+        return self.xpos[name]
+
+    def get_body_xquat(self, name):
+        return self.xquat[name]
+
+    def get_body_xvelp(self, name):
+        return self.xvelp.get(name, np.zeros(3))
+
+    def get_body_jacp(self, name):
+        return self.jacp[name].reshape(-1)
+
+    def get_body_jacr(self, name):
+        return self.jacr[name].reshape(-1)
+
+    def get_site_xmat(self, name):
+        return self.site_xmat[name]
+
+
+class FakeSim:
+    """`sim` with `.model` and `.data`; state is loaded from arrays."""
+
+    def __init__(self, model):
+        self.model = model
+        self.data = _FakeData(model)
+
+    def forward(self):
+        pass
+
+    def load_instance(self, st: Dict[str, np.ndarray], target_names: Sequence[str], devices):
+        """st holds ONE instance with per-device arrays in TARGET order:
+        M (n,n), J6 (D,6,n), dq (n), bias (n), ee_xyz (D,3), ee_quat (D,4),
+        ft_xmat (D,9), ft_raw (D,6).  Sub-devices that are not targeted still get
+        pulled by `Robot.get_all_states` (robot.py:130-131); they are served zeros,
+        which cannot reach the output (their Jacobian is never stacked, osc.py:137-138)."""
+        m, d = self.model, self.data
+        n, nv = m.nv_robot, m.nv
+        Mfull = np.eye(nv) * 0.05
+        Mfull[:n, :n] = st["M"]
+        d.qM = Mfull.reshape(-1)
+        d.qvel[:] = 0.0
+        d.qvel[:n] = st["dq"]
+        d.qfrc_bias[:] = 0.0
+        d.qfrc_bias[:n] = st["bias"]
+        d.sensordata[:] = 0.0
+        slices = {"ur5right": 0, "ur5left": 6}      # dual_ur5.xml:289-293 via device.py:150-167
+        for dev in devices:
+            body = dev.EE
+            jp = np.zeros((3, nv))
+            jr = np.zeros((3, nv))
+            d.xpos[body] = np.zeros(3)
+            d.xquat[body] = np.array([1.0, 0.0, 0.0, 0.0])
+            if dev.name in slices:
+                d.site_xmat["ft_frame_" + dev.name] = np.eye(3)
+            if dev.name in target_names:
+                i = list(target_names).index(dev.name)
+                jp[:, :n] = st["J6"][i, :3]
+                jr[:, :n] = st["J6"][i, 3:]
+                d.xpos[body] = np.asarray(st["ee_xyz"][i], dtype=np.float64)
+                d.xquat[body] = np.asarray(st["ee_quat"][i], dtype=np.float64)
+                if dev.name in slices:
+                    d.site_xmat["ft_frame_" + dev.name] = np.asarray(st["ft_xmat"][i]).reshape(3, 3)
+                    o = slices[dev.name]
+                    d.sensordata[o:o + 6] = st["ft_raw"][i]
+            d.jacp[body], d.jacr[body] = jp, jr
+
+
+class ReferenceRunner:
+    """Builds the reference's Device/Robot/OSC once and evaluates `OSC.generate`
+    instance by instance on supplied state arrays."""
+
+    def __init__(self, model, robot_cfg: Dict, osc_device_cfgs: Sequence, target_names: Sequence[str],
+                 nullspace_cfg: Optional[Dict], use_g: bool = True, admittance: bool = False):
+        Device, Robot, OSC, Target, DeviceState, RobotState = import_reference()
+        self.Target = Target
+        self.sim = FakeSim(model)
+        self.devices = [Device(d, model, self.sim, True) for d in robot_cfg["devices"]]
+        ids = robot_cfg["robots"][0]["device_ids"]
+        self.robot = Robot([self.devices[i] for i in ids], robot_cfg["robots"][0]["name"], self.sim, True)
+        cfg_by_name = {c["name"]: c for c in robot_cfg["controller_configs"]}
+        # the reference mutates these dicts (osc.py:38-39): give it private copies
+        dev_cfgs = [(name, dict(cfg_by_name[cfg_name])) for name, cfg_name in osc_device_cfgs]
+        ns = dict(cfg_by_name[nullspace_cfg]) if nullspace_cfg else None
+        self.osc = OSC(self.robot, self.sim, dev_cfgs, ns, use_g=use_g, admittance=admittance)
+        self.target_names = list(target_names)
+        self.n = self.robot.num_joints_total
+
+    def run(self, st: Dict[str, np.ndarray], tgt_xyz, tgt_quat, tgt_vel=None, max_vel=None):
+        """tgt_*: arrays indexed like `target_names`.  Returns dict with the packed forces
+        (list per target), ctrl index lists, the full joint vector u_all and the branch flag."""
+        self.sim.load_instance(st, self.target_names, self.devices)
+        targets = {}
+        for i, name in enumerate(self.target_names):
+            t = self.Target()
+            t.set_xyz(np.array(tgt_xyz[i], dtype=np.float64))
+            t.set_quat(np.array(tgt_quat[i], dtype=np.float64))
+            if tgt_vel is not None:
+                t.set_xyz_vel(np.array(tgt_vel[i][:3], dtype=np.float64))
+                t.set_abg_vel(np.array(tgt_vel[i][3:], dtype=np.float64))
+            targets[name] = t
+            if max_vel is not None:
+                self.robot.get_device(name).max_vel = [float(max_vel[i][0]), float(max_vel[i][1])]
+        calls = {"pinv": 0}
+        real_pinv = np.linalg.pinv
+
+        def counting_pinv(*a, **k):
+            calls["pinv"] += 1
+            return real_pinv(*a, **k)
+
+        np.linalg.pinv = counting_pinv
+        try:
+            idxs, forces = self.osc.generate(targets)
+            # second pass with every joint "actuated" to expose the internal u_all
+            saved = {}
+            first = self.target_names[0]
+            dev0 = self.robot.get_device(first)
+            saved = dev0.actuator_trnids
+            dev0.actuator_trnids = np.arange(self.n)
+            try:
+                _, full = self.osc.generate(targets)
+            finally:
+                dev0.actuator_trnids = saved
+        finally:
+            np.linalg.pinv = real_pinv
+        return {
+            "ctrl_idxs": [np.asarray(i) for i in idxs],
+            "forces": [np.asarray(f, dtype=np.float64) for f in forces],
+            "u_all": np.asarray(full[0], dtype=np.float64),
+            "pinv": calls["pinv"] > 0,
+            # what osc.py:172 actually sees: abg_vel goes Euler -> quaternion -> Euler inside Target
+            "target_vel_seen": np.stack([np.hstack([targets[nm].get_xyz_vel(), targets[nm].get_abg_vel()])
+                                         for nm in self.target_names]),
+        }
+
+    def calc_error(self, st, name, tgt_xyz, tgt_quat):
+        self.sim.load_instance(st, self.target_names, self.devices)
+        t = self.Target()
+        t.set_xyz(np.array(tgt_xyz, dtype=np.float64))
+        t.set_quat(np.array(tgt_quat, dtype=np.float64))
+        return self.osc.calc_error(t, self.robot.get_device(name))

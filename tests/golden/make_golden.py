@@ -1,0 +1,130 @@
+#!/usr/bin/env python3
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference `OSC.generate`.
+
+Run in the build container (needs /root/reference; the GPU box does not have it):
+
+    python tests/golden/make_golden.py
+
+For every scenario of SURVEY.md section 8 (gain_test, admit_test, insertion,
+worst_case k = 13) plus the quirk cases (non-zero target velocity N3/N4,
+near-singular start pose N2, per-instance max_vel schedule) it draws seeded
+states with `irl_control_b200.synthetic.synth_batch`, feeds each instance to
+the reference's own Device / Robot / OSC classes through oracle/ref_harness.py
+(stub mujoco_py / transforms3d, fake sim) and stores inputs + outputs:
+
+    inputs : M, J6, dq, bias, ee_xyz, ee_quat, ft_xmat, ft_raw, target_xyz,
+             target_quat, target_vel, max_vel            (per-device arrays in target order)
+    outputs: ctrl (packed forces, target order), u_all (n), pinv (branch flag)
+    meta   : layout_json (the flattened controller description), scenario, seed
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from irl_control_b200.dual_ur5 import DualUR5Model  # noqa: E402
+from irl_control_b200.synthetic import SCENARIOS, build_scenario, synth_batch  # noqa: E402
+from irl_control_b200.configs import SCENE_FREE_OBJECTS  # noqa: E402
+from oracle import ref_harness  # noqa: E402
+
+
+def reference_runner(scenario: str):
+    sc = SCENARIOS[scenario]
+    yaml_name = sc["config"].replace("+start_body", "")
+    cfg = ref_harness.load_reference_yaml(yaml_name, inject_start_body=True)
+    model = DualUR5Model(n_free_objects=SCENE_FREE_OBJECTS[sc["scene"]])
+    return ref_harness.ReferenceRunner(model, cfg, sc["device_cfgs"], sc["targets"], "nullspace",
+                                       use_g=True, admittance=sc["admittance"])
+
+
+def run_case(name, scenario, B, seed, mutate=None, insertion_schedule=False):
+    _, _, targets, layout = build_scenario(scenario)
+    st = synth_batch(layout, B, seed=seed, insertion_schedule=insertion_schedule)
+    st = {k: v.numpy() for k, v in st.items()}
+    st["target_vel"] = np.zeros((B, layout.D, 6))
+    if mutate is not None:
+        mutate(st, layout)
+    runner = reference_runner(scenario)
+    # the host layer's index maps must be the reference's own
+    for dl in layout.devices:
+        ref_dev = runner.robot.get_device(dl.name)
+        assert list(ref_dev.joint_ids_all) == list(dl.joint_ids_all), dl.name
+        assert list(ref_dev.actuator_trnids) == list(dl.actuator_trnids), dl.name
+        assert list(ref_dev.ctrl_idxs) == list(dl.ctrl_idxs), dl.name
+    ctrl, u_all, pinv, raised = [], [], [], []
+    for i in range(B):
+        inst = {k: v[i] for k, v in st.items()}
+        tv = st["target_vel"][i] if np.any(st["target_vel"][i] != 0) else None
+        try:
+            r = runner.run(inst, st["target_xyz"][i], st["target_quat"][i], tgt_vel=tv, max_vel=st["max_vel"][i])
+            ctrl.append(np.concatenate(r["forces"]))
+            u_all.append(r["u_all"])
+            pinv.append(r["pinv"])
+            raised.append(False)
+            st["target_vel"][i] = r["target_vel_seen"]
+        except IndexError:
+            ctrl.append(np.full(layout.n_ctrl, np.nan))
+            u_all.append(np.full(layout.n, np.nan))
+            pinv.append(False)
+            raised.append(True)
+    out = dict(st)
+    out.pop("J")
+    out.update(ctrl=np.stack(ctrl), u_all=np.stack(u_all), pinv=np.array(pinv), index_error=np.array(raised),
+               layout_json=np.array(json.dumps(layout.as_dict())), scenario=np.array(scenario), seed=np.array(seed))
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("%-28s B=%3d k=%2d pinv=%2d index_error=%2d  max|ctrl|=%.3e -> %s" % (
+        name, B, layout.k, int(np.sum(pinv)), int(np.sum(raised)), np.nanmax(np.abs(out["ctrl"])),
+        os.path.relpath(path, ROOT)))
+
+
+def vel_all_nonzero(st, layout):
+    rng = np.random.default_rng(5)
+    B = st["dq"].shape[0]
+    tv = rng.normal(0.0, 0.2, size=(B, layout.D, 6))
+    tv[np.abs(tv) < 1e-3] = 0.05
+    # odd instances: one zero component on device 0 -> that device falls back to the zero branch (N4)
+    tv[1::2, 0, 4] = 0.0
+    st["target_vel"] = tv
+
+
+def singular_pose(st, layout):
+    """Right arm at its all-zero start angles (default_xyz_abg.yaml:17): kinematic singularity (N2)."""
+    from irl_control_b200.dual_ur5 import dynamics
+    model = DualUR5Model()
+    B = st["dq"].shape[0]
+    rng = np.random.default_rng(11)
+    q = rng.uniform(-np.pi, np.pi, size=(B, 25))
+    q[:, 1:7] = rng.normal(0.0, 1e-3, size=(B, 6)) * np.linspace(0, 1, B)[:, None]
+    q[:, 7:13] = 0.0
+    q[:, 19:25] = 0.0
+    dyn = dynamics(model, torch.from_numpy(q), torch.from_numpy(st["dq"]))
+    ee = {"base": "ur_stand_dummy", "ur5right": "ur_EE_ur5right", "ur5left": "ur_EE_ur5left"}
+    st["M"] = dyn.M.numpy()
+    st["bias"] = dyn.bias.numpy()
+    for d, dl in enumerate(layout.devices):
+        b = model.body_name2id(ee[dl.name])
+        jp, jr = dyn.jac_body(b)
+        st["J6"][:, d] = torch.cat([jp, jr], 1).numpy()
+        delta = st["target_xyz"][:, d] - st["ee_xyz"][:, d]
+        st["ee_xyz"][:, d] = dyn.xpos[:, b].numpy()
+        st["ee_quat"][:, d] = dyn.xquat[:, b].numpy()
+        st["target_xyz"][:, d] = st["ee_xyz"][:, d] + delta
+
+
+if __name__ == "__main__":
+    assert ref_harness.reference_available(), "needs /root/reference"
+    run_case("gain_test_s0", "gain_test", 24, 0)
+    run_case("admit_test_s1", "admit_test", 24, 1)
+    run_case("insertion_s2", "insertion", 24, 2, insertion_schedule=True)
+    run_case("worst_case_s3", "worst_case", 24, 3)
+    run_case("gain_test_vel_s4", "gain_test", 12, 4, mutate=vel_all_nonzero)
+    run_case("worst_case_vel_s5", "worst_case", 12, 5, mutate=vel_all_nonzero)
+    run_case("insertion_vel_s6", "insertion", 8, 6, mutate=vel_all_nonzero)
+    run_case("admit_singular_s7", "admit_test", 16, 7, mutate=singular_pose)
