@@ -243,6 +243,7 @@ static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream
 extern "C" int32_t irlosc_step(irlosc_handle *h, int64_t B, const irlosc_io *io, void *cuda_stream) {
     if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
     if (B < 0) return fail(IRLOSC_ERR_INVALID, "B=%lld is negative", (long long)B);
+    if (B == 0) return IRLOSC_OK;   // empty batch: nothing to read or write (array pointers may be null)
     KIo k;
     int32_t rc = resolve_io(h, io, k);
     if (rc != IRLOSC_OK) return rc;
@@ -303,6 +304,7 @@ static int32_t ensure_cap(Staging &s, int slot, size_t bytes) {
 extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io *io) {
     if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
     if (B < 0) return fail(IRLOSC_ERR_INVALID, "B is negative");
+    if (B == 0) return IRLOSC_OK;
     KIo hk;   // host-pointer view with resolved strides
     int32_t rc = resolve_io(h, io, hk);
     if (rc != IRLOSC_OK) return rc;

@@ -199,34 +199,26 @@ class BatchedOSC:
         return err
 
 
+class _PinnedBlock:
+    """Owns one cudaHostAlloc block; freed when the last array viewing it dies."""
+
+    def __init__(self, nbytes: int):
+        self.lib = _native.load()
+        self.ptr = C.c_void_p()
+        _native.check(self.lib.irlosc_host_alloc(C.byref(self.ptr), int(nbytes)))
+
+    def __del__(self):
+        try:
+            self.lib.irlosc_host_free(self.ptr)
+        except Exception:
+            pass
+
+
 def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
-    """numpy array backed by pinned host memory from `irlosc_host_alloc` (kept alive by the array)."""
-    lib = _native.load()
-    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-    ptr = C.c_void_p()
-    _native.check(lib.irlosc_host_alloc(C.byref(ptr), nbytes))
-    buf = (C.c_char * max(nbytes, 1)).from_address(ptr.value)
-
-    class _Owner:
-        def __init__(self, p):
-            self.p = p
-
-        def __del__(self):
-            try:
-                lib.irlosc_host_free(self.p)
-            except Exception:
-                pass
-    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
-    owner = _Owner(ptr)
-    # tie lifetime of the pinned block to the array
-    holder = np.ndarray.__new__(_PinnedArray, shape, dtype, buffer=buf)
-    holder._owner = owner
-    return holder
-
-
-class _PinnedArray(np.ndarray):
-    _owner = None
-
-    def __array_finalize__(self, obj):
-        if obj is not None and getattr(obj, "_owner", None) is not None:
-            self._owner = obj._owner
+    """Uninitialised numpy array in pinned host memory (`irlosc_host_alloc`), for `step_host`."""
+    count = int(np.prod(shape))
+    nbytes = max(count * np.dtype(dtype).itemsize, 1)
+    block = _PinnedBlock(nbytes)
+    cbuf = (C.c_char * nbytes).from_address(block.ptr.value)
+    cbuf._block = block          # the numpy array references cbuf, cbuf keeps the block alive
+    return np.frombuffer(cbuf, dtype=dtype, count=count).reshape(shape)

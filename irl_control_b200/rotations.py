@@ -23,7 +23,7 @@ _EPS4 = 4.0 * _EPS
 
 def normalized_vector(v):
     v = np.asarray(v, dtype=np.float64).reshape(-1)
-    return v / math.sqrt(float(np.dot(v, v)))
+    return v / math.sqrt(float((v ** 2).sum()))
 
 
 def qconjugate(q):

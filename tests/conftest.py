@@ -1,0 +1,41 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+
+
+@pytest.fixture(scope="session")
+def native_lib():
+    """Build (if stale) and load libirlosc.so; no compute calls."""
+    import __graft_entry__ as g
+    g.build()
+    from irl_control_b200 import _native
+    return _native.load()
+
+
+def load_golden(name):
+    import json
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    layout = json.loads(str(g["layout_json"]))
+    return g, layout
+
+
+GOLDEN_CASES = ["gain_test_s0", "admit_test_s1", "insertion_s2", "worst_case_s3",
+                "gain_test_vel_s4", "worst_case_vel_s5", "insertion_vel_s6", "admit_singular_s7"]
+
+
+def golden_oracle_batch(g):
+    """Golden arrays in the oracle's field names."""
+    return dict(M=g["M"], J=g["J6"], dq=g["dq"], bias=g["bias"], ee_xyz=g["ee_xyz"], ee_quat=g["ee_quat"],
+                ft_xmat=g["ft_xmat"], ft_raw=g["ft_raw"], tgt_xyz=g["target_xyz"], tgt_quat=g["target_quat"],
+                tgt_vel=g["target_vel"], max_vel=g["max_vel"])

@@ -1,0 +1,124 @@
+"""CPU: the host mirror of the reference API (index maps, error behaviour, layout flattening)."""
+import numpy as np
+import pytest
+
+import irl_control_b200 as pkg
+from irl_control_b200.synthetic import SCENARIOS, build_scenario
+from irl_control_b200.dual_ur5 import DualUR5Model, dynamics, sample_joint_states
+
+
+def _app(cfg="default_xyz_abg.yaml+start_body", scene="gain_test_scene.xml"):
+    return pkg.MujocoApp(cfg, scene)
+
+
+def test_device_index_maps_match_survey_a1():
+    r = _app().get_robot("DualUR5")
+    base, right, left = (r.get_device(n) for n in ("base", "ur5right", "ur5left"))
+    assert list(base.joint_ids_all) == [0] and list(base.ctrl_idxs) == [0] and list(base.actuator_trnids) == [0]
+    assert list(right.joint_ids) == [1, 2, 3, 4, 5, 6] and list(right.gripper_ids) == list(range(7, 13))
+    assert list(right.ctrl_idxs) == [1, 2, 3, 4, 5, 6, 7] and list(right.actuator_trnids) == [1, 2, 3, 4, 5, 6, 10]
+    assert list(left.joint_ids_all) == list(range(13, 25))
+    assert list(left.ctrl_idxs) == list(range(8, 15)) and list(left.actuator_trnids) == [13, 14, 15, 16, 17, 18, 22]
+    assert r.num_joints_total == 25 and list(r.joint_ids_all) == list(range(25))
+    assert right.joint_names[0] == "joint0_ur5right"
+
+
+def test_shipped_yaml_without_start_body_fails_like_reference():
+    # 7 chain joints vs 6 start angles -> numpy shape error in Device.__init__
+    with pytest.raises(ValueError):
+        _app("default_xyz_abg.yaml")
+
+
+def test_scene_free_objects_keep_robot_ids():
+    app = _app(scene="insertion_task_scene.xml")
+    assert app.sim.model.nv == 49
+    r = app.get_robot("DualUR5")
+    assert list(r.joint_ids_all) == list(range(25))
+    M = r.get_state(pkg.RobotState.M)
+    assert M.shape == (25, 25)
+    Js, J_idxs = r.get_state(pkg.RobotState.J)
+    assert Js["ur5right"].shape == (6, 25) and list(J_idxs["ur5left"]) == list(range(7, 13))
+
+
+def test_layout_rows_and_dx_idx_order():
+    for name, k, n_ctrl in (("gain_test", 7, 15), ("admit_test", 12, 14), ("insertion", 12, 14), ("worst_case", 13, 15)):
+        _, _, targets, L = build_scenario(name)
+        assert (L.k, L.n_ctrl, L.D) == (k, n_ctrl, len(targets))
+    _, _, _, L = build_scenario("gain_test")
+    # J_idxs follow sub-device order base, right, left (robot.py:52-55), targets are right, left, base
+    assert [d.dx_idx for d in L.devices] == [(1, 2, 3), (4, 5, 6), (0,)]
+    _, _, _, L = build_scenario("admit_test")
+    # base is a sub-device of the robot even when it is not targeted -> left arm indexes past k = 12 (N3)
+    assert L.admittance and [d.dx_idx for d in L.devices] == [tuple(range(1, 7)), tuple(range(7, 13))]
+
+
+def test_osc_constructor_mutates_caller_config_like_reference():
+    app = _app()
+    cfg = app.get_controller_config("osc2")
+    pkg.OSC(app.get_robot("DualUR5"), app.sim, [("ur5right", cfg)], app.get_controller_config("nullspace"))
+    assert np.array_equal(cfg["task_space_gains"], [200] * 6) and np.allclose(cfg["lamb"], 4.0)
+
+
+def test_thread_mode_asserts():
+    app = pkg.MujocoApp("default_xyz_abg.yaml+start_body", "gain_test_scene.xml", use_sim=False)
+    r = app.get_robot("DualUR5")
+    osc = pkg.OSC(r, app.sim, [("ur5right", app.get_controller_config("osc2"))])
+    with pytest.raises(AssertionError):
+        osc.generate({"ur5right": pkg.Target()})      # osc.py:129-130
+    app2 = _app()
+    with pytest.raises(AssertionError):
+        app2.get_robot("DualUR5").get_device("base").update_state()   # device.py:203
+    with pytest.raises(AssertionError):
+        app2.get_robot("DualUR5").stop()                              # robot.py:119
+
+
+def test_unknown_names_raise_keyerror():
+    app = _app()
+    r = app.get_robot("DualUR5")
+    with pytest.raises(KeyError):
+        r.get_device("nope")
+    osc = pkg.OSC(r, app.sim, [("ur5right", app.get_controller_config("osc2"))])
+    with pytest.raises(KeyError):
+        osc.layout_for(["ur5left"])     # no controller config for that device (osc.py:160)
+
+
+def test_target_defaults_and_setters():
+    t = pkg.Target()
+    assert np.array_equal(t.get_quat(), [1, 0, 0, 0]) and np.array_equal(t.get_abg_vel(), [0, 0, 0])
+    t.set_all_abg([1, 2, 3], [0.1, -0.2, 0.3])
+    assert np.allclose(t.get_abg(), [0.1, -0.2, 0.3]) and np.array_equal(t.get_xyz(), [1, 2, 3])
+    with pytest.raises(AssertionError):
+        t.set_quat([1, 0, 0])
+    assert t.velocity6().shape == (6,)
+
+
+def test_calc_error_matches_oracle():
+    from oracle import osc_numpy
+    app, osc, targets, L = build_scenario("admit_test")
+    sim = app.sim
+    sim.data.qpos[:25] = sample_joint_states(1, 3)[0][0]
+    sim.forward()
+    dev = app.get_robot("DualUR5").get_device("ur5left")
+    t = pkg.Target([0.1, 0.2, 0.3, 0.3, -0.4, 0.2])
+    got = osc.calc_error(t, dev)
+    want = osc_numpy.calc_error(L.as_dict()["devices"][1], dev.get_state(pkg.DeviceState.EE_XYZ),
+                                dev.get_state(pkg.DeviceState.EE_QUAT), t.get_xyz(), t.get_quat())
+    assert np.array_equal(got, want)
+
+
+def test_dynamics_model_consistency():
+    import torch
+    m = DualUR5Model()
+    q, dq = sample_joint_states(8, 5)
+    q, dq = torch.from_numpy(q), torch.from_numpy(dq)
+    d = dynamics(m, q, dq)
+    assert torch.linalg.eigvalsh(d.M).min() > 0
+    z = torch.zeros_like(dq)
+    for j in (0, 3, 10, 24):
+        e = torch.zeros_like(dq)
+        e[:, j] = 1.0
+        col = dynamics(m, q, z, ddq=e, need_M=False, gravity=(0, 0, 0)).bias
+        assert (col - d.M[:, :, j]).abs().max() < 1e-12      # CRBA == RNEA columns
+    ee = m.body_name2id("ur_EE_ur5left")
+    jp, jr = d.jac_body(ee)
+    assert jp[:, :, 1:13].abs().max() == 0 and jp[:, :, 19:].abs().max() == 0   # other arm / own gripper columns
