@@ -52,13 +52,13 @@ __device__ void jacobi_eigen(GenericSmem &S, int k, int lane) {
         }
         off = warp_sum(off);
         dia = warp_sum(dia);
-        if (off <= 1e-32 * dia || off == 0.0) break;
+        if (off <= 1e-28 * dia || off == 0.0) break;
         for (int p = 0; p < k - 1; ++p) {
             for (int q = p + 1; q < k; ++q) {
                 const double apq = S.As[p][q];
                 const double app = S.As[p][p], aqq = S.As[q][q];
                 __syncwarp();
-                if (fabs(apq) <= 1e-300) continue;   // warp-uniform (same smem values)
+                if (fabs(apq) <= 1e-300 || apq * apq <= 1e-31 * fabs(app * aqq)) continue;   // warp-uniform (same smem values)
                 const double theta = (aqq - app) / (2.0 * apq);
                 const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double c = 1.0 / sqrt(tt * tt + 1.0);

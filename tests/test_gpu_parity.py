@@ -54,7 +54,7 @@ def _rel_err(got, want):
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-@pytest.mark.parametrize("packed_M,full6_J", [(False, False), (True, True)])
+@pytest.mark.parametrize("packed_M,full6_J", [(False, False), (True, True), (True, False)])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
 def test_cuda_matches_reference_golden(case, packed_M, full6_J, kernel):
     torch = _torch()
@@ -134,8 +134,13 @@ def test_size_independent_properties_at_full_batch():
     half = {k: v[B // 2:].contiguous() for k, v in kernel_inputs(st, layout).items()}
     d = eng.step(half)
     assert torch.equal(d["ctrl"], a["ctrl"][B // 2:])
-    e = eng.step(kernel_inputs(st, layout, packed_M=True, full6_J=True), want_u_all=True)
+    # packed vs dense M: same kernel family, same arithmetic -> bit-identical
+    e = eng.step(kernel_inputs(st, layout, packed_M=True), want_u_all=True)
     assert torch.equal(e["u_all"], a["u_all"])
+    # full-6 Jacobian layout is served by the generic kernel: equal within the parity tolerance
+    f = eng.step(kernel_inputs(st, layout, packed_M=True, full6_J=True), want_u_all=True)
+    scale = a["u_all"].abs().amax(dim=1, keepdim=True)
+    assert ((f["u_all"] - a["u_all"]).abs() / scale).max().item() < REL_TOL
     # ctrl is exactly the gather of u_all at the actuated joints (osc.py:203-208)
     cols = [j for dl in layout.devices for j in dl.actuator_trnids]
     assert torch.equal(a["ctrl"], a["u_all"][:, cols])
