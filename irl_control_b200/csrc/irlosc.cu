@@ -12,7 +12,7 @@
 #include "../../include/irlosc.h"
 #include "irlosc_device.cuh"
 #include "osc_generic.cuh"
-#include "osc_tiled.cuh"
+#include "osc_dispatch.cuh"
 
 using namespace irlosc;
 
@@ -181,7 +181,7 @@ extern "C" int64_t irlosc_kernel_launches(const irlosc_handle *h) { return h ? h
 extern "C" const char *irlosc_last_kernel(const irlosc_handle *h) { return h ? h->last_kernel : "none"; }
 
 extern "C" int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which) {
-    if (!h || which < 0 || which > 2) return fail(IRLOSC_ERR_INVALID, "kernel selector must be 0, 1 or 2");
+    if (!h || which < 0 || which > 9) return fail(IRLOSC_ERR_INVALID, "kernel selector must be 0 (auto), 1 (generic) or 2+v (tiled variant v)");
     h->kernel_choice = which;
     return IRLOSC_OK;
 }
@@ -222,11 +222,12 @@ static int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k) {
 static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st) {
     if (B == 0) return IRLOSC_OK;
     bool use_tiled = false;
-    if (h->kernel_choice != 1) use_tiled = tiled_supported(h->kp, k);
-    if (h->kernel_choice == 2 && !use_tiled)
+    const int variant = h->kernel_choice >= 2 ? h->kernel_choice - 2 : 0;
+    if (h->kernel_choice != 1) use_tiled = tiled_supported(h->kp, k, variant);
+    if (h->kernel_choice >= 2 && !use_tiled)
         return fail(IRLOSC_ERR_INVALID, "tiled kernel requested but this shape/layout is not supported (n=%d k=%d)", h->kp.n, h->kp.k);
     if (use_tiled) {
-        cudaError_t e = tiled_launch(h->kp, k, B, h->sm_count, st, &h->last_kernel);
+        cudaError_t e = tiled_launch(h->kp, k, B, h->sm_count, st, &h->last_kernel, variant);
         if (e != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "tiled kernel launch: %s", cudaGetErrorString(e));
     } else {
         const int64_t blocks_needed = (B + kGenericWarps - 1) / kGenericWarps;

@@ -195,8 +195,8 @@ __device__ void eigen_solve(double (*A)[K + 1], double (*V)[K + 1], const double
     __syncwarp();
 }
 
-template <int N, int K, int D, int G, bool PACKED>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+template <int N, int K, int D, int G, bool PACKED, int MINB>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, MINB)
 osc_step_tiled(const KParams P, const KIo io, const int64_t B) {
     using T = Tile<N, K, G>;
     using WS = WarpSmem<N, K, D, G, PACKED>;
@@ -597,74 +597,5 @@ osc_step_tiled(const KParams P, const KIo io, const int64_t B) {
 }
 
 }  // namespace tiled
-
-// ---- host side: instantiations and dispatch --------------------------------------------
-struct TiledEntry {
-    int n, k, d;
-    bool packed;
-    const void *fn;
-    size_t smem_per_cta;
-    const char *name;
-};
-
-template <int N, int K, int D, int G, bool PACKED>
-inline TiledEntry tiled_entry(const char *name) {
-    return TiledEntry{N, K, D, PACKED, (const void *)tiled::osc_step_tiled<N, K, D, G, PACKED>,
-                      sizeof(tiled::WarpSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name};
-}
-
-inline const TiledEntry *tiled_table(int *count) {
-    static const TiledEntry table[] = {
-        tiled_entry<25, 7, 3, 8, true>("osc_step_tiled<n25,k7,D3,G8,packed>"),
-        tiled_entry<25, 7, 3, 8, false>("osc_step_tiled<n25,k7,D3,G8,dense>"),
-        tiled_entry<25, 12, 2, 16, true>("osc_step_tiled<n25,k12,D2,G16,packed>"),
-        tiled_entry<25, 12, 2, 16, false>("osc_step_tiled<n25,k12,D2,G16,dense>"),
-        tiled_entry<25, 13, 3, 16, true>("osc_step_tiled<n25,k13,D3,G16,packed>"),
-        tiled_entry<25, 13, 3, 16, false>("osc_step_tiled<n25,k13,D3,G16,dense>"),
-    };
-    *count = (int)(sizeof(table) / sizeof(table[0]));
-    return table;
-}
-
-inline int32_t tiled_prepare() {
-    int cnt = 0;
-    const TiledEntry *t = tiled_table(&cnt);
-    for (int i = 0; i < cnt; ++i) {
-        if (cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t[i].smem_per_cta) != cudaSuccess)
-            return IRLOSC_ERR_CUDA;
-    }
-    return IRLOSC_OK;
-}
-
-inline const TiledEntry *tiled_find(const KParams &P, const KIo &io) {
-    auto al16 = [](const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-    if (io.j_layout != IRLOSC_J_ROWS || io.ldj != P.n || io.j_stride != (int64_t)P.n * P.k) return nullptr;
-    const bool packed = io.m_layout == IRLOSC_M_PACKED;
-    if (packed && io.m_stride != (int64_t)P.n * (P.n + 1) / 2) return nullptr;
-    if (!packed && (io.ldm != P.n || io.m_stride != (int64_t)P.n * P.n)) return nullptr;
-    if (!(al16(io.M) && al16(io.J) && al16(io.dq) && al16(io.bias) && al16(io.ee_xyz) && al16(io.ee_quat) &&
-          al16(io.target_xyz) && al16(io.target_quat) && al16(io.target_vel) && al16(io.max_vel) &&
-          al16(io.ft_xmat) && al16(io.ft_raw)))
-        return nullptr;
-    int cnt = 0;
-    const TiledEntry *t = tiled_table(&cnt);
-    for (int i = 0; i < cnt; ++i)
-        if (t[i].n == P.n && t[i].k == P.k && t[i].d == P.D && t[i].packed == packed) return &t[i];
-    return nullptr;
-}
-
-inline bool tiled_supported(const KParams &P, const KIo &io) { return tiled_find(P, io) != nullptr; }
-
-inline cudaError_t tiled_launch(const KParams &P, const KIo &io, int64_t B, int sm_count, cudaStream_t st,
-                                const char **name) {
-    const TiledEntry *e = tiled_find(P, io);
-    if (!e) return cudaErrorNotSupported;
-    const int wi_g8 = 4;
-    (void)wi_g8;
-    int grid = sm_count * 2;
-    void *args[] = {(void *)&P, (void *)&io, (void *)&B};
-    *name = e->name;
-    return cudaLaunchKernel(e->fn, dim3(grid), dim3(tiled::kWarpsPerCta * 32), args, e->smem_per_cta, st);
-}
 
 }  // namespace irlosc
