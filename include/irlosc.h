@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IRLOSC_ABI_VERSION 1
+#define IRLOSC_ABI_VERSION 2
 #define IRLOSC_MAX_DEVICES 4   /* target devices per controller (DualUR5: base + 2 arms) */
 #define IRLOSC_MAX_N 32        /* robot DoF, Robot.num_joints_total (robot.py:32); DualUR5: 25 */
 #define IRLOSC_MAX_K 24        /* stacked task rows, sum of ctrlr_dof over targets; DualUR5: <= 13 */
@@ -45,6 +45,8 @@ extern "C" {
 #define IRLOSC_ST_VEL_BRANCH 0x08   /* >=1 device took the non-zero target-velocity branch (osc.py:175-177) */
 #define IRLOSC_ST_DX_RANGE 0x10     /* that branch indexed dx out of range: the reference raises IndexError
                                        (robot.py:52-55 vs osc.py:150,176); outputs are NaN               */
+#define IRLOSC_ST_SPARSITY 0x20     /* check_topology was set and M / J had a non-zero where the declared
+                                       kinematic tree says zero; outputs are NaN                         */
 
 /* layouts of the inertia / Jacobian inputs */
 #define IRLOSC_M_DENSE 0        /* [B][ldm rows used: n][ldm]  row-major n x n block, row stride ldm   */
@@ -66,6 +68,10 @@ typedef struct irlosc_device_params {
     double max_vel[2];                    /* default when io.max_vel == NULL      (device.py:31)       */
     double kp, kv, ko;                    /* controller_configs entry             (osc.py:36)          */
     double k[3], d[3];                    /* stiffness / damping, xyz part        (osc.py:160-161)     */
+    int32_t ee_joint;                     /* robot-local id of the deepest joint that moves the EE body,
+                                             i.e. the last entry of Device.joint_ids (device.py:62-64);
+                                             -1 = unknown (only read when has_topology)                 */
+    int32_t reserved_;
 } irlosc_device_params;
 
 typedef struct irlosc_params {
@@ -76,6 +82,16 @@ typedef struct irlosc_params {
     int32_t admittance;                   /* OSC(admittance=...)                  (osc.py:184)         */
     int32_t has_nullspace;                /* nullspace_config is not None         (osc.py:195)         */
     double nullspace_kv;                  /* nullspace_config['kv']               (osc.py:196)         */
+    /* Optional kinematic-tree description (what Device.__init__ walks, device.py:41-64).  When
+     * has_topology != 0 the caller guarantees the sparsity every MuJoCo state has:
+     *   M[i][j] == 0 unless joint i is an ancestor of joint j or vice versa (mj_fullM),
+     *   row r of a device's Jacobian == 0 outside the ancestors-or-self of its ee_joint (mj_jacBody).
+     * Kernels specialised for a topology (DualUR5) then skip the structural zeros - the result is
+     * the same as the dense elimination.  check_topology makes the step verify the zeros
+     * (IRLOSC_ST_SPARSITY).  Without topology the dense kernels are used. */
+    int32_t has_topology;
+    int32_t check_topology;
+    int32_t joint_parent[IRLOSC_MAX_N];   /* robot-local parent joint, -1 for a root                   */
     irlosc_device_params dev[IRLOSC_MAX_DEVICES];
 } irlosc_params;
 
@@ -143,7 +159,8 @@ int32_t irlosc_calc_error(irlosc_handle *h, int64_t B, const double *ee_xyz, con
 int32_t irlosc_host_alloc(void **ptr, int64_t bytes);
 int32_t irlosc_host_free(void *ptr);
 
-/* Kernel selection: 0 = auto, 1 = generic (any n, k), 2 = register-tiled DualUR5 kernel. */
+/* Kernel selection: 0 = auto, 1 = generic (any n, k, layout), 2 + v = variant v of the specialised
+ * DualUR5 kernels (v = 0 is what auto picks; others exist for A/B measurements). */
 int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which);
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t irlosc_kernel_launches(const irlosc_handle *h);

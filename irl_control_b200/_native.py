@@ -12,13 +12,14 @@ from typing import Optional
 MAX_DEVICES = 4
 MAX_N = 32
 MAX_K = 24
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ST_PINV = 0x01
 ST_M_NOT_PD = 0x02
 ST_EIGEN = 0x04
 ST_VEL_BRANCH = 0x08
 ST_DX_RANGE = 0x10
+ST_SPARSITY = 0x20
 
 M_DENSE, M_PACKED = 0, 1
 J_ROWS, J_FULL6 = 0, 1
@@ -48,6 +49,7 @@ class DeviceParams(C.Structure):
         ("max_vel", C.c_double * 2),
         ("kp", C.c_double), ("kv", C.c_double), ("ko", C.c_double),
         ("k", C.c_double * 3), ("d", C.c_double * 3),
+        ("ee_joint", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -60,6 +62,9 @@ class Params(C.Structure):
         ("admittance", C.c_int32),
         ("has_nullspace", C.c_int32),
         ("nullspace_kv", C.c_double),
+        ("has_topology", C.c_int32),
+        ("check_topology", C.c_int32),
+        ("joint_parent", C.c_int32 * MAX_N),
         ("dev", DeviceParams * MAX_DEVICES),
     ]
 

@@ -83,6 +83,13 @@ static int32_t build_kparams(const irlosc_params &u, KParams &kp) {
     kp.admittance = u.admittance != 0;
     kp.has_nullspace = u.has_nullspace != 0;
     kp.nullspace_kv = u.nullspace_kv;
+    kp.has_topology = u.has_topology != 0;
+    kp.check_topology = u.check_topology != 0;
+    for (int j = 0; j < IRLOSC_MAX_N; ++j) {
+        const int pj = (kp.has_topology && j < u.n) ? u.joint_parent[j] : -1;
+        if (pj < -1 || pj >= u.n) return fail(IRLOSC_ERR_INVALID, "joint_parent[%d]=%d outside -1..%d", j, pj, u.n - 1);
+        kp.joint_parent[j] = (int8_t)pj;
+    }
     int row = 0, ctrl = 0;
     for (int d = 0; d < u.n_devices; ++d) {
         const irlosc_device_params &s = u.dev[d];
@@ -131,6 +138,7 @@ static int32_t build_kparams(const irlosc_params &u, KParams &kp) {
             if (j < 0 || j >= u.n) return fail(IRLOSC_ERR_INVALID, "device %d: actuator joint %d outside 0..%d", d, j, u.n - 1);
             t.actuator[i] = (int8_t)j;
         }
+        t.ee_joint = (s.ee_joint >= 0 && s.ee_joint < u.n) ? s.ee_joint : -1;
         ctrl += s.n_ctrl;
     }
     if (row < 1) return fail(IRLOSC_ERR_INVALID, "no controlled task rows");

@@ -36,6 +36,7 @@ struct KDevice {
     double stiff[6];          // k + [1,1,1]     (osc.py:160)
     double damp[6];           // d + [1,1,1]     (osc.py:161)
     uint32_t joint_mask;      // bit j set <=> j in joint_ids_all
+    int32_t ee_joint;         // deepest joint moving the EE body (-1 unknown)
     int8_t actuator[IRLOSC_MAX_N];
 };
 
@@ -45,6 +46,8 @@ struct KParams {
     double nullspace_kv;
     int8_t row_dev[IRLOSC_MAX_K];   // stacked row -> device
     int8_t row_comp[IRLOSC_MAX_K];  // stacked row -> component 0..5 of [xyz, abg]
+    int32_t has_topology, check_topology;
+    int8_t joint_parent[IRLOSC_MAX_N];
     KDevice dev[IRLOSC_MAX_DEVICES];
 };
 

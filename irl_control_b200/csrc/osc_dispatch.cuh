@@ -1,48 +1,71 @@
-// Kernel table and dispatch for the register-tiled OSC kernels.
+// Kernel table and dispatch for the specialised DualUR5 OSC kernels.
+//
+//   kind 0  dense register-tiled kernels (osc_tiled.cuh: column/scratch, osc_rows.cuh: row/shuffle)
+//   kind 1  kinematic-tree-sparse kernel (osc_tree.cuh) - needs irlosc_params.has_topology and the
+//           DualUR5 tree; default whenever eligible
+// variant 0 of a shape is what irlosc_step dispatches to; the others are kept for A/B
+// measurements (irlosc_set_kernel(h, 2 + variant)).
 #pragma once
 #include "osc_tiled.cuh"
 #include "osc_rows.cuh"
+#include "osc_tree.cuh"
 
 namespace irlosc {
 
-// ---- host side: instantiations and dispatch --------------------------------------------
 struct TiledEntry {
-    int n, k, d;
+    int kind;             // 0 dense, 1 tree
+    int n, k, d;          // shape served (tree: k and d follow from kd / has_base)
     bool packed;
-    int variant;          // 0 = default choice for this shape; others are selectable for experiments
+    int variant;
     int ctas_per_sm;
     const void *fn;
     size_t smem_per_cta;
     const char *name;
+    int kd;               // tree only
+    bool has_base;        // tree only
 };
 
 template <int N, int K, int D, int G, bool PACKED, int MINB>
 inline TiledEntry tiled_entry(int variant, const char *name) {
-    return TiledEntry{N, K, D, PACKED, variant, MINB,
+    return TiledEntry{0, N, K, D, PACKED, variant, MINB,
                       (const void *)tiled::osc_step_tiled<N, K, D, G, PACKED, MINB>,
-                      sizeof(tiled::WarpSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name};
+                      sizeof(tiled::WarpSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name, 0, false};
 }
 
 template <int N, int K, int D, int G, bool PACKED, int MINB>
 inline TiledEntry rows_entry(int variant, const char *name) {
-    return TiledEntry{N, K, D, PACKED, variant, MINB,
+    return TiledEntry{0, N, K, D, PACKED, variant, MINB,
                       (const void *)rows::osc_step_rows<N, K, D, G, PACKED, MINB>,
-                      sizeof(rows::RowSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name};
+                      sizeof(rows::RowSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name, 0, false};
 }
 
-// variant 0 is what irlosc_step dispatches to; the others exist for A/B measurements
-// (irlosc_set_kernel(h, 2 + variant)).
+template <int KD, bool HAS_BASE, bool PACKED, int MINB>
+inline TiledEntry tree_entry(int variant, const char *name) {
+    using WS = tree::TreeSmem<KD, HAS_BASE, PACKED>;
+    return TiledEntry{1, tree::kN, WS::K, WS::D, PACKED, variant, MINB,
+                      (const void *)tree::osc_step_tree<KD, HAS_BASE, PACKED, MINB>,
+                      sizeof(WS) * tree::kTreeWarps, name, KD, HAS_BASE};
+}
+
 inline const TiledEntry *tiled_table(int *count) {
     static const TiledEntry table[] = {
-        rows_entry<25, 7, 3, 8, true, 2>(0, "osc_step_rows<n25,k7,D3,G8,packed>"),
-        rows_entry<25, 7, 3, 8, false, 2>(0, "osc_step_rows<n25,k7,D3,G8,dense>"),
-        tiled_entry<25, 7, 3, 8, true, 2>(1, "osc_step_tiled<n25,k7,D3,G8,packed>"),
-        rows_entry<25, 12, 2, 16, true, 2>(1, "osc_step_rows<n25,k12,D2,G16,packed>"),
-                tiled_entry<25, 12, 2, 16, true, 2>(0, "osc_step_tiled<n25,k12,D2,G16,packed>"),
-        tiled_entry<25, 12, 2, 16, false, 2>(0, "osc_step_tiled<n25,k12,D2,G16,dense>"),
-        rows_entry<25, 13, 3, 16, true, 2>(1, "osc_step_rows<n25,k13,D3,G16,packed>"),
-                tiled_entry<25, 13, 3, 16, true, 2>(0, "osc_step_tiled<n25,k13,D3,G16,packed>"),
-        tiled_entry<25, 13, 3, 16, false, 2>(0, "osc_step_tiled<n25,k13,D3,G16,dense>"),
+        // ---- kinematic-tree-sparse (default when the topology is declared)
+        tree_entry<3, true, true, 1>(0, "osc_step_tree<kd3,base,packed>"),
+        tree_entry<3, true, false, 1>(0, "osc_step_tree<kd3,base,dense>"),
+        tree_entry<6, false, true, 1>(0, "osc_step_tree<kd6,packed>"),
+        tree_entry<6, false, false, 1>(0, "osc_step_tree<kd6,dense>"),
+        tree_entry<6, true, true, 1>(0, "osc_step_tree<kd6,base,packed>"),
+        tree_entry<6, true, false, 1>(0, "osc_step_tree<kd6,base,dense>"),
+        // ---- dense (default without topology; variants 1/2 with topology)
+        rows_entry<25, 7, 3, 8, true, 2>(1, "osc_step_rows<n25,k7,D3,G8,packed>"),
+        rows_entry<25, 7, 3, 8, false, 2>(1, "osc_step_rows<n25,k7,D3,G8,dense>"),
+        tiled_entry<25, 7, 3, 8, true, 2>(2, "osc_step_tiled<n25,k7,D3,G8,packed>"),
+        tiled_entry<25, 12, 2, 16, true, 2>(1, "osc_step_tiled<n25,k12,D2,G16,packed>"),
+        tiled_entry<25, 12, 2, 16, false, 2>(1, "osc_step_tiled<n25,k12,D2,G16,dense>"),
+        rows_entry<25, 12, 2, 16, true, 2>(2, "osc_step_rows<n25,k12,D2,G16,packed>"),
+        tiled_entry<25, 13, 3, 16, true, 2>(1, "osc_step_tiled<n25,k13,D3,G16,packed>"),
+        tiled_entry<25, 13, 3, 16, false, 2>(1, "osc_step_tiled<n25,k13,D3,G16,dense>"),
+        rows_entry<25, 13, 3, 16, true, 2>(2, "osc_step_rows<n25,k13,D3,G16,packed>"),
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;
@@ -58,7 +81,32 @@ inline int32_t tiled_prepare() {
     return IRLOSC_OK;
 }
 
-inline const TiledEntry *tiled_find(const KParams &P, const KIo &io, int variant = 0) {
+// Does the controller description match what osc_tree.cuh is specialised for?
+inline bool tree_roles(const KParams &P, tree::Roles &R, int &kd, bool &has_base) {
+    R.dev_arm[0] = R.dev_arm[1] = R.dev_base = -1;
+    R.row_arm[0] = R.row_arm[1] = R.row_base = 0;
+    if (!P.has_topology || P.n != tree::kN || P.D < 2 || P.D > 3) return false;
+    for (int j = 0; j < tree::kN; ++j)
+        if (P.joint_parent[j] != tree::kDualUr5Parent[j]) return false;
+    for (int d = 0; d < P.D; ++d) {
+        const KDevice &dv = P.dev[d];
+        if (dv.ee_joint == 6 && R.dev_arm[0] < 0) { R.dev_arm[0] = d; R.row_arm[0] = dv.row0; }
+        else if (dv.ee_joint == 18 && R.dev_arm[1] < 0) { R.dev_arm[1] = d; R.row_arm[1] = dv.row0; }
+        else if (dv.ee_joint == 0 && R.dev_base < 0) { R.dev_base = d; R.row_base = dv.row0; }
+        else return false;
+    }
+    if (R.dev_arm[0] < 0 || R.dev_arm[1] < 0) return false;
+    kd = P.dev[R.dev_arm[0]].kdev;
+    if (P.dev[R.dev_arm[1]].kdev != kd || (kd != 3 && kd != 6)) return false;
+    has_base = R.dev_base >= 0;
+    if (has_base && P.dev[R.dev_base].kdev != 1) return false;
+    if ((P.D == 3) != has_base) return false;
+    return true;
+}
+
+// Dispatch order for variant v: with a matching topology the tree kernels are variant 0 and the
+// dense ones follow (v >= 1); without topology the dense variants shift down by one.
+inline const TiledEntry *tiled_find(const KParams &P, const KIo &io, int variant, tree::Roles *roles_out) {
     auto al16 = [](const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     if (io.j_layout != IRLOSC_J_ROWS || io.ldj != P.n || io.j_stride != (int64_t)P.n * P.k) return nullptr;
     const bool packed = io.m_layout == IRLOSC_M_PACKED;
@@ -68,22 +116,44 @@ inline const TiledEntry *tiled_find(const KParams &P, const KIo &io, int variant
           al16(io.target_xyz) && al16(io.target_quat) && al16(io.target_vel) && al16(io.max_vel) &&
           al16(io.ft_xmat) && al16(io.ft_raw)))
         return nullptr;
+    tree::Roles R;
+    int kd = 0;
+    bool has_base = false;
+    const bool tree_ok = tree_roles(P, R, kd, has_base);
+    if (roles_out) *roles_out = R;
+    const int want = tree_ok ? variant : variant + 1;     // dense variants are numbered from 1 in the table
     int cnt = 0;
     const TiledEntry *t = tiled_table(&cnt);
-    for (int i = 0; i < cnt; ++i)
-        if (t[i].n == P.n && t[i].k == P.k && t[i].d == P.D && t[i].packed == packed && t[i].variant == variant) return &t[i];
+    for (int i = 0; i < cnt; ++i) {
+        if (t[i].packed != packed || t[i].variant != want) continue;
+        if (t[i].kind == 1) {
+            if (tree_ok && t[i].kd == kd && t[i].has_base == has_base) return &t[i];
+        } else if (t[i].n == P.n && t[i].k == P.k && t[i].d == P.D) {
+            return &t[i];
+        }
+    }
     return nullptr;
 }
 
-inline bool tiled_supported(const KParams &P, const KIo &io, int variant = 0) { return tiled_find(P, io, variant) != nullptr; }
+inline bool tiled_supported(const KParams &P, const KIo &io, int variant = 0) {
+    return tiled_find(P, io, variant, nullptr) != nullptr;
+}
 
 inline cudaError_t tiled_launch(const KParams &P, const KIo &io, int64_t B, int sm_count, cudaStream_t st,
                                 const char **name, int variant = 0) {
-    const TiledEntry *e = tiled_find(P, io, variant);
+    tree::Roles R;
+    const TiledEntry *e = tiled_find(P, io, variant, &R);
     if (!e) return cudaErrorNotSupported;
-    const int grid = sm_count * e->ctas_per_sm;
-    void *args[] = {(void *)&P, (void *)&io, (void *)&B};
+    int ctas = e->ctas_per_sm;
+    if (e->kind == 1) ctas = (int)((227 * 1024) / (e->smem_per_cta + 1024));   // as many CTAs as shared memory holds
+    if (ctas < 1) ctas = 1;
+    const int grid = sm_count * ctas;
     *name = e->name;
+    if (e->kind == 1) {
+        void *args[] = {(void *)&P, (void *)&io, (void *)&B, (void *)&R};
+        return cudaLaunchKernel(e->fn, dim3(grid), dim3(tree::kTreeWarps * 32), args, e->smem_per_cta, st);
+    }
+    void *args[] = {(void *)&P, (void *)&io, (void *)&B};
     return cudaLaunchKernel(e->fn, dim3(grid), dim3(tiled::kWarpsPerCta * 32), args, e->smem_per_cta, st);
 }
 

@@ -32,6 +32,7 @@ class DeviceLayout:
     ko: float
     k: tuple
     d: tuple
+    ee_joint: int = -1          # robot-local id of the last joint of Device.joint_ids (device.py:62-64)
 
     @property
     def n_rows(self) -> int:
@@ -45,6 +46,8 @@ class OscLayout:
     use_g: bool = True
     admittance: bool = False
     nullspace_kv: Optional[float] = None
+    joint_parent: Optional[tuple] = None    # robot-local parent joint per joint (-1 root); None = unknown
+    check_topology: bool = False
 
     @property
     def D(self) -> int:
@@ -70,11 +73,13 @@ class OscLayout:
         return {
             "n": self.n, "use_g": self.use_g, "admittance": self.admittance,
             "nullspace_kv": self.nullspace_kv,
+            "joint_parent": None if self.joint_parent is None else list(self.joint_parent),
             "devices": [{
                 "name": d.name, "ctrlr_dof": list(d.ctrlr_dof), "joint_ids_all": list(d.joint_ids_all),
                 "actuator_trnids": list(d.actuator_trnids), "ctrl_idxs": list(d.ctrl_idxs),
                 "dx_idx": list(d.dx_idx), "has_max_vel": d.has_max_vel, "max_vel": list(d.max_vel),
                 "kp": d.kp, "kv": d.kv, "ko": d.ko, "k": list(d.k), "d": list(d.d),
+                "ee_joint": d.ee_joint,
             } for d in self.devices],
         }
 
@@ -89,6 +94,13 @@ class OscLayout:
         p.admittance = int(self.admittance)
         p.has_nullspace = int(self.nullspace_kv is not None)
         p.nullspace_kv = float(self.nullspace_kv or 0.0)
+        p.has_topology = int(self.joint_parent is not None)
+        p.check_topology = int(self.check_topology)
+        for j in range(_native.MAX_N):
+            p.joint_parent[j] = -1
+        if self.joint_parent is not None:
+            for j, v in enumerate(self.joint_parent):
+                p.joint_parent[j] = int(v)
         for i, d in enumerate(self.devices):
             c = p.dev[i]
             for j in range(6):
@@ -107,11 +119,36 @@ class OscLayout:
             for j in range(3):
                 c.k[j] = float(d.k[j])
                 c.d[j] = float(d.d[j])
+            c.ee_joint = int(d.ee_joint)
         return p
 
 
+def joint_parents(model, joint_ids_all) -> Optional[tuple]:
+    """Robot-local parent joint of every robot joint (-1 for roots), from the same body tree that
+    `Device.__init__` walks (device.py:41-64).  None when the model lacks `jnt_bodyid`."""
+    if not hasattr(model, "jnt_bodyid"):
+        return None
+    local = {int(g): i for i, g in enumerate(joint_ids_all)}
+    out = []
+    for g in joint_ids_all:
+        g = int(g)
+        body = int(model.jnt_bodyid[g])
+        parent = -1
+        if g > int(model.body_jntadr[body]):           # several joints on one body: chained
+            parent = g - 1
+        else:
+            b = int(model.body_parentid[body])
+            while b != 0 and int(model.body_jntnum[b]) == 0:
+                b = int(model.body_parentid[b])
+            if b != 0:
+                parent = int(model.body_jntadr[b]) + int(model.body_jntnum[b]) - 1
+        out.append(local.get(parent, -1))
+    return tuple(out)
+
+
 def compile_layout(robot, device_configs: Dict[str, Dict], target_names: Sequence[str],
-                   nullspace_config: Optional[Dict], use_g: bool, admittance: bool) -> OscLayout:
+                   nullspace_config: Optional[Dict], use_g: bool, admittance: bool,
+                   check_topology: bool = False) -> OscLayout:
     """Build the layout for one target order.
 
     robot          : a `Robot` (ours or anything with sub_devices_dict / joint_ids_all)
@@ -140,8 +177,11 @@ def compile_layout(robot, device_configs: Dict[str, Dict], target_names: Sequenc
             max_vel=(float(mv[0]), float(mv[1])) if mv is not None else (0.0, 0.0),
             kp=float(cfg['kp']), kv=float(cfg['kv']), ko=float(cfg['ko']),
             k=tuple(float(x) for x in cfg['k']), d=tuple(float(x) for x in cfg['d']),
+            ee_joint=local.get(int(dev.joint_ids[-1]), -1) if len(dev.joint_ids) else -1,
         ))
     return OscLayout(
         n=int(robot.num_joints_total), devices=tuple(devs), use_g=bool(use_g),
         admittance=bool(admittance),
-        nullspace_kv=None if nullspace_config is None else float(nullspace_config['kv']))
+        nullspace_kv=None if nullspace_config is None else float(nullspace_config['kv']),
+        joint_parent=joint_parents(robot.sim.model, robot.joint_ids_all),
+        check_topology=bool(check_topology))
