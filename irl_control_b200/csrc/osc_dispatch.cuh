@@ -6,6 +6,7 @@
 // variant 0 of a shape is what irlosc_step dispatches to; the others are kept for A/B
 // measurements (irlosc_set_kernel(h, 2 + variant)).
 #pragma once
+#include <cstdlib>
 #include "osc_tiled.cuh"
 #include "osc_rows.cuh"
 #include "osc_tree.cuh"
@@ -23,39 +24,50 @@ struct TiledEntry {
     const char *name;
     int kd;               // tree only
     bool has_base;        // tree only
+    int warps, slots;     // tree only: warps per CTA, input slots per CTA
+    int slot_fixed, priv; // tree only: bytes of the fixed slot part / per-warp scratch
 };
 
 template <int N, int K, int D, int G, bool PACKED, int MINB>
 inline TiledEntry tiled_entry(int variant, const char *name) {
     return TiledEntry{0, N, K, D, PACKED, variant, MINB,
                       (const void *)tiled::osc_step_tiled<N, K, D, G, PACKED, MINB>,
-                      sizeof(tiled::WarpSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name, 0, false};
+                      sizeof(tiled::WarpSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name, 0, false, 0, 0, 0, 0};
 }
 
 template <int N, int K, int D, int G, bool PACKED, int MINB>
 inline TiledEntry rows_entry(int variant, const char *name) {
     return TiledEntry{0, N, K, D, PACKED, variant, MINB,
                       (const void *)rows::osc_step_rows<N, K, D, G, PACKED, MINB>,
-                      sizeof(rows::RowSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name, 0, false};
+                      sizeof(rows::RowSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name, 0, false, 0, 0, 0, 0};
 }
 
-template <int KD, bool HAS_BASE, bool PACKED, int MINB>
+constexpr size_t kTreeSmemLimit = 227 * 1024;
+constexpr int kTreeHeader = 64;
+
+template <int KD, bool HAS_BASE, bool PACKED, int W, int NS, int GW = 1>
 inline TiledEntry tree_entry(int variant, const char *name) {
-    using WS = tree::TreeSmem<KD, HAS_BASE, PACKED>;
-    return TiledEntry{1, tree::kN, WS::K, WS::D, PACKED, variant, MINB,
-                      (const void *)tree::osc_step_tree<KD, HAS_BASE, PACKED, MINB>,
-                      sizeof(WS) * tree::kTreeWarps, name, KD, HAS_BASE};
+    using SLT = tree::TreeSlot<KD, HAS_BASE, PACKED>;
+    using PVT = tree::TreePriv<KD, HAS_BASE>;
+    return TiledEntry{1, tree::kN, SLT::K, SLT::D, PACKED, variant, 1,
+                      (const void *)tree::osc_step_tree<KD, HAS_BASE, PACKED, W, NS, GW>,
+                      kTreeSmemLimit, name, KD, HAS_BASE, W, NS,
+                      (int)(sizeof(SLT) - 16), (int)((sizeof(PVT) + 15) & ~size_t(15))};
 }
 
 inline const TiledEntry *tiled_table(int *count) {
     static const TiledEntry table[] = {
-        // ---- kinematic-tree-sparse (default when the topology is declared)
-        tree_entry<3, true, true, 1>(0, "osc_step_tree<kd3,base,packed>"),
-        tree_entry<3, true, false, 1>(0, "osc_step_tree<kd3,base,dense>"),
-        tree_entry<6, false, true, 1>(0, "osc_step_tree<kd6,packed>"),
-        tree_entry<6, false, false, 1>(0, "osc_step_tree<kd6,dense>"),
-        tree_entry<6, true, true, 1>(0, "osc_step_tree<kd6,base,packed>"),
-        tree_entry<6, true, false, 1>(0, "osc_step_tree<kd6,base,dense>"),
+        // ---- kinematic-tree-sparse (default when the topology is declared); for one variant number
+        //      the first entry whose shared-memory plan fits is taken
+        tree_entry<3, true, true, 7, 3, 1>(0, "osc_step_tree<kd3,base,packed,w7,s3,g1>"),
+        tree_entry<3, true, true, 6, 2, 1>(0, "osc_step_tree<kd3,base,packed,w6,s2,g1>"),
+        tree_entry<3, true, false, 6, 2, 1>(0, "osc_step_tree<kd3,base,dense,w6,s2,g1>"),
+        tree_entry<6, false, true, 4, 2, 1>(0, "osc_step_tree<kd6,packed,w4,s2,g1>"),
+        tree_entry<6, false, false, 3, 2, 1>(0, "osc_step_tree<kd6,dense,w3,s2,g1>"),
+        tree_entry<6, true, true, 4, 2, 1>(0, "osc_step_tree<kd6,base,packed,w4,s2,g1>"),
+        tree_entry<6, true, false, 3, 2, 1>(0, "osc_step_tree<kd6,base,dense,w3,s2,g1>"),
+        tree_entry<3, true, true, 6, 3, 3>(3, "osc_step_tree<kd3,base,packed,w6,s3,g3>"),
+        tree_entry<3, true, true, 4, 4, 1>(4, "osc_step_tree<kd3,base,packed,w4,s4,g1>"),
         // ---- dense (default without topology; variants 1/2 with topology)
         rows_entry<25, 7, 3, 8, true, 2>(1, "osc_step_rows<n25,k7,D3,G8,packed>"),
         rows_entry<25, 7, 3, 8, false, 2>(1, "osc_step_rows<n25,k7,D3,G8,dense>"),
@@ -95,6 +107,8 @@ inline bool tree_roles(const KParams &P, tree::Roles &R, int &kd, bool &has_base
         else if (dv.ee_joint == 0 && R.dev_base < 0) { R.dev_base = d; R.row_base = dv.row0; }
         else return false;
     }
+    R.opt_tvel = R.opt_mvel = R.opt_ftx = R.opt_ftr = -1;
+    R.opt_doubles = R.slot_bytes = R.priv_bytes = 0;
     if (R.dev_arm[0] < 0 || R.dev_arm[1] < 0) return false;
     kd = P.dev[R.dev_arm[0]].kdev;
     if (P.dev[R.dev_arm[1]].kdev != kd || (kd != 3 && kd != 6)) return false;
@@ -127,7 +141,20 @@ inline const TiledEntry *tiled_find(const KParams &P, const KIo &io, int variant
     for (int i = 0; i < cnt; ++i) {
         if (t[i].packed != packed || t[i].variant != want) continue;
         if (t[i].kind == 1) {
-            if (tree_ok && t[i].kd == kd && t[i].has_base == has_base) return &t[i];
+            if (!(tree_ok && t[i].kd == kd && t[i].has_base == has_base)) continue;
+            // shared-memory plan: optional per-instance arrays go to the slot tail
+            int at = 0;
+            const int per = tree::kWI * P.D;
+            if (io.target_vel) { R.opt_tvel = at; at += 6 * per; }
+            if (io.max_vel) { R.opt_mvel = at; at += 2 * per; }
+            if (P.admittance) { R.opt_ftx = at; at += 9 * per; R.opt_ftr = at; at += 6 * per; }
+            R.opt_doubles = at;
+            R.slot_bytes = t[i].slot_fixed + ((at * 8 + 15) & ~15);
+            R.priv_bytes = t[i].priv - 16 + ((at * 8 + 15) & ~15);
+            const size_t total = kTreeHeader + (size_t)t[i].slots * R.slot_bytes + (size_t)t[i].warps * R.priv_bytes;
+            if (total > kTreeSmemLimit) continue;
+            if (roles_out) *roles_out = R;
+            return &t[i];
         } else if (t[i].n == P.n && t[i].k == P.k && t[i].d == P.D) {
             return &t[i];
         }
@@ -144,14 +171,13 @@ inline cudaError_t tiled_launch(const KParams &P, const KIo &io, int64_t B, int 
     tree::Roles R;
     const TiledEntry *e = tiled_find(P, io, variant, &R);
     if (!e) return cudaErrorNotSupported;
-    int ctas = e->ctas_per_sm;
-    if (e->kind == 1) ctas = (int)((227 * 1024) / (e->smem_per_cta + 1024));   // as many CTAs as shared memory holds
-    if (ctas < 1) ctas = 1;
-    const int grid = sm_count * ctas;
+    int grid = sm_count * e->ctas_per_sm;
+    if (const char *g = getenv("IRLOSC_GRID")) grid = atoi(g) > 0 ? atoi(g) : grid;   // experiments only
     *name = e->name;
     if (e->kind == 1) {
+        const size_t smem = kTreeHeader + (size_t)e->slots * R.slot_bytes + (size_t)e->warps * R.priv_bytes;
         void *args[] = {(void *)&P, (void *)&io, (void *)&B, (void *)&R};
-        return cudaLaunchKernel(e->fn, dim3(grid), dim3(tree::kTreeWarps * 32), args, e->smem_per_cta, st);
+        return cudaLaunchKernel(e->fn, dim3(grid), dim3(e->warps * 32), args, smem, st);
     }
     void *args[] = {(void *)&P, (void *)&io, (void *)&B};
     return cudaLaunchKernel(e->fn, dim3(grid), dim3(tiled::kWarpsPerCta * 32), args, e->smem_per_cta, st);

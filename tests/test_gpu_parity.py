@@ -12,7 +12,10 @@ from conftest import GOLDEN_CASES, golden_oracle_batch, load_golden
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-6          # well inside the 1e-4 bar of BASELINE.json
-KERNELS = [1, 0]        # 1 = generic kernel, 0 = auto (tiled where instantiated)
+KERNELS = [1, 0, 3]     # 1 = generic kernel, 0 = auto (tree-sparse kernel when the topology is declared,
+                        # dense register-tiled kernel otherwise), 3 = next specialised variant
+DUAL_UR5_PARENT = (-1, 0, 1, 2, 3, 4, 5, 6, 7, 6, 6, 10, 6, 0, 13, 14, 15, 16, 17, 18, 19, 18, 18, 22, 18)
+EE_JOINT = {"base": 0, "ur5right": 6, "ur5left": 18}
 
 
 def _torch():
@@ -21,14 +24,18 @@ def _torch():
     return torch
 
 
-def _layout_from_dict(ld):
+def _layout_from_dict(ld, topology=False, check=False):
+    """Layout stored with a golden file; `topology` declares the DualUR5 kinematic tree (what the
+    host layer derives from the model), which makes the tree-sparse kernel eligible."""
     from irl_control_b200.layout import DeviceLayout, OscLayout
     devs = tuple(DeviceLayout(name=d["name"], ctrlr_dof=tuple(d["ctrlr_dof"]), joint_ids_all=tuple(d["joint_ids_all"]),
                               actuator_trnids=tuple(d["actuator_trnids"]), ctrl_idxs=tuple(d["ctrl_idxs"]),
                               dx_idx=tuple(d["dx_idx"]), has_max_vel=d["has_max_vel"], max_vel=tuple(d["max_vel"]),
-                              kp=d["kp"], kv=d["kv"], ko=d["ko"], k=tuple(d["k"]), d=tuple(d["d"])) for d in ld["devices"])
+                              kp=d["kp"], kv=d["kv"], ko=d["ko"], k=tuple(d["k"]), d=tuple(d["d"]),
+                              ee_joint=EE_JOINT[d["name"]] if topology else -1) for d in ld["devices"])
     return OscLayout(n=ld["n"], devices=devs, use_g=ld["use_g"], admittance=ld["admittance"],
-                     nullspace_kv=ld["nullspace_kv"])
+                     nullspace_kv=ld["nullspace_kv"], joint_parent=DUAL_UR5_PARENT if topology else None,
+                     check_topology=check)
 
 
 def _golden_state(g, layout, torch, packed_M, full6_J):
@@ -53,16 +60,18 @@ def _rel_err(got, want):
     return (np.abs(got - want) / scale).max(axis=1)
 
 
-@pytest.mark.parametrize("kernel", KERNELS)
+@pytest.mark.parametrize("kernel,topology", [(1, False), (0, False), (0, True), (3, True)])
 @pytest.mark.parametrize("packed_M,full6_J", [(False, False), (True, True), (True, False)])
 @pytest.mark.parametrize("case", GOLDEN_CASES)
-def test_cuda_matches_reference_golden(case, packed_M, full6_J, kernel):
+def test_cuda_matches_reference_golden(case, packed_M, full6_J, kernel, topology):
     torch = _torch()
     from irl_control_b200 import _native
     from irl_control_b200.engine import BatchedOSC
     g, ld = load_golden(case)
-    layout = _layout_from_dict(ld)
+    layout = _layout_from_dict(ld, topology=topology, check=topology)
     eng = BatchedOSC(layout, device=0)
+    if kernel == 3 and full6_J:
+        pytest.skip("specialised variants need the row-stacked Jacobian layout")
     eng.set_kernel(kernel)
     out = eng.step(_golden_state(g, layout, torch, packed_M, full6_J), want_u_all=True)
     torch.cuda.synchronize()
@@ -73,7 +82,7 @@ def test_cuda_matches_reference_golden(case, packed_M, full6_J, kernel):
     ok = ~bad
     if ok.any():
         assert np.array_equal((status[ok] & _native.ST_PINV) != 0, g["pinv"][ok])
-        assert not np.any(status[ok] & (_native.ST_M_NOT_PD | _native.ST_DX_RANGE))
+        assert not np.any(status[ok] & (_native.ST_M_NOT_PD | _native.ST_DX_RANGE | _native.ST_SPARSITY))
         e_u = _rel_err(u_all[ok], g["u_all"][ok])
         e_c = np.abs(ctrl[ok] - g["ctrl"][ok]).max(axis=1) / np.abs(g["u_all"][ok]).max(axis=1)
         print("%s kernel=%s worst rel err u_all %.2e ctrl %.2e" % (case, eng.last_kernel, e_u.max(), e_c.max()))
@@ -96,7 +105,7 @@ def test_cuda_matches_oracle_on_baseline_configs(scenario, B, kernel):
     st = synth_batch(layout, B, seed=B + 1, device="cuda:0", insertion_schedule=(scenario == "insertion"))
     eng = BatchedOSC(layout, device=0)
     eng.set_kernel(kernel)
-    out = eng.step(kernel_inputs(st, layout), want_u_all=True)
+    out = eng.step(kernel_inputs(st, layout, packed_M=(kernel == 3)), want_u_all=True)
     torch.cuda.synchronize()
     u_all, status = out["u_all"].cpu().numpy(), out["status"].cpu().numpy()
     assert np.isfinite(u_all).all() and not np.any(status & (_native.ST_M_NOT_PD | _native.ST_DX_RANGE))
@@ -226,3 +235,41 @@ def test_calc_error_kernel_matches_oracle():
             want = osc_numpy.calc_error(ld["devices"][d], h["ee_xyz"][i, d], h["ee_quat"][i, d],
                                         h["target_xyz"][i, d], h["target_quat"][i, d])
             assert np.abs(err[i, d] - want).max() < 1e-12
+
+
+def test_tree_kernel_is_the_default_for_the_dual_ur5_and_checks_its_contract():
+    """With the kinematic tree declared (what the host layer derives from the model) the sparse
+    kernel runs; check_topology flags instances whose M / J break the declared zeros."""
+    torch = _torch()
+    import dataclasses
+    from irl_control_b200 import _native
+    from irl_control_b200.engine import BatchedOSC
+    from irl_control_b200.synthetic import scenario_layout, synth_batch, kernel_inputs
+    for scenario in ("gain_test", "admit_test", "worst_case"):
+        layout = dataclasses.replace(scenario_layout(scenario), check_topology=True)
+        assert layout.joint_parent == DUAL_UR5_PARENT
+        B = 1001
+        st = synth_batch(layout, B, seed=21, device="cuda:0")
+        kin = kernel_inputs(st, layout, packed_M=True)
+        eng = BatchedOSC(layout, device=0)
+        good = eng.step(kin, want_u_all=True)
+        assert "osc_step_tree" in eng.last_kernel
+        assert not (good["status"] & _native.ST_SPARSITY).any()
+        # dense specialised kernel (variant 1) and generic kernel agree with it
+        eng.set_kernel(3)
+        dense = eng.step(kin, want_u_all=True)
+        assert "osc_step_tree" not in eng.last_kernel
+        scale = dense["u_all"].abs().amax(dim=1, keepdim=True)
+        assert ((good["u_all"] - dense["u_all"]).abs() / scale).max().item() < REL_TOL
+        # break the contract on two instances: right-arm / left-arm coupling in M, gripper column in J
+        bad = {k: v.clone() for k, v in kin.items()}
+        i, j = 15, 3                               # left arm joint 15 x right arm joint 3
+        bad["M"][5, i * (i + 1) // 2 + j] = 1e-3
+        bad["J"][7, 0, 9] = 1e-3                   # first task row, gripper joint column
+        eng.set_kernel(0)
+        out = eng.step(bad, want_u_all=True)
+        flagged = (out["status"] & _native.ST_SPARSITY) != 0
+        assert flagged[5] and flagged[7] and int(flagged.sum()) == 2
+        assert torch.isnan(out["ctrl"][5]).all() and torch.isnan(out["ctrl"][7]).all()
+        ok = ~flagged
+        assert torch.equal(out["ctrl"][ok], good["ctrl"][ok])
