@@ -125,6 +125,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU")
     ap.add_argument("--m-layout", default="packed", choices=["packed", "dense"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")
+    ap.add_argument("--sm-margin", type=int, default=8, help="SMs left to NCCL when --gpus > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -173,6 +174,7 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")     # 8 MB gather: a handful of channels saturates it
         dist.init_process_group("nccl", device_id=dev)
 
     st = synth_batch(layout, B, seed=1000 * rank, device=dev)
@@ -181,23 +183,41 @@ def main():
     config["l2_policy"] = "inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (in_bytes / 1e6)
     eng = BatchedOSC(layout, device=local_rank)
     eng.set_kernel(args.kernel)
-    out = {"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)}
-    gathered = torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) if world > 1 else None
+    if world > 1 and args.sm_margin > 0:
+        eng.set_sm_margin(args.sm_margin)      # the NCCL gather needs a few SMs to overlap the next step's kernel
+    # two output buffers: the NCCL gather of step i (on NCCL's own stream) overlaps the kernel of step i+1
+    outs = [{"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)} for _ in range(2)]
+    out = outs[0]
+    gathered = [torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    pending = [None, None]
+    step_no = [0]
 
     def one_step():
-        eng.step(kin, out=out, want_status=False)
+        b = step_no[0] & 1
+        step_no[0] += 1
+        if pending[b] is not None:
+            pending[b].wait()      # the buffer's previous gather must be done before the kernel overwrites it
+            pending[b] = None
+        eng.step(kin, out=outs[b], want_status=False)
         if world > 1:      # result gather over NVLink (the only exchange on this path)
-            dist.all_gather_into_tensor(gathered, out["ctrl"])
+            pending[b] = dist.all_gather_into_tensor(gathered[b], outs[b]["ctrl"], async_op=True)
+
+    def drain():
+        for b in range(2):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
 
     for _ in range(max(args.warmup, 3)):
         one_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    drain()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()          # all ranks enter the timed region together (after rank 0's sampler start-up)
     launches0 = eng.kernel_launches
     torch.cuda.synchronize()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
@@ -206,11 +226,14 @@ def main():
     for i in range(args.steps):
         one_step()
         ev[i + 1].record()
+    drain()
+    ev_end = torch.cuda.Event(enable_timing=True)
+    ev_end.record()
     torch.cuda.synchronize()
     t_wall1 = time.time()
     if world > 1:
         dist.barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms = ev[0].elapsed_time(ev_end)      # includes the last gather
     launches = eng.kernel_launches - launches0
     # kernel-only time for the roofline: events around the kernel alone, same stream
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

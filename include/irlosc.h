@@ -162,6 +162,10 @@ int32_t irlosc_host_free(void *ptr);
 /* Kernel selection: 0 = auto, 1 = generic (any n, k, layout), 2 + v = variant v of the specialised
  * DualUR5 kernels (v = 0 is what auto picks; others exist for A/B measurements). */
 int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which);
+/* Leave `sms` streaming multiprocessors free when launching the step kernel (default 0), so that a
+ * collective running on another stream (the NCCL gather of ctrl) can overlap instead of queueing
+ * behind a grid that fills every SM. */
+int32_t irlosc_set_sm_margin(irlosc_handle *h, int32_t sms);
 /* Number of kernels this handle has launched since creation (bench.py "gpu_launches"). */
 int64_t irlosc_kernel_launches(const irlosc_handle *h);
 /* Name of the kernel the last step dispatched to (static string). */

@@ -88,7 +88,7 @@ class Io(C.Structure):
 EXPORTS = [
     "irlosc_last_error", "irlosc_abi_version", "irlosc_create", "irlosc_destroy",
     "irlosc_num_task_rows", "irlosc_num_ctrl", "irlosc_step", "irlosc_step_host",
-    "irlosc_calc_error", "irlosc_host_alloc", "irlosc_host_free", "irlosc_set_kernel",
+    "irlosc_calc_error", "irlosc_host_alloc", "irlosc_host_free", "irlosc_set_kernel", "irlosc_set_sm_margin",
     "irlosc_kernel_launches", "irlosc_last_kernel",
 ]
 
@@ -135,6 +135,8 @@ def load() -> C.CDLL:
     lib.irlosc_host_free.argtypes = [C.c_void_p]
     lib.irlosc_set_kernel.restype = C.c_int32
     lib.irlosc_set_kernel.argtypes = [C.c_void_p, C.c_int32]
+    lib.irlosc_set_sm_margin.restype = C.c_int32
+    lib.irlosc_set_sm_margin.argtypes = [C.c_void_p, C.c_int32]
     lib.irlosc_kernel_launches.restype = C.c_int64
     lib.irlosc_kernel_launches.argtypes = [C.c_void_p]
     lib.irlosc_last_kernel.restype = C.c_char_p

@@ -63,7 +63,8 @@ struct irlosc_handle {
     KParams kp;
     int device = 0;
     int sm_count = 0;
-    int kernel_choice = 0;    // 0 auto, 1 generic, 2 tiled
+    int kernel_choice = 0;    // 0 auto, 1 generic, 2 + v specialised variant v
+    int sm_margin = 0;        // SMs left free for overlapping collectives
     int64_t launches = 0;
     const char *last_kernel = "none";
     Staging stage[kPipeDepth];
@@ -188,6 +189,12 @@ extern "C" int32_t irlosc_num_ctrl(const irlosc_handle *h) { return h ? h->kp.n_
 extern "C" int64_t irlosc_kernel_launches(const irlosc_handle *h) { return h ? h->launches : -1; }
 extern "C" const char *irlosc_last_kernel(const irlosc_handle *h) { return h ? h->last_kernel : "none"; }
 
+extern "C" int32_t irlosc_set_sm_margin(irlosc_handle *h, int32_t sms) {
+    if (!h || sms < 0 || sms >= h->sm_count) return fail(IRLOSC_ERR_INVALID, "sm margin must be in 0..%d", h ? h->sm_count - 1 : 0);
+    h->sm_margin = sms;
+    return IRLOSC_OK;
+}
+
 extern "C" int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which) {
     if (!h || which < 0 || which > 9) return fail(IRLOSC_ERR_INVALID, "kernel selector must be 0 (auto), 1 (generic) or 2+v (tiled variant v)");
     h->kernel_choice = which;
@@ -235,11 +242,11 @@ static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream
     if (h->kernel_choice >= 2 && !use_tiled)
         return fail(IRLOSC_ERR_INVALID, "tiled kernel requested but this shape/layout is not supported (n=%d k=%d)", h->kp.n, h->kp.k);
     if (use_tiled) {
-        cudaError_t e = tiled_launch(h->kp, k, B, h->sm_count, st, &h->last_kernel, variant);
+        cudaError_t e = tiled_launch(h->kp, k, B, h->sm_count - h->sm_margin, st, &h->last_kernel, variant);
         if (e != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "tiled kernel launch: %s", cudaGetErrorString(e));
     } else {
         const int64_t blocks_needed = (B + kGenericWarps - 1) / kGenericWarps;
-        const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)h->sm_count * 8);
+        const int grid = (int)std::min<int64_t>(blocks_needed, (int64_t)(h->sm_count - h->sm_margin) * 8);
         osc_step_generic<<<grid, kGenericWarps * 32, sizeof(GenericSmem) * kGenericWarps, st>>>(h->kp, k, B);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "generic kernel launch: %s", cudaGetErrorString(e));

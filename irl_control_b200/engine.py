@@ -65,6 +65,10 @@ class BatchedOSC:
     def set_kernel(self, which: int):
         _native.check(self.lib.irlosc_set_kernel(self._handle, int(which)))
 
+    def set_sm_margin(self, sms: int):
+        """Leave `sms` SMs free so a collective on another stream can overlap the step kernel."""
+        _native.check(self.lib.irlosc_set_sm_margin(self._handle, int(sms)))
+
     @property
     def kernel_launches(self) -> int:
         return int(self.lib.irlosc_kernel_launches(self._handle))
