@@ -45,11 +45,6 @@ namespace {
 
 constexpr int kPipeDepth = 3;   // chunks in flight in irlosc_step_host
 
-struct FieldSpec {            // one per-instance array of irlosc_io
-    size_t in_elems;          // doubles per instance to copy host->device (0 = absent)
-    size_t out_elems;         // doubles (or bytes for status) per instance device->host
-};
-
 struct Staging {
     cudaStream_t stream = nullptr;
     void *buf[16] = {nullptr};
@@ -117,6 +112,8 @@ static int32_t build_kparams(const irlosc_params &u, KParams &kp) {
         t.max_vel[0] = s.max_vel[0];
         t.max_vel[1] = s.max_vel[1];
         t.kp = s.kp; t.kv = s.kv; t.ko = s.ko;
+        t.kv_over_kp = s.kp != 0.0 ? s.kv / s.kp : 0.0;
+        t.kv_over_ko = s.ko != 0.0 ? s.kv / s.ko : 0.0;
         if (!(s.kv != 0.0)) return fail(IRLOSC_ERR_INVALID, "device %d: kv must be non-zero", d);
         for (int i = 0; i < 6; ++i) {
             t.gain[i] = (i < 3) ? s.kp : s.ko;

@@ -31,6 +31,7 @@ struct KDevice {
     int32_t dx_idx[6];
     double max_vel[2];
     double kp, kv, ko;
+    double kv_over_kp, kv_over_ko;   // saturation gains of osc.py:83,90 (max_vel / kp * kv)
     double gain[6];           // task_space_gains (osc.py:37)
     double lamb[6];           // gains / kv      (osc.py:39)
     double stiff[6];          // k + [1,1,1]     (osc.py:160)
@@ -60,6 +61,35 @@ struct KIo {
     double *u_all, *ctrl; uint8_t *status;
 };
 
+// ---------------------------------------------------------------- fast fp64 reciprocal / sqrt
+// IEEE division and sqrt expand to ~25-30 instructions with a slow path each; the task law has a
+// dozen of them on one or two lanes per instance.  Hardware seed + Newton steps give <= 1 ulp-level
+// results in 5-7 instructions (differences vs. the reference's correctly rounded numpy values are
+// ~1e-16 relative, far inside the parity tolerance).
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ double fast_sqrt(double x) {     // x >= 0 and not denormal-small; sqrt(0) = 0
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    // two Newton steps on r ~ 1/sqrt(x), then one correction of s = x r
+    double h = 0.5 * r;
+    double e = fma(-x * r, h, 0.5);
+    r = fma(r, e, r);
+    h = 0.5 * r;
+    e = fma(-x * r, h, 0.5);
+    r = fma(r, e, r);
+    double s = x * r;
+    s = fma(fma(-s, s, x), 0.5 * r, s);
+    return x > 0.0 ? s : 0.0;
+}
+
 // ---------------------------------------------------------------- rotations
 __device__ __forceinline__ void quat_mul(const double *a, const double *b, double *o) {
     o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
@@ -74,7 +104,7 @@ __device__ __forceinline__ void quat_to_euler_sxyz(const double *q, double *e) {
     const double nq = w * w + x * x + y * y + z * z;
     double m00 = 1.0, m10 = 0.0, m20 = 0.0, m21 = 0.0, m22 = 1.0, m11 = 1.0, m12 = 0.0;
     if (nq >= kEps) {
-        const double s = 2.0 / nq;
+        const double s = 2.0 * fast_rcp(nq);
         const double X = x * s, Y = y * s, Z = z * s;
         const double wX = w * X, wY = w * Y, wZ = w * Z;
         const double xX = x * X, xY = x * Y, xZ = x * Z;
@@ -87,7 +117,7 @@ __device__ __forceinline__ void quat_to_euler_sxyz(const double *q, double *e) {
         m11 = 1.0 - (xX + zZ);
         m12 = yZ - wX;
     }
-    const double cy = sqrt(m00 * m00 + m10 * m10);
+    const double cy = fast_sqrt(m00 * m00 + m10 * m10);
     if (cy > 4.0 * kEps) {
         e[0] = atan2(m21, m22);
         e[1] = atan2(-m20, cy);
@@ -110,9 +140,9 @@ __device__ __forceinline__ void device_pose_error(const KDevice &dv, const doubl
         for (int i = 0; i < 3; ++i) u[i] = ee_xyz[i] - t_xyz[i];
     }
     if (dv.any_abg) {
-        const double nn = sqrt(t_quat[0] * t_quat[0] + t_quat[1] * t_quat[1] +
-                               t_quat[2] * t_quat[2] + t_quat[3] * t_quat[3]);
-        const double qd[4] = {t_quat[0] / nn, t_quat[1] / nn, t_quat[2] / nn, t_quat[3] / nn};
+        const double n2 = t_quat[0] * t_quat[0] + t_quat[1] * t_quat[1] + t_quat[2] * t_quat[2] + t_quat[3] * t_quat[3];
+        const double inn = fast_rcp(fast_sqrt(n2));
+        const double qd[4] = {t_quat[0] * inn, t_quat[1] * inn, t_quat[2] * inn, t_quat[3] * inn};
         const double qc[4] = {ee_quat[0], -ee_quat[1], -ee_quat[2], -ee_quat[3]};
         double qr[4];
         quat_mul(qd, qc, qr);
@@ -144,12 +174,12 @@ __device__ __forceinline__ bool device_task_signal(const KDevice &dv, const doub
     if (dv.has_max_vel) {
         // osc.py:79-94
         double sc_xyz = 1.0, sc_abg = 1.0;
-        const double n_xyz = sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
-        const double sat_xyz = max_vel[0] / dv.kp * dv.kv;
-        if (n_xyz > sat_xyz) sc_xyz = sat_xyz / n_xyz;
-        const double n_abg = sqrt(u[3] * u[3] + u[4] * u[4] + u[5] * u[5]);
-        const double sat_abg = max_vel[1] / dv.ko * dv.kv;
-        if (n_abg > sat_abg) sc_abg = sat_abg / n_abg;
+        const double n_xyz = fast_sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        const double sat_xyz = max_vel[0] * dv.kv_over_kp;
+        if (n_xyz > sat_xyz) sc_xyz = sat_xyz * fast_rcp(n_xyz);
+        const double n_abg = fast_sqrt(u[3] * u[3] + u[4] * u[4] + u[5] * u[5]);
+        const double sat_abg = max_vel[1] * dv.kv_over_ko;
+        if (n_abg > sat_abg) sc_abg = sat_abg * fast_rcp(n_abg);
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
             const double sc = (i < 3) ? sc_xyz : sc_abg;

@@ -304,8 +304,8 @@ osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
             const int ro = rowoff(jb + i - 1);
             sfor<0, i + 1>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
-                double v = Ms[ro + ccol(j)];
-                v = (h == 0) ? v : 0.0;                       // the h = 1 copy accumulates updates only
+                double v = 0.0;                               // the h = 1 copy accumulates updates only
+                if (h == 0) v = Ms[ro + ccol(j)];
                 c[i * (i + 1) / 2 + j] = v;
                 uvC[i] = fma(v, dqc[j], uvC[i]);
                 if constexpr (j != i) uvC[j] = fma(v, dqc[i], uvC[j]);
