@@ -372,7 +372,7 @@ osc_step_rows(const KParams P, const KIo io, const int64_t B) {
             hard_mask &= hard_mask - 1;
             const int gi = src / G;
             const bool gi_abad = __shfl_sync(FULL, a_bad ? 1 : 0, src) != 0;
-            tiled::eigen_solve<K>(S.As[gi], S.Vs, S.g[gi], S.w[gi], S.u[gi], !gi_abad, lane, &S.flags[gi]);
+            tiled::eigen_solve<K>(S.As[gi], S.Vs, S.g[gi], S.w[gi], S.u[gi], S.dx[gi], !gi_abad, lane, &S.flags[gi]);
         }
         __syncwarp();
 

@@ -132,11 +132,24 @@ struct WarpSmem {
     alignas(8) unsigned long long bar_v;
 };
 
-// Warp-cooperative symmetric eigen-solve for one instance (pinv / indefinite fallback).
-// A (destroyed) and V have leading dimension K+1; result w = V f(lambda) V^T g.
+// Warp-cooperative symmetric eigen-solve for one instance (pinv / indefinite fallback):
+// parallel-order Jacobi.  A round-robin schedule gives K/2 disjoint (p, q) pairs per round, so one
+// round applies K/2 rotations with three passes over the matrix (columns of A and V, rows of A,
+// clean-up) instead of one barrier-separated pass per rotation.
+// A (destroyed) and V have leading dimension K+1; cbuf / sbuf hold >= K doubles each;
+// result w = V f(lambda) V^T g.
 template <int K>
-__device__ void eigen_solve(double (*A)[K + 1], double (*V)[K + 1], const double *g, double *w, double *tmp,
-                            bool force_pinv, int lane, int *flags_out) {
+__device__ void eigen_solve(double (*A)[K + 1], double (*V)[K + 1], const double *g, double *w, double *cbuf,
+                            double *sbuf, bool force_pinv, int lane, int *flags_out) {
+    constexpr int M = (K % 2 == 0) ? K : K + 1;      // players of the round-robin (one dummy when K is odd)
+    constexpr int KP = M / 2;                        // pairs per round
+    auto pair_of = [](int r, int t, int &p, int &q) {
+        int a, b;
+        if (t == 0) { a = M - 1; b = r % (M - 1); }
+        else { a = (r + t) % (M - 1); b = (r - t + 2 * (M - 1)) % (M - 1); }
+        p = a < b ? a : b;
+        q = a < b ? b : a;
+    };
     for (int i = lane; i < K * K; i += 32) V[i / K][i % K] = (i / K == i % K) ? 1.0 : 0.0;
     __syncwarp();
     for (int sweep = 0; sweep < 60; ++sweep) {
@@ -148,31 +161,58 @@ __device__ void eigen_solve(double (*A)[K + 1], double (*V)[K + 1], const double
         off = warp_sum(off);
         dia = warp_sum(dia);
         if (off <= 1e-28 * dia || off == 0.0) break;
-        for (int p = 0; p < K - 1; ++p)
-            for (int q = p + 1; q < K; ++q) {
-                const double apq = A[p][q], app = A[p][p], aqq = A[q][q];
-                __syncwarp();
-                if (fabs(apq) <= 1e-300 || apq * apq <= 1e-31 * fabs(app * aqq)) continue;
-                const double theta = (aqq - app) / (2.0 * apq);
-                const double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(tt * tt + 1.0), s = tt * c;
-                if (lane < K) {
-                    const int i = lane;
-                    if (i != p && i != q) {
-                        const double aip = A[i][p], aiq = A[i][q];
-                        const double nip = c * aip - s * aiq, niq = s * aip + c * aiq;
-                        A[i][p] = nip; A[p][i] = nip; A[i][q] = niq; A[q][i] = niq;
+        for (int r = 0; r < M - 1; ++r) {
+            if (lane < KP) {                         // rotation of pair `lane`
+                int p, q;
+                pair_of(r, lane, p, q);
+                double c = 1.0, sn = 0.0;
+                if (q < K) {
+                    const double apq = A[p][q], app = A[p][p], aqq = A[q][q];
+                    if (!(fabs(apq) <= 1e-300 || apq * apq <= 1e-31 * fabs(app * aqq))) {
+                        const double theta = (aqq - app) * fast_rcp(2.0 * apq);
+                        const double tt = (theta >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(theta) + fast_sqrt(theta * theta + 1.0));
+                        c = fast_rcp(fast_sqrt(tt * tt + 1.0));
+                        sn = tt * c;
                     }
-                    const double vip = V[i][p], viq = V[i][q];
-                    V[i][p] = c * vip - s * viq;
-                    V[i][q] = s * vip + c * viq;
                 }
-                if (lane == 0) {
-                    A[p][p] = app - tt * apq; A[q][q] = aqq + tt * apq;
-                    A[p][q] = 0.0; A[q][p] = 0.0;
-                }
-                __syncwarp();
+                cbuf[lane] = c;
+                sbuf[lane] = sn;
             }
+            __syncwarp();
+            for (int e = lane; e < K * KP; e += 32) {        // A <- A J, V <- V J (columns p, q)
+                const int i = e / KP, t = e % KP;
+                int p, q;
+                pair_of(r, t, p, q);
+                if (q < K) {
+                    const double c = cbuf[t], sn = sbuf[t];
+                    const double aip = A[i][p], aiq = A[i][q];
+                    A[i][p] = c * aip - sn * aiq;
+                    A[i][q] = sn * aip + c * aiq;
+                    const double vip = V[i][p], viq = V[i][q];
+                    V[i][p] = c * vip - sn * viq;
+                    V[i][q] = sn * vip + c * viq;
+                }
+            }
+            __syncwarp();
+            for (int e = lane; e < K * KP; e += 32) {        // A <- J^T A (rows p, q)
+                const int j = e / KP, t = e % KP;
+                int p, q;
+                pair_of(r, t, p, q);
+                if (q < K) {
+                    const double c = cbuf[t], sn = sbuf[t];
+                    const double apj = A[p][j], aqj = A[q][j];
+                    A[p][j] = c * apj - sn * aqj;
+                    A[q][j] = sn * apj + c * aqj;
+                }
+            }
+            __syncwarp();
+            if (lane < KP) {                         // the rotated pair is exactly decoupled
+                int p, q;
+                pair_of(r, lane, p, q);
+                if (q < K && sbuf[lane] != 0.0) { A[p][q] = 0.0; A[q][p] = 0.0; }
+            }
+            __syncwarp();
+        }
     }
     __syncwarp();
     double lmax = 0.0, det = 1.0;
@@ -183,12 +223,12 @@ __device__ void eigen_solve(double (*A)[K + 1], double (*V)[K + 1], const double
         double proj = 0.0;
         for (int i = 0; i < K; ++i) proj += V[i][lane] * g[i];
         const bool keep = pinv ? (fabs(lam) > kPinvRcond * lmax) : true;
-        tmp[lane] = keep ? proj / lam : 0.0;
+        cbuf[lane] = keep ? proj / lam : 0.0;
     }
     __syncwarp();
     if (lane < K) {
         double acc = 0.0;
-        for (int c = 0; c < K; ++c) acc += V[lane][c] * tmp[c];
+        for (int c = 0; c < K; ++c) acc += V[lane][c] * cbuf[c];
         w[lane] = acc;
     }
     if (lane == 0) *flags_out |= IRLOSC_ST_EIGEN | (pinv ? IRLOSC_ST_PINV : 0);
@@ -551,7 +591,7 @@ osc_step_tiled(const KParams P, const KIo io, const int64_t B) {
             hard_mask &= hard_mask - 1;
             const int gi = src / G;
             const bool gi_abad = __shfl_sync(0xffffffffu, a_bad ? 1 : 0, src) != 0;
-            eigen_solve<K>(S.As[gi], S.Vs, S.g[gi], S.w[gi], S.u[gi], !gi_abad, lane, &S.flags[gi]);
+            eigen_solve<K>(S.As[gi], S.Vs, S.g[gi], S.w[gi], S.u[gi], S.dx[gi], !gi_abad, lane, &S.flags[gi]);
         }
         __syncwarp();
 

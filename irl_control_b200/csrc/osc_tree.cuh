@@ -608,7 +608,7 @@ osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
             hard_mask &= hard_mask - 1;
             const int gi = src / G;
             const bool gi_abad = __shfl_sync(FULL, a_bad ? 1 : 0, src) != 0;
-            tiled::eigen_solve<K>(PV.As[gi], PV.Vs, PV.g[gi], PV.w[gi], PV.dx[gi], !gi_abad, lane, &PV.flags[gi]);
+            tiled::eigen_solve<K>(PV.As[gi], PV.Vs, PV.g[gi], PV.w[gi], PV.dx[gi], PV.j0[gi], !gi_abad, lane, &PV.flags[gi]);
         }
         __syncwarp();
 
