@@ -68,16 +68,15 @@ inline const TiledEntry *tiled_table(int *count) {
         tree_entry<6, true, false, 3, 2, 1>(0, "osc_step_tree<kd6,base,dense,w3,s2,g1>"),
         tree_entry<3, true, true, 6, 3, 3>(3, "osc_step_tree<kd3,base,packed,w6,s3,g3>"),
         tree_entry<3, true, true, 4, 4, 1>(4, "osc_step_tree<kd3,base,packed,w4,s4,g1>"),
-        // ---- dense (default without topology; variants 1/2 with topology)
+        // ---- dense: default without topology (variant 1 when a topology is declared), all DualUR5 shapes;
+        //      variant 2 keeps the column/scratch kernel of the headline shape for A/B runs
         rows_entry<25, 7, 3, 8, true, 2>(1, "osc_step_rows<n25,k7,D3,G8,packed>"),
         rows_entry<25, 7, 3, 8, false, 2>(1, "osc_step_rows<n25,k7,D3,G8,dense>"),
         tiled_entry<25, 7, 3, 8, true, 2>(2, "osc_step_tiled<n25,k7,D3,G8,packed>"),
         tiled_entry<25, 12, 2, 16, true, 2>(1, "osc_step_tiled<n25,k12,D2,G16,packed>"),
         tiled_entry<25, 12, 2, 16, false, 2>(1, "osc_step_tiled<n25,k12,D2,G16,dense>"),
-        rows_entry<25, 12, 2, 16, true, 2>(2, "osc_step_rows<n25,k12,D2,G16,packed>"),
         tiled_entry<25, 13, 3, 16, true, 2>(1, "osc_step_tiled<n25,k13,D3,G16,packed>"),
         tiled_entry<25, 13, 3, 16, false, 2>(1, "osc_step_tiled<n25,k13,D3,G16,dense>"),
-        rows_entry<25, 13, 3, 16, true, 2>(2, "osc_step_rows<n25,k13,D3,G16,packed>"),
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;

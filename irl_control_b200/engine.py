@@ -117,11 +117,14 @@ class BatchedOSC:
 
     # ------------------------------------------------------------------
     def step(self, state: Dict, out: Optional[Dict] = None, want_u_all: bool = False,
-             want_status: bool = True) -> Dict:
+             want_status: bool = True, strides: Optional[Dict[str, int]] = None) -> Dict:
         """One control step for B instances resident on the GPU.
 
-        state : dict of CUDA float64 contiguous tensors (see module docstring)
-        out   : optional preallocated {"ctrl", "u_all", "status"} tensors
+        state   : dict of CUDA float64 contiguous tensors (see module docstring)
+        out     : optional preallocated {"ctrl", "u_all", "status"} tensors
+        strides : optional {"ldm", "m_stride", "ldj", "j_stride"} in doubles when M / J are views into
+                  larger buffers, e.g. the robot block of the scene's nv x nv `mj_fullM` output
+                  (robot.py:69-71) - `M` is then `[B, nv, nv]` and ldm = nv, m_stride = nv * nv.
         """
         import torch
         M = state["M"]
@@ -130,6 +133,11 @@ class BatchedOSC:
         B = int(M.shape[0])
         m_layout, j_layout = self._infer_layouts(state)
         shapes = self._shapes(B, m_layout, j_layout)
+        strides = strides or {}
+        if "ldm" in strides:
+            shapes["M"] = tuple(M.shape)            # a view: the caller vouches for ldm / m_stride
+        if "ldj" in strides:
+            shapes["J"] = tuple(state["J"].shape)
 
         def ok(name, t):
             if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device == M.device):
@@ -150,6 +158,8 @@ class BatchedOSC:
         io.ctrl = out["ctrl"].data_ptr()
         io.u_all = out["u_all"].data_ptr() if "u_all" in out else None
         io.status = out["status"].data_ptr() if "status" in out else None
+        io.ldm, io.m_stride = int(strides.get("ldm", 0)), int(strides.get("m_stride", 0))
+        io.ldj, io.j_stride = int(strides.get("ldj", 0)), int(strides.get("j_stride", 0))
         stream = torch.cuda.current_stream(M.device).cuda_stream
         with torch.cuda.device(M.device):
             _native.check(self.lib.irlosc_step(self._handle, B, C.byref(io), C.c_void_p(stream)))

@@ -273,3 +273,38 @@ def test_tree_kernel_is_the_default_for_the_dual_ur5_and_checks_its_contract():
         assert torch.isnan(out["ctrl"][5]).all() and torch.isnan(out["ctrl"][7]).all()
         ok = ~flagged
         assert torch.equal(out["ctrl"][ok], good["ctrl"][ok])
+
+
+def test_scene_sized_views_and_bad_inputs():
+    """M handed over as the robot block of the scene's nv x nv matrix (robot.py:69-71: nv = 49 in the
+    insertion scene) and J with nv columns, through explicit strides; and a non-PD M is flagged."""
+    torch = _torch()
+    from irl_control_b200 import _native
+    from irl_control_b200.engine import BatchedOSC
+    from irl_control_b200.synthetic import scenario_layout, synth_batch, kernel_inputs
+    layout = scenario_layout("insertion")
+    B, n, nv = 257, 25, 49
+    st = synth_batch(layout, B, seed=33, device="cuda:0", insertion_schedule=True)
+    kin = kernel_inputs(st, layout)
+    eng = BatchedOSC(layout, device=0)
+    ref = eng.step(kin, want_u_all=True)
+    ref = {k: v.clone() for k, v in ref.items()}
+    Mfull = torch.zeros(B, nv, nv, dtype=torch.float64, device="cuda:0")
+    Mfull[:, :n, :n] = kin["M"]
+    Mfull[:, n:, n:] = 0.05 * torch.eye(nv - n, dtype=torch.float64, device="cuda:0")
+    Jfull = torch.zeros(B, layout.k, nv, dtype=torch.float64, device="cuda:0")
+    Jfull[:, :, :n] = kin["J"]
+    view = dict(kin, M=Mfull, J=Jfull)
+    out = eng.step(view, want_u_all=True, strides={"ldm": nv, "m_stride": nv * nv, "ldj": nv, "j_stride": layout.k * nv})
+    assert eng.last_kernel == "osc_step_generic"
+    scale = ref["u_all"].abs().amax(dim=1, keepdim=True)
+    assert ((out["u_all"] - ref["u_all"]).abs() / scale).max().item() < REL_TOL
+    assert torch.equal(out["status"] & _native.ST_PINV, ref["status"] & _native.ST_PINV)
+    # an indefinite inertia matrix cannot be factorised: flagged, outputs NaN, neighbours untouched
+    bad = {k: v.clone() for k, v in kin.items()}
+    bad["M"][3, 4, 4] = -1.0
+    out = eng.step(bad, want_u_all=True)
+    assert (out["status"][3] & _native.ST_M_NOT_PD) != 0 and torch.isnan(out["ctrl"][3]).all()
+    keep = torch.ones(B, dtype=torch.bool, device="cuda:0")
+    keep[3] = False
+    assert torch.equal(out["ctrl"][keep], ref["ctrl"][keep])

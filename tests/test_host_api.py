@@ -122,3 +122,34 @@ def test_dynamics_model_consistency():
     ee = m.body_name2id("ur_EE_ur5left")
     jp, jr = d.jac_body(ee)
     assert jp[:, :, 1:13].abs().max() == 0 and jp[:, :, 19:].abs().max() == 0   # other arm / own gripper columns
+
+
+def test_topology_is_derived_from_the_model_tree():
+    """joint_parent / ee_joint come from the same body tree Device.__init__ walks (device.py:41-64)."""
+    _, _, _, L = build_scenario("gain_test")
+    assert L.joint_parent == (-1, 0, 1, 2, 3, 4, 5, 6, 7, 6, 6, 10, 6, 0, 13, 14, 15, 16, 17, 18, 19, 18, 18, 22, 18)
+    assert [d.ee_joint for d in L.devices] == [6, 18, 0]
+    p = L.to_c_params()
+    assert p.has_topology == 1 and p.check_topology == 0 and p.dev[0].ee_joint == 6
+    assert list(p.joint_parent)[:25] == list(L.joint_parent)
+    # structural zeros promised by that tree really are exact zeros in the synthetic states
+    import torch
+    from irl_control_b200.synthetic import synth_batch
+    st = synth_batch(L, 16, seed=2)
+    anc = []
+    for i in range(25):
+        a, j = set(), i
+        while j >= 0:
+            a.add(j)
+            j = L.joint_parent[j]
+        anc.append(a)
+    M = st["M"].numpy()
+    for i in range(25):
+        for j in range(i):
+            if j not in anc[i]:
+                assert (M[:, i, j] == 0).all()
+    J = st["J6"].numpy()
+    for d, dl in enumerate(L.devices):
+        for j in range(25):
+            if j not in anc[dl.ee_joint]:
+                assert (J[:, d, :, j] == 0).all()
