@@ -125,7 +125,9 @@ def main():
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU")
     ap.add_argument("--m-layout", default="packed", choices=["packed", "dense"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")
-    ap.add_argument("--sm-margin", type=int, default=8, help="SMs left to NCCL when --gpus > 1")
+    ap.add_argument("--sm-margin", type=int, default=-1,
+                    help="SMs left free for the gather when --gpus > 1 (-1: 0 for the fused gather, 8 for NCCL)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="result gather for --gpus > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -183,29 +185,67 @@ def main():
     config["l2_policy"] = "inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (in_bytes / 1e6)
     eng = BatchedOSC(layout, device=local_rank)
     eng.set_kernel(args.kernel)
-    if world > 1 and args.sm_margin > 0:
-        eng.set_sm_margin(args.sm_margin)      # the NCCL gather needs a few SMs to overlap the next step's kernel
-    # two output buffers: the NCCL gather of step i (on NCCL's own stream) overlaps the kernel of step i+1
+    # Result gather for N > 1 (the only exchange on this path), two output buffers so that the gather
+    # of step i overlaps the kernel of step i+1:
+    #   fused : the step kernel stores its ctrl rows straight into every rank's gathered array through
+    #           peer-mapped symmetric memory (NVLink stores), followed by a symmetric-memory barrier
+    #   nccl  : all_gather_into_tensor on NCCL's stream (fallback, or --gather nccl)
     outs = [{"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)} for _ in range(2)]
     out = outs[0]
-    gathered = [torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    gathered = None
     pending = [None, None]
     step_no = [0]
+    gather_mode = "none"
+    if world > 1:
+        gather_mode = "nccl"
+        if args.gather == "fused":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                gathered = [symm_mem.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(2)]
+                handles = [symm_mem.rendezvous(t, dist.group.WORLD) for t in gathered]
+                peer_ptrs = [[int(h.buffer_ptrs[r]) for r in range(world)] for h in handles]
+                side = torch.cuda.Stream(device=dev)
+                gather_mode = "fused"
+            except Exception as exc:          # no symmetric memory on this box: NCCL gather
+                sys.stderr.write("fused gather unavailable (%s), using NCCL\n" % exc)
+        if gather_mode == "nccl":
+            gathered = [torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(2)]
+
+    margin = args.sm_margin if args.sm_margin >= 0 else (8 if gather_mode == "nccl" else 0)
+    if world > 1 and margin > 0:
+        eng.set_sm_margin(margin)      # the NCCL gather kernel needs a few SMs to overlap the next step's kernel
 
     def one_step():
         b = step_no[0] & 1
         step_no[0] += 1
-        if pending[b] is not None:
-            pending[b].wait()      # the buffer's previous gather must be done before the kernel overwrites it
+        if pending[b] is not None:          # the buffer's previous gather must be complete before it is overwritten
+            if gather_mode == "fused":
+                torch.cuda.current_stream().wait_event(pending[b])
+            else:
+                pending[b].wait()
             pending[b] = None
-        eng.step(kin, out=outs[b], want_status=False)
-        if world > 1:      # result gather over NVLink (the only exchange on this path)
-            pending[b] = dist.all_gather_into_tensor(gathered[b], outs[b]["ctrl"], async_op=True)
+        if gather_mode == "fused":
+            eng.step(kin, out=outs[b], want_status=False, gather=(peer_ptrs[b], rank * B))
+            done = torch.cuda.Event()
+            done.record()
+            with torch.cuda.stream(side):   # cross-GPU barrier off the critical path of the next kernel
+                side.wait_event(done)
+                handles[b].barrier(channel=b)
+                fin = torch.cuda.Event()
+                fin.record()
+            pending[b] = fin
+        else:
+            eng.step(kin, out=outs[b], want_status=False)
+            if gather_mode == "nccl":
+                pending[b] = dist.all_gather_into_tensor(gathered[b], outs[b]["ctrl"], async_op=True)
 
     def drain():
         for b in range(2):
             if pending[b] is not None:
-                pending[b].wait()
+                if gather_mode == "fused":
+                    torch.cuda.current_stream().wait_event(pending[b])
+                else:
+                    pending[b].wait()
                 pending[b] = None
 
     for _ in range(max(args.warmup, 3)):
@@ -307,6 +347,7 @@ def main():
         nsample = (os.cpu_count() or 1) * 192
         sub = {k: v[:nsample] for k, v in st.items()}
         cb = cpu_baseline(layout, oracle_inputs(sub, layout))
+    config["gather"] = gather_mode
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,

@@ -27,10 +27,11 @@
 extern "C" {
 #endif
 
-#define IRLOSC_ABI_VERSION 2
+#define IRLOSC_ABI_VERSION 3
 #define IRLOSC_MAX_DEVICES 4   /* target devices per controller (DualUR5: base + 2 arms) */
 #define IRLOSC_MAX_N 32        /* robot DoF, Robot.num_joints_total (robot.py:32); DualUR5: 25 */
 #define IRLOSC_MAX_K 24        /* stacked task rows, sum of ctrlr_dof over targets; DualUR5: <= 13 */
+#define IRLOSC_MAX_PEERS 8     /* GPUs of one NVSwitch domain the result gather can be fused over */
 
 /* return codes */
 #define IRLOSC_OK 0
@@ -123,6 +124,15 @@ typedef struct irlosc_io {
     double *u_all;            /* [B][n]      out, optional: joint-space signal before packing (osc.py:152-200) */
     double *ctrl;             /* [B][n_ctrl] out: u_all[actuator_trnids] per target, concatenated (osc.py:203-208) */
     uint8_t *status;          /* [B]         out, optional: IRLOSC_ST_* bits                           */
+    /* Fused result gather (irlosc_step only).  When the batch is sharded over the GPUs of one box,
+     * the step kernel can write its packed ctrl rows straight into the gathered [B_total][n_ctrl]
+     * array of every rank through peer-mapped pointers (NVLink 5 / NVSwitch stores) instead of a
+     * separate all-gather: row (gather_offset + i) of each ctrl_gather[g].  The caller provides the
+     * cross-GPU barrier before anyone reads the gathered arrays. */
+    int32_t n_gather;         /* number of entries of ctrl_gather, 0 = no fused gather               */
+    int32_t reserved_;
+    int64_t gather_offset;    /* first gathered row of this rank's shard                             */
+    double *ctrl_gather[IRLOSC_MAX_PEERS];
 } irlosc_io;
 
 typedef struct irlosc_handle irlosc_handle;

@@ -12,7 +12,8 @@ from typing import Optional
 MAX_DEVICES = 4
 MAX_N = 32
 MAX_K = 24
-ABI_VERSION = 2
+MAX_PEERS = 8
+ABI_VERSION = 3
 
 ST_PINV = 0x01
 ST_M_NOT_PD = 0x02
@@ -82,6 +83,8 @@ class Io(C.Structure):
         ("target_vel", C.c_void_p), ("max_vel", C.c_void_p),
         ("ft_xmat", C.c_void_p), ("ft_raw", C.c_void_p),
         ("u_all", C.c_void_p), ("ctrl", C.c_void_p), ("status", C.c_void_p),
+        ("n_gather", C.c_int32), ("reserved_", C.c_int32), ("gather_offset", C.c_int64),
+        ("ctrl_gather", C.c_void_p * MAX_PEERS),
     ]
 
 

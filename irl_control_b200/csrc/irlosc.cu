@@ -228,6 +228,12 @@ static int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k) {
     k.target_xyz = io->target_xyz; k.target_quat = io->target_quat; k.target_vel = io->target_vel;
     k.max_vel = io->max_vel; k.ft_xmat = io->ft_xmat; k.ft_raw = io->ft_raw;
     k.u_all = io->u_all; k.ctrl = io->ctrl; k.status = io->status;
+    if (io->n_gather < 0 || io->n_gather > IRLOSC_MAX_PEERS) return fail(IRLOSC_ERR_INVALID, "n_gather=%d outside 0..%d", io->n_gather, IRLOSC_MAX_PEERS);
+    k.n_gather = io->n_gather; k.gather_offset = io->gather_offset;
+    for (int g = 0; g < IRLOSC_MAX_PEERS; ++g) {
+        k.ctrl_gather[g] = g < io->n_gather ? io->ctrl_gather[g] : nullptr;
+        if (g < io->n_gather && !k.ctrl_gather[g]) return fail(IRLOSC_ERR_INVALID, "ctrl_gather[%d] is null", g);
+    }
     return IRLOSC_OK;
 }
 
@@ -322,6 +328,7 @@ extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io
     int32_t rc = resolve_io(h, io, hk);
     if (rc != IRLOSC_OK) return rc;
     if (B == 0) return IRLOSC_OK;
+    if (hk.n_gather != 0) return fail(IRLOSC_ERR_INVALID, "the fused gather is only available with irlosc_step (device pointers)");
     const KParams &P = h->kp;
     CUDA_TRY(cudaSetDevice(h->device));
     for (int s = 0; s < kPipeDepth; ++s)

@@ -59,7 +59,16 @@ struct KIo {
     const double *dq, *bias, *ee_xyz, *ee_quat, *target_xyz, *target_quat;
     const double *target_vel, *max_vel, *ft_xmat, *ft_raw;
     double *u_all, *ctrl; uint8_t *status;
+    int32_t n_gather; int64_t gather_offset;
+    double *ctrl_gather[IRLOSC_MAX_PEERS];
 };
+
+// Packed control output (osc.py:203-208): local array plus, when the gather is fused, the same
+// row in every peer's gathered array (plain stores to peer-mapped memory travel over NVLink).
+__device__ __forceinline__ void store_ctrl(const KIo &io, int n_ctrl, int64_t inst, int c, double v) {
+    io.ctrl[inst * n_ctrl + c] = v;
+    for (int g = 0; g < io.n_gather; ++g) io.ctrl_gather[g][(io.gather_offset + inst) * n_ctrl + c] = v;
+}
 
 // ---------------------------------------------------------------- fast fp64 reciprocal / sqrt
 // IEEE division and sqrt expand to ~25-30 instructions with a slow path each; the task law has a

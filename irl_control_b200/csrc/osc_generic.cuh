@@ -292,7 +292,7 @@ osc_step_generic(const KParams P, const KIo io, const int64_t B) {
         if (lane < P.n_ctrl) {
             int d = 0;
             while (d + 1 < D && lane >= P.dev[d + 1].ctrl0) ++d;
-            io.ctrl[b * P.n_ctrl + lane] = S.u[P.dev[d].actuator[lane - P.dev[d].ctrl0]];
+            store_ctrl(io, P.n_ctrl, b, lane, S.u[P.dev[d].actuator[lane - P.dev[d].ctrl0]]);
         }
         if (io.status && lane == 0)
             io.status[b] = (uint8_t)(S.flags | fl | (m_bad ? IRLOSC_ST_M_NOT_PD : 0));

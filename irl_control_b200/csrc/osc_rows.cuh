@@ -407,7 +407,7 @@ osc_step_rows(const KParams P, const KIo io, const int64_t B) {
             if (c < P.n_ctrl && valid) {
                 int d = 0;
                 while (d + 1 < D && c >= P.dev[d + 1].ctrl0) ++d;
-                io.ctrl[inst * P.n_ctrl + c] = S.u[grp][P.dev[d].actuator[c - P.dev[d].ctrl0]];
+                store_ctrl(io, P.n_ctrl, inst, c, S.u[grp][P.dev[d].actuator[c - P.dev[d].ctrl0]]);
             }
         }
         if (io.status && valid && l == 0) io.status[inst] = (uint8_t)flg;

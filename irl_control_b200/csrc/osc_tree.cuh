@@ -659,7 +659,7 @@ osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
             if (cidx < P.n_ctrl && valid) {
                 int d = 0;
                 while (d + 1 < D && cidx >= P.dev[d + 1].ctrl0) ++d;
-                io.ctrl[inst * P.n_ctrl + cidx] = PV.uv[grp][P.dev[d].actuator[cidx - P.dev[d].ctrl0]];
+                store_ctrl(io, P.n_ctrl, inst, cidx, PV.uv[grp][P.dev[d].actuator[cidx - P.dev[d].ctrl0]]);
             }
         }
         if (io.status && valid && l == 0) io.status[inst] = (uint8_t)flg;

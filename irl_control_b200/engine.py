@@ -117,7 +117,8 @@ class BatchedOSC:
 
     # ------------------------------------------------------------------
     def step(self, state: Dict, out: Optional[Dict] = None, want_u_all: bool = False,
-             want_status: bool = True, strides: Optional[Dict[str, int]] = None) -> Dict:
+             want_status: bool = True, strides: Optional[Dict[str, int]] = None,
+             gather: Optional[tuple] = None) -> Dict:
         """One control step for B instances resident on the GPU.
 
         state   : dict of CUDA float64 contiguous tensors (see module docstring)
@@ -125,6 +126,10 @@ class BatchedOSC:
         strides : optional {"ldm", "m_stride", "ldj", "j_stride"} in doubles when M / J are views into
                   larger buffers, e.g. the robot block of the scene's nv x nv `mj_fullM` output
                   (robot.py:69-71) - `M` is then `[B, nv, nv]` and ldm = nv, m_stride = nv * nv.
+        gather  : optional (peer_ptrs, row_offset): device pointers of every rank's gathered
+                  `[B_total, n_ctrl]` array (peer-mapped, e.g. torch symmetric memory `buffer_ptrs`);
+                  the kernel then also stores its ctrl rows at row_offset + i of each of them
+                  (fused NVLink gather, see `irlosc_io.ctrl_gather`).
         """
         import torch
         M = state["M"]
@@ -158,6 +163,13 @@ class BatchedOSC:
         io.ctrl = out["ctrl"].data_ptr()
         io.u_all = out["u_all"].data_ptr() if "u_all" in out else None
         io.status = out["status"].data_ptr() if "status" in out else None
+        if gather is not None:
+            ptrs, offset = gather
+            if len(ptrs) > _native.MAX_PEERS:
+                raise ValueError("at most %d peers" % _native.MAX_PEERS)
+            io.n_gather, io.gather_offset = len(ptrs), int(offset)
+            for gi, ptr in enumerate(ptrs):
+                io.ctrl_gather[gi] = int(ptr)
         io.ldm, io.m_stride = int(strides.get("ldm", 0)), int(strides.get("m_stride", 0))
         io.ldj, io.j_stride = int(strides.get("ldj", 0)), int(strides.get("j_stride", 0))
         stream = torch.cuda.current_stream(M.device).cuda_stream
