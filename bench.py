@@ -127,7 +127,9 @@ def main():
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")
     ap.add_argument("--sm-margin", type=int, default=-1,
                     help="SMs left free for the gather when --gpus > 1 (-1: 0 for the fused gather, 8 for NCCL)")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl"], help="result gather for --gpus > 1")
+    ap.add_argument("--gather-buffers", type=int, default=3, help="gathered output buffers in flight (>= 2)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "peer", "nccl"],
+                    help="result gather for --gpus > 1: fused = multicast stores if the box has NVLS, else peer stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -185,47 +187,53 @@ def main():
     config["l2_policy"] = "inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (in_bytes / 1e6)
     eng = BatchedOSC(layout, device=local_rank)
     eng.set_kernel(args.kernel)
-    # Result gather for N > 1 (the only exchange on this path), two output buffers so that the gather
+    # Result gather for N > 1 (the only exchange on this path), NBUF output buffers so that the gather
     # of step i overlaps the kernel of step i+1:
     #   fused : the step kernel stores its ctrl rows straight into every rank's gathered array through
     #           peer-mapped symmetric memory (NVLink stores), followed by a symmetric-memory barrier
     #   nccl  : all_gather_into_tensor on NCCL's stream (fallback, or --gather nccl)
-    outs = [{"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)} for _ in range(2)]
+    NBUF = max(2, args.gather_buffers)
+    outs = [{"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)} for _ in range(NBUF)]
     out = outs[0]
     gathered = None
-    pending = [None, None]
+    pending = [None] * NBUF
     step_no = [0]
     gather_mode = "none"
     if world > 1:
         gather_mode = "nccl"
-        if args.gather == "fused":
+        if args.gather in ("fused", "peer"):
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                gathered = [symm_mem.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(2)]
+                gathered = [symm_mem.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(NBUF)]
                 handles = [symm_mem.rendezvous(t, dist.group.WORLD) for t in gathered]
-                peer_ptrs = [[int(h.buffer_ptrs[r]) for r in range(world)] for h in handles]
+                mc_ptrs = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles]
+                if args.gather == "fused" and all(mc_ptrs):       # one multimem store per row through the switch
+                    gather_args = [([], rank * B, mc_ptrs[b]) for b in range(NBUF)]
+                    gather_mode = "fused-multicast"
+                else:                                             # one store per row per peer
+                    gather_args = [([int(h.buffer_ptrs[r]) for r in range(world)], rank * B) for h in handles]
+                    gather_mode = "fused-peer"
                 side = torch.cuda.Stream(device=dev)
-                gather_mode = "fused"
             except Exception as exc:          # no symmetric memory on this box: NCCL gather
                 sys.stderr.write("fused gather unavailable (%s), using NCCL\n" % exc)
         if gather_mode == "nccl":
-            gathered = [torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(2)]
+            gathered = [torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(NBUF)]
 
     margin = args.sm_margin if args.sm_margin >= 0 else (8 if gather_mode == "nccl" else 0)
     if world > 1 and margin > 0:
         eng.set_sm_margin(margin)      # the NCCL gather kernel needs a few SMs to overlap the next step's kernel
 
     def one_step():
-        b = step_no[0] & 1
+        b = step_no[0] % NBUF
         step_no[0] += 1
         if pending[b] is not None:          # the buffer's previous gather must be complete before it is overwritten
-            if gather_mode == "fused":
+            if gather_mode.startswith("fused"):
                 torch.cuda.current_stream().wait_event(pending[b])
             else:
                 pending[b].wait()
             pending[b] = None
-        if gather_mode == "fused":
-            eng.step(kin, out=outs[b], want_status=False, gather=(peer_ptrs[b], rank * B))
+        if gather_mode.startswith("fused"):
+            eng.step(kin, out=outs[b], want_status=False, gather=gather_args[b])
             done = torch.cuda.Event()
             done.record()
             with torch.cuda.stream(side):   # cross-GPU barrier off the critical path of the next kernel
@@ -240,9 +248,9 @@ def main():
                 pending[b] = dist.all_gather_into_tensor(gathered[b], outs[b]["ctrl"], async_op=True)
 
     def drain():
-        for b in range(2):
+        for b in range(NBUF):
             if pending[b] is not None:
-                if gather_mode == "fused":
+                if gather_mode.startswith("fused"):
                     torch.cuda.current_stream().wait_event(pending[b])
                 else:
                     pending[b].wait()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IRLOSC_ABI_VERSION 3
+#define IRLOSC_ABI_VERSION 4
 #define IRLOSC_MAX_DEVICES 4   /* target devices per controller (DualUR5: base + 2 arms) */
 #define IRLOSC_MAX_N 32        /* robot DoF, Robot.num_joints_total (robot.py:32); DualUR5: 25 */
 #define IRLOSC_MAX_K 24        /* stacked task rows, sum of ctrlr_dof over targets; DualUR5: <= 13 */
@@ -133,6 +133,11 @@ typedef struct irlosc_io {
     int32_t reserved_;
     int64_t gather_offset;    /* first gathered row of this rank's shard                             */
     double *ctrl_gather[IRLOSC_MAX_PEERS];
+    /* Same gather through an NVSwitch multicast (NVLS) mapping of the gathered array: ONE
+     * multimem store per row reaches every GPU bound to the mapping (this one included), so the
+     * NVLink egress of a rank is its own shard once instead of once per peer.  When non-NULL it
+     * is used instead of ctrl_gather[] (n_gather may be 0). */
+    double *ctrl_multicast;
 } irlosc_io;
 
 typedef struct irlosc_handle irlosc_handle;

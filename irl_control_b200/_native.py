@@ -13,7 +13,7 @@ MAX_DEVICES = 4
 MAX_N = 32
 MAX_K = 24
 MAX_PEERS = 8
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 ST_PINV = 0x01
 ST_M_NOT_PD = 0x02
@@ -85,6 +85,7 @@ class Io(C.Structure):
         ("u_all", C.c_void_p), ("ctrl", C.c_void_p), ("status", C.c_void_p),
         ("n_gather", C.c_int32), ("reserved_", C.c_int32), ("gather_offset", C.c_int64),
         ("ctrl_gather", C.c_void_p * MAX_PEERS),
+        ("ctrl_multicast", C.c_void_p),
     ]
 
 

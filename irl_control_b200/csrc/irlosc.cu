@@ -234,6 +234,7 @@ static int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k) {
         k.ctrl_gather[g] = g < io->n_gather ? io->ctrl_gather[g] : nullptr;
         if (g < io->n_gather && !k.ctrl_gather[g]) return fail(IRLOSC_ERR_INVALID, "ctrl_gather[%d] is null", g);
     }
+    k.ctrl_mc = io->ctrl_multicast;
     return IRLOSC_OK;
 }
 
@@ -328,7 +329,7 @@ extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io
     int32_t rc = resolve_io(h, io, hk);
     if (rc != IRLOSC_OK) return rc;
     if (B == 0) return IRLOSC_OK;
-    if (hk.n_gather != 0) return fail(IRLOSC_ERR_INVALID, "the fused gather is only available with irlosc_step (device pointers)");
+    if (hk.n_gather != 0 || hk.ctrl_mc) return fail(IRLOSC_ERR_INVALID, "the fused gather is only available with irlosc_step (device pointers)");
     const KParams &P = h->kp;
     CUDA_TRY(cudaSetDevice(h->device));
     for (int s = 0; s < kPipeDepth; ++s)

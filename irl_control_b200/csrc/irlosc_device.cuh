@@ -61,12 +61,22 @@ struct KIo {
     double *u_all, *ctrl; uint8_t *status;
     int32_t n_gather; int64_t gather_offset;
     double *ctrl_gather[IRLOSC_MAX_PEERS];
+    double *ctrl_mc;
 };
 
 // Packed control output (osc.py:203-208): local array plus, when the gather is fused, the same
-// row in every peer's gathered array (plain stores to peer-mapped memory travel over NVLink).
+// row in every peer's gathered array: one multimem store through the NVSwitch multicast mapping,
+// or plain stores to each peer-mapped array (both travel over NVLink).
+__device__ __forceinline__ void multimem_st(double *p, double v) {
+    asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st(double2 *p, double2 v) {      // 16-byte form (v2.f64 does not exist)
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(__double2loint(v.x)),
+                 "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)), "r"(__double2hiint(v.y)) : "memory");
+}
 __device__ __forceinline__ void store_ctrl(const KIo &io, int n_ctrl, int64_t inst, int c, double v) {
     io.ctrl[inst * n_ctrl + c] = v;
+    if (io.ctrl_mc) { multimem_st(io.ctrl_mc + (io.gather_offset + inst) * n_ctrl + c, v); return; }
     for (int g = 0; g < io.n_gather; ++g) io.ctrl_gather[g][(io.gather_offset + inst) * n_ctrl + c] = v;
 }
 

@@ -107,7 +107,7 @@ inline bool tree_roles(const KParams &P, tree::Roles &R, int &kd, bool &has_base
         else return false;
     }
     R.opt_tvel = R.opt_mvel = R.opt_ftx = R.opt_ftr = -1;
-    R.opt_doubles = R.slot_bytes = R.priv_bytes = 0;
+    R.opt_doubles = R.slot_bytes = R.priv_bytes = R.ctrl_vec = 0;
     if (R.dev_arm[0] < 0 || R.dev_arm[1] < 0) return false;
     kd = P.dev[R.dev_arm[0]].kdev;
     if (P.dev[R.dev_arm[1]].kdev != kd || (kd != 3 && kd != 6)) return false;
@@ -148,6 +148,9 @@ inline const TiledEntry *tiled_find(const KParams &P, const KIo &io, int variant
             if (io.max_vel) { R.opt_mvel = at; at += 2 * per; }
             if (P.admittance) { R.opt_ftx = at; at += 9 * per; R.opt_ftr = at; at += 6 * per; }
             R.opt_doubles = at;
+            R.ctrl_vec = al16(io.ctrl) && ((io.gather_offset * (int64_t)P.n_ctrl) % 2 == 0);
+            for (int g = 0; g < io.n_gather; ++g) R.ctrl_vec = R.ctrl_vec && al16(io.ctrl_gather[g]);
+            R.ctrl_vec = R.ctrl_vec && al16(io.ctrl_mc);
             R.slot_bytes = t[i].slot_fixed + ((at * 8 + 15) & ~15);
             R.priv_bytes = t[i].priv - 16 + ((at * 8 + 15) & ~15);
             const size_t total = kTreeHeader + (size_t)t[i].slots * R.slot_bytes + (size_t)t[i].warps * R.priv_bytes;

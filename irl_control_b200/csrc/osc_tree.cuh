@@ -72,6 +72,7 @@ struct Roles {            // which target device plays which part (indices into 
     int opt_tvel, opt_mvel, opt_ftx, opt_ftr;   // double offsets of the optional arrays in a slot's tail, -1 = absent
     int opt_doubles;                            // doubles in the optional tail (per slot and per warp scratch)
     int slot_bytes, priv_bytes;
+    int ctrl_vec;         // ctrl (and every gather target) is 16-byte aligned: packed rows go out as double2
 };
 
 // Fixed part of an input slot; the optional per-instance arrays follow in a tail.
@@ -103,7 +104,7 @@ struct TreePriv {
     double As[WI][K][K + 1];
     double Vs[K][K + 1];
     double uv[WI][N];            // M dq, overwritten in place by the joint-space signal u
-    double bias[WI][N];
+    alignas(16) double bias[WI][N];   // reused as the packed-output staging tile after assembly
     double dx[WI][K], g[WI][K], j0[WI][K];
     double jc[WI][2][KD][7];     // original J entries of the arm rows on [stand, arm joints] (for J^T w)
     double jst[WI];              // J[base row][stand]
@@ -653,14 +654,35 @@ osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
         }
         __syncwarp();
         // -------------------------------------------------- packing (osc.py:203-208)
+        // The tile's rows are contiguous in every destination: stage them in the (now dead) bias
+        // scratch and write 16-byte vectors, so the peer stores of the fused gather leave the SM as
+        // full 512-byte requests instead of 32-byte pieces (NVLink packet efficiency).
+        double *ct = &PV.bias[0][0];
 #pragma unroll
         for (int t = 0; t < (32 + G - 1) / G; ++t) {
             const int cidx = l + G * t;
-            if (cidx < P.n_ctrl && valid) {
+            if (cidx < P.n_ctrl) {
                 int d = 0;
                 while (d + 1 < D && cidx >= P.dev[d + 1].ctrl0) ++d;
-                store_ctrl(io, P.n_ctrl, inst, cidx, PV.uv[grp][P.dev[d].actuator[cidx - P.dev[d].ctrl0]]);
+                ct[grp * P.n_ctrl + cidx] = PV.uv[grp][P.dev[d].actuator[cidx - P.dev[d].ctrl0]];
             }
+        }
+        __syncwarp();
+        if (tile_full(tile) && R.ctrl_vec) {
+            const double2 *src = reinterpret_cast<const double2 *>(ct);
+            const int64_t row0 = tile * WI * (int64_t)P.n_ctrl;
+            double2 *dst = reinterpret_cast<double2 *>(io.ctrl + row0);
+            for (int e = lane; e < (WI / 2) * P.n_ctrl; e += 32) {
+                const double2 v = src[e];
+                dst[e] = v;
+                if (io.ctrl_mc)
+                    multimem_st(reinterpret_cast<double2 *>(io.ctrl_mc + io.gather_offset * P.n_ctrl + row0) + e, v);
+                else
+                    for (int g = 0; g < io.n_gather; ++g)
+                        reinterpret_cast<double2 *>(io.ctrl_gather[g] + io.gather_offset * P.n_ctrl + row0)[e] = v;
+            }
+        } else if (valid) {
+            for (int cidx = l; cidx < P.n_ctrl; cidx += G) store_ctrl(io, P.n_ctrl, inst, cidx, ct[grp * P.n_ctrl + cidx]);
         }
         if (io.status && valid && l == 0) io.status[inst] = (uint8_t)flg;
         __syncwarp();

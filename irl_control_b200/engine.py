@@ -129,7 +129,10 @@ class BatchedOSC:
         gather  : optional (peer_ptrs, row_offset): device pointers of every rank's gathered
                   `[B_total, n_ctrl]` array (peer-mapped, e.g. torch symmetric memory `buffer_ptrs`);
                   the kernel then also stores its ctrl rows at row_offset + i of each of them
-                  (fused NVLink gather, see `irlosc_io.ctrl_gather`).
+                  (fused NVLink gather, see `irlosc_io.ctrl_gather`).  A third element, the
+                  multicast (NVLS) address of the gathered array (symmetric memory
+                  `multicast_ptr`), makes the kernel write each row once through the switch
+                  instead of once per peer (`irlosc_io.ctrl_multicast`).
         """
         import torch
         M = state["M"]
@@ -164,7 +167,9 @@ class BatchedOSC:
         io.u_all = out["u_all"].data_ptr() if "u_all" in out else None
         io.status = out["status"].data_ptr() if "status" in out else None
         if gather is not None:
-            ptrs, offset = gather
+            ptrs, offset = gather[0], gather[1]
+            if len(gather) > 2 and gather[2]:
+                io.ctrl_multicast = int(gather[2])
             if len(ptrs) > _native.MAX_PEERS:
                 raise ValueError("at most %d peers" % _native.MAX_PEERS)
             io.n_gather, io.gather_offset = len(ptrs), int(offset)

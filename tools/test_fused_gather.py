@@ -1,4 +1,5 @@
-"""2+ GPUs: the fused peer-store gather of irlosc_step equals an NCCL all_gather of the local outputs."""
+"""2+ GPUs: the fused gather of irlosc_step (peer stores, and NVSwitch multicast stores when the box
+offers them) equals an NCCL all_gather of the local outputs."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -9,7 +10,9 @@ dist.init_process_group("nccl", device_id=dev)
 from irl_control_b200.engine import BatchedOSC
 from irl_control_b200.synthetic import scenario_layout, synth_batch, kernel_inputs
 ok = True
-for scenario, B, kern in (("gain_test", 4099, 0), ("admit_test", 1024, 0), ("gain_test", 777, 1)):
+for scenario, B, kern, mode in (("gain_test", 4099, 0, "peer"), ("admit_test", 1024, 0, "peer"), ("gain_test", 777, 1, "peer"),
+                                ("gain_test", 4096, 0, "peer"), ("gain_test", 4096, 0, "multicast"),
+                                ("gain_test", 4099, 0, "multicast"), ("admit_test", 1031, 2, "multicast")):
     layout = scenario_layout(scenario)
     st = synth_batch(layout, B, seed=100 + rank, device=dev)
     kin = kernel_inputs(st, layout, packed_M=True)
@@ -17,15 +20,20 @@ for scenario, B, kern in (("gain_test", 4099, 0), ("admit_test", 1024, 0), ("gai
     g = symm_mem.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev)
     g.fill_(float("nan"))
     h = symm_mem.rendezvous(g, dist.group.WORLD)
+    mc = int(getattr(h, "multicast_ptr", 0) or 0)
+    if mode == "multicast" and mc == 0:
+        if rank == 0: print(scenario, B, "multicast mapping not available on this box: skipped")
+        continue
     h.barrier(channel=0)
-    out = eng.step(kin, want_status=False, gather=([int(p) for p in h.buffer_ptrs], rank * B))
+    gather = ([int(p) for p in h.buffer_ptrs], rank * B) if mode == "peer" else ([], rank * B, mc)
+    out = eng.step(kin, want_status=False, gather=gather)
     h.barrier(channel=0)
     torch.cuda.synchronize()
     ref = torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(ref, out["ctrl"])
     same = torch.equal(g, ref)
     ok = ok and same
-    if rank == 0: print(scenario, B, eng.last_kernel, "fused gather == nccl all_gather:", same)
+    if rank == 0: print(scenario, B, eng.last_kernel, mode, "fused gather == nccl all_gather:", same)
 flag = torch.tensor([1 if ok else 0], device=dev); dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0: print("ALL OK" if flag.item() == 1 else "MISMATCH")
 dist.destroy_process_group()
