@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IRLOSC_ABI_VERSION 4
+#define IRLOSC_ABI_VERSION 5
 #define IRLOSC_MAX_DEVICES 4   /* target devices per controller (DualUR5: base + 2 arms) */
 #define IRLOSC_MAX_N 32        /* robot DoF, Robot.num_joints_total (robot.py:32); DualUR5: 25 */
 #define IRLOSC_MAX_K 24        /* stacked task rows, sum of ctrlr_dof over targets; DualUR5: <= 13 */
@@ -140,6 +140,62 @@ typedef struct irlosc_io {
     double *ctrl_multicast;
 } irlosc_io;
 
+/* ------------------------------------------------------------------------------------------
+ * Fused state provider: the step BEFORE the path.  The reference pulls M, J,
+ * qfrc_bias and the EE poses out of MuJoCo every timestep (robot.py:68-72 mj_fullM,
+ * device.py:115-133 mj_jacBody via get_body_jacp/jacr, osc.py:191 qfrc_bias, device.py:93-95
+ * xpos/xquat, device.py:135-143 site_xmat).  With a rigid-body description of the robot the
+ * library computes all of that on the GPU from (q, dq) inside the same kernel as the control
+ * law, so only ~0.6 KB per instance crosses HBM / PCIe instead of ~4.9 KB.
+ *
+ * The description is the MuJoCo model reduced to its joints: bodies without joints are folded
+ * into the nearest ancestor body that has one (frames composed, inertias lumped).  All hinge,
+ * anchored at the body origin (true for every joint of scenes/dual_ur5.xml:55-251). */
+typedef struct irlosc_joint_model {
+    int32_t parent;           /* robot-local parent joint, -1 = attached to the world               */
+    int32_t reserved_;
+    double pos[3];            /* body frame origin in the parent joint's body frame (body_pos chain) */
+    double quat[4];           /* body frame orientation likewise, w x y z          (body_quat chain) */
+    double axis[3];           /* hinge axis in the body frame, unit                 (jnt_axis)       */
+    double mass;              /* lumped mass of the body and everything welded to it (body_mass)     */
+    double com[3];            /* centre of mass, body frame                          (body_ipos)     */
+    double inertia[6];        /* about the COM, body-frame axes: xx yy zz xy xz yz   (body_inertia, body_iquat) */
+} irlosc_joint_model;
+
+typedef struct irlosc_frame_model {
+    int32_t joint;            /* robot-local joint whose body carries the frame; -1 = frame absent   */
+    int32_t reserved_;
+    double pos[3];            /* in that body's frame                                                */
+    double quat[4];           /* w x y z                                                             */
+} irlosc_frame_model;
+
+typedef struct irlosc_model {
+    int32_t n_joints;         /* == params.n                                                         */
+    int32_t reserved_;
+    double gravity[3];        /* mjOption.gravity, world frame                                       */
+    irlosc_joint_model joint[IRLOSC_MAX_N];
+    irlosc_frame_model ee[IRLOSC_MAX_DEVICES]; /* per TARGET device: its EE body (device.py:93-95,125-128) */
+    irlosc_frame_model ft[IRLOSC_MAX_DEVICES]; /* per TARGET device: its F/T site (device.py:135-143);
+                                                  joint = -1: no sensor, force = torque = 0 (device.py:162-170) */
+} irlosc_model;
+
+/* Per-step arrays of the fused step; DEVICE pointers for irlosc_step_fused, HOST pointers for
+ * irlosc_step_fused_host.  Same conventions as irlosc_io. */
+typedef struct irlosc_fused_io {
+    const double *q;          /* [B][n]    sim.data.qpos[joint_ids_all]                              */
+    const double *dq;         /* [B][n]    sim.data.qvel[joint_ids_all]   (robot.py:60-65)           */
+    const double *target_xyz; /* [B][D][3]                                                           */
+    const double *target_quat;/* [B][D][4]                                                           */
+    const double *target_vel; /* [B][D][6] optional                                                  */
+    const double *max_vel;    /* [B][D][2] optional                                                  */
+    const double *ft_raw;     /* [B][D][6] sensor-frame force|torque; NULL iff !admittance           */
+    double *ctrl;             /* [B][n_ctrl] out                                                     */
+    double *u_all;            /* [B][n]      out, optional                                           */
+    uint8_t *status;          /* [B]         out, optional                                           */
+    double *ee_xyz;           /* [B][D][3]   out, optional: DeviceState.EE_XYZ the step computed     */
+    double *ee_quat;          /* [B][D][4]   out, optional: DeviceState.EE_QUAT (w x y z, w >= 0 branch) */
+} irlosc_fused_io;
+
 typedef struct irlosc_handle irlosc_handle;
 
 /* Thread-local, human-readable description of the last failure on this thread. */
@@ -163,6 +219,19 @@ int32_t irlosc_step(irlosc_handle *h, int64_t B, const irlosc_io *io_device, voi
  * status back and returns when they are valid.  Work is pipelined in chunks over internal
  * streams; buffers from irlosc_host_alloc (pinned) make the copies asynchronous. */
 int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io *io_host);
+
+/* Attach the rigid-body description used by the fused step.  Validates that the joint tree is the
+ * DualUR5 one the kernels are specialised for and that every EE / F-T frame hangs off the joint
+ * its device's Jacobian ends at. */
+int32_t irlosc_set_model(irlosc_handle *h, const irlosc_model *model);
+
+/* Replaces: Robot.get_all_states + Device.get_all_states + OSC.generate (robot.py:125-136,
+ * device.py:183-197, osc.py:120-210) for B instances given only joint positions / velocities and
+ * targets.  Asynchronous on `cuda_stream`; launches the fused kernel and a fix-up kernel for the
+ * instances that need the eigen-decomposition (pinv) branch. */
+int32_t irlosc_step_fused(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_device, void *cuda_stream);
+/* Same with HOST buffers, pipelined in chunks like irlosc_step_host. */
+int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_host);
 
 /* Replaces: OSC.calc_error (osc.py:101-118), also called by insertion_task.py:173-179.
  * err[B][D][6] (unmasked), device pointers, asynchronous. */

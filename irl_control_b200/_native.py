@@ -13,7 +13,7 @@ MAX_DEVICES = 4
 MAX_N = 32
 MAX_K = 24
 MAX_PEERS = 8
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 ST_PINV = 0x01
 ST_M_NOT_PD = 0x02
@@ -89,7 +89,40 @@ class Io(C.Structure):
     ]
 
 
+class JointModel(C.Structure):
+    _fields_ = [
+        ("parent", C.c_int32), ("reserved_", C.c_int32),
+        ("pos", C.c_double * 3), ("quat", C.c_double * 4), ("axis", C.c_double * 3),
+        ("mass", C.c_double), ("com", C.c_double * 3), ("inertia", C.c_double * 6),
+    ]
+
+
+class FrameModel(C.Structure):
+    _fields_ = [("joint", C.c_int32), ("reserved_", C.c_int32), ("pos", C.c_double * 3), ("quat", C.c_double * 4)]
+
+
+class Model(C.Structure):
+    _fields_ = [
+        ("n_joints", C.c_int32), ("reserved_", C.c_int32),
+        ("gravity", C.c_double * 3),
+        ("joint", JointModel * MAX_N),
+        ("ee", FrameModel * MAX_DEVICES),
+        ("ft", FrameModel * MAX_DEVICES),
+    ]
+
+
+class FusedIo(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("dq", C.c_void_p),
+        ("target_xyz", C.c_void_p), ("target_quat", C.c_void_p),
+        ("target_vel", C.c_void_p), ("max_vel", C.c_void_p), ("ft_raw", C.c_void_p),
+        ("ctrl", C.c_void_p), ("u_all", C.c_void_p), ("status", C.c_void_p),
+        ("ee_xyz", C.c_void_p), ("ee_quat", C.c_void_p),
+    ]
+
+
 EXPORTS = [
+    "irlosc_set_model", "irlosc_step_fused", "irlosc_step_fused_host",
     "irlosc_last_error", "irlosc_abi_version", "irlosc_create", "irlosc_destroy",
     "irlosc_num_task_rows", "irlosc_num_ctrl", "irlosc_step", "irlosc_step_host",
     "irlosc_calc_error", "irlosc_host_alloc", "irlosc_host_free", "irlosc_set_kernel", "irlosc_set_sm_margin",
@@ -131,6 +164,12 @@ def load() -> C.CDLL:
     lib.irlosc_step.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Io), C.c_void_p]
     lib.irlosc_step_host.restype = C.c_int32
     lib.irlosc_step_host.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Io)]
+    lib.irlosc_set_model.restype = C.c_int32
+    lib.irlosc_set_model.argtypes = [C.c_void_p, C.POINTER(Model)]
+    lib.irlosc_step_fused.restype = C.c_int32
+    lib.irlosc_step_fused.argtypes = [C.c_void_p, C.c_int64, C.POINTER(FusedIo), C.c_void_p]
+    lib.irlosc_step_fused_host.restype = C.c_int32
+    lib.irlosc_step_fused_host.argtypes = [C.c_void_p, C.c_int64, C.POINTER(FusedIo)]
     lib.irlosc_calc_error.restype = C.c_int32
     lib.irlosc_calc_error.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_void_p]
     lib.irlosc_host_alloc.restype = C.c_int32

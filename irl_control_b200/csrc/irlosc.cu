@@ -10,7 +10,8 @@
 #include <cuda_runtime.h>
 
 #include "../../include/irlosc.h"
-#include "irlosc_device.cuh"
+#include "irlosc_internal.h"
+#include "irlosc_build.h"
 #include "osc_generic.cuh"
 #include "osc_dispatch.cuh"
 
@@ -19,7 +20,7 @@ using namespace irlosc;
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_last_error;
 
-static int32_t fail(int32_t rc, const char *fmt, ...) {
+int32_t irlosc::fail(int32_t rc, const char *fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -29,122 +30,8 @@ static int32_t fail(int32_t rc, const char *fmt, ...) {
     return rc;
 }
 
-#define CUDA_TRY(expr)                                                                        \
-    do {                                                                                      \
-        cudaError_t e_ = (expr);                                                              \
-        if (e_ != cudaSuccess)                                                                \
-            return fail(IRLOSC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
-                        __FILE__, __LINE__);                                                  \
-    } while (0)
-
 extern "C" const char *irlosc_last_error(void) { return g_last_error.c_str(); }
 extern "C" int32_t irlosc_abi_version(void) { return IRLOSC_ABI_VERSION; }
-
-// ------------------------------------------------------------------ handle
-namespace {
-
-constexpr int kPipeDepth = 3;   // chunks in flight in irlosc_step_host
-
-struct Staging {
-    cudaStream_t stream = nullptr;
-    void *buf[16] = {nullptr};
-    size_t cap[16] = {0};
-};
-
-}  // namespace
-
-struct irlosc_handle {
-    irlosc_params user;
-    KParams kp;
-    int device = 0;
-    int sm_count = 0;
-    int kernel_choice = 0;    // 0 auto, 1 generic, 2 + v specialised variant v
-    int sm_margin = 0;        // SMs left free for overlapping collectives
-    int64_t launches = 0;
-    const char *last_kernel = "none";
-    Staging stage[kPipeDepth];
-    int64_t host_chunk = 8192;
-};
-
-static int32_t build_kparams(const irlosc_params &u, KParams &kp) {
-    memset(&kp, 0, sizeof kp);
-    if (u.abi_version != IRLOSC_ABI_VERSION)
-        return fail(IRLOSC_ERR_INVALID, "abi_version %d, library is %d", u.abi_version, IRLOSC_ABI_VERSION);
-    if (u.n < 1 || u.n > IRLOSC_MAX_N) return fail(IRLOSC_ERR_INVALID, "n=%d outside 1..%d", u.n, IRLOSC_MAX_N);
-    if (u.n_devices < 1 || u.n_devices > IRLOSC_MAX_DEVICES)
-        return fail(IRLOSC_ERR_INVALID, "n_devices=%d outside 1..%d", u.n_devices, IRLOSC_MAX_DEVICES);
-    kp.n = u.n;
-    kp.D = u.n_devices;
-    kp.use_g = u.use_g != 0;
-    kp.admittance = u.admittance != 0;
-    kp.has_nullspace = u.has_nullspace != 0;
-    kp.nullspace_kv = u.nullspace_kv;
-    kp.has_topology = u.has_topology != 0;
-    kp.check_topology = u.check_topology != 0;
-    for (int j = 0; j < IRLOSC_MAX_N; ++j) {
-        const int pj = (kp.has_topology && j < u.n) ? u.joint_parent[j] : -1;
-        if (pj < -1 || pj >= u.n) return fail(IRLOSC_ERR_INVALID, "joint_parent[%d]=%d outside -1..%d", j, pj, u.n - 1);
-        kp.joint_parent[j] = (int8_t)pj;
-    }
-    int row = 0, ctrl = 0;
-    for (int d = 0; d < u.n_devices; ++d) {
-        const irlosc_device_params &s = u.dev[d];
-        KDevice &t = kp.dev[d];
-        t.row0 = row;
-        t.ctrl0 = ctrl;
-        int kd = 0;
-        for (int i = 0; i < 6; ++i) {
-            t.dof[i] = s.ctrlr_dof[i] != 0;
-            if (t.dof[i]) {
-                if (row >= IRLOSC_MAX_K) return fail(IRLOSC_ERR_INVALID, "more than %d task rows", IRLOSC_MAX_K);
-                kp.row_dev[row] = (int8_t)d;
-                kp.row_comp[row] = (int8_t)i;
-                t.dx_idx[kd] = s.dx_idx[kd];
-                if (s.dx_idx[kd] < 0) return fail(IRLOSC_ERR_INVALID, "device %d: negative dx_idx", d);
-                ++row;
-                ++kd;
-            }
-        }
-        t.kdev = kd;
-        t.any_xyz = (t.dof[0] + t.dof[1] + t.dof[2]) > 0;
-        t.any_abg = (t.dof[3] + t.dof[4] + t.dof[5]) > 0;
-        t.has_max_vel = s.has_max_vel != 0;
-        t.max_vel[0] = s.max_vel[0];
-        t.max_vel[1] = s.max_vel[1];
-        t.kp = s.kp; t.kv = s.kv; t.ko = s.ko;
-        t.kv_over_kp = s.kp != 0.0 ? s.kv / s.kp : 0.0;
-        t.kv_over_ko = s.ko != 0.0 ? s.kv / s.ko : 0.0;
-        if (!(s.kv != 0.0)) return fail(IRLOSC_ERR_INVALID, "device %d: kv must be non-zero", d);
-        for (int i = 0; i < 6; ++i) {
-            t.gain[i] = (i < 3) ? s.kp : s.ko;
-            t.lamb[i] = t.gain[i] / s.kv;
-            t.stiff[i] = (i < 3) ? s.k[i] : 1.0;
-            t.damp[i] = (i < 3) ? s.d[i] : 1.0;
-        }
-        if (s.n_joints_all < 0 || s.n_joints_all > u.n)
-            return fail(IRLOSC_ERR_INVALID, "device %d: n_joints_all=%d", d, s.n_joints_all);
-        t.n_joints_all = s.n_joints_all;
-        for (int i = 0; i < s.n_joints_all; ++i) {
-            const int j = s.joint_ids_all[i];
-            if (j < 0 || j >= u.n) return fail(IRLOSC_ERR_INVALID, "device %d: joint id %d outside 0..%d", d, j, u.n - 1);
-            t.joint_mask |= (1u << j);
-        }
-        if (s.n_ctrl < 0 || s.n_ctrl > u.n) return fail(IRLOSC_ERR_INVALID, "device %d: n_ctrl=%d", d, s.n_ctrl);
-        t.n_ctrl = s.n_ctrl;
-        for (int i = 0; i < s.n_ctrl; ++i) {
-            const int j = s.actuator_trnids[i];
-            if (j < 0 || j >= u.n) return fail(IRLOSC_ERR_INVALID, "device %d: actuator joint %d outside 0..%d", d, j, u.n - 1);
-            t.actuator[i] = (int8_t)j;
-        }
-        t.ee_joint = (s.ee_joint >= 0 && s.ee_joint < u.n) ? s.ee_joint : -1;
-        ctrl += s.n_ctrl;
-    }
-    if (row < 1) return fail(IRLOSC_ERR_INVALID, "no controlled task rows");
-    if (ctrl < 1 || ctrl > 32) return fail(IRLOSC_ERR_INVALID, "n_ctrl=%d outside 1..32", ctrl);
-    kp.k = row;
-    kp.n_ctrl = ctrl;
-    return IRLOSC_OK;
-}
 
 extern "C" int32_t irlosc_create(const irlosc_params *params, irlosc_handle **out) {
     if (!params || !out) return fail(IRLOSC_ERR_INVALID, "null argument");
@@ -173,10 +60,16 @@ extern "C" int32_t irlosc_create(const irlosc_params *params, irlosc_handle **ou
 extern "C" int32_t irlosc_destroy(irlosc_handle *h) {
     if (!h) return IRLOSC_OK;
     for (int s = 0; s < kPipeDepth; ++s) {
-        for (int i = 0; i < 16; ++i)
+        for (int i = 0; i < 16; ++i) {
             if (h->stage[s].buf[i]) cudaFree(h->stage[s].buf[i]);
+            if (h->fstage[s].buf[i]) cudaFree(h->fstage[s].buf[i]);
+        }
         if (h->stage[s].stream) cudaStreamDestroy(h->stage[s].stream);
+        if (h->fstage[s].stream) cudaStreamDestroy(h->fstage[s].stream);
     }
+    if (h->hard_count) cudaFree(h->hard_count);
+    if (h->hard_inst) cudaFree(h->hard_inst);
+    if (h->hard_rec) cudaFree(h->hard_rec);
     delete h;
     return IRLOSC_OK;
 }
@@ -313,7 +206,7 @@ extern "C" int32_t irlosc_host_free(void *ptr) {
     return IRLOSC_OK;
 }
 
-static int32_t ensure_cap(Staging &s, int slot, size_t bytes) {
+int32_t irlosc::ensure_cap(Staging &s, int slot, size_t bytes) {
     if (bytes <= s.cap[slot]) return IRLOSC_OK;
     if (s.buf[slot]) { CUDA_TRY(cudaFree(s.buf[slot])); s.buf[slot] = nullptr; s.cap[slot] = 0; }
     CUDA_TRY(cudaMalloc(&s.buf[slot], bytes));

@@ -1,0 +1,198 @@
+// Host-side flattening of the C-ABI parameter blocks into what the kernels read:
+// irlosc_params -> KParams (index maps, gains; device.py:41-74, robot.py:26-32, osc.py:26-39) and
+// irlosc_model -> fused::KModel.  Shared by the translation units of libirlosc.so and by the
+// host-compiled test harness (tests/host_fused).
+#pragma once
+#include <cmath>
+#include <cstring>
+#include "irlosc_internal.h"
+
+namespace irlosc {
+
+inline int32_t build_kparams(const irlosc_params &u, KParams &kp) {
+    memset(&kp, 0, sizeof kp);
+    if (u.abi_version != IRLOSC_ABI_VERSION)
+        return fail(IRLOSC_ERR_INVALID, "abi_version %d, library is %d", u.abi_version, IRLOSC_ABI_VERSION);
+    if (u.n < 1 || u.n > IRLOSC_MAX_N) return fail(IRLOSC_ERR_INVALID, "n=%d outside 1..%d", u.n, IRLOSC_MAX_N);
+    if (u.n_devices < 1 || u.n_devices > IRLOSC_MAX_DEVICES)
+        return fail(IRLOSC_ERR_INVALID, "n_devices=%d outside 1..%d", u.n_devices, IRLOSC_MAX_DEVICES);
+    kp.n = u.n;
+    kp.D = u.n_devices;
+    kp.use_g = u.use_g != 0;
+    kp.admittance = u.admittance != 0;
+    kp.has_nullspace = u.has_nullspace != 0;
+    kp.nullspace_kv = u.nullspace_kv;
+    kp.has_topology = u.has_topology != 0;
+    kp.check_topology = u.check_topology != 0;
+    for (int j = 0; j < IRLOSC_MAX_N; ++j) {
+        const int pj = (kp.has_topology && j < u.n) ? u.joint_parent[j] : -1;
+        if (pj < -1 || pj >= u.n) return fail(IRLOSC_ERR_INVALID, "joint_parent[%d]=%d outside -1..%d", j, pj, u.n - 1);
+        kp.joint_parent[j] = (int8_t)pj;
+    }
+    int row = 0, ctrl = 0;
+    for (int d = 0; d < u.n_devices; ++d) {
+        const irlosc_device_params &s = u.dev[d];
+        KDevice &t = kp.dev[d];
+        t.row0 = row;
+        t.ctrl0 = ctrl;
+        int kd = 0;
+        for (int i = 0; i < 6; ++i) {
+            t.dof[i] = s.ctrlr_dof[i] != 0;
+            if (t.dof[i]) {
+                if (row >= IRLOSC_MAX_K) return fail(IRLOSC_ERR_INVALID, "more than %d task rows", IRLOSC_MAX_K);
+                kp.row_dev[row] = (int8_t)d;
+                kp.row_comp[row] = (int8_t)i;
+                t.dx_idx[kd] = s.dx_idx[kd];
+                if (s.dx_idx[kd] < 0) return fail(IRLOSC_ERR_INVALID, "device %d: negative dx_idx", d);
+                ++row;
+                ++kd;
+            }
+        }
+        t.kdev = kd;
+        t.any_xyz = (t.dof[0] + t.dof[1] + t.dof[2]) > 0;
+        t.any_abg = (t.dof[3] + t.dof[4] + t.dof[5]) > 0;
+        t.has_max_vel = s.has_max_vel != 0;
+        t.max_vel[0] = s.max_vel[0];
+        t.max_vel[1] = s.max_vel[1];
+        t.kp = s.kp; t.kv = s.kv; t.ko = s.ko;
+        t.kv_over_kp = s.kp != 0.0 ? s.kv / s.kp : 0.0;
+        t.kv_over_ko = s.ko != 0.0 ? s.kv / s.ko : 0.0;
+        if (!(s.kv != 0.0)) return fail(IRLOSC_ERR_INVALID, "device %d: kv must be non-zero", d);
+        for (int i = 0; i < 6; ++i) {
+            t.gain[i] = (i < 3) ? s.kp : s.ko;
+            t.lamb[i] = t.gain[i] / s.kv;
+            t.stiff[i] = (i < 3) ? s.k[i] : 1.0;
+            t.damp[i] = (i < 3) ? s.d[i] : 1.0;
+        }
+        if (s.n_joints_all < 0 || s.n_joints_all > u.n)
+            return fail(IRLOSC_ERR_INVALID, "device %d: n_joints_all=%d", d, s.n_joints_all);
+        t.n_joints_all = s.n_joints_all;
+        for (int i = 0; i < s.n_joints_all; ++i) {
+            const int j = s.joint_ids_all[i];
+            if (j < 0 || j >= u.n) return fail(IRLOSC_ERR_INVALID, "device %d: joint id %d outside 0..%d", d, j, u.n - 1);
+            t.joint_mask |= (1u << j);
+        }
+        if (s.n_ctrl < 0 || s.n_ctrl > u.n) return fail(IRLOSC_ERR_INVALID, "device %d: n_ctrl=%d", d, s.n_ctrl);
+        t.n_ctrl = s.n_ctrl;
+        for (int i = 0; i < s.n_ctrl; ++i) {
+            const int j = s.actuator_trnids[i];
+            if (j < 0 || j >= u.n) return fail(IRLOSC_ERR_INVALID, "device %d: actuator joint %d outside 0..%d", d, j, u.n - 1);
+            t.actuator[i] = (int8_t)j;
+        }
+        t.ee_joint = (s.ee_joint >= 0 && s.ee_joint < u.n) ? s.ee_joint : -1;
+        ctrl += s.n_ctrl;
+    }
+    if (row < 1) return fail(IRLOSC_ERR_INVALID, "no controlled task rows");
+    if (ctrl < 1 || ctrl > 32) return fail(IRLOSC_ERR_INVALID, "n_ctrl=%d outside 1..32", ctrl);
+    kp.k = row;
+    kp.n_ctrl = ctrl;
+    return IRLOSC_OK;
+}
+
+
+namespace fused_build {
+using fused::KJoint;
+using fused::KFrame;
+using fused::FRoles;
+using fused::kN;
+constexpr int kDualUr5Parent[kN] = {-1, 0, 1, 2, 3, 4, 5, 6, 7, 6, 6, 10, 6, 0, 13, 14, 15, 16, 17, 18, 19, 18, 18, 22, 18};
+
+inline void quat_to_mat(const double *q, double *R) {
+    const double w = q[0], x = q[1], y = q[2], z = q[3];
+    const double s = 2.0 / (w * w + x * x + y * y + z * z);
+    const double xs = x * s, ys = y * s, zs = z * s;
+    R[0] = 1.0 - (y * ys + z * zs); R[1] = x * ys - w * zs;         R[2] = x * zs + w * ys;
+    R[3] = x * ys + w * zs;         R[4] = 1.0 - (x * xs + z * zs); R[5] = y * zs - w * xs;
+    R[6] = x * zs - w * ys;         R[7] = y * zs + w * xs;         R[8] = 1.0 - (x * xs + y * ys);
+}
+
+inline int32_t build_joint(const irlosc_joint_model &m, int j, KJoint &k) {
+    const double an = std::sqrt(m.axis[0] * m.axis[0] + m.axis[1] * m.axis[1] + m.axis[2] * m.axis[2]);
+    if (!(an > 0.0)) return fail(IRLOSC_ERR_INVALID, "joint %d: zero hinge axis", j);
+    if (!(m.mass >= 0.0)) return fail(IRLOSC_ERR_INVALID, "joint %d: negative mass", j);
+    const double a[3] = {m.axis[0] / an, m.axis[1] / an, m.axis[2] / an};
+    double Rf[9];
+    quat_to_mat(m.quat, Rf);
+    const double ax[9] = {0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0};
+    double Ra[3];
+    for (int i = 0; i < 3; ++i) Ra[i] = Rf[3 * i] * a[0] + Rf[3 * i + 1] * a[1] + Rf[3 * i + 2] * a[2];
+    for (int i = 0; i < 3; ++i)
+        for (int c = 0; c < 3; ++c) {
+            double p1 = 0.0;
+            for (int t = 0; t < 3; ++t) p1 += Rf[3 * i + t] * ax[3 * t + c];
+            k.P1[3 * i + c] = p1;
+            k.P2[3 * i + c] = Ra[i] * a[c];
+            k.Q0[3 * i + c] = Rf[3 * i + c] - k.P2[3 * i + c];
+        }
+    for (int i = 0; i < 3; ++i) { k.pos[i] = m.pos[i]; k.axp[i] = Ra[i]; k.com[i] = m.com[i]; }
+    k.mass = m.mass;
+    for (int i = 0; i < 6; ++i) k.ic[i] = m.inertia[i];
+    return IRLOSC_OK;
+}
+
+inline int32_t build_frame(const irlosc_frame_model &f, int want_joint, const char *what, int d, KFrame &k) {
+    memset(&k, 0, sizeof k);
+    if (f.joint < 0) { k.joint = -1; k.has = 0; k.R[0] = k.R[4] = k.R[8] = 1.0; return IRLOSC_OK; }
+    if (f.joint != want_joint)
+        return fail(IRLOSC_ERR_INVALID, "%s frame of device %d hangs off joint %d, its Jacobian ends at joint %d", what, d,
+                    f.joint, want_joint);
+    k.joint = f.joint;
+    k.has = 1;
+    for (int i = 0; i < 3; ++i) k.pos[i] = f.pos[i];
+    quat_to_mat(f.quat, k.R);
+    return IRLOSC_OK;
+}
+
+// which devices play which role; same contract as tree_roles in osc_dispatch.cuh
+inline bool fused_roles(const KParams &P, FRoles &R, int &kd, bool &has_base) {
+    R.dev_arm[0] = R.dev_arm[1] = R.dev_base = -1;
+    R.row_arm[0] = R.row_arm[1] = R.row_base = 0;
+    if (!P.has_topology || P.n != kN || P.D < 2 || P.D > 3) return false;
+    for (int j = 0; j < kN; ++j)
+        if (P.joint_parent[j] != kDualUr5Parent[j]) return false;
+    for (int d = 0; d < P.D; ++d) {
+        const KDevice &dv = P.dev[d];
+        if (dv.ee_joint == 6 && R.dev_arm[0] < 0) { R.dev_arm[0] = d; R.row_arm[0] = dv.row0; }
+        else if (dv.ee_joint == 18 && R.dev_arm[1] < 0) { R.dev_arm[1] = d; R.row_arm[1] = dv.row0; }
+        else if (dv.ee_joint == 0 && R.dev_base < 0) { R.dev_base = d; R.row_base = dv.row0; }
+        else return false;
+    }
+    if (R.dev_arm[0] < 0 || R.dev_arm[1] < 0) return false;
+    kd = P.dev[R.dev_arm[0]].kdev;
+    if (P.dev[R.dev_arm[1]].kdev != kd || (kd != 3 && kd != 6)) return false;
+    has_base = R.dev_base >= 0;
+    if (has_base && P.dev[R.dev_base].kdev != 1) return false;
+    if ((P.D == 3) != has_base) return false;
+    return true;
+}
+
+}  // namespace fused_build
+using fused_build::fused_roles;
+using fused_build::build_joint;
+using fused_build::build_frame;
+
+// irlosc_model -> kernel constants (frames as matrices, Rodrigues terms folded with the fixed frames).
+inline int32_t build_kmodel(const KParams &P, const irlosc_model &m, fused::KModel &K) {
+    using namespace fused;
+    memset(&K, 0, sizeof K);
+    for (int i = 0; i < 3; ++i) K.gravity[i] = m.gravity[i];
+    int32_t rc = build_joint(m.joint[0], 0, K.stand);
+    for (int a = 0; a < 2 && rc == IRLOSC_OK; ++a) {
+        const int jb = 1 + 12 * a;
+        for (int i = 0; i < 6 && rc == IRLOSC_OK; ++i) rc = build_joint(m.joint[jb + i], jb + i, K.arm[a][i]);
+        for (int hf = 0; hf < 2 && rc == IRLOSC_OK; ++hf)
+            for (int r = 0; r < 3 && rc == IRLOSC_OK; ++r)
+                rc = build_joint(m.joint[jb + 6 + 3 * hf + r], jb + 6 + 3 * hf + r, K.grip[a][hf][r]);
+    }
+    if (rc != IRLOSC_OK) return rc;
+    for (int d = 0; d < P.D; ++d) {
+        const int want = P.dev[d].ee_joint;
+        if (m.ee[d].joint < 0) return fail(IRLOSC_ERR_INVALID, "device %d has no EE frame", d);
+        rc = build_frame(m.ee[d], want, "EE", d, K.ee[d]);
+        if (rc == IRLOSC_OK) rc = build_frame(m.ft[d], want, "F/T", d, K.ft[d]);
+        if (rc != IRLOSC_OK) return rc;
+    }
+    return IRLOSC_OK;
+}
+
+}  // namespace irlosc

@@ -12,6 +12,10 @@
 #include <cuda_runtime.h>
 #include "../../include/irlosc.h"
 
+// Functions shared with the host-compiled test harness (tests/host_fused) are host + device;
+// nothing in the product calls them on the host.
+#define IRLOSC_HD __host__ __device__ __forceinline__
+
 namespace irlosc {
 
 constexpr double kDetThreshold = 1e-4;   // osc.py:51
@@ -85,7 +89,10 @@ __device__ __forceinline__ void store_ctrl(const KIo &io, int n_ctrl, int64_t in
 // dozen of them on one or two lanes per instance.  Hardware seed + Newton steps give <= 1 ulp-level
 // results in 5-7 instructions (differences vs. the reference's correctly rounded numpy values are
 // ~1e-16 relative, far inside the parity tolerance).
-__device__ __forceinline__ double fast_rcp(double d) {
+IRLOSC_HD double fast_rcp(double d) {
+#ifndef __CUDA_ARCH__
+    return 1.0 / d;
+#else
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
     double e = fma(-d, r, 1.0);
@@ -93,8 +100,12 @@ __device__ __forceinline__ double fast_rcp(double d) {
     e = fma(-d, r, 1.0);
     r = fma(r, e, r);
     return r;
+#endif
 }
-__device__ __forceinline__ double fast_sqrt(double x) {     // x >= 0 and not denormal-small; sqrt(0) = 0
+IRLOSC_HD double fast_sqrt(double x) {     // x >= 0 and not denormal-small; sqrt(0) = 0
+#ifndef __CUDA_ARCH__
+    return sqrt(x);
+#else
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     // two Newton steps on r ~ 1/sqrt(x), then one correction of s = x r
@@ -107,10 +118,11 @@ __device__ __forceinline__ double fast_sqrt(double x) {     // x >= 0 and not de
     double s = x * r;
     s = fma(fma(-s, s, x), 0.5 * r, s);
     return x > 0.0 ? s : 0.0;
+#endif
 }
 
 // ---------------------------------------------------------------- rotations
-__device__ __forceinline__ void quat_mul(const double *a, const double *b, double *o) {
+IRLOSC_HD void quat_mul(const double *a, const double *b, double *o) {
     o[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
     o[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
     o[2] = a[0] * b[2] + a[2] * b[0] + a[3] * b[1] - a[1] * b[3];
@@ -118,7 +130,7 @@ __device__ __forceinline__ void quat_mul(const double *a, const double *b, doubl
 }
 
 // quat2euler(q) = mat2euler(quat2mat(q)), static x-y-z angles.
-__device__ __forceinline__ void quat_to_euler_sxyz(const double *q, double *e) {
+IRLOSC_HD void quat_to_euler_sxyz(const double *q, double *e) {
     const double w = q[0], x = q[1], y = q[2], z = q[3];
     const double nq = w * w + x * x + y * y + z * z;
     double m00 = 1.0, m10 = 0.0, m20 = 0.0, m21 = 0.0, m22 = 1.0, m11 = 1.0, m12 = 0.0;
@@ -149,7 +161,7 @@ __device__ __forceinline__ void quat_to_euler_sxyz(const double *q, double *e) {
 }
 
 // osc.py:101-118 - unmasked 6-vector [ee - target ; euler(conj(q_d * conj(q_ee)))].
-__device__ __forceinline__ void device_pose_error(const KDevice &dv, const double *ee_xyz,
+IRLOSC_HD void device_pose_error(const KDevice &dv, const double *ee_xyz,
                                                   const double *ee_quat, const double *t_xyz,
                                                   const double *t_quat, double *u) {
 #pragma unroll
@@ -171,7 +183,7 @@ __device__ __forceinline__ void device_pose_error(const KDevice &dv, const doubl
 }
 
 // device.py:135-170 - world-frame [force ; torque] of one device.
-__device__ __forceinline__ void rotate_wrench(const double *R, const double *raw, double *out) {
+IRLOSC_HD void rotate_wrench(const double *R, const double *raw, double *out) {
 #pragma unroll
     for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -184,7 +196,7 @@ __device__ __forceinline__ void rotate_wrench(const double *R, const double *raw
 //   u      out: 6-vector AFTER gains, stiffness and (if taken) the velocity-tracking term
 //   returns true when the non-zero-target-velocity branch was taken (osc.py:175-177)
 //   dx / k are only read on that branch; *dx_oob is set when dx_idx runs past k (IndexError in numpy)
-__device__ __forceinline__ bool device_task_signal(const KDevice &dv, const double *ee_xyz,
+IRLOSC_HD bool device_task_signal(const KDevice &dv, const double *ee_xyz,
                                                    const double *ee_quat, const double *t_xyz,
                                                    const double *t_quat, const double *t_vel,
                                                    const double *max_vel, const double *dx, int k,

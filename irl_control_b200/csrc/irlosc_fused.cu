@@ -1,0 +1,219 @@
+// C ABI of the fused state provider + OSC step (include/irlosc.h: irlosc_set_model,
+// irlosc_step_fused, irlosc_step_fused_host).  Kernels: osc_fused.cuh.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <cuda_runtime.h>
+
+#include "irlosc_internal.h"
+#include "irlosc_build.h"
+#include "osc_eigen.cuh"      // tiled::eigen_solve for the fix-up kernel
+#include "osc_fused.cuh"
+
+using namespace irlosc;
+using namespace irlosc::fused;
+
+namespace {
+
+using fused_build::kDualUr5Parent;
+constexpr int kFusedThreads = 256;
+
+struct FusedEntry {
+    int kd;
+    bool has_base;
+    const void *step, *fixup;
+    int rec_doubles;
+    const char *name;
+};
+
+template <int KD, bool HB>
+FusedEntry entry(const char *name) {
+    return FusedEntry{KD, HB, (const void *)osc_step_fused<KD, HB, kFusedThreads>, (const void *)osc_fused_fixup<KD, HB>,
+                      Rec<KD, HB>::SIZE, name};
+}
+
+const FusedEntry *fused_table(int *count) {
+    static const FusedEntry t[] = {
+        entry<3, true>("osc_step_fused<kd3,base>"),
+        entry<6, false>("osc_step_fused<kd6>"),
+        entry<6, true>("osc_step_fused<kd6,base>"),
+        entry<3, false>("osc_step_fused<kd3>"),
+    };
+    *count = (int)(sizeof t / sizeof t[0]);
+    return t;
+}
+
+const FusedEntry *fused_find(int kd, bool has_base) {
+    int cnt = 0;
+    const FusedEntry *t = fused_table(&cnt);
+    for (int i = 0; i < cnt; ++i)
+        if (t[i].kd == kd && t[i].has_base == has_base) return &t[i];
+    return nullptr;
+}
+
+constexpr size_t kFusedSmem = (size_t)kScratchDoubles * kFusedThreads * sizeof(double);
+
+int32_t ensure_queue(irlosc_handle *h, int64_t B, int rec_doubles) {
+    if (!h->hard_count) CUDA_TRY(cudaMalloc(&h->hard_count, sizeof(int)));
+    if (B > h->hard_cap || rec_doubles != h->hard_rec_doubles) {
+        if (h->hard_inst) { CUDA_TRY(cudaFree(h->hard_inst)); h->hard_inst = nullptr; }
+        if (h->hard_rec) { CUDA_TRY(cudaFree(h->hard_rec)); h->hard_rec = nullptr; }
+        h->hard_cap = 0;
+        CUDA_TRY(cudaMalloc(&h->hard_inst, (size_t)B * sizeof(int64_t)));
+        CUDA_TRY(cudaMalloc(&h->hard_rec, (size_t)B * rec_doubles * sizeof(double)));
+        h->hard_cap = B;
+        h->hard_rec_doubles = rec_doubles;
+    }
+    return IRLOSC_OK;
+}
+
+int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
+    if (!io) return fail(IRLOSC_ERR_INVALID, "io is null");
+    if (!io->q || !io->dq || !io->target_xyz || !io->target_quat || !io->ctrl)
+        return fail(IRLOSC_ERR_INVALID, "a required array (q, dq, target_xyz, target_quat, ctrl) is null");
+    if (h->kp.admittance && !io->ft_raw) return fail(IRLOSC_ERR_INVALID, "admittance is set but ft_raw is null");
+    k.q = io->q; k.dq = io->dq; k.target_xyz = io->target_xyz; k.target_quat = io->target_quat;
+    k.target_vel = io->target_vel; k.max_vel = io->max_vel; k.ft_raw = io->ft_raw;
+    k.ctrl = io->ctrl; k.u_all = io->u_all; k.status = io->status; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    return IRLOSC_OK;
+}
+
+int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st) {
+    const FusedEntry *e = fused_find(h->fused_kd, h->fused_base);
+    if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d", h->fused_kd, (int)h->fused_base);
+    int32_t rc = ensure_queue(h, B, e->rec_doubles);
+    if (rc != IRLOSC_OK) return rc;
+    CUDA_TRY(cudaMemsetAsync(h->hard_count, 0, sizeof(int), st));
+    HardQueue hq{h->hard_count, (int)std::min<int64_t>(h->hard_cap, INT32_MAX), e->rec_doubles, h->hard_rec, h->hard_inst};
+    const int sms = std::max(1, h->sm_count - h->sm_margin);
+    const int grid = (int)std::min<int64_t>((B + kFusedThreads - 1) / kFusedThreads, (int64_t)sms);
+    void *args[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr, (void *)&hq};
+    cudaError_t err = cudaLaunchKernel(e->step, dim3(grid), dim3(kFusedThreads), args, kFusedSmem, st);
+    if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fused kernel launch: %s", cudaGetErrorString(err));
+    const int fgrid = (int)std::min<int64_t>((B + 3) / 4, (int64_t)sms * 4);
+    void *fargs[] = {(void *)&h->kp, (void *)&k, (void *)&h->fr, (void *)&hq};
+    err = cudaLaunchKernel(e->fixup, dim3(fgrid), dim3(128), fargs, 0, st);
+    if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fix-up kernel launch: %s", cudaGetErrorString(err));
+    h->launches += 2;
+    h->last_kernel = e->name;
+    return IRLOSC_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t irlosc_set_model(irlosc_handle *h, const irlosc_model *m) {
+    if (!h || !m) return fail(IRLOSC_ERR_INVALID, "null argument");
+    h->has_model = false;
+    if (m->n_joints != h->kp.n) return fail(IRLOSC_ERR_INVALID, "model has %d joints, controller n=%d", m->n_joints, h->kp.n);
+    int kd = 0;
+    bool has_base = false;
+    if (!fused_roles(h->kp, h->fr, kd, has_base))
+        return fail(IRLOSC_ERR_INVALID, "the fused step needs the DualUR5 topology (has_topology, two arm devices with 3 or 6 "
+                                        "rows each, optionally the base with one row)");
+    for (int j = 0; j < kN; ++j)
+        if (m->joint[j].parent != kDualUr5Parent[j])
+            return fail(IRLOSC_ERR_INVALID, "model joint %d has parent %d, the DualUR5 tree has %d", j, m->joint[j].parent,
+                        kDualUr5Parent[j]);
+    if (!fused_find(kd, has_base)) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d", kd, (int)has_base);
+    int32_t rc = build_kmodel(h->kp, *m, h->km);
+    if (rc != IRLOSC_OK) return rc;
+    int cnt = 0;
+    const FusedEntry *t = fused_table(&cnt);
+    for (int i = 0; i < cnt; ++i)
+        CUDA_TRY(cudaFuncSetAttribute(t[i].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+    h->fused_kd = kd;
+    h->fused_base = has_base;
+    h->has_model = true;
+    return IRLOSC_OK;
+}
+
+extern "C" int32_t irlosc_step_fused(irlosc_handle *h, int64_t B, const irlosc_fused_io *io, void *cuda_stream) {
+    if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
+    if (!h->has_model) return fail(IRLOSC_ERR_INVALID, "irlosc_set_model has not been called");
+    if (B < 0) return fail(IRLOSC_ERR_INVALID, "B=%lld is negative", (long long)B);
+    if (B == 0) return IRLOSC_OK;
+    FIo k;
+    int32_t rc = check_fio(h, io, k);
+    if (rc != IRLOSC_OK) return rc;
+    return launch_fused(h, B, k, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irlosc_fused_io *io) {
+    if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
+    if (!h->has_model) return fail(IRLOSC_ERR_INVALID, "irlosc_set_model has not been called");
+    if (B < 0) return fail(IRLOSC_ERR_INVALID, "B is negative");
+    if (B == 0) return IRLOSC_OK;
+    FIo hk;
+    int32_t rc = check_fio(h, io, hk);
+    if (rc != IRLOSC_OK) return rc;
+    const KParams &P = h->kp;
+    CUDA_TRY(cudaSetDevice(h->device));
+    for (int s = 0; s < kPipeDepth; ++s)
+        if (!h->fstage[s].stream) CUDA_TRY(cudaStreamCreateWithFlags(&h->fstage[s].stream, cudaStreamNonBlocking));
+    const size_t D = P.D, n = P.n;
+    struct In { const double *src; size_t per; } ins[7] = {
+        {hk.q, n}, {hk.dq, n}, {hk.target_xyz, 3 * D}, {hk.target_quat, 4 * D},
+        {hk.target_vel, 6 * D}, {hk.max_vel, 2 * D}, {hk.ft_raw, 6 * D}};
+    // The queue of eigen-path instances is per launch, so chunks are serialised on the kernel side by
+    // using ONE compute stream; copies of the next chunk overlap through the per-stage streams.
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(4 * h->host_chunk, B));
+    cudaEvent_t done[kPipeDepth] = {nullptr};
+    int turn = 0;
+    int32_t result = IRLOSC_OK;
+    for (int64_t b0 = 0; b0 < B && result == IRLOSC_OK; b0 += chunk, ++turn) {
+        const int64_t nb = std::min<int64_t>(chunk, B - b0);
+        Staging &S = h->fstage[turn % kPipeDepth];
+        const double *dptr[7];
+        for (int i = 0; i < 7 && result == IRLOSC_OK; ++i) {
+            dptr[i] = nullptr;
+            if (!ins[i].src) continue;
+            result = ensure_cap(S, i, ins[i].per * (size_t)chunk * sizeof(double));
+            if (result != IRLOSC_OK) break;
+            CUDA_TRY(cudaMemcpyAsync(S.buf[i], ins[i].src + ins[i].per * (size_t)b0, ins[i].per * (size_t)nb * sizeof(double),
+                                     cudaMemcpyHostToDevice, S.stream));
+            dptr[i] = (const double *)S.buf[i];
+        }
+        if (result == IRLOSC_OK) result = ensure_cap(S, 8, (size_t)chunk * P.n_ctrl * sizeof(double));
+        if (result == IRLOSC_OK && hk.u_all) result = ensure_cap(S, 9, (size_t)chunk * n * sizeof(double));
+        if (result == IRLOSC_OK && hk.status) result = ensure_cap(S, 10, (size_t)chunk);
+        if (result == IRLOSC_OK && hk.ee_xyz) result = ensure_cap(S, 11, (size_t)chunk * 3 * D * sizeof(double));
+        if (result == IRLOSC_OK && hk.ee_quat) result = ensure_cap(S, 12, (size_t)chunk * 4 * D * sizeof(double));
+        if (result != IRLOSC_OK) break;
+        FIo dk;
+        dk.q = dptr[0]; dk.dq = dptr[1]; dk.target_xyz = dptr[2]; dk.target_quat = dptr[3];
+        dk.target_vel = dptr[4]; dk.max_vel = dptr[5]; dk.ft_raw = dptr[6];
+        dk.ctrl = (double *)S.buf[8];
+        dk.u_all = hk.u_all ? (double *)S.buf[9] : nullptr;
+        dk.status = hk.status ? (uint8_t *)S.buf[10] : nullptr;
+        dk.ee_xyz = hk.ee_xyz ? (double *)S.buf[11] : nullptr;
+        dk.ee_quat = hk.ee_quat ? (double *)S.buf[12] : nullptr;
+        // the shared queue: wait for the previous chunk's kernels before this chunk's start
+        if (turn > 0) {
+            cudaEvent_t prev = done[(turn - 1) % kPipeDepth];
+            CUDA_TRY(cudaStreamWaitEvent(S.stream, prev, 0));
+        }
+        result = launch_fused(h, nb, dk, S.stream);
+        if (result != IRLOSC_OK) break;
+        if (!done[turn % kPipeDepth]) CUDA_TRY(cudaEventCreateWithFlags(&done[turn % kPipeDepth], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(done[turn % kPipeDepth], S.stream));
+        CUDA_TRY(cudaMemcpyAsync(hk.ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
+                                 cudaMemcpyDeviceToHost, S.stream));
+        if (hk.u_all)
+            CUDA_TRY(cudaMemcpyAsync(hk.u_all + (size_t)b0 * n, dk.u_all, (size_t)nb * n * sizeof(double),
+                                     cudaMemcpyDeviceToHost, S.stream));
+        if (hk.status) CUDA_TRY(cudaMemcpyAsync(hk.status + b0, dk.status, (size_t)nb, cudaMemcpyDeviceToHost, S.stream));
+        if (hk.ee_xyz)
+            CUDA_TRY(cudaMemcpyAsync(hk.ee_xyz + (size_t)b0 * 3 * D, dk.ee_xyz, (size_t)nb * 3 * D * sizeof(double),
+                                     cudaMemcpyDeviceToHost, S.stream));
+        if (hk.ee_quat)
+            CUDA_TRY(cudaMemcpyAsync(hk.ee_quat + (size_t)b0 * 4 * D, dk.ee_quat, (size_t)nb * 4 * D * sizeof(double),
+                                     cudaMemcpyDeviceToHost, S.stream));
+    }
+    for (int s = 0; s < kPipeDepth; ++s) {
+        cudaError_t e = cudaStreamSynchronize(h->fstage[s].stream);
+        if (e != cudaSuccess && result == IRLOSC_OK) result = fail(IRLOSC_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
+        if (done[s]) cudaEventDestroy(done[s]);
+    }
+    return result;
+}

@@ -1,0 +1,58 @@
+// Plain data types of the fused state provider + OSC step (kernels: osc_fused.cuh).
+#pragma once
+#include <cstdint>
+#include "../../include/irlosc.h"
+
+namespace irlosc {
+namespace fused {
+
+constexpr int kN = 25;
+
+struct KJoint {
+    double Q0[9], P1[9], P2[9];   // R_local(q) = cos q Q0 + sin q P1 + P2 (row-major; fixed frame folded in)
+    double pos[3];                // body origin in the parent joint body's frame
+    double axp[3];                // hinge axis in the parent joint body's frame
+    double mass, com[3], ic[6];   // lumped body: COM (body frame), inertia about it (xx yy zz xy xz yz)
+};
+struct KFrame {
+    int32_t joint, has;
+    double pos[3], R[9];
+};
+struct KModel {
+    double gravity[3], pad_;
+    KJoint stand;                 // joint 0
+    KJoint arm[2][6];             // joints 1..6 / 13..18
+    KJoint grip[2][2][3];         // [arm][half]: g0 (child of arm joint 6), g1 (child of g0), g2 (child of arm joint 6)
+    KFrame ee[IRLOSC_MAX_DEVICES], ft[IRLOSC_MAX_DEVICES];
+};
+struct FRoles {
+    int dev_arm[2], dev_base, row_arm[2], row_base;
+};
+struct FIo {
+    const double *q, *dq, *target_xyz, *target_quat, *target_vel, *max_vel, *ft_raw;
+    double *ctrl, *u_all;
+    uint8_t *status;
+    double *ee_xyz, *ee_quat;
+};
+// Instances that need the eigen path: one record each, finished by osc_fused_fixup.
+struct HardQueue {
+    int *count;
+    int capacity;
+    int rec_doubles;
+    double *rec;
+    int64_t *inst;
+};
+template <int KD, bool HAS_BASE>
+struct Rec {                       // record layout in doubles
+    static constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
+    static constexpr int A = 0;                    // K x K row-major
+    static constexpr int G = A + K * K;            // rhs g
+    static constexpr int BASE = G + K;             // base[13]: stand, arm0 joints 1..6, arm1 joints 1..6
+    static constexpr int JST = BASE + 13;          // J[r][stand], r < K
+    static constexpr int JARM = JST + K;           // J[row_arm[a] + cr][arm joint i]: [a][i][cr]
+    static constexpr int ABAD = JARM + 2 * 6 * KD; // 1.0 when the LDL^T pivots failed
+    static constexpr int SIZE = ABAD + 1;
+};
+
+}  // namespace fused
+}  // namespace irlosc

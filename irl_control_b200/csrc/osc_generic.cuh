@@ -14,6 +14,7 @@
 //   osc.py:203-208 packing u_all[actuator_trnids] per target
 #pragma once
 #include "irlosc_device.cuh"
+#include "osc_eigen.cuh"
 
 namespace irlosc {
 
@@ -32,11 +33,6 @@ struct GenericSmem {
     int flags;
 };
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // Cyclic Jacobi eigen-decomposition of the symmetric k x k matrix in S.As (destroyed:
 // eigenvalues end on its diagonal); eigenvectors in the columns of S.Ls.  Warp-cooperative.

@@ -217,6 +217,104 @@ class BatchedOSC:
             _native.check(self.lib.irlosc_step_host(self._handle, B, C.byref(io)))
         return out
 
+    # ------------------------------------------------------------------ fused state provider
+    _FUSED_FIELDS = ("q", "dq", "target_xyz", "target_quat", "target_vel", "max_vel", "ft_raw")
+
+    def set_model(self, model: "_native.Model"):
+        """Attach the rigid-body description (`rigid_model.reduce_model`) the fused step needs."""
+        _native.check(self.lib.irlosc_set_model(self._handle, C.byref(model)))
+        self._has_model = True
+
+    def _fused_shapes(self, B: int) -> Dict[str, tuple]:
+        n, D = self.n, self.D
+        return {"q": (B, n), "dq": (B, n), "target_xyz": (B, D, 3), "target_quat": (B, D, 4),
+                "target_vel": (B, D, 6), "max_vel": (B, D, 2), "ft_raw": (B, D, 6)}
+
+    def _fused_check(self, state, B, is_ok):
+        shapes = self._fused_shapes(B)
+        for name in self._FUSED_FIELDS:
+            arr = state.get(name)
+            if arr is None:
+                if name in ("target_vel", "max_vel", "ft_raw"):
+                    continue
+                raise ValueError("state['%s'] is required" % name)
+            if tuple(arr.shape) != shapes[name]:
+                raise ValueError("state['%s'] has shape %s, expected %s" % (name, tuple(arr.shape), shapes[name]))
+            is_ok(name, arr)
+        if self.layout.admittance and state.get("ft_raw") is None:
+            raise ValueError("admittance is set: state['ft_raw'] is required")
+
+    def step_fused(self, state: Dict, out: Optional[Dict] = None, want_u_all: bool = False,
+                   want_status: bool = True, want_ee: bool = False) -> Dict:
+        """One control step from joint states: what `Robot.get_all_states` + `OSC.generate` do together
+        (robot.py:125-136, osc.py:120-210), with M, J, qfrc_bias and the EE poses computed on the GPU
+        from `state["q"]`, `state["dq"]` (CUDA float64 `[B, n]`) instead of read from a simulator."""
+        import torch
+        q = state["q"]
+        if not q.is_cuda:
+            raise ValueError("BatchedOSC.step_fused expects CUDA tensors; use step_fused_host for host arrays")
+        B = int(q.shape[0])
+
+        def ok(name, t):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device == q.device):
+                raise ValueError("state['%s'] must be a contiguous float64 CUDA tensor on %s" % (name, q.device))
+        self._fused_check(state, B, ok)
+        out = {} if out is None else out
+        new = lambda *shape, dtype=torch.float64: torch.empty(*shape, dtype=dtype, device=q.device)
+        if "ctrl" not in out:
+            out["ctrl"] = new(B, self.n_ctrl)
+        if want_u_all and "u_all" not in out:
+            out["u_all"] = new(B, self.n)
+        if want_status and "status" not in out:
+            out["status"] = new(B, dtype=torch.uint8)
+        if want_ee:
+            out.setdefault("ee_xyz", new(B, self.D, 3))
+            out.setdefault("ee_quat", new(B, self.D, 4))
+        io = _native.FusedIo()
+        for name in self._FUSED_FIELDS:
+            t = state.get(name)
+            setattr(io, name, t.data_ptr() if t is not None else None)
+        for name in ("ctrl", "u_all", "status", "ee_xyz", "ee_quat"):
+            setattr(io, name, out[name].data_ptr() if name in out else None)
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        with torch.cuda.device(q.device):
+            _native.check(self.lib.irlosc_step_fused(self._handle, B, C.byref(io), C.c_void_p(stream)))
+        return out
+
+    def step_fused_host(self, state: Dict, out: Optional[Dict] = None, want_u_all: bool = False,
+                        want_status: bool = True, want_ee: bool = False) -> Dict:
+        """`step_fused` with HOST numpy arrays; blocks until the results are valid."""
+        q = state["q"]
+        B = int(q.shape[0])
+
+        def ok(name, a):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("state['%s'] must be a C-contiguous float64 numpy array" % name)
+        self._fused_check(state, B, ok)
+        out = {} if out is None else out
+        if "ctrl" not in out:
+            out["ctrl"] = np.empty((B, self.n_ctrl), dtype=np.float64)
+        if want_u_all and "u_all" not in out:
+            out["u_all"] = np.empty((B, self.n), dtype=np.float64)
+        if want_status and "status" not in out:
+            out["status"] = np.empty((B,), dtype=np.uint8)
+        if want_ee:
+            out.setdefault("ee_xyz", np.empty((B, self.D, 3), dtype=np.float64))
+            out.setdefault("ee_quat", np.empty((B, self.D, 4), dtype=np.float64))
+        io = _native.FusedIo()
+        for name in self._FUSED_FIELDS:
+            a = state.get(name)
+            setattr(io, name, a.ctypes.data if a is not None else None)
+        for name in ("ctrl", "u_all", "status", "ee_xyz", "ee_quat"):
+            setattr(io, name, out[name].ctypes.data if name in out else None)
+        if self._torch_device is not None:
+            import torch
+            with torch.cuda.device(self._torch_device):
+                _native.check(self.lib.irlosc_step_fused_host(self._handle, B, C.byref(io)))
+        else:
+            _native.check(self.lib.irlosc_step_fused_host(self._handle, B, C.byref(io)))
+        return out
+
     def calc_error(self, ee_xyz, ee_quat, target_xyz, target_quat):
         """Batched `OSC.calc_error` (osc.py:101-118) on CUDA tensors -> (B, D, 6)."""
         import torch

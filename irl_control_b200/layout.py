@@ -33,6 +33,7 @@ class DeviceLayout:
     k: tuple
     d: tuple
     ee_joint: int = -1          # robot-local id of the last joint of Device.joint_ids (device.py:62-64)
+    ee_body: str = ""           # Device.EE, the body whose pose / Jacobian the device reads (device.py:93-95,125)
 
     @property
     def n_rows(self) -> int:
@@ -178,6 +179,7 @@ def compile_layout(robot, device_configs: Dict[str, Dict], target_names: Sequenc
             kp=float(cfg['kp']), kv=float(cfg['kv']), ko=float(cfg['ko']),
             k=tuple(float(x) for x in cfg['k']), d=tuple(float(x) for x in cfg['d']),
             ee_joint=local.get(int(dev.joint_ids[-1]), -1) if len(dev.joint_ids) else -1,
+            ee_body=str(getattr(dev, 'EE', '')),
         ))
     return OscLayout(
         n=int(robot.num_joints_total), devices=tuple(devs), use_g=bool(use_g),

@@ -103,7 +103,7 @@ def synth_batch(layout: OscLayout, B: int, seed: int = 0, device="cpu", model: O
     deul = rng.uniform(-0.5, 0.5, size=(B, D, 3))
     ft_raw = np.concatenate([rng.normal(0.0, 5.0, size=(B, D, 3)), rng.normal(0.0, 0.5, size=(B, D, 3))], -1)
     out: Dict[str, List[torch.Tensor]] = {k: [] for k in
-                                          ("M", "J6", "dq", "bias", "ee_xyz", "ee_quat", "ft_xmat")}
+                                          ("M", "J6", "q", "dq", "bias", "ee_xyz", "ee_quat", "ft_xmat")}
     for s in range(0, B, chunk):
         q = torch.from_numpy(q_np[s:s + chunk]).to(dev)
         dq = torch.from_numpy(dq_np[s:s + chunk]).to(dev)
@@ -120,6 +120,7 @@ def synth_batch(layout: OscLayout, B: int, seed: int = 0, device="cpu", model: O
             else:
                 fx.append(torch.eye(3, dtype=torch.float64, device=dev).reshape(1, 9).expand(q.shape[0], 9))
         out["M"].append(dyn.M)
+        out["q"].append(q)
         out["J6"].append(torch.stack(j6, 1))
         out["dq"].append(dq)
         out["bias"].append(dyn.bias)
@@ -145,6 +146,26 @@ def synth_batch(layout: OscLayout, B: int, seed: int = 0, device="cpu", model: O
             mv[:, 0, 0] = torch.clamp(6.0 * err, 0.1, 3.0)
         st["max_vel"] = mv.contiguous()
     return st
+
+
+def fused_inputs(st: Dict[str, torch.Tensor], layout: OscLayout, with_vel: bool = False) -> Dict[str, torch.Tensor]:
+    """Fields `BatchedOSC.step_fused` consumes: joint states and targets only (no M / J / bias / EE)."""
+    keep = {"q": st["q"], "dq": st["dq"], "target_xyz": st["target_xyz"], "target_quat": st["target_quat"]}
+    if "max_vel" in st:
+        keep["max_vel"] = st["max_vel"]
+    if layout.admittance:
+        keep["ft_raw"] = st["ft_raw"]
+    if with_vel and "target_vel" in st:
+        keep["target_vel"] = st["target_vel"]
+    return keep
+
+
+def scenario_model(name: str):
+    """(layout, irlosc_model) of a named scenario for the fused step."""
+    from .rigid_model import model_for_layout
+    app, _osc, _names, layout = build_scenario(name)
+    robot = app.get_robot("DualUR5")
+    return layout, model_for_layout(app.sim.model, robot.joint_ids_all, layout)
 
 
 def kernel_inputs(st: Dict[str, torch.Tensor], layout: OscLayout, packed_M: bool = False,

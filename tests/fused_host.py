@@ -1,0 +1,68 @@
+"""TEST INFRASTRUCTURE: builds and drives tests/host_fused/fused_host.cu, which runs the
+per-instance function of the fused CUDA kernel (osc_fused.cuh, __host__ __device__) on the CPU.
+Never imported by the package."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from irl_control_b200 import _native
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_fused", "fused_host.cu")
+LIB = os.path.join(HERE, "_build", "libfused_host.so")
+CSRC = os.path.join(os.path.dirname(HERE), "irl_control_b200", "csrc")
+_lib = None
+
+
+def build():
+    deps = [SRC, os.path.join(os.path.dirname(HERE), "include", "irlosc.h")] + [
+        os.path.join(CSRC, f) for f in ("osc_fused.cuh", "osc_fused_types.h", "irlosc_device.cuh",
+                                        "irlosc_build.h", "irlosc_internal.h")]
+    if os.path.isfile(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in deps):
+        return LIB
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    cmd = [os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+           "-shared", "-Xcompiler", "-fPIC", "-o", LIB, SRC]
+    subprocess.check_call(cmd)
+    return LIB
+
+
+def load():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.fused_host_run.restype = C.c_int64
+        _lib.fused_host_run.argtypes = [C.POINTER(_native.Params), C.POINTER(_native.Model), C.c_int64,
+                                        C.POINTER(_native.FusedIo)] + [C.c_void_p] * 6
+        _lib.fused_host_error.restype = C.c_char_p
+    return _lib
+
+
+def run(layout, model, inp, debug=False):
+    """inp: dict of numpy arrays q, dq, target_xyz, target_quat [, target_vel, max_vel, ft_raw]."""
+    lib = load()
+    B = int(inp["q"].shape[0])
+    n, D, k, nc = layout.n, layout.D, layout.k, layout.n_ctrl
+    keep = {k_: np.ascontiguousarray(v, dtype=np.float64) for k_, v in inp.items()}
+    out = {"ctrl": np.zeros((B, nc)), "u_all": np.zeros((B, n)), "status": np.zeros(B, dtype=np.uint8),
+           "ee_xyz": np.zeros((B, D, 3)), "ee_quat": np.zeros((B, D, 4))}
+    io = _native.FusedIo()
+    for name in ("q", "dq", "target_xyz", "target_quat", "target_vel", "max_vel", "ft_raw"):
+        setattr(io, name, keep[name].ctypes.data if name in keep else None)
+    for name in out:
+        setattr(io, name, out[name].ctypes.data)
+    dbg = {}
+    ptrs = [None] * 6
+    if debug:
+        dbg = {"A": np.zeros((B, k, k)), "g": np.zeros((B, k)), "uv": np.zeros((B, n)),
+               "bias": np.zeros((B, n)), "dx": np.zeros((B, k)), "J": np.zeros((B, k, n))}
+        ptrs = [dbg[x].ctypes.data for x in ("A", "g", "uv", "bias", "dx", "J")]
+    params = layout.to_c_params()
+    rc = lib.fused_host_run(C.byref(params), C.byref(model), B, C.byref(io), *ptrs)
+    if rc < 0:
+        raise RuntimeError(lib.fused_host_error().decode())
+    out["n_hard"] = int(rc)
+    out.update(dbg)
+    return out

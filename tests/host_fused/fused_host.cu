@@ -1,0 +1,132 @@
+// TEST INFRASTRUCTURE ONLY.  Runs the per-instance function of the fused CUDA kernel
+// (irl_control_b200/csrc/osc_fused.cuh, __host__ __device__) on the CPU so that the CPU test
+// suite can check the kernel's arithmetic against the oracle without a GPU.  Nothing in the
+// package loads this library; the product path is libirlosc.so on a GPU.
+#define IRLOSC_FUSED_NO_KERNELS 1
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../irl_control_b200/csrc/irlosc_internal.h"
+#include "../../irl_control_b200/csrc/irlosc_build.h"
+#include "../../irl_control_b200/csrc/osc_fused.cuh"
+
+static std::string g_err;
+int32_t irlosc::fail(int32_t rc, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return rc;
+}
+int32_t irlosc::ensure_cap(Staging &, int, size_t) { return IRLOSC_OK; }
+
+using namespace irlosc;
+using namespace irlosc::fused;
+
+// serial cyclic Jacobi + the truncation rule of tiled::eigen_solve (osc.py:52-55), test-only
+template <int K>
+static int host_eigen_solve(const double *A0, const double *g, bool force_pinv, double *w) {
+    double A[K][K], V[K][K];
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) { A[i][j] = A0[i * K + j]; V[i][j] = i == j; }
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0, dia = 0;
+        for (int i = 0; i < K; ++i)
+            for (int j = 0; j < K; ++j) (i == j ? dia : off) += A[i][j] * A[i][j];
+        if (off <= 1e-30 * dia) break;
+        for (int p = 0; p < K; ++p)
+            for (int q = p + 1; q < K; ++q) {
+                if (A[p][q] == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+                for (int i = 0; i < K; ++i) {
+                    const double aip = A[i][p], aiq = A[i][q];
+                    A[i][p] = c * aip - s * aiq; A[i][q] = s * aip + c * aiq;
+                    const double vip = V[i][p], viq = V[i][q];
+                    V[i][p] = c * vip - s * viq; V[i][q] = s * vip + c * viq;
+                }
+                for (int j = 0; j < K; ++j) {
+                    const double apj = A[p][j], aqj = A[q][j];
+                    A[p][j] = c * apj - s * aqj; A[q][j] = s * apj + c * aqj;
+                }
+            }
+    }
+    double lmax = 0, det = 1;
+    for (int i = 0; i < K; ++i) { lmax = fmax(lmax, fabs(A[i][i])); det *= A[i][i]; }
+    const bool pinv = force_pinv || !(fabs(det) >= kDetThreshold);
+    double c[K];
+    for (int e = 0; e < K; ++e) {
+        double proj = 0;
+        for (int i = 0; i < K; ++i) proj += V[i][e] * g[i];
+        const bool keep = pinv ? (fabs(A[e][e]) > kPinvRcond * lmax) : true;
+        c[e] = keep ? proj / A[e][e] : 0.0;
+    }
+    for (int i = 0; i < K; ++i) {
+        double acc = 0;
+        for (int e = 0; e < K; ++e) acc += V[i][e] * c[e];
+        w[i] = acc;
+    }
+    return IRLOSC_ST_EIGEN | (pinv ? IRLOSC_ST_PINV : 0);
+}
+
+template <int KD, bool HB>
+static int64_t run(const KParams &P, const KModel &M, const FRoles &R, const FIo &io, int64_t B, const Debug *dbg0) {
+    using RC = Rec<KD, HB>;
+    constexpr int K = RC::K;
+    std::vector<double> scratch(kScratchDoubles), rec(RC::SIZE);
+    int64_t n_hard = 0;
+    for (int64_t i = 0; i < B; ++i) {
+        Debug d, *dp = nullptr;
+        if (dbg0) {
+            d = *dbg0;
+            if (d.A) d.A += i * K * K;
+            if (d.g) d.g += i * K;
+            if (d.dx) d.dx += i * K;
+            if (d.uv) d.uv += i * kN;
+            if (d.bias) d.bias += i * kN;
+            if (d.J) d.J += i * K * kN;
+            dp = &d;
+        }
+        const Scratch scr{scratch.data(), 1};
+        const bool hard = fused_instance<KD, HB>(P, M, R, io, i, scr, rec.data(), dp);
+        if (hard) {
+            ++n_hard;
+            double w[K];
+            const int fl = host_eigen_solve<K>(&rec[RC::A], &rec[RC::G], rec[RC::ABAD] == 0.0, w);
+            fixup_finish<KD, HB>(P, R, io, i, rec.data(), w, 0, 1);
+            if (io.status) io.status[i] = (uint8_t)(io.status[i] | fl);
+        }
+    }
+    return n_hard;
+}
+
+extern "C" const char *fused_host_error(void) { return g_err.c_str(); }
+
+// Returns the number of instances that took the eigen path, or -1 on error.
+extern "C" int64_t fused_host_run(const irlosc_params *params, const irlosc_model *model, int64_t B,
+                                  const irlosc_fused_io *io, double *dbg_A, double *dbg_g, double *dbg_uv,
+                                  double *dbg_bias, double *dbg_dx, double *dbg_J) {
+    KParams P;
+    if (build_kparams(*params, P) != IRLOSC_OK) return -1;
+    FRoles R;
+    int kd = 0;
+    bool hb = false;
+    if (!fused_roles(P, R, kd, hb)) { irlosc::fail(1, "not the DualUR5 topology"); return -1; }
+    KModel M;
+    if (build_kmodel(P, *model, M) != IRLOSC_OK) return -1;
+    FIo k;
+    k.q = io->q; k.dq = io->dq; k.target_xyz = io->target_xyz; k.target_quat = io->target_quat;
+    k.target_vel = io->target_vel; k.max_vel = io->max_vel; k.ft_raw = io->ft_raw;
+    k.ctrl = io->ctrl; k.u_all = io->u_all; k.status = io->status; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    Debug d{dbg_A, dbg_g, dbg_uv, dbg_bias, dbg_dx, dbg_J};
+    const Debug *dp = (dbg_A || dbg_uv || dbg_J) ? &d : nullptr;
+    if (kd == 3 && hb) return run<3, true>(P, M, R, k, B, dp);
+    if (kd == 3 && !hb) return run<3, false>(P, M, R, k, B, dp);
+    if (kd == 6 && hb) return run<6, true>(P, M, R, k, B, dp);
+    return run<6, false>(P, M, R, k, B, dp);
+}

@@ -1,0 +1,123 @@
+"""CPU: arithmetic of the fused state provider + OSC step.
+
+`irl_control_b200/csrc/osc_fused.cuh` keeps its per-instance function `__host__ __device__`;
+tests/host_fused compiles exactly that function for the host (test infrastructure, never loaded
+by the package) so this suite can compare it with the oracle without a GPU:
+
+  * the provider part - M dq, qfrc_bias, J rows, dx = J dq, A = J M^-1 J^T, EE poses - against the
+    rigid-body model in `dual_ur5.py` (what the reference reads from MuJoCo);
+  * the joint-space signal against `oracle/osc_numpy.py` fed with that model's M / J / bias.
+
+The GPU suite (tests/test_gpu_fused.py) then checks the compiled kernel against the same oracle.
+"""
+import numpy as np
+import pytest
+
+import fused_host
+from irl_control_b200.dual_ur5 import sample_joint_states
+from irl_control_b200.rigid_model import model_for_layout
+from irl_control_b200.synthetic import build_scenario, oracle_inputs, synth_batch
+from oracle import osc_numpy
+
+REL_TOL = 1e-6      # same bar as tests/test_gpu_parity.py (BASELINE.json asks 1e-4)
+
+
+def _case(scenario, B, seed, with_vel=None):
+    app, _osc, _names, layout = build_scenario(scenario)
+    robot = app.get_robot("DualUR5")
+    model = model_for_layout(app.sim.model, robot.joint_ids_all, layout)
+    st = synth_batch(layout, B, seed=seed, insertion_schedule=(scenario == "insertion"))
+    q, dq = sample_joint_states(B, seed)
+    assert np.array_equal(q, st["q"].numpy()) and np.array_equal(dq, st["dq"].numpy())
+    inp = {"q": q, "dq": dq, "target_xyz": st["target_xyz"].numpy(), "target_quat": st["target_quat"].numpy(),
+           "max_vel": st["max_vel"].numpy()}
+    if layout.admittance:
+        inp["ft_raw"] = st["ft_raw"].numpy()
+    if with_vel is not None:
+        import torch
+        st["target_vel"] = torch.from_numpy(with_vel)
+        inp["target_vel"] = with_vel
+    return layout, model, st, inp
+
+
+def _rel(got, want):
+    scale = np.abs(want).max(axis=1, keepdims=True)
+    return (np.abs(got - want) / scale).max(axis=1)
+
+
+@pytest.mark.parametrize("scenario", ["gain_test", "admit_test", "insertion", "worst_case"])
+def test_provider_quantities_match_the_rigid_body_model(scenario):
+    layout, model, st, inp = _case(scenario, 96, seed=11)
+    out = fused_host.run(layout, model, inp, debug=True)
+    M, J, dq = st["M"].numpy(), st["J"].numpy(), st["dq"].numpy()
+    assert np.abs(out["uv"] - np.einsum("bij,bj->bi", M, dq)).max() < 1e-12
+    assert np.abs(out["bias"] - st["bias"].numpy()).max() < 1e-11
+    assert np.abs(out["J"] - J).max() < 1e-13
+    assert np.abs(out["dx"] - np.einsum("bkj,bj->bk", J, dq)).max() < 1e-13
+    A = J @ np.linalg.solve(M, J.transpose(0, 2, 1))
+    assert (np.abs(out["A"] - A).max(axis=(1, 2)) / np.abs(A).max(axis=(1, 2))).max() < 1e-11
+    assert np.abs(out["ee_xyz"] - st["ee_xyz"].numpy()).max() < 1e-13
+    eq = st["ee_quat"].numpy()
+    sgn = np.sign((out["ee_quat"] * eq).sum(-1, keepdims=True))
+    assert np.abs(out["ee_quat"] * sgn - eq).max() < 1e-13
+
+
+@pytest.mark.parametrize("scenario,B", [("gain_test", 512), ("admit_test", 512), ("insertion", 512), ("worst_case", 256)])
+def test_fused_step_matches_the_oracle(scenario, B):
+    layout, model, st, inp = _case(scenario, B, seed=3)
+    out = fused_host.run(layout, model, inp)
+    ref = osc_numpy.osc_batch(layout.as_dict(), oracle_inputs(st, layout))
+    rel = _rel(out["u_all"], ref["u_all"])
+    # instances within rounding of the pinv cutoff may legitimately differ; none are expected here
+    assert rel.max() < REL_TOL, (rel.max(), int(np.argmax(rel)))
+    assert np.array_equal((out["status"] & 1).astype(bool), np.asarray(ref["pinv"]).astype(bool))
+    # packing (osc.py:203-208)
+    want = np.concatenate([ref["u_all"][:, list(d.actuator_trnids)] for d in layout.devices], axis=1)
+    assert _rel(out["ctrl"], want).max() < REL_TOL
+    if scenario in ("admit_test", "insertion", "worst_case"):
+        assert out["n_hard"] > 0          # the eigen fix-up path is exercised
+
+
+def test_velocity_tracking_branch_and_index_error_flag():
+    """N4: the branch is taken only when all six target-velocity entries are non-zero; N3: in the
+    gain_test target order J_idxs runs past k for the left arm -> IndexError in the reference."""
+    from irl_control_b200 import _native
+    B = 64
+    rng = np.random.default_rng(0)
+    for scenario in ("admit_test", "gain_test"):
+        app, _o, _n, layout = build_scenario(scenario)
+        tv = rng.normal(0.0, 0.2, size=(B, layout.D, 6))
+        tv[: B // 2, :, 0] = 0.0                      # one zero entry -> "zero" branch (osc.py:173)
+        layout, model, st, inp = _case(scenario, B, seed=9, with_vel=tv)
+        out = fused_host.run(layout, model, inp)
+        ob = oracle_inputs(st, layout)
+        n_err = n_track = 0
+        for i in range(B):
+            try:
+                ref = osc_numpy.osc_step(layout.as_dict(), {k: v[i] for k, v in ob.items()})
+            except IndexError:                           # robot.py:52-55 vs osc.py:150,176
+                n_err += 1
+                assert out["status"][i] & _native.ST_DX_RANGE
+                assert np.isnan(out["u_all"][i]).all() and np.isnan(out["ctrl"][i]).all()
+                continue
+            assert not out["status"][i] & _native.ST_DX_RANGE
+            assert _rel(out["u_all"][i:i + 1], ref["u_all"][None]).max() < REL_TOL
+            tracking = bool(np.any(ref["vel_branch"]))
+            n_track += tracking
+            assert bool(out["status"][i] & _native.ST_VEL_BRANCH) == tracking
+        assert n_err + n_track == B // 2, (scenario, n_err, n_track)
+
+
+def test_reduced_model_lumps_welded_bodies():
+    from irl_control_b200.dual_ur5 import DualUR5Model
+    app, _o, _n, layout = build_scenario("gain_test")
+    robot = app.get_robot("DualUR5")
+    m = app.sim.model
+    model = model_for_layout(m, robot.joint_ids_all, layout)
+    assert model.n_joints == 25
+    assert [model.joint[j].parent for j in range(25)] == [-1, 0, 1, 2, 3, 4, 5, 6, 7, 6, 6, 10, 6,
+                                                          0, 13, 14, 15, 16, 17, 18, 19, 18, 18, 22, 18]
+    moving = sum(it[2] for b, it in enumerate(m.body_inertial) if it is not None and b < m.n_robot_bodies) - 100.0
+    assert abs(sum(model.joint[j].mass for j in range(25)) - moving) < 1e-12     # origin_base (100 kg) is welded to the world
+    assert [model.ee[d].joint for d in range(3)] == [6, 18, 0]
+    assert [model.ft[d].joint for d in range(3)] == [6, 18, -1]

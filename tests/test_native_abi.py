@@ -25,11 +25,15 @@ def test_struct_sizes_match_header(native_lib, tmp_path):
     from irl_control_b200 import _native
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "irlosc.h"\nint main(){printf("%zu %zu %zu\\n", '
-                   'sizeof(irlosc_device_params), sizeof(irlosc_params), sizeof(irlosc_io));return 0;}\n')
+                   'sizeof(irlosc_device_params), sizeof(irlosc_params), sizeof(irlosc_io));'
+                   'printf("%zu %zu %zu %zu\\n", sizeof(irlosc_joint_model), sizeof(irlosc_frame_model), '
+                   'sizeof(irlosc_model), sizeof(irlosc_fused_io));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)]).decode().split()
-    assert [int(x) for x in out] == [C.sizeof(_native.DeviceParams), C.sizeof(_native.Params), C.sizeof(_native.Io)]
+    assert [int(x) for x in out] == [C.sizeof(_native.DeviceParams), C.sizeof(_native.Params), C.sizeof(_native.Io),
+                                     C.sizeof(_native.JointModel), C.sizeof(_native.FrameModel),
+                                     C.sizeof(_native.Model), C.sizeof(_native.FusedIo)]
 
 
 def test_library_is_sm100a_only(native_lib):
@@ -61,6 +65,16 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_native, "library_path", lambda: str(tmp_path / "libirlosc.so"))
     with pytest.raises(_native.NativeLibraryError):
         _native.load()
+
+
+def test_product_never_loads_the_host_harness():
+    """tests/host_fused runs the fused kernel's per-instance function on the CPU for the tests; the
+    package must not know about it."""
+    pkg_dir = os.path.join(ROOT, "irl_control_b200")
+    for fn in os.listdir(pkg_dir):
+        if fn.endswith(".py"):
+            text = open(os.path.join(pkg_dir, fn)).read()
+            assert "fused_host" not in text and "host_fused" not in text, fn
 
 
 def test_product_never_imports_oracle():
