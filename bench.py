@@ -132,6 +132,7 @@ def main():
                     help="result gather for --gpus > 1: fused = multicast stores if the box has NVLS, else peer stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="skip the fused state-provider measurement (SURVEY 8 f1)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -328,6 +329,67 @@ def main():
                "api": "BatchedOSC.step_host -> irlosc_step_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)"}
         assert np.isfinite(host_out["ctrl"]).all()
 
+    # ------------------------------------------------------------ fused state provider
+    # Same control steps, but M / J / qfrc_bias / EE poses are computed on the GPU from (q, dq) inside
+    # the step kernel (irlosc_step_fused) instead of being read from HBM.  Its inputs (~0.6 KB per
+    # instance) fit in L2, so L2 is flushed between the individually timed steps.
+    fused = None
+    if not args.no_fused:
+        from irl_control_b200.synthetic import fused_inputs, scenario_model
+        _, model = scenario_model(args.workload)
+        eng.set_model(model)
+        fin = fused_inputs(st, layout)
+        fout = {"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)}
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(max(args.warmup, 3)):
+            eng.step_fused(fin, out=fout, want_status=False)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0 = eng.kernel_launches
+        fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in fev:
+            flush.zero_()
+            a.record()
+            eng.step_fused(fin, out=fout, want_status=False)
+            b.record()
+        torch.cuda.synchronize()
+        f_ms = sum(a.elapsed_time(b) for a, b in fev) / len(fev)
+        f_launches = eng.kernel_launches - l0
+        ft = torch.tensor([f_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
+        f_ms = float(ft.item())
+        f_in = sum(v.numel() * v.element_size() for v in fin.values())
+        fused = {"value": world * B / (f_ms * 1e-3), "unit": UNIT, "ms_per_step": f_ms, "kernel": eng.last_kernel,
+                 "gpu_launches": int(f_launches), "input_bytes_per_step": int(f_in // B),
+                 "l2_policy": "256 MB flush write between timed steps (inputs %.0f MB < L2)" % (f_in / 1e6),
+                 "api": "BatchedOSC.step_fused -> irlosc_step_fused (q, dq, targets in HBM)"}
+        if not args.no_e2e:
+            host_in = {}
+            for k, v in fin.items():
+                buf = pinned_empty(tuple(v.shape))
+                buf[...] = v.cpu().numpy()
+                host_in[k] = buf
+            host_out = {"ctrl": pinned_empty((B, layout.n_ctrl))}
+            for _ in range(2):
+                eng.step_fused_host(host_in, out=host_out, want_status=False)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            reps = max(3, min(args.steps, 10))
+            for _ in range(reps):
+                eng.step_fused_host(host_in, out=host_out, want_status=False)
+            dt = (time.perf_counter() - t0) / reps
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            assert np.isfinite(host_out["ctrl"]).all()
+            fused["e2e"] = {"value": world * B / float(tt.item()), "unit": UNIT,
+                            "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in.values())),
+                            "d2h_bytes_per_step": int(host_out["ctrl"].nbytes), "ms_per_step": 1e3 * float(tt.item()),
+                            "api": "BatchedOSC.step_fused_host -> irlosc_step_fused_host (pinned host buffers)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -359,7 +421,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb}
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb, "fused_state": fused}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

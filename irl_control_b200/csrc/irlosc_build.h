@@ -163,6 +163,14 @@ inline bool fused_roles(const KParams &P, FRoles &R, int &kd, bool &has_base) {
     has_base = R.dev_base >= 0;
     if (has_base && P.dev[R.dev_base].kdev != 1) return false;
     if ((P.D == 3) != has_base) return false;
+    // joint -> packed ctrl slot; a joint returned twice cannot be served by the single-store packing
+    for (int j = 0; j < IRLOSC_MAX_N; ++j) R.joint_slot[j] = -1;
+    for (int d = 0; d < P.D; ++d)
+        for (int c = 0; c < P.dev[d].n_ctrl; ++c) {
+            const int j = P.dev[d].actuator[c];
+            if (R.joint_slot[j] >= 0) return false;
+            R.joint_slot[j] = (int8_t)(P.dev[d].ctrl0 + c);
+        }
     return true;
 }
 

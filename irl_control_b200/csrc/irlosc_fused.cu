@@ -8,7 +8,6 @@
 
 #include "irlosc_internal.h"
 #include "irlosc_build.h"
-#include "osc_eigen.cuh"      // tiled::eigen_solve for the fix-up kernel
 #include "osc_fused.cuh"
 
 using namespace irlosc;
@@ -17,42 +16,49 @@ using namespace irlosc::fused;
 namespace {
 
 using fused_build::kDualUr5Parent;
-constexpr int kFusedThreads = 256;
 
 struct FusedEntry {
     int kd;
     bool has_base;
+    int variant;              // 0 = default; others for A/B measurements (irlosc_set_kernel(h, 2 + variant))
+    int threads;
+    size_t smem;
     const void *step, *fixup;
     int rec_doubles;
     const char *name;
 };
 
-template <int KD, bool HB>
-FusedEntry entry(const char *name) {
-    return FusedEntry{KD, HB, (const void *)osc_step_fused<KD, HB, kFusedThreads>, (const void *)osc_fused_fixup<KD, HB>,
+template <int KD, bool HB, int NT, bool SMEM>
+FusedEntry entry(int variant, const char *name) {
+    return FusedEntry{KD, HB, variant, NT, SMEM ? (size_t)kScratchDoubles * NT * sizeof(double) : 0,
+                      (const void *)osc_step_fused<KD, HB, NT, SMEM>, (const void *)osc_tail_fixup<KD, HB>,
                       Rec<KD, HB>::SIZE, name};
 }
 
 const FusedEntry *fused_table(int *count) {
     static const FusedEntry t[] = {
-        entry<3, true>("osc_step_fused<kd3,base>"),
-        entry<6, false>("osc_step_fused<kd6>"),
-        entry<6, true>("osc_step_fused<kd6,base>"),
-        entry<3, false>("osc_step_fused<kd3>"),
+        entry<3, true, 256, true>(0, "osc_step_fused<kd3,base,t256,smem>"),
+        entry<6, false, 256, true>(0, "osc_step_fused<kd6,t256,smem>"),
+        entry<6, true, 256, true>(0, "osc_step_fused<kd6,base,t256,smem>"),
+        entry<3, false, 256, true>(0, "osc_step_fused<kd3,t256,smem>"),
+        entry<3, true, 256, false>(1, "osc_step_fused<kd3,base,t256,local>"),
+        entry<6, false, 256, false>(1, "osc_step_fused<kd6,t256,local>"),
+        entry<3, true, 384, false>(2, "osc_step_fused<kd3,base,t384,local>"),
+        entry<6, false, 384, false>(2, "osc_step_fused<kd6,t384,local>"),
+        entry<3, true, 192, true>(3, "osc_step_fused<kd3,base,t192,smem>"),
+        entry<3, true, 128, false>(4, "osc_step_fused<kd3,base,t128,local>"),
     };
     *count = (int)(sizeof t / sizeof t[0]);
     return t;
 }
 
-const FusedEntry *fused_find(int kd, bool has_base) {
+const FusedEntry *fused_find(int kd, bool has_base, int variant = 0) {
     int cnt = 0;
     const FusedEntry *t = fused_table(&cnt);
     for (int i = 0; i < cnt; ++i)
-        if (t[i].kd == kd && t[i].has_base == has_base) return &t[i];
+        if (t[i].kd == kd && t[i].has_base == has_base && t[i].variant == variant) return &t[i];
     return nullptr;
 }
-
-constexpr size_t kFusedSmem = (size_t)kScratchDoubles * kFusedThreads * sizeof(double);
 
 int32_t ensure_queue(irlosc_handle *h, int64_t B, int rec_doubles) {
     if (!h->hard_count) CUDA_TRY(cudaMalloc(&h->hard_count, sizeof(int)));
@@ -80,19 +86,23 @@ int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
 }
 
 int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st) {
-    const FusedEntry *e = fused_find(h->fused_kd, h->fused_base);
-    if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d", h->fused_kd, (int)h->fused_base);
+    const int variant = h->kernel_choice >= 2 ? h->kernel_choice - 2 : 0;
+    const FusedEntry *e = fused_find(h->fused_kd, h->fused_base, variant);
+    if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d variant=%d", h->fused_kd, (int)h->fused_base, variant);
     int32_t rc = ensure_queue(h, B, e->rec_doubles);
     if (rc != IRLOSC_OK) return rc;
     CUDA_TRY(cudaMemsetAsync(h->hard_count, 0, sizeof(int), st));
     HardQueue hq{h->hard_count, (int)std::min<int64_t>(h->hard_cap, INT32_MAX), e->rec_doubles, h->hard_rec, h->hard_inst};
     const int sms = std::max(1, h->sm_count - h->sm_margin);
-    const int grid = (int)std::min<int64_t>((B + kFusedThreads - 1) / kFusedThreads, (int64_t)sms);
+    const int grid = (int)std::min<int64_t>((B + e->threads - 1) / e->threads, (int64_t)sms);
     void *args[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr, (void *)&hq};
-    cudaError_t err = cudaLaunchKernel(e->step, dim3(grid), dim3(kFusedThreads), args, kFusedSmem, st);
+    cudaError_t err = cudaLaunchKernel(e->step, dim3(grid), dim3(e->threads), args, e->smem, st);
     if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fused kernel launch: %s", cudaGetErrorString(err));
     const int fgrid = (int)std::min<int64_t>((B + 3) / 4, (int64_t)sms * 4);
-    void *fargs[] = {(void *)&h->kp, (void *)&k, (void *)&h->fr, (void *)&hq};
+    TailOut tout;
+    memset(&tout, 0, sizeof tout);
+    tout.u_all = k.u_all; tout.ctrl = k.ctrl; tout.status = k.status;
+    void *fargs[] = {(void *)&h->kp, (void *)&tout, (void *)&h->fr, (void *)&hq};
     err = cudaLaunchKernel(e->fixup, dim3(fgrid), dim3(128), fargs, 0, st);
     if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fix-up kernel launch: %s", cudaGetErrorString(err));
     h->launches += 2;
@@ -120,8 +130,11 @@ extern "C" int32_t irlosc_set_model(irlosc_handle *h, const irlosc_model *m) {
     if (rc != IRLOSC_OK) return rc;
     int cnt = 0;
     const FusedEntry *t = fused_table(&cnt);
-    for (int i = 0; i < cnt; ++i)
-        CUDA_TRY(cudaFuncSetAttribute(t[i].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem));
+    for (int i = 0; i < cnt; ++i) {
+        CUDA_TRY(cudaFuncSetAttribute(t[i].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t[i].smem));
+        if (t[i].smem == 0)    // scratch in local memory: give the whole SM to L1
+            CUDA_TRY(cudaFuncSetAttribute(t[i].step, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+    }
     h->fused_kd = kd;
     h->fused_base = has_base;
     h->has_model = true;

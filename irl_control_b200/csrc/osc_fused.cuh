@@ -35,6 +35,7 @@
 #include <cmath>
 #include "irlosc_device.cuh"
 #include "osc_fused_types.h"
+#include "osc_tail.cuh"
 
 namespace irlosc {
 namespace fused {
@@ -77,13 +78,6 @@ IRLOSC_HD void cross3_add(const double *a, const double *b, double *c) {
 }
 IRLOSC_HD double dot6(const double *a, const double *b) {
     return fma(a[5], b[5], fma(a[4], b[4], fma(a[3], b[3], fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])))));
-}
-IRLOSC_HD double rcp64(double d) {
-#ifdef __CUDA_ARCH__
-    return fast_rcp(d);
-#else
-    return 1.0 / d;
-#endif
 }
 IRLOSC_HD void sincos64(double x, double *s, double *c) {
 #ifdef __CUDA_ARCH__
@@ -199,13 +193,15 @@ IRLOSC_HD bool joint_up(double *IA, const double *s, double *f, double *inv_out)
 
 // Unit task force of component `comp` (0..2 xyz, 3..5 abg) at world point p.
 IRLOSC_HD void task_force(int comp, const double *p, double *e) {
-#pragma unroll
-    for (int i = 0; i < 6; ++i) e[i] = 0.0;
-    if (comp >= 3) { e[comp - 3] = 1.0; return; }
-    e[3 + comp] = 1.0;
-    if (comp == 0) { e[1] = p[2]; e[2] = -p[1]; }
-    else if (comp == 1) { e[0] = -p[2]; e[2] = p[0]; }
-    else { e[0] = p[1]; e[1] = -p[0]; }
+    const bool lin = comp < 3;                      // no dynamic indexing: e stays in registers
+    const int c = lin ? comp : comp - 3;
+    const double ux = (c == 0) ? 1.0 : 0.0, uy = (c == 1) ? 1.0 : 0.0, uz = (c == 2) ? 1.0 : 0.0;
+    e[0] = lin ? p[1] * uz - p[2] * uy : ux;
+    e[1] = lin ? p[2] * ux - p[0] * uz : uy;
+    e[2] = lin ? p[0] * uy - p[1] * ux : uz;
+    e[3] = lin ? ux : 0.0;
+    e[4] = lin ? uy : 0.0;
+    e[5] = lin ? uz : 0.0;
 }
 
 // Rotation matrix -> unit quaternion, w >= 0 (sign is irrelevant to osc.py:101-118).
@@ -228,29 +224,45 @@ IRLOSC_HD void mat_to_quat(const double *R, double *q) {
     if (q[0] < 0.0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
 }
 
-// Coefficient of (M dq)_j in u_j: the velocity term of the device that owns joint j when it took
-// the zero-target-velocity branch (osc.py:174, last device wins) plus the null-space term
-// (osc.py:195-200, collapsed form).
-IRLOSC_HD double coef_uv(const KParams &P, const int *vel_zero, int j) {
-    double c = 0.0;
+// ---------------------------------------------------------------- one instance
+// osc.py:159-168,179-181 for one device whose EE pose is known: the task signal before the
+// velocity-tracking term, plus the rotated F/T wrench when admittance is on -> gpre[row].
+IRLOSC_HD void device_signal_early(const KParams &P, const FIo &io, int64_t inst, int d, const double *ee_p,
+                                   const double *Ree, const double *Rft, bool has_ft, double *gpre) {
+    const int D = P.D;
+    const KDevice &dv = P.dev[d];
+    double ee_q[4];
+    mat_to_quat(Ree, ee_q);
+    double mv[2] = {dv.max_vel[0], dv.max_vel[1]};
+    if (io.max_vel) { mv[0] = io.max_vel[(inst * D + d) * 2]; mv[1] = io.max_vel[(inst * D + d) * 2 + 1]; }
+    double u6[6], txyz[3], tquat[4];
 #pragma unroll
-    for (int d = 0; d < IRLOSC_MAX_DEVICES; ++d)
-        if (d < P.D && vel_zero[d] && ((P.dev[d].joint_mask >> j) & 1u)) c = -1.0 * P.dev[d].kv;
-    if (P.has_nullspace) c -= P.nullspace_kv;
-    return c;
+    for (int i = 0; i < 3; ++i) txyz[i] = io.target_xyz[(inst * D + d) * 3 + i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tquat[i] = io.target_quat[(inst * D + d) * 4 + i];
+    bool oob = false;
+    device_task_signal(dv, ee_p, ee_q, txyz, tquat, nullptr, mv, nullptr, 0, u6, &oob);
+    if (P.admittance) {
+        double ft[6] = {0, 0, 0, 0, 0, 0};
+        if (has_ft) {
+            double raw[6];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) raw[i] = io.ft_raw[(inst * D + d) * 6 + i];
+            rotate_wrench(Rft, raw, ft);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) u6[i] += ft[i];
+    }
+    int r = dv.row0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        if (dv.dof[i]) gpre[r++] = u6[i];
+    if (io.ee_xyz)
+        for (int i = 0; i < 3; ++i) io.ee_xyz[(inst * D + d) * 3 + i] = ee_p[i];
+    if (io.ee_quat)
+        for (int i = 0; i < 4; ++i) io.ee_quat[(inst * D + d) * 4 + i] = ee_q[i];
 }
 
-// Optional taps for the host test harness (all pointers may be null).
-struct Debug {
-    double *A;      // K x K
-    double *g;      // K
-    double *uv;     // n: M dq
-    double *bias;   // n
-    double *dx;     // K
-    double *J;      // K x n
-};
-
-// ---------------------------------------------------------------- one instance
 // Returns true when the instance was queued for the eigen fix-up (outputs of the chain joints are
 // then written by osc_fused_fixup / fixup_finish).
 template <int KD, bool HAS_BASE>
@@ -258,6 +270,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
                               const Scratch &scr, double *hard_rec, const Debug *dbg) {
     constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
     constexpr int N = kN;
+    constexpr int KT = KD * (KD + 1) / 2;
     using RC = Rec<KD, HAS_BASE>;
     const int D = P.D;
     const double *q = io.q + inst * N;
@@ -266,7 +279,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
     int flags = 0;
 
     // which devices track a target velocity (osc.py:172-177): known from the inputs alone
-    int vel_zero[IRLOSC_MAX_DEVICES];
+    unsigned vel_zero = 0;
 #pragma unroll
     for (int d = 0; d < IRLOSC_MAX_DEVICES; ++d) {
         bool tracking = false;
@@ -274,47 +287,44 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
             tracking = true;
             for (int i = 0; i < 6; ++i) tracking = tracking && (io.target_vel[(inst * D + d) * 6 + i] != 0.0);
         }
-        vel_zero[d] = tracking ? 0 : 1;
+        if (!tracking) vel_zero |= 1u << d;
     }
 
-    double u[N];                        // joint-space signal (osc.py:152-200)
-    double As[K][K], j0[K], dxr[K];     // blocks of A = J M^-1 J^T before the stand joint couples them
-    double jarm[2][6][KD], base_arm[2][6], jst[K];
-    double ee_p[IRLOSC_MAX_DEVICES][3], ee_q[IRLOSC_MAX_DEVICES][4], ft_R[IRLOSC_MAX_DEVICES][9];
-#pragma unroll
-    for (int i = 0; i < K; ++i)
-#pragma unroll
-        for (int j = 0; j < K; ++j) As[i][j] = 0.0;
+    // what survives the arm loop (dynamic indices -> local memory; kept as small as possible)
+    double akA[2][KT];                  // the arms' diagonal blocks of A = J M^-1 J^T before the stand joint
+    double j0[K], jst[K], dxr[K], g[K]; // stand column of the reduced / original J, dx = J dq, task signal
+    double jarm[2][6][KD], base_arm[2][6];
 
     // ------------------------------------------------------------ stand joint (world -> joint 0)
-    Body W;
-#pragma unroll
-    for (int e = 0; e < 9; ++e) W.R[e] = (e % 4 == 0) ? 1.0 : 0.0;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { W.o[i] = 0.0; W.v[i] = W.v[3 + i] = 0.0; W.a[i] = 0.0; W.a[3 + i] = -Mdl.gravity[i]; }
     Body S0;
-    double s0[6], r0[3], Iw0[6], h0[6], fb0[6];
-    joint_down(Mdl.stand, W, q[0], dq[0], S0, s0, r0, Iw0);
-    body_wrench(Mdl.stand.mass, r0, Iw0, S0.v, S0.a, h0, fb0);
+    double s0[6];
     double IA0[21], Htot[6], FBtot[6];
+    {
+        Body W;
 #pragma unroll
-    for (int e = 0; e < 21; ++e) IA0[e] = 0.0;
-    add_rigid(IA0, Mdl.stand.mass, r0, Iw0);
+        for (int e = 0; e < 9; ++e) W.R[e] = (e % 4 == 0) ? 1.0 : 0.0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { Htot[i] = h0[i]; FBtot[i] = fb0[i]; }
+        for (int i = 0; i < 3; ++i) { W.o[i] = 0.0; W.v[i] = W.v[3 + i] = 0.0; W.a[i] = 0.0; W.a[3 + i] = -Mdl.gravity[i]; }
+        double r0[3], Iw0[6];
+        joint_down(Mdl.stand, W, q[0], dq[0], S0, s0, r0, Iw0);
+        body_wrench(Mdl.stand.mass, r0, Iw0, S0.v, S0.a, Htot, FBtot);
+#pragma unroll
+        for (int e = 0; e < 21; ++e) IA0[e] = 0.0;
+        add_rigid(IA0, Mdl.stand.mass, r0, Iw0);
+    }
     bool m_ok = true;
 
     if (HAS_BASE) {
         const int d = R.dev_base;
         const KFrame &F = Mdl.ee[d];
-        double t[3], Re[9];
+        double t[3], Re[9], p[3];
         mat3_vec(S0.R, F.pos, t);
-        for (int i = 0; i < 3; ++i) ee_p[d][i] = S0.o[i] + t[i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) p[i] = S0.o[i] + t[i];
         mat3_mul(S0.R, F.R, Re);
-        mat_to_quat(Re, ee_q[d]);
-        for (int e = 0; e < 9; ++e) ft_R[d][e] = (e % 4 == 0) ? 1.0 : 0.0;
+        device_signal_early(P, io, inst, d, p, Re, Re, false, g);
         double e6[6];
-        task_force(P.row_comp[R.row_base], ee_p[d], e6);
+        task_force(P.row_comp[R.row_base], p, e6);
         const double jb0 = dot6(s0, e6);
         j0[R.row_base] = jb0;
         jst[R.row_base] = jb0;
@@ -357,24 +367,24 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
             Bc = Bn;
         }
         // Bc = arm link 6; Hpre / FBpre = sums over the arm links (grippers are added below)
-        // ---- EE pose, F/T frame, task forces (device.py:93-95,125-143)
-        double E[KD][6];
+        // ---- EE pose, F/T frame, task signal and task forces (device.py:93-95,125-143; osc.py:156-181)
+        double ee_p[3];
         {
             const KFrame &F = Mdl.ee[dev];
-            double t[3], Re[9];
+            double t[3], Re[9], Rf[9];
             mat3_vec(Bc.R, F.pos, t);
-            for (int i = 0; i < 3; ++i) ee_p[dev][i] = Bc.o[i] + t[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) ee_p[i] = Bc.o[i] + t[i];
             mat3_mul(Bc.R, F.R, Re);
-            mat_to_quat(Re, ee_q[dev]);
             const KFrame &T = Mdl.ft[dev];
-            if (T.has) mat3_mul(Bc.R, T.R, ft_R[dev]);
-            else
-                for (int e = 0; e < 9; ++e) ft_R[dev][e] = 0.0;
+            if (P.admittance && T.has) mat3_mul(Bc.R, T.R, Rf);
+            device_signal_early(P, io, inst, dev, ee_p, Re, Rf, T.has != 0, g);
 #pragma unroll
             for (int cr = 0; cr < KD; ++cr) {
-                task_force(P.row_comp[row_a + cr], ee_p[dev], E[cr]);
-                dxr[row_a + cr] = dot6(E[cr], Bc.v);           // dx = J dq (osc.py:150)
-                jst[row_a + cr] = dot6(E[cr], s0);             // J[r][stand]
+                double e0[6];
+                task_force(P.row_comp[row_a + cr], ee_p, e0);
+                dxr[row_a + cr] = dot6(e0, Bc.v);              // dx = J dq (osc.py:150)
+                jst[row_a + cr] = dot6(e0, s0);                // J[r][stand]
             }
         }
         // ---- gripper halves: leaves g1 -> g0 and g2, eliminated into link 6's articulated inertia
@@ -396,7 +406,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
                 body_wrench(Mdl.grip[arm][half][1].mass, rb, Iwb, B1.v, B1.a, hb, fbb);
                 const double cu1 = coef_uv(P, vel_zero, gj + 1);
                 const double uv1 = dot6(sb, hb), b1 = dot6(sb, fbb);
-                u[gj + 1] = fma(cu1, uv1, gb * b1);
+                put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj + 1, fma(cu1, uv1, gb * b1));
                 if (dbg && dbg->uv) { dbg->uv[gj + 1] = uv1; dbg->bias[gj + 1] = b1; }
 #pragma unroll
                 for (int e = 0; e < 6; ++e) { ha[e] += hb[e]; fba[e] += fbb[e]; }     // subtree sums of g0
@@ -407,7 +417,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
             }
             const double cu0 = coef_uv(P, vel_zero, gj);
             const double uv0 = dot6(sa, ha), b0 = dot6(sa, fba);
-            u[gj] = fma(cu0, uv0, gb * b0);
+            put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj, fma(cu0, uv0, gb * b0));
             if (dbg && dbg->uv) { dbg->uv[gj] = uv0; dbg->bias[gj] = b0; }
 #pragma unroll
             for (int e = 0; e < 6; ++e) { Hpre[e] += ha[e]; FBpre[e] += fba[e]; }
@@ -422,7 +432,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
                 body_wrench(Mdl.grip[arm][half][2].mass, rc, Iwc, B2.v, B2.a, hc, fbc);
                 const double cu2 = coef_uv(P, vel_zero, gj + 2);
                 const double uv2 = dot6(sc, hc), b2 = dot6(sc, fbc);
-                u[gj + 2] = fma(cu2, uv2, gb * b2);
+                put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj + 2, fma(cu2, uv2, gb * b2));
                 if (dbg && dbg->uv) { dbg->uv[gj + 2] = uv2; dbg->bias[gj + 2] = b2; }
 #pragma unroll
                 for (int e = 0; e < 6; ++e) { Hpre[e] += hc[e]; FBpre[e] += fbc[e]; }
@@ -438,9 +448,11 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 #pragma unroll
         for (int e = 0; e < 6; ++e) { Htot[e] += Hpre[e]; FBtot[e] += FBpre[e]; }
         // ---- upward articulated sweep over arm joints 6..1 with the arm's task rows
-        double ak[KD * (KD + 1) / 2];
+        double ak[KT], E[KD][6];
 #pragma unroll
-        for (int e = 0; e < KD * (KD + 1) / 2; ++e) ak[e] = 0.0;
+        for (int e = 0; e < KT; ++e) ak[e] = 0.0;
+#pragma unroll
+        for (int cr = 0; cr < KD; ++cr) task_force(P.row_comp[row_a + cr], ee_p, E[cr]);
 #pragma unroll 1
         for (int i = 5; i >= 0; --i) {
             const int o = i * kBodyScratch;
@@ -461,7 +473,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 #pragma unroll
             for (int cr = 0; cr < KD; ++cr) {
                 double e0[6];
-                task_force(P.row_comp[row_a + cr], ee_p[dev], e0);
+                task_force(P.row_comp[row_a + cr], ee_p, e0);
                 jarm[arm][i][cr] = dot6(s, e0);                 // original J[r][joint] for J^T w
             }
             add_rigid(IA, Mdl.arm[arm][i].mass, r, Iw);
@@ -483,14 +495,9 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 #pragma unroll
         for (int e = 0; e < 21; ++e) IA0[e] += IA[e];
 #pragma unroll
-        for (int cr = 0; cr < KD; ++cr) {
-            j0[row_a + cr] = dot6(s0, E[cr]);
+        for (int cr = 0; cr < KD; ++cr) j0[row_a + cr] = dot6(s0, E[cr]);
 #pragma unroll
-            for (int c2 = 0; c2 <= cr; ++c2) {
-                As[row_a + cr][row_a + c2] = ak[cr * (cr + 1) / 2 + c2];
-                As[row_a + c2][row_a + cr] = ak[cr * (cr + 1) / 2 + c2];
-            }
-        }
+        for (int e = 0; e < KT; ++e) akA[arm][e] = ak[e];
     }
 
     // ------------------------------------------------------------ stand joint couples the arms
@@ -501,221 +508,25 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
     const double base_st = fma(cu_st, uv_st, gb * b_st);
     if (dbg && dbg->uv) { dbg->uv[0] = uv_st; dbg->bias[0] = b_st; }
 
-    // ------------------------------------------------------------ per-device task signal (osc.py:156-181)
-    double g[K];
-#pragma unroll 1
-    for (int d = 0; d < D; ++d) {
-        const KDevice &dv = P.dev[d];
-        double mv[2] = {dv.max_vel[0], dv.max_vel[1]};
-        if (io.max_vel) { mv[0] = io.max_vel[(inst * D + d) * 2]; mv[1] = io.max_vel[(inst * D + d) * 2 + 1]; }
-        double tv[6], u6[6], txyz[3], tquat[4];
-        if (io.target_vel)
-            for (int i = 0; i < 6; ++i) tv[i] = io.target_vel[(inst * D + d) * 6 + i];
-        for (int i = 0; i < 3; ++i) txyz[i] = io.target_xyz[(inst * D + d) * 3 + i];
-        for (int i = 0; i < 4; ++i) tquat[i] = io.target_quat[(inst * D + d) * 4 + i];
-        bool oob = false;
-        const bool tracking = device_task_signal(dv, ee_p[d], ee_q[d], txyz, tquat, io.target_vel ? tv : nullptr, mv,
-                                                 dxr, K, u6, &oob);
-        double ft[6] = {0, 0, 0, 0, 0, 0};
-        if (P.admittance) {
-            double raw[6];
-            for (int i = 0; i < 6; ++i) raw[i] = io.ft_raw[(inst * D + d) * 6 + i];
-            rotate_wrench(ft_R[d], raw, ft);
-        }
-        int r = dv.row0;
-        const double kvn = P.has_nullspace ? P.nullspace_kv : 0.0;
-        for (int i = 0; i < 6; ++i)
-            if (dv.dof[i]) {
-                const double v = P.admittance ? u6[i] + ft[i] : u6[i];
-                g[r] = v - kvn * dxr[r];
-                ++r;
-            }
-        flags |= (tracking ? IRLOSC_ST_VEL_BRANCH : 0) | (oob ? IRLOSC_ST_DX_RANGE : 0);
-        if (io.ee_xyz)
-            for (int i = 0; i < 3; ++i) io.ee_xyz[(inst * D + d) * 3 + i] = ee_p[d][i];
-        if (io.ee_quat)
-            for (int i = 0; i < 4; ++i) io.ee_quat[(inst * D + d) * 4 + i] = ee_q[d][i];
-    }
-
-    // ------------------------------------------------------------ A = blocks + j0 j0^T / d0, LDL^T solve
-    double a[K * (K + 1) / 2];
-    double fro2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        const double ji = j0[i] * inv0;
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-            const double v = fma(ji, j0[j], As[i][j]);
-            a[i * (i + 1) / 2 + j] = v;
-            fro2 = fma(v, (i == j) ? v : 2.0 * v, fro2);
-        }
-    }
-    if (dbg && dbg->A) {
-        for (int i = 0; i < K; ++i)
-            for (int j = 0; j <= i; ++j) { dbg->A[i * K + j] = a[i * (i + 1) / 2 + j]; dbg->A[j * K + i] = a[i * (i + 1) / 2 + j]; }
-        for (int i = 0; i < K; ++i) { dbg->g[i] = g[i]; dbg->dx[i] = dxr[i]; }
-    }
-    if (!m_ok) flags |= IRLOSC_ST_M_NOT_PD;
-    const bool poison = (flags & (IRLOSC_ST_M_NOT_PD | IRLOSC_ST_DX_RANGE)) != 0;
-
-    // in-place LDL^T: a[i][p] becomes l_ip, diagonal keeps d_p; dinv[p] = 1 / d_p
-    double dinv[K], w[K];
-    double detinv = 1.0;
-    bool a_bad = false;
-#pragma unroll
-    for (int p = 0; p < K; ++p) {
-        const double inv = rcp64(a[p * (p + 1) / 2 + p]);
-        dinv[p] = inv;
-        detinv *= inv;
-        a_bad = a_bad || !(inv > 0.0);
-#pragma unroll
-        for (int i = p + 1; i < K; ++i) {
-            const double aip = a[i * (i + 1) / 2 + p];
-            const double l = aip * inv;
-#pragma unroll
-            for (int j = p + 1; j <= i; ++j) a[i * (i + 1) / 2 + j] = fma(-l, a[j * (j + 1) / 2 + p], a[i * (i + 1) / 2 + j]);
-        }
-#pragma unroll
-        for (int i = p + 1; i < K; ++i) a[i * (i + 1) / 2 + p] *= inv;
-    }
-    // w = A^-1 g
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        double z = g[i];
-#pragma unroll
-        for (int j = 0; j < i; ++j) z = fma(-a[i * (i + 1) / 2 + j], w[j], z);
-        w[i] = z;
-    }
-#pragma unroll
-    for (int i = 0; i < K; ++i) w[i] *= dinv[i];
-#pragma unroll
-    for (int i = K - 1; i >= 0; --i) {
-        double z = w[i];
-#pragma unroll
-        for (int j = i + 1; j < K; ++j) z = fma(-a[j * (j + 1) / 2 + i], w[j], z);
-        w[i] = z;
-    }
-    // osc.py:52-55: |det| >= 1e-4 -> inverse.  Otherwise pinv(rcond = 1e-5), which equals the inverse
-    // unless an eigenvalue is <= 1e-5 lambda_max.  lambda_max <= ||A||_F and 1 / lambda_min <= tr(A^-1),
-    // so ||A||_F tr(A^-1) < 1e5 certifies that nothing is cut.  tr(A^-1) = sum_p dinv_p |row p of L^-1|^2.
-    const bool small_det = !(fabs(detinv) <= 1.0 / kDetThreshold);
-    bool certified = true;
-    if (small_det && !a_bad) {
-        // X = L^-1 in place (unit lower triangular), column by column
-        double tr_inv = 0.0;
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            double x[K];
-            x[j] = 1.0;
-            double acc = dinv[j];
-#pragma unroll
-            for (int i = j + 1; i < K; ++i) {
-                double z = -a[i * (i + 1) / 2 + j];
-#pragma unroll
-                for (int m = j + 1; m < i; ++m) z = fma(-a[i * (i + 1) / 2 + m], x[m], z);
-                x[i] = z;
-                acc = fma(z * z, dinv[i], acc);
-            }
-            tr_inv += acc;
-        }
-        certified = (fro2 * tr_inv * tr_inv < (1.0 / kPinvRcond) * (1.0 / kPinvRcond));
-    }
-    const bool hard = !poison && (a_bad || (small_det && !certified));
-    if (small_det && !a_bad) flags |= IRLOSC_ST_PINV;
-
-    // ------------------------------------------------------------ joint-space assembly + packing
-    if (hard && hard_rec != nullptr) {
-        // full A again (the factorisation overwrote it)
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            const double ji = j0[i] * inv0;
-#pragma unroll
-            for (int j = 0; j < K; ++j) hard_rec[RC::A + i * K + j] = fma(ji, j0[j], As[i][j]);
-            hard_rec[RC::G + i] = g[i];
-            hard_rec[RC::JST + i] = jst[i];
-        }
-        hard_rec[RC::BASE] = base_st;
-        for (int am = 0; am < 2; ++am)
-            for (int i = 0; i < 6; ++i) {
-                hard_rec[RC::BASE + 1 + 6 * am + i] = base_arm[am][i];
-                for (int cr = 0; cr < KD; ++cr) hard_rec[RC::JARM + (am * 6 + i) * KD + cr] = jarm[am][i][cr];
-            }
-        hard_rec[RC::ABAD] = a_bad ? 1.0 : 0.0;
-    }
-    {
-        double jt = 0.0;
-#pragma unroll
-        for (int r = 0; r < K; ++r) jt = fma(jst[r], w[r], jt);
-        u[0] = base_st - jt;
-    }
-#pragma unroll
-    for (int am = 0; am < 2; ++am)
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            double jt = 0.0;
-#pragma unroll
-            for (int cr = 0; cr < KD; ++cr) jt = fma(jarm[am][i][cr], w[R.row_arm[am] + cr], jt);
-            u[1 + 12 * am + i] = base_arm[am][i] - jt;
-        }
-    if (poison) {
-        const double qnan = nan("");
-        for (int j = 0; j < N; ++j) u[j] = qnan;
-    }
-    if (io.u_all)
-        for (int j = 0; j < N; ++j) io.u_all[inst * N + j] = u[j];
-    for (int d = 0; d < D; ++d) {
-        const KDevice &dv = P.dev[d];
-        for (int c = 0; c < dv.n_ctrl; ++c) io.ctrl[inst * P.n_ctrl + dv.ctrl0 + c] = u[dv.actuator[c]];
-    }
-    if (io.status) io.status[inst] = (uint8_t)flags;
-    if (dbg && dbg->J) {
-        for (int e = 0; e < K * N; ++e) dbg->J[e] = 0.0;
-        for (int r = 0; r < K; ++r) dbg->J[r * N] = jst[r];
-        for (int am = 0; am < 2; ++am)
-            for (int i = 0; i < 6; ++i)
-                for (int cr = 0; cr < KD; ++cr) dbg->J[(R.row_arm[am] + cr) * N + 1 + 12 * am + i] = jarm[am][i][cr];
-    }
-    return hard && hard_rec != nullptr;
-}
-
-// Finish one queued instance given w = pinv(A) g: the 13 joints that have Jacobian columns.
-template <int KD, bool HAS_BASE>
-IRLOSC_HD void fixup_finish(const KParams &P, const FRoles &R, const FIo &io, int64_t inst, const double *rec,
-                            const double *w, int j_lo, int j_step) {
-    using RC = Rec<KD, HAS_BASE>;
-    constexpr int K = RC::K;
-    // joint slots: 0 = stand, 1 + 6 a + i = arm a joint i
-    for (int sl = j_lo; sl < 13; sl += j_step) {
-        double jt = 0.0;
-        int joint = 0;
-        if (sl == 0) {
-            for (int r = 0; r < K; ++r) jt = fma(rec[RC::JST + r], w[r], jt);
-        } else {
-            const int am = (sl - 1) / 6, i = (sl - 1) % 6;
-            joint = 1 + 12 * am + i;
-            for (int cr = 0; cr < KD; ++cr) jt = fma(rec[RC::JARM + (am * 6 + i) * KD + cr], w[R.row_arm[am] + cr], jt);
-        }
-        const double uj = rec[RC::BASE + sl] - jt;
-        if (io.u_all) io.u_all[inst * kN + joint] = uj;
-        for (int d = 0; d < P.D; ++d) {
-            const KDevice &dv = P.dev[d];
-            for (int c = 0; c < dv.n_ctrl; ++c)
-                if (dv.actuator[c] == joint) io.ctrl[inst * P.n_ctrl + dv.ctrl0 + c] = uj;
-        }
-    }
+    return osc_tail<KD, HAS_BASE>(P, R, io.target_vel ? io.target_vel + inst * D * 6 : nullptr, vel_zero, flags, m_ok, akA, j0,
+                                  jst, dxr, g, jarm, base_arm, base_st, inv0, io.u_all ? io.u_all + inst * N : nullptr,
+                                  io.ctrl + inst * P.n_ctrl, io.status ? io.status + inst : nullptr, hard_rec, dbg);
 }
 
 #if defined(__CUDACC__) && !defined(IRLOSC_FUSED_NO_KERNELS)
 // ---------------------------------------------------------------- kernels
-template <int KD, bool HAS_BASE, int NT>
+// SMEM = true: the per-thread chain scratch lives in shared memory (strided, conflict-free);
+// SMEM = false: in local memory, leaving the whole 256 KB of the SM to L1, which then also catches
+// the register spills and the small dynamically indexed arrays.
+template <int KD, bool HAS_BASE, int NT, bool SMEM>
 __global__ void __launch_bounds__(NT, 1)
-osc_step_fused(const __grid_constant__ KParams P, const __grid_constant__ KModel Mdl, const FIo io, const int64_t B,
-               const FRoles R, const HardQueue hq) {
+osc_step_fused(const __grid_constant__ KParams P, const __grid_constant__ KModel Mdl, const __grid_constant__ FIo io,
+               const int64_t B, const __grid_constant__ FRoles R, const __grid_constant__ HardQueue hq) {
     extern __shared__ __align__(16) double fused_smem[];
-    const Scratch scr{fused_smem + threadIdx.x, NT};
+    double chain[SMEM ? 1 : kScratchDoubles];
+    const Scratch scr = SMEM ? Scratch{fused_smem + threadIdx.x, NT} : Scratch{chain, 1};
     for (int64_t inst = (int64_t)blockIdx.x * NT + threadIdx.x; inst < B; inst += (int64_t)gridDim.x * NT) {
-        // queue slot claimed only when needed: build the record in place
-        // (record memory is per instance slot = inst while capacity >= B, so no atomics for the body)
+        // record memory is indexed by instance (capacity >= B): only the queue slot needs an atomic
         double *rec = hq.rec ? hq.rec + (size_t)inst * hq.rec_doubles : nullptr;
         const bool hard = fused_instance<KD, HAS_BASE>(P, Mdl, R, io, inst, scr, rec, nullptr);
         if (hard) {
@@ -725,37 +536,6 @@ osc_step_fused(const __grid_constant__ KParams P, const __grid_constant__ KModel
     }
 }
 
-// One warp per queued instance: eigen-decomposition of A (tiled::eigen_solve), w = pinv(A) g, then the
-// joints with Jacobian columns are rewritten.
-template <int KD, bool HAS_BASE>
-__global__ void __launch_bounds__(128, 1)
-osc_fused_fixup(const __grid_constant__ KParams P, const FIo io, const FRoles R, const HardQueue hq) {
-    using RC = Rec<KD, HAS_BASE>;
-    constexpr int K = RC::K;
-    struct WarpSmem {
-        double As[K][K + 1], Vs[K][K + 1];
-        double g[K], w[K], cbuf[32], sbuf[32];
-        int flags;
-    };
-    __shared__ WarpSmem sm[4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    WarpSmem &S = sm[warp];
-    const int n_hard = *hq.count;
-    for (int slot = blockIdx.x * 4 + warp; slot < n_hard; slot += gridDim.x * 4) {
-        const int64_t inst = hq.inst[slot];
-        const double *rec = hq.rec + (size_t)inst * hq.rec_doubles;
-        for (int e = lane; e < K * K; e += 32) S.As[e / K][e % K] = rec[RC::A + e];
-        if (lane < K) S.g[lane] = rec[RC::G + lane];
-        if (lane == 0) S.flags = 0;
-        __syncwarp();
-        const bool a_bad = rec[RC::ABAD] != 0.0;
-        tiled::eigen_solve<K>(S.As, S.Vs, S.g, S.w, S.cbuf, S.sbuf, !a_bad, lane, &S.flags);
-        __syncwarp();
-        fixup_finish<KD, HAS_BASE>(P, R, io, inst, rec, S.w, lane, 32);
-        if (io.status && lane == 0) io.status[inst] = (uint8_t)(io.status[inst] | S.flags);
-        __syncwarp();
-    }
-}
 #endif  // __CUDACC__
 
 }  // namespace fused

@@ -27,6 +27,7 @@ struct KModel {
 };
 struct FRoles {
     int dev_arm[2], dev_base, row_arm[2], row_base;
+    int8_t joint_slot[IRLOSC_MAX_N];   // packed ctrl slot of joint j (osc.py:203-208), -1 = not returned
 };
 struct FIo {
     const double *q, *dq, *target_xyz, *target_quat, *target_vel, *max_vel, *ft_raw;

@@ -98,7 +98,7 @@ static int64_t run(const KParams &P, const KModel &M, const FRoles &R, const FIo
             ++n_hard;
             double w[K];
             const int fl = host_eigen_solve<K>(&rec[RC::A], &rec[RC::G], rec[RC::ABAD] == 0.0, w);
-            fixup_finish<KD, HB>(P, R, io, i, rec.data(), w, 0, 1);
+            fixup_finish<KD, HB>(R, io.u_all ? io.u_all + i * kN : nullptr, io.ctrl + i * P.n_ctrl, rec.data(), w, 0, 1);
             if (io.status) io.status[i] = (uint8_t)(io.status[i] | fl);
         }
     }

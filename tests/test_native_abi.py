@@ -74,7 +74,7 @@ def test_product_never_loads_the_host_harness():
     for fn in os.listdir(pkg_dir):
         if fn.endswith(".py"):
             text = open(os.path.join(pkg_dir, fn)).read()
-            assert "fused_host" not in text and "host_fused" not in text, fn
+            assert "libfused_host" not in text and "host_fused" not in text and "import fused_host" not in text, fn
 
 
 def test_product_never_imports_oracle():
