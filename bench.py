@@ -292,6 +292,7 @@ def main():
         b.record()
     torch.cuda.synchronize()
     kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
+    kernel_name = eng.last_kernel
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
     tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -410,7 +411,7 @@ def main():
         key = "%s_B%d_%s" % (args.workload, B, args.m_layout)
         traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": eng.last_kernel, "kernel_ms": kernel_ms,
+                "traffic": traffic, "kernel": kernel_name, "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_step": abytes, "peak_source": peak_src}
     cb = None
     if world == 1 and not args.no_cpu_baseline:

@@ -243,8 +243,9 @@ int32_t irlosc_calc_error(irlosc_handle *h, int64_t B, const double *ee_xyz, con
 int32_t irlosc_host_alloc(void **ptr, int64_t bytes);
 int32_t irlosc_host_free(void *ptr);
 
-/* Kernel selection: 0 = auto, 1 = generic (any n, k, layout), 2 + v = variant v of the specialised
- * DualUR5 kernels (v = 0 is what auto picks; others exist for A/B measurements). */
+/* Kernel selection: 0 = auto, 1 = generic (any n, k, layout), 2 + v = variant v of the 4-lane DualUR5
+ * kernels (v = 0: tree-sparse), 9 = streaming thread-per-instance kernel; for the fused step 2 + v
+ * selects its variant v.  Non-default choices exist for A/B measurements, see DESIGN.md. */
 int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which);
 /* Leave `sms` streaming multiprocessors free when launching the step kernel (default 0), so that a
  * collective running on another stream (the NCCL gather of ctrl) can overlap instead of queueing

@@ -67,9 +67,11 @@ extern "C" int32_t irlosc_destroy(irlosc_handle *h) {
         if (h->stage[s].stream) cudaStreamDestroy(h->stage[s].stream);
         if (h->fstage[s].stream) cudaStreamDestroy(h->fstage[s].stream);
     }
-    if (h->hard_count) cudaFree(h->hard_count);
-    if (h->hard_inst) cudaFree(h->hard_inst);
-    if (h->hard_rec) cudaFree(h->hard_rec);
+    for (int q = 0; q < kQueues; ++q) {
+        if (h->hard[q].count) cudaFree(h->hard[q].count);
+        if (h->hard[q].inst) cudaFree(h->hard[q].inst);
+        if (h->hard[q].rec) cudaFree(h->hard[q].rec);
+    }
     delete h;
     return IRLOSC_OK;
 }
@@ -131,11 +133,24 @@ static int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k) {
     return IRLOSC_OK;
 }
 
-static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st) {
+// Kernel selection (irlosc_set_kernel): 0 auto, 1 generic, 2 + v tiled-table variant v, 9 streaming.
+//   auto, DualUR5 topology declared: 3-row arm devices (gain_test) -> tree-sparse 4-lane kernel when
+//   the layout is one it stages (tight packed / dense M, row-stacked J), 6-row arm devices -> streaming
+//   kernel; anything the tree kernel does not stage (strided views, full-6 J) -> streaming kernel;
+//   check_topology -> the kernels that read every entry.  No topology: dense kernels / generic.
+constexpr int kKernelStream = 9;
+
+static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st, int queue = 0) {
     if (B == 0) return IRLOSC_OK;
+    const bool stream_ok = stream_supported(h, k);
+    if (h->kernel_choice == kKernelStream) {
+        if (!stream_ok) return fail(IRLOSC_ERR_INVALID, "streaming kernel requested but the DualUR5 topology is not declared (or check_topology is set)");
+        return stream_launch(h, B, k, st, queue);
+    }
     bool use_tiled = false;
     const int variant = h->kernel_choice >= 2 ? h->kernel_choice - 2 : 0;
     if (h->kernel_choice != 1) use_tiled = tiled_supported(h->kp, k, variant);
+    if (h->kernel_choice == 0 && stream_ok && (stream_preferred(h) || !use_tiled)) return stream_launch(h, B, k, st, queue);
     if (h->kernel_choice >= 2 && !use_tiled)
         return fail(IRLOSC_ERR_INVALID, "tiled kernel requested but this shape/layout is not supported (n=%d k=%d)", h->kp.n, h->kp.k);
     if (use_tiled) {
@@ -261,7 +276,7 @@ extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io
         dk.ctrl = (double *)S.buf[12];
         dk.u_all = hk.u_all ? (double *)S.buf[13] : nullptr;
         dk.status = hk.status ? (uint8_t *)S.buf[14] : nullptr;
-        rc = launch_step(h, nb, dk, S.stream);
+        rc = launch_step(h, nb, dk, S.stream, 1 + turn % kPipeDepth);
         if (rc != IRLOSC_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(hk.ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
                                  cudaMemcpyDeviceToHost, S.stream));

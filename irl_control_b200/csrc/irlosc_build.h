@@ -6,6 +6,9 @@
 #include <cmath>
 #include <cstring>
 #include "irlosc_internal.h"
+#include "osc_stream.cuh"
+#include <vector>
+#include <algorithm>
 
 namespace irlosc {
 
@@ -199,6 +202,110 @@ inline int32_t build_kmodel(const KParams &P, const irlosc_model &m, fused::KMod
         rc = build_frame(m.ee[d], want, "EE", d, K.ee[d]);
         if (rc == IRLOSC_OK) rc = build_frame(m.ft[d], want, "F/T", d, K.ft[d]);
         if (rc != IRLOSC_OK) return rc;
+    }
+    return IRLOSC_OK;
+}
+
+// Copy plan of the streaming step (osc_stream.cuh): which doubles of an instance's arrays go to which
+// stage entry of which group, as 8-entry chunks with per-lane byte offsets.  Works for every M / J
+// layout and stride of irlosc_io because a chunk carries its array's base pointer and stride.
+inline int32_t build_stream_plan(const KParams &P, const KIo &io, const fused::FRoles &R, int kd, bool has_base,
+                                 stream::Plan &plan) {
+    using namespace stream;
+    struct Item { const void *base; int64_t stride; int64_t off; int dst; };
+    std::vector<Item> groups[kGroups];
+    const int n = P.n, D = P.D;
+    auto M_at = [&](int i, int j) -> Item {        // i >= j
+        const int64_t e = io.m_layout == IRLOSC_M_PACKED ? (int64_t)i * (i + 1) / 2 + j : (int64_t)i * io.ldm + j;
+        return Item{io.M, io.m_stride * 8, e * 8, 0};
+    };
+    auto J_at = [&](int row, int j) -> Item {
+        const int64_t r = io.j_layout == IRLOSC_J_ROWS ? row : (int64_t)P.row_dev[row] * 6 + P.row_comp[row];
+        return Item{io.J, io.j_stride * 8, (r * io.ldj + j) * 8, 0};
+    };
+    auto vec = [&](const double *base, int per, int idx) -> Item { return Item{base, (int64_t)per * 8, (int64_t)idx * 8, 0}; };
+    auto put = [&](int g, Item it, int dst) { it.dst = dst; groups[g].push_back(it); };
+    const double *bias = io.bias ? io.bias : io.dq;      // use_g == 0: any finite value (multiplied by 0)
+    auto device_block = [&](int g, int d, int e0) {
+        for (int i = 0; i < 3; ++i) { put(g, vec(io.ee_xyz, 3 * D, d * 3 + i), e0 + kEeXyz + i); put(g, vec(io.target_xyz, 3 * D, d * 3 + i), e0 + kTXyz + i); }
+        for (int i = 0; i < 4; ++i) { put(g, vec(io.ee_quat, 4 * D, d * 4 + i), e0 + kEeQuat + i); put(g, vec(io.target_quat, 4 * D, d * 4 + i), e0 + kTQuat + i); }
+        if (io.max_vel)
+            for (int i = 0; i < 2; ++i) put(g, vec(io.max_vel, 2 * D, d * 2 + i), e0 + kMaxVel + i);
+        if (P.admittance) {
+            for (int i = 0; i < 9; ++i) put(g, vec(io.ft_xmat, 9 * D, d * 9 + i), e0 + kFtX + i);
+            for (int i = 0; i < 6; ++i) put(g, vec(io.ft_raw, 6 * D, d * 6 + i), e0 + kFtRaw + i);
+        }
+    };
+    int max_entries = kG1Entries;
+    // G0
+    put(0, vec(bias, n, 0), kG0Bias0);
+    if (has_base) {
+        put(0, J_at(R.row_base, 0), kG0Jbase);
+        device_block(0, R.dev_base, kG0Dev);
+        max_entries = std::max(max_entries, kG0Dev + kDevEntries);
+    }
+    for (int arm = 0; arm < 2; ++arm) {
+        const int jb = 1 + 12 * arm, g0 = 1 + 5 * arm;
+        auto C = [&](int i) { return i == 0 ? 0 : jb + i - 1; };
+        for (int i = 0; i < 7; ++i) {
+            for (int j = 0; j <= i; ++j) put(g0, M_at(C(i), C(j)), kCC + i * (i + 1) / 2 + j);
+            put(g0, vec(io.dq, n, C(i)), kDqC + i);
+        }
+        for (int half = 0; half < 2; ++half) {
+            const int g = g0 + 1 + half, gj = jb + 6 + 3 * half;
+            for (int i = 0; i < 7; ++i) {
+                put(g, M_at(gj + 1, C(i)), kRg1 + i);
+                put(g, M_at(gj, C(i)), kRg0 + i);
+                put(g, M_at(gj + 2, C(i)), kRg2 + i);
+            }
+            put(g, M_at(gj + 1, gj), kE10);
+            put(g, M_at(gj + 1, gj + 1), kD1);
+            put(g, M_at(gj, gj), kD0);
+            put(g, M_at(gj + 2, gj + 2), kD2);
+            for (int r = 0; r < 3; ++r) { put(g, vec(io.dq, n, gj + r), kDqG + r); put(g, vec(bias, n, gj + r), kBiasG + r); }
+        }
+        for (int cr = 0; cr < kd; ++cr)
+            for (int i = 0; i < 7; ++i) put(g0 + 3, J_at(R.row_arm[arm] + cr, C(i)), cr * 7 + i);
+        for (int i = 0; i < 6; ++i) put(g0 + 3, vec(bias, n, jb + i), kd * 7 + i);
+        max_entries = std::max(max_entries, kd * 7 + 6);
+        device_block(g0 + 4, R.dev_arm[arm], 0);
+    }
+    memset(&plan, 0, sizeof plan);
+    plan.has_mvel = io.max_vel != nullptr;
+    const int trash = max_entries;
+    plan.stage_entries = max_entries + 1;
+    int nc = 0;
+    for (int g = 0; g < kGroups; ++g) {
+        plan.first[g] = nc;
+        std::vector<Item> &v = groups[g];
+        std::stable_sort(v.begin(), v.end(), [](const Item &a, const Item &b) {
+            return a.base != b.base ? a.base < b.base : a.off < b.off;
+        });
+        size_t at = 0;
+        while (at < v.size()) {
+            if (nc >= kMaxChunks) return fail(IRLOSC_ERR_INVALID, "stream plan needs more than %d chunks", kMaxChunks);
+            Chunk &c = plan.ch[nc++];
+            c.base = (uint64_t)(uintptr_t)v[at].base;
+            c.stride = (int32_t)v[at].stride;
+            if ((int64_t)c.stride != v[at].stride) return fail(IRLOSC_ERR_INVALID, "instance stride too large for the streaming kernel");
+            int l = 0;
+            for (; l < 8 && at < v.size() && v[at].base == (const void *)(uintptr_t)c.base && v[at].stride == c.stride; ++l, ++at) {
+                if (v[at].off > INT32_MAX) return fail(IRLOSC_ERR_INVALID, "record too large for the streaming kernel");
+                c.off[l] = (int32_t)v[at].off;
+                c.dst[l] = (int16_t)v[at].dst;
+            }
+            for (; l < 8; ++l) { c.off[l] = c.off[0]; c.dst[l] = (int16_t)trash; }
+        }
+    }
+    plan.first[kGroups] = nc;
+    plan.n_chunks = nc;
+    for (int c = 0; c < nc; ++c) {               // distinct arrays, for the whole-tile L2 prefetch
+        bool seen = false;
+        for (int a = 0; a < plan.n_arrays; ++a) seen = seen || plan.arr_base[a] == plan.ch[c].base;
+        if (!seen && plan.n_arrays < kMaxArrays) {
+            plan.arr_base[plan.n_arrays] = plan.ch[c].base;
+            plan.arr_stride[plan.n_arrays++] = plan.ch[c].stride;
+        }
     }
     return IRLOSC_OK;
 }

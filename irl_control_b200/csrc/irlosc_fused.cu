@@ -9,6 +9,8 @@
 #include "irlosc_internal.h"
 #include "irlosc_build.h"
 #include "osc_fused.cuh"
+#include "osc_stream.cuh"
+#include <cstdlib>
 
 using namespace irlosc;
 using namespace irlosc::fused;
@@ -60,16 +62,17 @@ const FusedEntry *fused_find(int kd, bool has_base, int variant = 0) {
     return nullptr;
 }
 
-int32_t ensure_queue(irlosc_handle *h, int64_t B, int rec_doubles) {
-    if (!h->hard_count) CUDA_TRY(cudaMalloc(&h->hard_count, sizeof(int)));
-    if (B > h->hard_cap || rec_doubles != h->hard_rec_doubles) {
-        if (h->hard_inst) { CUDA_TRY(cudaFree(h->hard_inst)); h->hard_inst = nullptr; }
-        if (h->hard_rec) { CUDA_TRY(cudaFree(h->hard_rec)); h->hard_rec = nullptr; }
-        h->hard_cap = 0;
-        CUDA_TRY(cudaMalloc(&h->hard_inst, (size_t)B * sizeof(int64_t)));
-        CUDA_TRY(cudaMalloc(&h->hard_rec, (size_t)B * rec_doubles * sizeof(double)));
-        h->hard_cap = B;
-        h->hard_rec_doubles = rec_doubles;
+int32_t ensure_queue(irlosc_handle *h, int q, int64_t B, int rec_doubles) {
+    HardBuffers &hb = h->hard[q];
+    if (!hb.count) CUDA_TRY(cudaMalloc(&hb.count, sizeof(int)));
+    if (B > hb.cap || rec_doubles != hb.rec_doubles) {
+        if (hb.inst) { CUDA_TRY(cudaFree(hb.inst)); hb.inst = nullptr; }
+        if (hb.rec) { CUDA_TRY(cudaFree(hb.rec)); hb.rec = nullptr; }
+        hb.cap = 0;
+        CUDA_TRY(cudaMalloc(&hb.inst, (size_t)B * sizeof(int64_t)));
+        CUDA_TRY(cudaMalloc(&hb.rec, (size_t)B * rec_doubles * sizeof(double)));
+        hb.cap = B;
+        hb.rec_doubles = rec_doubles;
     }
     return IRLOSC_OK;
 }
@@ -86,13 +89,14 @@ int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
 }
 
 int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st) {
-    const int variant = h->kernel_choice >= 2 ? h->kernel_choice - 2 : 0;
+    const int variant = (h->kernel_choice >= 2 && h->kernel_choice < 9) ? h->kernel_choice - 2 : 0;
     const FusedEntry *e = fused_find(h->fused_kd, h->fused_base, variant);
     if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d variant=%d", h->fused_kd, (int)h->fused_base, variant);
-    int32_t rc = ensure_queue(h, B, e->rec_doubles);
+    int32_t rc = ensure_queue(h, 0, B, e->rec_doubles);
     if (rc != IRLOSC_OK) return rc;
-    CUDA_TRY(cudaMemsetAsync(h->hard_count, 0, sizeof(int), st));
-    HardQueue hq{h->hard_count, (int)std::min<int64_t>(h->hard_cap, INT32_MAX), e->rec_doubles, h->hard_rec, h->hard_inst};
+    HardBuffers &hb = h->hard[0];
+    CUDA_TRY(cudaMemsetAsync(hb.count, 0, sizeof(int), st));
+    HardQueue hq{hb.count, (int)std::min<int64_t>(hb.cap, INT32_MAX), e->rec_doubles, hb.rec, hb.inst};
     const int sms = std::max(1, h->sm_count - h->sm_margin);
     const int grid = (int)std::min<int64_t>((B + e->threads - 1) / e->threads, (int64_t)sms);
     void *args[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr, (void *)&hq};
@@ -110,7 +114,114 @@ int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st)
     return IRLOSC_OK;
 }
 
+// ------------------------------------------------------------------ streaming step (state in HBM)
+struct StreamEntry {
+    int kd;
+    bool has_base;
+    int max_threads;
+    const void *step, *fixup;
+    int rec_doubles;
+    const char *name;
+};
+
+template <int KD, bool HB, int NT>
+StreamEntry sentry(const char *name) {
+    return StreamEntry{KD, HB, NT, (const void *)stream::osc_step_stream<KD, HB, NT>, (const void *)osc_tail_fixup<KD, HB>,
+                       Rec<KD, HB>::SIZE, name};
+}
+
+const StreamEntry *stream_table(int *count) {
+    static const StreamEntry t[] = {
+        sentry<3, true, 256>("osc_step_stream<kd3,base>"),
+        sentry<6, false, 256>("osc_step_stream<kd6>"),
+        sentry<6, true, 256>("osc_step_stream<kd6,base>"),
+        sentry<3, false, 256>("osc_step_stream<kd3>"),
+    };
+    *count = (int)(sizeof t / sizeof t[0]);
+    return t;
+}
+
+constexpr size_t kSmemLimit = 227 * 1024;
+bool g_stream_ready = false;
+
 }  // namespace
+
+bool irlosc::stream_supported(const irlosc_handle *h, const KIo &) {
+    FRoles R;
+    int kd = 0;
+    bool hb = false;
+    return !h->kp.check_topology && fused_roles(h->kp, R, kd, hb);
+}
+
+bool irlosc::stream_preferred(const irlosc_handle *h) {
+    FRoles R;
+    int kd = 0;
+    bool hb = false;
+    return fused_roles(h->kp, R, kd, hb) && kd == 6;
+}
+
+int32_t irlosc::stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaStream_t st, int queue) {
+    FRoles R;
+    int kd = 0;
+    bool has_base = false;
+    if (!fused_roles(h->kp, R, kd, has_base)) return fail(IRLOSC_ERR_INVALID, "streaming kernel: not the DualUR5 topology");
+    int cnt = 0;
+    const StreamEntry *t = stream_table(&cnt), *e = nullptr;
+    for (int i = 0; i < cnt; ++i)
+        if (t[i].kd == kd && t[i].has_base == has_base) e = &t[i];
+    if (!e) return fail(IRLOSC_ERR_INVALID, "no streaming kernel for kd=%d base=%d", kd, (int)has_base);
+    if (!g_stream_ready) {
+        for (int i = 0; i < cnt; ++i)
+            CUDA_TRY(cudaFuncSetAttribute(t[i].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        g_stream_ready = true;
+    }
+    stream::Plan plan;
+    int32_t rc = build_stream_plan(h->kp, io, R, kd, has_base, plan);
+    if (rc != IRLOSC_OK) return rc;
+    rc = ensure_queue(h, queue, B, e->rec_doubles);
+    if (rc != IRLOSC_OK) return rc;
+    HardBuffers &hb = h->hard[queue];
+    CUDA_TRY(cudaMemsetAsync(hb.count, 0, sizeof(int), st));
+    HardQueue hq{hb.count, (int)std::min<int64_t>(hb.cap, INT32_MAX), e->rec_doubles, hb.rec, hb.inst};
+    // shared-memory plan: tables, then per warp two stages and the packed ctrl tile
+    const int stage_bytes = (plan.stage_entries * stream::kPitch * 8 + 15) & ~15;
+    const int warp_bytes = 2 * stage_bytes + ((32 * h->kp.n_ctrl * 8 + 15) & ~15);
+    const size_t head = (sizeof(stream::Plan) + 15) & ~size_t(15);
+    int warps = (int)std::min<size_t>(e->max_threads / 32, (kSmemLimit - head) / warp_bytes);
+    if (const char *w = getenv("IRLOSC_STREAM_WARPS")) warps = std::max(1, std::min(warps, atoi(w)));   // experiments only
+    if (warps < 1) return fail(IRLOSC_ERR_INVALID, "streaming kernel: a stage does not fit in shared memory");
+    const size_t smem = head + (size_t)warps * warp_bytes;
+    stream::Outputs out{io.u_all, io.ctrl, io.status, io.target_vel};
+    auto al16 = [](const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    stream::Gather G;
+    memset(&G, 0, sizeof G);
+    G.n_gather = io.n_gather;
+    G.gather_offset = io.gather_offset;
+    G.ctrl_mc = io.ctrl_mc;
+    G.ctrl_vec = al16(io.ctrl) && ((io.gather_offset * (int64_t)h->kp.n_ctrl) % 2 == 0) && al16(io.ctrl_mc);
+    for (int g = 0; g < io.n_gather; ++g) { G.ctrl_gather[g] = io.ctrl_gather[g]; G.ctrl_vec = G.ctrl_vec && al16(io.ctrl_gather[g]); }
+    const int sms = std::max(1, h->sm_count - h->sm_margin);
+    const int64_t n_tiles = (B + 31) / 32;
+    const int grid = (int)std::min<int64_t>((n_tiles + warps - 1) / warps, (int64_t)sms);
+    int mode = 0;
+    if (const char *m = getenv("IRLOSC_STREAM_MODE")) mode = atoi(m);                                   // experiments only
+    void *args[] = {(void *)&h->kp, (void *)&plan, (void *)&out, (void *)&B, (void *)&R, (void *)&hq, (void *)&G,
+                    (void *)&stage_bytes, (void *)&warp_bytes, (void *)&mode};
+    cudaError_t err = cudaLaunchKernel(e->step, dim3(grid), dim3(warps * 32), args, smem, st);
+    if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "streaming kernel launch: %s", cudaGetErrorString(err));
+    TailOut tout;
+    memset(&tout, 0, sizeof tout);
+    tout.u_all = io.u_all; tout.ctrl = io.ctrl; tout.status = io.status;
+    tout.n_gather = io.n_gather; tout.gather_offset = io.gather_offset; tout.ctrl_mc = io.ctrl_mc;
+    for (int g = 0; g < io.n_gather; ++g) tout.ctrl_gather[g] = io.ctrl_gather[g];
+    const int fgrid = (int)std::min<int64_t>((B + 3) / 4, (int64_t)sms * 4);
+    void *fargs[] = {(void *)&h->kp, (void *)&tout, (void *)&R, (void *)&hq};
+    err = cudaLaunchKernel(e->fixup, dim3(fgrid), dim3(128), fargs, 0, st);
+    if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fix-up kernel launch: %s", cudaGetErrorString(err));
+    h->launches += 2;
+    h->last_kernel = e->name;
+    return IRLOSC_OK;
+}
 
 extern "C" int32_t irlosc_set_model(irlosc_handle *h, const irlosc_model *m) {
     if (!h || !m) return fail(IRLOSC_ERR_INVALID, "null argument");

@@ -118,7 +118,12 @@ IRLOSC_HD void joint_down(const KJoint &jm, const Body &p, double q, double dq, 
     mat3_vec(c.R, jm.com, t);
 #pragma unroll
     for (int i = 0; i < 3; ++i) r[i] = c.o[i] + t[i];
-    // Iw = R Ic R^T
+    // Iw = R Ic R^T; an isotropic tensor (every UR5 link of scenes/dual_ur5.xml) is rotation invariant
+    if (jm.ic[3] == 0.0 && jm.ic[4] == 0.0 && jm.ic[5] == 0.0 && jm.ic[0] == jm.ic[1] && jm.ic[1] == jm.ic[2]) {
+        Iw[0] = Iw[1] = Iw[2] = jm.ic[0];
+        Iw[3] = Iw[4] = Iw[5] = 0.0;
+        return;
+    }
     const double ic[9] = {jm.ic[0], jm.ic[3], jm.ic[4], jm.ic[3], jm.ic[1], jm.ic[5], jm.ic[4], jm.ic[5], jm.ic[2]};
     double T[9];
     mat3_mul(c.R, ic, T);
@@ -342,12 +347,17 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
         double Hpre[6], FBpre[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { Hpre[i] = 0.0; FBpre[i] = 0.0; }
+        // joint angles / rates are fetched one joint ahead so that their latency hides behind a joint's work
+        double q_nx = q[jb], dq_nx = dq[jb];
 #pragma unroll 1
         for (int i = 0; i < 6; ++i) {
             const KJoint &jm = Mdl.arm[arm][i];
             Body Bn;
             double s[6], r[3], Iw[6], h[6], fb[6];
-            joint_down(jm, Bc, q[jb + i], dq[jb + i], Bn, s, r, Iw);
+            const double q_i = q_nx, dq_i = dq_nx;
+            q_nx = q[jb + i + 1];                  // i = 5: first gripper joint, still inside the row
+            dq_nx = dq[jb + i + 1];
+            joint_down(jm, Bc, q_i, dq_i, Bn, s, r, Iw);
             body_wrench(jm.mass, r, Iw, Bn.v, Bn.a, h, fb);
             const double cu = coef_uv(P, vel_zero, jb + i);
             double x[6];
@@ -394,15 +404,17 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const int gj = jb + 6 + 3 * half;
+            const double qg0 = q[gj], qg1 = q[gj + 1], qg2 = q[gj + 2];
+            const double dqg0 = dq[gj], dqg1 = dq[gj + 1], dqg2 = dq[gj + 2];
             double IAg[21], f[6], inv;
             Body B0;
             double sa[6], ra[3], Iwa[6], ha[6], fba[6];
-            joint_down(Mdl.grip[arm][half][0], Bc, q[gj], dq[gj], B0, sa, ra, Iwa);
+            joint_down(Mdl.grip[arm][half][0], Bc, qg0, dqg0, B0, sa, ra, Iwa);
             body_wrench(Mdl.grip[arm][half][0].mass, ra, Iwa, B0.v, B0.a, ha, fba);
             {
                 Body B1;
                 double sb[6], rb[3], Iwb[6], hb[6], fbb[6];
-                joint_down(Mdl.grip[arm][half][1], B0, q[gj + 1], dq[gj + 1], B1, sb, rb, Iwb);
+                joint_down(Mdl.grip[arm][half][1], B0, qg1, dqg1, B1, sb, rb, Iwb);
                 body_wrench(Mdl.grip[arm][half][1].mass, rb, Iwb, B1.v, B1.a, hb, fbb);
                 const double cu1 = coef_uv(P, vel_zero, gj + 1);
                 const double uv1 = dot6(sb, hb), b1 = dot6(sb, fbb);
@@ -428,7 +440,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
             {   // g2
                 Body B2;
                 double sc[6], rc[3], Iwc[6], hc[6], fbc[6];
-                joint_down(Mdl.grip[arm][half][2], Bc, q[gj + 2], dq[gj + 2], B2, sc, rc, Iwc);
+                joint_down(Mdl.grip[arm][half][2], Bc, qg2, dqg2, B2, sc, rc, Iwc);
                 body_wrench(Mdl.grip[arm][half][2].mass, rc, Iwc, B2.v, B2.a, hc, fbc);
                 const double cu2 = coef_uv(P, vel_zero, gj + 2);
                 const double uv2 = dot6(sc, hc), b2 = dot6(sc, fbc);
@@ -470,11 +482,16 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
             for (int e = 0; e < 6; ++e) x[e] = fma(cu, Hpre[e], gb * FBpre[e]);
             base_arm[arm][i] = dot6(s, x) - scr(o + 15);
             if (dbg && dbg->uv) { dbg->uv[jb + i] += dot6(s, Hpre); dbg->bias[jb + i] += dot6(s, FBpre); }
+            {   // original J[r][joint] for J^T w: [jacp; jacr] column = [a x (p - c); a] = [s_ang x p + s_lin; s_ang]
+                double jp[3];
+                cross3(s, ee_p, jp);
 #pragma unroll
-            for (int cr = 0; cr < KD; ++cr) {
-                double e0[6];
-                task_force(P.row_comp[row_a + cr], ee_p, e0);
-                jarm[arm][i][cr] = dot6(s, e0);                 // original J[r][joint] for J^T w
+                for (int e = 0; e < 3; ++e) jp[e] += s[3 + e];
+#pragma unroll
+                for (int cr = 0; cr < KD; ++cr) {
+                    const int comp = P.row_comp[row_a + cr];
+                    jarm[arm][i][cr] = comp == 0 ? jp[0] : comp == 1 ? jp[1] : comp == 2 ? jp[2] : comp == 3 ? s[0] : comp == 4 ? s[1] : s[2];
+                }
             }
             add_rigid(IA, Mdl.arm[arm][i].mass, r, Iw);
             double f[6], inv;

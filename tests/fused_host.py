@@ -18,13 +18,13 @@ _lib = None
 
 def build():
     deps = [SRC, os.path.join(os.path.dirname(HERE), "include", "irlosc.h")] + [
-        os.path.join(CSRC, f) for f in ("osc_fused.cuh", "osc_fused_types.h", "irlosc_device.cuh",
-                                        "irlosc_build.h", "irlosc_internal.h")]
+        os.path.join(CSRC, f) for f in ("osc_fused.cuh", "osc_fused_types.h", "irlosc_device.cuh", "osc_tail.cuh",
+                                        "osc_stream.cuh", "irlosc_build.h", "irlosc_internal.h")]
     if os.path.isfile(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in deps):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     cmd = [os.environ.get("NVCC", "nvcc"), "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-shared", "-Xcompiler", "-fPIC", "-o", LIB, SRC]
+           "-diag-suppress", "20014,20011", "-shared", "-Xcompiler", "-fPIC", "-o", LIB, SRC]
     subprocess.check_call(cmd)
     return LIB
 
@@ -37,6 +37,8 @@ def load():
         _lib.fused_host_run.argtypes = [C.POINTER(_native.Params), C.POINTER(_native.Model), C.c_int64,
                                         C.POINTER(_native.FusedIo)] + [C.c_void_p] * 6
         _lib.fused_host_error.restype = C.c_char_p
+        _lib.stream_host_run.restype = C.c_int64
+        _lib.stream_host_run.argtypes = [C.POINTER(_native.Params), C.c_int64, C.POINTER(_native.Io)] + [C.c_void_p] * 6
     return _lib
 
 
@@ -64,5 +66,40 @@ def run(layout, model, inp, debug=False):
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
     out["n_hard"] = int(rc)
+    out.update(dbg)
+    return out
+
+
+def run_stream(layout, state, debug=False, strides=None):
+    """The streaming step (osc_stream.cuh) on the CPU.  state: numpy arrays in `BatchedOSC.step` field names."""
+    lib = load()
+    keep = {k_: np.ascontiguousarray(v, dtype=np.float64) if k_ not in (strides or {}).get("views", ()) else v
+            for k_, v in state.items()}
+    B = int(keep["dq"].shape[0])
+    n, D, k, nc = layout.n, layout.D, layout.k, layout.n_ctrl
+    out = {"ctrl": np.zeros((B, nc)), "u_all": np.zeros((B, n)), "status": np.zeros(B, dtype=np.uint8)}
+    io = _native.Io()
+    io.m_layout = _native.M_DENSE if keep["M"].ndim == 3 else _native.M_PACKED
+    io.j_layout = _native.J_FULL6 if keep["J"].ndim == 4 else _native.J_ROWS
+    for name in ("M", "J", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat", "target_vel", "max_vel",
+                 "ft_xmat", "ft_raw"):
+        setattr(io, name, keep[name].ctypes.data if name in keep else None)
+    for name in out:
+        setattr(io, name, out[name].ctypes.data)
+    for key in ("ldm", "m_stride", "ldj", "j_stride"):
+        setattr(io, key, int((strides or {}).get(key, 0)))
+    dbg = {}
+    ptrs = [None] * 5
+    if debug:
+        dbg = {"A": np.zeros((B, k, k)), "g": np.zeros((B, k)), "uv": np.zeros((B, n)), "dx": np.zeros((B, k)),
+               "J": np.zeros((B, k, n))}
+        ptrs = [dbg[x].ctypes.data for x in ("A", "g", "uv", "dx", "J")]
+    params = layout.to_c_params()
+    nch = C.c_int32(0)
+    rc = lib.stream_host_run(C.byref(params), B, C.byref(io), *ptrs, C.byref(nch))
+    if rc < 0:
+        raise RuntimeError(lib.fused_host_error().decode())
+    out["n_hard"] = int(rc)
+    out["n_chunks"] = int(nch.value)
     out.update(dbg)
     return out

@@ -11,6 +11,7 @@
 #include "../../irl_control_b200/csrc/irlosc_internal.h"
 #include "../../irl_control_b200/csrc/irlosc_build.h"
 #include "../../irl_control_b200/csrc/osc_fused.cuh"
+#include "../../irl_control_b200/csrc/osc_stream.cuh"
 
 static std::string g_err;
 int32_t irlosc::fail(int32_t rc, const char *fmt, ...) {
@@ -129,4 +130,98 @@ extern "C" int64_t fused_host_run(const irlosc_params *params, const irlosc_mode
     if (kd == 3 && !hb) return run<3, false>(P, M, R, k, B, dp);
     if (kd == 6 && hb) return run<6, true>(P, M, R, k, B, dp);
     return run<6, false>(P, M, R, k, B, dp);
+}
+
+// ------------------------------------------------------------------ streaming step (state given)
+// Emulates the staging of osc_step_stream on the CPU: every group of the host-built copy plan is
+// gathered into a stage exactly as the cp.async chunks would, then the per-instance consumers
+// (the same __host__ __device__ code the kernel runs) read it.
+namespace {
+struct HostGroups {
+    const stream::Plan &plan;
+    int64_t inst;
+    std::vector<double> stage;
+    struct Reader {
+        const double *st;
+        __host__ __device__ double operator()(int e) const { return st[e]; }
+    };
+    __host__ __device__ Reader operator()(int g) {
+#ifndef __CUDA_ARCH__
+        std::fill(stage.begin(), stage.end(), std::nan(""));      // anything not copied must not be used
+        for (int c = plan.first[g]; c < plan.first[g + 1]; ++c) {
+            const stream::Chunk &ch = plan.ch[c];
+            for (int l = 0; l < 8; ++l) {
+                const unsigned char *src = reinterpret_cast<const unsigned char *>(ch.base) + inst * (int64_t)ch.stride + ch.off[l];
+                stage[ch.dst[l]] = *reinterpret_cast<const double *>(src);
+            }
+        }
+        return Reader{stage.data()};
+#else
+        return Reader{nullptr};
+#endif
+    }
+};
+
+template <int KD, bool HB>
+int64_t run_stream(const KParams &P, const FRoles &R, const stream::Plan &plan, const stream::Outputs &out, int64_t B,
+                   const Debug *dbg0) {
+    using RC = Rec<KD, HB>;
+    constexpr int K = RC::K;
+    std::vector<double> rec(RC::SIZE);
+    int64_t n_hard = 0;
+    for (int64_t i = 0; i < B; ++i) {
+        Debug d, *dp = nullptr;
+        if (dbg0) {
+            d = *dbg0;
+            if (d.A) d.A += i * K * K;
+            if (d.g) d.g += i * K;
+            if (d.dx) d.dx += i * K;
+            if (d.uv) d.uv += i * kN;
+            if (d.bias) d.bias = nullptr;
+            if (d.J) d.J += i * K * kN;
+            dp = &d;
+        }
+        HostGroups groups{plan, i, std::vector<double>(plan.stage_entries)};
+        double *ctrl_row = out.ctrl + i * P.n_ctrl;
+        const bool hard = stream::stream_instance<KD, HB>(P, R, plan, out, i, groups, ctrl_row, rec.data(), dp);
+        if (hard) {
+            ++n_hard;
+            double w[K];
+            const int fl = host_eigen_solve<K>(&rec[RC::A], &rec[RC::G], rec[RC::ABAD] == 0.0, w);
+            fixup_finish<KD, HB>(R, out.u_all ? out.u_all + i * kN : nullptr, ctrl_row, rec.data(), w, 0, 1);
+            if (out.status) out.status[i] = (uint8_t)(out.status[i] | fl);
+        }
+    }
+    return n_hard;
+}
+}  // namespace
+
+extern "C" int64_t stream_host_run(const irlosc_params *params, int64_t B, const irlosc_io *io, double *dbg_A,
+                                   double *dbg_g, double *dbg_uv, double *dbg_dx, double *dbg_J, int32_t *n_chunks) {
+    KParams P;
+    if (build_kparams(*params, P) != IRLOSC_OK) return -1;
+    FRoles R;
+    int kd = 0;
+    bool hb = false;
+    if (!fused_roles(P, R, kd, hb)) { irlosc::fail(1, "not the DualUR5 topology"); return -1; }
+    KIo k;
+    memset(&k, 0, sizeof k);
+    k.M = io->M; k.m_layout = io->m_layout;
+    if (io->m_layout == IRLOSC_M_DENSE) { k.ldm = io->ldm ? io->ldm : P.n; k.m_stride = io->m_stride ? io->m_stride : (int64_t)k.ldm * P.n; }
+    else { k.ldm = 0; k.m_stride = io->m_stride ? io->m_stride : (int64_t)P.n * (P.n + 1) / 2; }
+    k.J = io->J; k.j_layout = io->j_layout; k.ldj = io->ldj ? io->ldj : P.n;
+    k.j_stride = io->j_stride ? io->j_stride : (io->j_layout == IRLOSC_J_ROWS ? (int64_t)k.ldj * P.k : (int64_t)k.ldj * 6 * P.D);
+    k.dq = io->dq; k.bias = io->bias; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    k.target_xyz = io->target_xyz; k.target_quat = io->target_quat; k.target_vel = io->target_vel;
+    k.max_vel = io->max_vel; k.ft_xmat = io->ft_xmat; k.ft_raw = io->ft_raw;
+    stream::Plan plan;
+    if (build_stream_plan(P, k, R, kd, hb, plan) != IRLOSC_OK) return -1;
+    if (n_chunks) *n_chunks = plan.n_chunks;
+    stream::Outputs out{io->u_all, io->ctrl, io->status, io->target_vel};
+    Debug d{dbg_A, dbg_g, dbg_uv, nullptr, dbg_dx, dbg_J};
+    const Debug *dp = (dbg_A || dbg_uv || dbg_J) ? &d : nullptr;
+    if (kd == 3 && hb) return run_stream<3, true>(P, R, plan, out, B, dp);
+    if (kd == 3 && !hb) return run_stream<3, false>(P, R, plan, out, B, dp);
+    if (kd == 6 && hb) return run_stream<6, true>(P, R, plan, out, B, dp);
+    return run_stream<6, false>(P, R, plan, out, B, dp);
 }

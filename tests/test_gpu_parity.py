@@ -12,8 +12,9 @@ from conftest import GOLDEN_CASES, golden_oracle_batch, load_golden
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-6          # well inside the 1e-4 bar of BASELINE.json
-KERNELS = [1, 0, 3]     # 1 = generic kernel, 0 = auto (tree-sparse kernel when the topology is declared,
-                        # dense register-tiled kernel otherwise), 3 = next specialised variant
+KERNELS = [1, 0, 2, 3, 9]  # 1 = generic kernel, 0 = auto (DualUR5 topology declared: tree-sparse 4-lane kernel for
+                           # 3-row arm devices, streaming thread-per-instance kernel for 6-row ones), 2 = tree-sparse
+                           # kernel, 3 = dense register-tiled variant, 9 = streaming kernel
 DUAL_UR5_PARENT = (-1, 0, 1, 2, 3, 4, 5, 6, 7, 6, 6, 10, 6, 0, 13, 14, 15, 16, 17, 18, 19, 18, 18, 22, 18)
 EE_JOINT = {"base": 0, "ur5right": 6, "ur5left": 18}
 
@@ -91,6 +92,36 @@ def test_cuda_matches_reference_golden(case, packed_M, full6_J, kernel, topology
         assert np.array_equal((status[ok] & _native.ST_VEL_BRANCH) != 0, vel[ok])
 
 
+@pytest.mark.parametrize("packed_M,full6_J", [(False, False), (True, True), (True, False)])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_streaming_kernel_matches_reference_golden(case, packed_M, full6_J):
+    """The default DualUR5 kernel (osc_stream.cuh, thread per instance) on the reference's goldens,
+    every M / J layout."""
+    torch = _torch()
+    from irl_control_b200 import _native
+    from irl_control_b200.engine import BatchedOSC
+    g, ld = load_golden(case)
+    layout = _layout_from_dict(ld, topology=True, check=False)
+    eng = BatchedOSC(layout, device=0)
+    eng.set_kernel(9)
+    out = eng.step(_golden_state(g, layout, torch, packed_M, full6_J), want_u_all=True)
+    torch.cuda.synchronize()
+    assert eng.last_kernel.startswith("osc_step_stream"), eng.last_kernel
+    ctrl, u_all, status = (out[k].cpu().numpy() for k in ("ctrl", "u_all", "status"))
+    bad = g["index_error"]
+    assert np.all((status[bad] & _native.ST_DX_RANGE) != 0) and np.all(np.isnan(ctrl[bad])) and np.all(np.isnan(u_all[bad]))
+    ok = ~bad
+    if ok.any():
+        assert np.array_equal((status[ok] & _native.ST_PINV) != 0, g["pinv"][ok])
+        assert not np.any(status[ok] & (_native.ST_M_NOT_PD | _native.ST_DX_RANGE | _native.ST_SPARSITY))
+        e_u = _rel_err(u_all[ok], g["u_all"][ok])
+        e_c = np.abs(ctrl[ok] - g["ctrl"][ok]).max(axis=1) / np.abs(g["u_all"][ok]).max(axis=1)
+        print("%s kernel=%s worst rel err u_all %.2e ctrl %.2e" % (case, eng.last_kernel, e_u.max(), e_c.max()))
+        assert e_u.max() < REL_TOL and e_c.max() < REL_TOL
+        vel = (np.asarray(g["target_vel"]) != 0).all(axis=-1).any(axis=-1)
+        assert np.array_equal((status[ok] & _native.ST_VEL_BRANCH) != 0, vel[ok])
+
+
 @pytest.mark.parametrize("kernel", KERNELS)
 @pytest.mark.parametrize("scenario,B", [("gain_test", 4096), ("admit_test", 8192), ("insertion", 16384), ("worst_case", 4096)])
 def test_cuda_matches_oracle_on_baseline_configs(scenario, B, kernel):
@@ -146,7 +177,7 @@ def test_size_independent_properties_at_full_batch():
     # packed vs dense M: same kernel family, same arithmetic -> bit-identical
     e = eng.step(kernel_inputs(st, layout, packed_M=True), want_u_all=True)
     assert torch.equal(e["u_all"], a["u_all"])
-    # full-6 Jacobian layout is served by the generic kernel: equal within the parity tolerance
+    # full-6 Jacobian layout: same entries through another copy plan
     f = eng.step(kernel_inputs(st, layout, packed_M=True, full6_J=True), want_u_all=True)
     scale = a["u_all"].abs().amax(dim=1, keepdim=True)
     assert ((f["u_all"] - a["u_all"]).abs() / scale).max().item() < REL_TOL
@@ -237,7 +268,7 @@ def test_calc_error_kernel_matches_oracle():
             assert np.abs(err[i, d] - want).max() < 1e-12
 
 
-def test_tree_kernel_is_the_default_for_the_dual_ur5_and_checks_its_contract():
+def test_tree_kernel_checks_the_sparsity_contract():
     """With the kinematic tree declared (what the host layer derives from the model) the sparse
     kernel runs; check_topology flags instances whose M / J break the declared zeros."""
     torch = _torch()
@@ -296,8 +327,13 @@ def test_scene_sized_views_and_bad_inputs():
     Jfull[:, :, :n] = kin["J"]
     view = dict(kin, M=Mfull, J=Jfull)
     out = eng.step(view, want_u_all=True, strides={"ldm": nv, "m_stride": nv * nv, "ldj": nv, "j_stride": layout.k * nv})
+    assert eng.last_kernel.startswith("osc_step_stream")      # strided views are just another copy plan
+    eng.set_kernel(1)
+    gen = eng.step(view, want_u_all=True, strides={"ldm": nv, "m_stride": nv * nv, "ldj": nv, "j_stride": layout.k * nv})
     assert eng.last_kernel == "osc_step_generic"
+    eng.set_kernel(0)
     scale = ref["u_all"].abs().amax(dim=1, keepdim=True)
+    assert ((gen["u_all"] - ref["u_all"]).abs() / scale).max().item() < REL_TOL
     assert ((out["u_all"] - ref["u_all"]).abs() / scale).max().item() < REL_TOL
     assert torch.equal(out["status"] & _native.ST_PINV, ref["status"] & _native.ST_PINV)
     # an indefinite inertia matrix cannot be factorised: flagged, outputs NaN, neighbours untouched
