@@ -12,7 +12,11 @@ from irl_control_b200.synthetic import scenario_layout, synth_batch, kernel_inpu
 ok = True
 for scenario, B, kern, mode in (("gain_test", 4099, 0, "peer"), ("admit_test", 1024, 0, "peer"), ("gain_test", 777, 1, "peer"),
                                 ("gain_test", 4096, 0, "peer"), ("gain_test", 4096, 0, "multicast"),
-                                ("gain_test", 4099, 0, "multicast"), ("admit_test", 1031, 2, "multicast")):
+                                ("gain_test", 4099, 0, "multicast"), ("admit_test", 1031, 2, "multicast"),
+                                # streaming kernel (kernel 9; auto for 6-row arm devices), incl. eigen fix-ups
+                                ("gain_test", 4099, 9, "peer"), ("gain_test", 4096, 9, "multicast"),
+                                ("worst_case", 2051, 9, "multicast"), ("worst_case", 2048, 0, "peer"),
+                                ("admit_test", 4096, 0, "multicast")):
     layout = scenario_layout(scenario)
     st = synth_batch(layout, B, seed=100 + rank, device=dev)
     kin = kernel_inputs(st, layout, packed_M=True)
