@@ -366,6 +366,33 @@ def main():
                  "gpu_launches": int(f_launches), "input_bytes_per_step": int(f_in // B),
                  "l2_policy": "256 MB flush write between timed steps (inputs %.0f MB < L2)" % (f_in / 1e6),
                  "api": "BatchedOSC.step_fused -> irlosc_step_fused (q, dq, targets in HBM)"}
+        # caller loop fused in: the insertion demo's WP / GRIP state machine per instance
+        try:
+            from irl_control_b200.sequence import ActionSequence
+            acts = [{"action": "WP"}, {"action": "GRIP", "gripper_force": -0.08, "gripper_duration": 1.0},
+                    {"action": "WP", "gripper_force": -0.08}, {"action": "GRIP", "gripper_force": 0.2, "gripper_duration": 2.0},
+                    {"action": "WP", "gripper_force": 0.2}]
+            seq = ActionSequence(layout, acts, active_arm="ur5right")
+            ia = seq.active_device
+            wp_xyz = (st["ee_xyz"][:, ia, None, :] + 0.05 * torch.randn(B, len(acts), 3, dtype=torch.float64, device=dev)).contiguous()
+            wp_quat = st["ee_quat"][:, ia, None, :].expand(B, len(acts), 4).contiguous()
+            sst = seq.new_state(B, wp_xyz, wp_quat, device=dev)
+            sin = {k: v for k, v in fin.items() if k not in ("target_xyz", "target_quat")}
+            for _ in range(3):
+                eng.step_sequence(sin, seq, sst, out=fout, want_status=False)
+            torch.cuda.synchronize()
+            sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+            for a, b in sev:
+                flush.zero_()
+                a.record()
+                eng.step_sequence(sin, seq, sst, out=fout, want_status=False)
+                b.record()
+            torch.cuda.synchronize()
+            s_ms = sum(a.elapsed_time(b) for a, b in sev) / len(sev)
+            fused["sequence"] = {"value": B / (s_ms * 1e-3), "unit": "episode-steps/s per GPU", "ms_per_step": s_ms,
+                                 "api": "BatchedOSC.step_sequence -> irlosc_step_sequence (5-action insertion sequence)"}
+        except Exception as exc:      # the sequence step needs two arm devices in the layout
+            fused["sequence"] = {"unavailable": str(exc)}
         if not args.no_e2e:
             host_in = {}
             for k, v in fin.items():

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IRLOSC_ABI_VERSION 5
+#define IRLOSC_ABI_VERSION 6
 #define IRLOSC_MAX_DEVICES 4   /* target devices per controller (DualUR5: base + 2 arms) */
 #define IRLOSC_MAX_N 32        /* robot DoF, Robot.num_joints_total (robot.py:32); DualUR5: 25 */
 #define IRLOSC_MAX_K 24        /* stacked task rows, sum of ctrlr_dof over targets; DualUR5: <= 13 */
@@ -196,6 +196,48 @@ typedef struct irlosc_fused_io {
     double *ee_quat;          /* [B][D][4]   out, optional: DeviceState.EE_QUAT (w x y z, w >= 0 branch) */
 } irlosc_fused_io;
 
+/* ------------------------------------------------------------------------------------------
+ * Action sequences: the step AFTER the path.  The reference's insertion demo drives
+ * `OSC.generate` from a per-robot state machine - `run_sequence` over WP / GRIP actions
+ * (examples/insertion_task.py:312-317), `go_to_waypoint` (279-297: loop until the pose error of the
+ * active arm is <= max_error, max_vel[0] = clip(kp * error, min_speed, max_speed) every step),
+ * `grip` (190-204: hold for a duration), `send_forces` (146-179: gripper force override, error
+ * update) and `set_waypoint_targets` (206-268: the passive arm holds the xyz it has when a WP starts).
+ * `irlosc_step_sequence` runs that state machine per instance inside the fused step, so a batch of
+ * episodes advances without host round trips. */
+#define IRLOSC_MAX_ACTIONS 16
+#define IRLOSC_ACT_WP 0
+#define IRLOSC_ACT_GRIP 1
+
+typedef struct irlosc_action {
+    int32_t type;             /* IRLOSC_ACT_WP | IRLOSC_ACT_GRIP                   (insertion_task.py:22-29) */
+    int32_t grip_steps;       /* GRIP: control steps the action lasts (gripper_duration / step period)        */
+    double kp, max_error, min_speed_xyz, max_speed_xyz;     /* WP parameters      (insertion_task.py:88-96) */
+    double gripper_force;     /* written to the gripper's ctrl slot when non-zero  (insertion_task.py:160-161) */
+} irlosc_action;
+
+typedef struct irlosc_sequence {
+    int32_t n_actions;
+    int32_t active_device;    /* target-order index of the active arm              (insertion_task.py:115-128) */
+    int32_t gripper_slot;     /* packed ctrl slot that receives gripper_force (sim.data.ctrl[7] / [14]), -1 none */
+    int32_t reserved_;
+    double passive_quat[4];   /* DEFAULT_EE_QUAT, target orientation of the passive arm (insertion_task.py:213) */
+    irlosc_action action[IRLOSC_MAX_ACTIONS];
+} irlosc_sequence;
+
+/* Per-instance episode state and waypoints (device pointers). */
+typedef struct irlosc_sequence_io {
+    const double *wp_xyz;     /* [B][n_actions][3] active-arm target of every WP action (set_waypoint_targets) */
+    const double *wp_quat;    /* [B][n_actions][4]                                                             */
+    int32_t *action;          /* [B] in/out: current action, n_actions = sequence finished (holds last targets) */
+    int32_t *entered;         /* [B] in/out: 1 once the current action has run its first step                  */
+    int32_t *timer;           /* [B] in/out: remaining steps of a GRIP action                                  */
+    double *err;              /* [B] in/out: self.errors[active arm] (inf when a WP starts)                    */
+    double *max_vel0;         /* [B] in/out: active_arm.max_vel[0], persists across actions (insertion_task.py:294) */
+    double *target_xyz;       /* [B][D][3] in/out: self.targets, used instead of irlosc_fused_io.target_xyz    */
+    double *target_quat;      /* [B][D][4] in/out                                                              */
+} irlosc_sequence_io;
+
 typedef struct irlosc_handle irlosc_handle;
 
 /* Thread-local, human-readable description of the last failure on this thread. */
@@ -232,6 +274,10 @@ int32_t irlosc_set_model(irlosc_handle *h, const irlosc_model *model);
 int32_t irlosc_step_fused(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_device, void *cuda_stream);
 /* Same with HOST buffers, pipelined in chunks like irlosc_step_host. */
 int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_host);
+/* One control step of B episodes of an action sequence: state machine + fused step in one kernel.
+ * io->target_xyz / target_quat are ignored (the targets live in sio). */
+int32_t irlosc_step_sequence(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_device, const irlosc_sequence *seq,
+                             const irlosc_sequence_io *sio_device, void *cuda_stream);
 
 /* Replaces: OSC.calc_error (osc.py:101-118), also called by insertion_task.py:173-179.
  * err[B][D][6] (unmasked), device pointers, asynchronous. */

@@ -13,7 +13,9 @@ MAX_DEVICES = 4
 MAX_N = 32
 MAX_K = 24
 MAX_PEERS = 8
-ABI_VERSION = 5
+ABI_VERSION = 6
+MAX_ACTIONS = 16
+ACT_WP, ACT_GRIP = 0, 1
 
 ST_PINV = 0x01
 ST_M_NOT_PD = 0x02
@@ -121,8 +123,24 @@ class FusedIo(C.Structure):
     ]
 
 
+class Action(C.Structure):
+    _fields_ = [("type", C.c_int32), ("grip_steps", C.c_int32), ("kp", C.c_double), ("max_error", C.c_double),
+                ("min_speed_xyz", C.c_double), ("max_speed_xyz", C.c_double), ("gripper_force", C.c_double)]
+
+
+class Sequence(C.Structure):
+    _fields_ = [("n_actions", C.c_int32), ("active_device", C.c_int32), ("gripper_slot", C.c_int32),
+                ("reserved_", C.c_int32), ("passive_quat", C.c_double * 4), ("action", Action * MAX_ACTIONS)]
+
+
+class SequenceIo(C.Structure):
+    _fields_ = [("wp_xyz", C.c_void_p), ("wp_quat", C.c_void_p), ("action", C.c_void_p), ("entered", C.c_void_p),
+                ("timer", C.c_void_p), ("err", C.c_void_p), ("max_vel0", C.c_void_p),
+                ("target_xyz", C.c_void_p), ("target_quat", C.c_void_p)]
+
+
 EXPORTS = [
-    "irlosc_set_model", "irlosc_step_fused", "irlosc_step_fused_host",
+    "irlosc_set_model", "irlosc_step_fused", "irlosc_step_fused_host", "irlosc_step_sequence",
     "irlosc_last_error", "irlosc_abi_version", "irlosc_create", "irlosc_destroy",
     "irlosc_num_task_rows", "irlosc_num_ctrl", "irlosc_step", "irlosc_step_host",
     "irlosc_calc_error", "irlosc_host_alloc", "irlosc_host_free", "irlosc_set_kernel", "irlosc_set_sm_margin",
@@ -170,6 +188,9 @@ def load() -> C.CDLL:
     lib.irlosc_step_fused.argtypes = [C.c_void_p, C.c_int64, C.POINTER(FusedIo), C.c_void_p]
     lib.irlosc_step_fused_host.restype = C.c_int32
     lib.irlosc_step_fused_host.argtypes = [C.c_void_p, C.c_int64, C.POINTER(FusedIo)]
+    lib.irlosc_step_sequence.restype = C.c_int32
+    lib.irlosc_step_sequence.argtypes = [C.c_void_p, C.c_int64, C.POINTER(FusedIo), C.POINTER(Sequence),
+                                         C.POINTER(SequenceIo), C.c_void_p]
     lib.irlosc_calc_error.restype = C.c_int32
     lib.irlosc_calc_error.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_void_p]
     lib.irlosc_host_alloc.restype = C.c_int32

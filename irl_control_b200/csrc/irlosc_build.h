@@ -206,6 +206,31 @@ inline int32_t build_kmodel(const KParams &P, const irlosc_model &m, fused::KMod
     return IRLOSC_OK;
 }
 
+// irlosc_sequence -> kernel constants, validated against the controller description.
+inline int32_t build_kseq(const KParams &P, const fused::FRoles &R, const irlosc_sequence &u, fused::KSeq &Q) {
+    memset(&Q, 0, sizeof Q);
+    if (u.n_actions < 1 || u.n_actions > IRLOSC_MAX_ACTIONS)
+        return fail(IRLOSC_ERR_INVALID, "n_actions=%d outside 1..%d", u.n_actions, IRLOSC_MAX_ACTIONS);
+    if (u.active_device != R.dev_arm[0] && u.active_device != R.dev_arm[1])
+        return fail(IRLOSC_ERR_INVALID, "active_device=%d is not one of the arm devices", u.active_device);
+    if (u.gripper_slot < -1 || u.gripper_slot >= P.n_ctrl) return fail(IRLOSC_ERR_INVALID, "gripper_slot=%d outside -1..%d", u.gripper_slot, P.n_ctrl - 1);
+    Q.n_actions = u.n_actions;
+    Q.active_dev = u.active_device;
+    Q.gripper_slot = u.gripper_slot;
+    for (int i = 0; i < 4; ++i) Q.passive_quat[i] = u.passive_quat[i];
+    for (int a = 0; a < u.n_actions; ++a) {
+        const irlosc_action &s = u.action[a];
+        if (s.type != IRLOSC_ACT_WP && s.type != IRLOSC_ACT_GRIP) return fail(IRLOSC_ERR_INVALID, "action %d: unknown type %d", a, s.type);
+        if (s.type == IRLOSC_ACT_GRIP && s.grip_steps < 0) return fail(IRLOSC_ERR_INVALID, "action %d: negative grip_steps", a);
+        Q.act[a].type = s.type;
+        Q.act[a].grip_steps = s.grip_steps;
+        Q.act[a].kp = s.kp; Q.act[a].max_error = s.max_error;
+        Q.act[a].min_speed = s.min_speed_xyz; Q.act[a].max_speed = s.max_speed_xyz;
+        Q.act[a].gripper_force = s.gripper_force;
+    }
+    return IRLOSC_OK;
+}
+
 // Copy plan of the streaming step (osc_stream.cuh): which doubles of an instance's arrays go to which
 // stage entry of which group, as 8-entry chunks with per-lane byte offsets.  Works for every M / J
 // layout and stride of irlosc_io because a chunk carries its array's base pointer and stride.

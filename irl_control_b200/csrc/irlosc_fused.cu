@@ -28,13 +28,16 @@ struct FusedEntry {
     const void *step, *fixup;
     int rec_doubles;
     const char *name;
+    const void *step_seq;     // same kernel with the action-sequence state machine compiled in (variant 0 only)
 };
 
 template <int KD, bool HB, int NT, bool SMEM>
 FusedEntry entry(int variant, const char *name) {
+    const void *seq = nullptr;
+    if constexpr (NT == 256 && SMEM) seq = (const void *)osc_step_fused<KD, HB, NT, SMEM, true>;
     return FusedEntry{KD, HB, variant, NT, SMEM ? (size_t)kScratchDoubles * NT * sizeof(double) : 0,
                       (const void *)osc_step_fused<KD, HB, NT, SMEM>, (const void *)osc_tail_fixup<KD, HB>,
-                      Rec<KD, HB>::SIZE, name};
+                      Rec<KD, HB>::SIZE, name, seq};
 }
 
 const FusedEntry *fused_table(int *count) {
@@ -85,10 +88,13 @@ int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
     k.q = io->q; k.dq = io->dq; k.target_xyz = io->target_xyz; k.target_quat = io->target_quat;
     k.target_vel = io->target_vel; k.max_vel = io->max_vel; k.ft_raw = io->ft_raw;
     k.ctrl = io->ctrl; k.u_all = io->u_all; k.status = io->status; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    k.wp_xyz = k.wp_quat = nullptr;
+    k.seq_action = k.seq_entered = k.seq_timer = nullptr;
+    k.seq_err = k.seq_mv0 = k.seq_tgt_xyz = k.seq_tgt_quat = nullptr;
     return IRLOSC_OK;
 }
 
-int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st) {
+int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st, const KSeq *seq = nullptr) {
     const int variant = (h->kernel_choice >= 2 && h->kernel_choice < 9) ? h->kernel_choice - 2 : 0;
     const FusedEntry *e = fused_find(h->fused_kd, h->fused_base, variant);
     if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d variant=%d", h->fused_kd, (int)h->fused_base, variant);
@@ -99,8 +105,15 @@ int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st)
     HardQueue hq{hb.count, (int)std::min<int64_t>(hb.cap, INT32_MAX), e->rec_doubles, hb.rec, hb.inst};
     const int sms = std::max(1, h->sm_count - h->sm_margin);
     const int grid = (int)std::min<int64_t>((B + e->threads - 1) / e->threads, (int64_t)sms);
-    void *args[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr, (void *)&hq};
-    cudaError_t err = cudaLaunchKernel(e->step, dim3(grid), dim3(e->threads), args, e->smem, st);
+    static const KSeq no_seq = {};
+    const void *fn = e->step;
+    if (seq) {
+        if (!e->step_seq) return fail(IRLOSC_ERR_INVALID, "the action-sequence step exists for fused variant 0 only");
+        fn = e->step_seq;
+    }
+    void *args[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr, (void *)&hq,
+                    (void *)(seq ? seq : &no_seq)};
+    cudaError_t err = cudaLaunchKernel(fn, dim3(grid), dim3(e->threads), args, e->smem, st);
     if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fused kernel launch: %s", cudaGetErrorString(err));
     const int fgrid = (int)std::min<int64_t>((B + 3) / 4, (int64_t)sms * 4);
     TailOut tout;
@@ -243,6 +256,8 @@ extern "C" int32_t irlosc_set_model(irlosc_handle *h, const irlosc_model *m) {
     const FusedEntry *t = fused_table(&cnt);
     for (int i = 0; i < cnt; ++i) {
         CUDA_TRY(cudaFuncSetAttribute(t[i].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t[i].smem));
+        if (t[i].step_seq)
+            CUDA_TRY(cudaFuncSetAttribute(t[i].step_seq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t[i].smem));
         if (t[i].smem == 0)    // scratch in local memory: give the whole SM to L1
             CUDA_TRY(cudaFuncSetAttribute(t[i].step, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
     }
@@ -261,6 +276,31 @@ extern "C" int32_t irlosc_step_fused(irlosc_handle *h, int64_t B, const irlosc_f
     int32_t rc = check_fio(h, io, k);
     if (rc != IRLOSC_OK) return rc;
     return launch_fused(h, B, k, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int32_t irlosc_step_sequence(irlosc_handle *h, int64_t B, const irlosc_fused_io *io, const irlosc_sequence *seq,
+                                        const irlosc_sequence_io *sio, void *cuda_stream) {
+    if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
+    if (!h->has_model) return fail(IRLOSC_ERR_INVALID, "irlosc_set_model has not been called");
+    if (!io || !seq || !sio) return fail(IRLOSC_ERR_INVALID, "null argument");
+    if (B < 0) return fail(IRLOSC_ERR_INVALID, "B=%lld is negative", (long long)B);
+    if (B == 0) return IRLOSC_OK;
+    if (!sio->wp_xyz || !sio->wp_quat || !sio->action || !sio->entered || !sio->timer || !sio->err || !sio->max_vel0 ||
+        !sio->target_xyz || !sio->target_quat)
+        return fail(IRLOSC_ERR_INVALID, "every array of irlosc_sequence_io is required");
+    KSeq Q;
+    int32_t rc = build_kseq(h->kp, h->fr, *seq, Q);
+    if (rc != IRLOSC_OK) return rc;
+    irlosc_fused_io io2 = *io;
+    io2.target_xyz = sio->target_xyz;            // the targets live in the episode state
+    io2.target_quat = sio->target_quat;
+    FIo k;
+    rc = check_fio(h, &io2, k);
+    if (rc != IRLOSC_OK) return rc;
+    k.wp_xyz = sio->wp_xyz; k.wp_quat = sio->wp_quat;
+    k.seq_action = sio->action; k.seq_entered = sio->entered; k.seq_timer = sio->timer;
+    k.seq_err = sio->err; k.seq_mv0 = sio->max_vel0; k.seq_tgt_xyz = sio->target_xyz; k.seq_tgt_quat = sio->target_quat;
+    return launch_fused(h, B, k, (cudaStream_t)cuda_stream, &Q);
 }
 
 extern "C" int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irlosc_fused_io *io) {

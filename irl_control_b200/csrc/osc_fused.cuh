@@ -36,6 +36,7 @@
 #include "irlosc_device.cuh"
 #include "osc_fused_types.h"
 #include "osc_tail.cuh"
+#include "osc_sequence.cuh"
 
 namespace irlosc {
 namespace fused {
@@ -233,13 +234,13 @@ IRLOSC_HD void mat_to_quat(const double *R, double *q) {
 // osc.py:159-168,179-181 for one device whose EE pose is known: the task signal before the
 // velocity-tracking term, plus the rotated F/T wrench when admittance is on -> gpre[row].
 IRLOSC_HD void device_signal_early(const KParams &P, const FIo &io, int64_t inst, int d, const double *ee_p,
-                                   const double *Ree, const double *Rft, bool has_ft, double *gpre) {
+                                   const double *ee_q, const double *Rft, bool has_ft, double mv0_override,
+                                   double *gpre) {
     const int D = P.D;
     const KDevice &dv = P.dev[d];
-    double ee_q[4];
-    mat_to_quat(Ree, ee_q);
     double mv[2] = {dv.max_vel[0], dv.max_vel[1]};
     if (io.max_vel) { mv[0] = io.max_vel[(inst * D + d) * 2]; mv[1] = io.max_vel[(inst * D + d) * 2 + 1]; }
+    if (mv0_override >= 0.0) mv[0] = mv0_override;            // action-sequence mode: active_arm.max_vel[0]
     double u6[6], txyz[3], tquat[4];
 #pragma unroll
     for (int i = 0; i < 3; ++i) txyz[i] = io.target_xyz[(inst * D + d) * 3 + i];
@@ -270,9 +271,9 @@ IRLOSC_HD void device_signal_early(const KParams &P, const FIo &io, int64_t inst
 
 // Returns true when the instance was queued for the eigen fix-up (outputs of the chain joints are
 // then written by osc_fused_fixup / fixup_finish).
-template <int KD, bool HAS_BASE>
+template <int KD, bool HAS_BASE, bool SEQ = false>
 IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles &R, const FIo &io, int64_t inst,
-                              const Scratch &scr, double *hard_rec, const Debug *dbg) {
+                              const Scratch &scr, double *hard_rec, const Debug *dbg, const KSeq *Q = nullptr) {
     constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
     constexpr int N = kN;
     constexpr int KT = KD * (KD + 1) / 2;
@@ -322,12 +323,13 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
     if (HAS_BASE) {
         const int d = R.dev_base;
         const KFrame &F = Mdl.ee[d];
-        double t[3], Re[9], p[3];
+        double t[3], Re[9], p[3], eq[4];
         mat3_vec(S0.R, F.pos, t);
 #pragma unroll
         for (int i = 0; i < 3; ++i) p[i] = S0.o[i] + t[i];
         mat3_mul(S0.R, F.R, Re);
-        device_signal_early(P, io, inst, d, p, Re, Re, false, g);
+        mat_to_quat(Re, eq);
+        device_signal_early(P, io, inst, d, p, eq, Re, false, -1.0, g);
         double e6[6];
         task_force(P.row_comp[R.row_base], p, e6);
         const double jb0 = dot6(s0, e6);
@@ -337,8 +339,16 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
     }
 
     // ------------------------------------------------------------ the two arms
+    // (action-sequence mode: the active arm first - its pose decides whether a waypoint starts, and the
+    //  passive arm then latches its own xyz as target, insertion_task.py:211-213)
+    SeqResult seq{false, 0.0};
 #pragma unroll 1
-    for (int arm = 0; arm < 2; ++arm) {
+    for (int it = 0; it < 2; ++it) {
+        int arm = it;
+        if (SEQ) {
+            const int act_arm = (R.dev_arm[0] == Q->active_dev) ? 0 : 1;
+            arm = it == 0 ? act_arm : 1 - act_arm;
+        }
         const int jb = 1 + 12 * arm;
         const int dev = R.dev_arm[arm];
         const int row_a = R.row_arm[arm];
@@ -386,9 +396,20 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 #pragma unroll
             for (int i = 0; i < 3; ++i) ee_p[i] = Bc.o[i] + t[i];
             mat3_mul(Bc.R, F.R, Re);
+            double ee_q[4], mv0 = -1.0;
+            mat_to_quat(Re, ee_q);
+            if (SEQ) {
+                if (dev == Q->active_dev) {
+                    seq = seq_advance(*Q, P.dev[dev], io, inst, D, ee_p, ee_q);
+                    mv0 = io.seq_mv0[inst];
+                } else if (seq.entered_wp) {
+                    for (int i = 0; i < 3; ++i) io.seq_tgt_xyz[(inst * D + dev) * 3 + i] = ee_p[i];
+                    for (int i = 0; i < 4; ++i) io.seq_tgt_quat[(inst * D + dev) * 4 + i] = Q->passive_quat[i];
+                }
+            }
             const KFrame &T = Mdl.ft[dev];
             if (P.admittance && T.has) mat3_mul(Bc.R, T.R, Rf);
-            device_signal_early(P, io, inst, dev, ee_p, Re, Rf, T.has != 0, g);
+            device_signal_early(P, io, inst, dev, ee_p, ee_q, Rf, T.has != 0, mv0, g);
 #pragma unroll
             for (int cr = 0; cr < KD; ++cr) {
                 double e0[6];
@@ -525,9 +546,13 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
     const double base_st = fma(cu_st, uv_st, gb * b_st);
     if (dbg && dbg->uv) { dbg->uv[0] = uv_st; dbg->bias[0] = b_st; }
 
-    return osc_tail<KD, HAS_BASE>(P, R, io.target_vel ? io.target_vel + inst * D * 6 : nullptr, vel_zero, flags, m_ok, akA, j0,
-                                  jst, dxr, g, jarm, base_arm, base_st, inv0, io.u_all ? io.u_all + inst * N : nullptr,
-                                  io.ctrl + inst * P.n_ctrl, io.status ? io.status + inst : nullptr, hard_rec, dbg);
+    const bool hard = osc_tail<KD, HAS_BASE>(P, R, io.target_vel ? io.target_vel + inst * D * 6 : nullptr, vel_zero, flags,
+                                             m_ok, akA, j0, jst, dxr, g, jarm, base_arm, base_st, inv0,
+                                             io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl,
+                                             io.status ? io.status + inst : nullptr, hard_rec, dbg);
+    // send_forces: `if gripper_force: sim.data.ctrl[gripper_idx] = gripper_force` (insertion_task.py:160-161)
+    if (SEQ && seq.gripper_force != 0.0 && Q->gripper_slot >= 0) io.ctrl[inst * P.n_ctrl + Q->gripper_slot] = seq.gripper_force;
+    return hard;
 }
 
 #if defined(__CUDACC__) && !defined(IRLOSC_FUSED_NO_KERNELS)
@@ -535,17 +560,18 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 // SMEM = true: the per-thread chain scratch lives in shared memory (strided, conflict-free);
 // SMEM = false: in local memory, leaving the whole 256 KB of the SM to L1, which then also catches
 // the register spills and the small dynamically indexed arrays.
-template <int KD, bool HAS_BASE, int NT, bool SMEM>
+template <int KD, bool HAS_BASE, int NT, bool SMEM, bool SEQ = false>
 __global__ void __launch_bounds__(NT, 1)
 osc_step_fused(const __grid_constant__ KParams P, const __grid_constant__ KModel Mdl, const __grid_constant__ FIo io,
-               const int64_t B, const __grid_constant__ FRoles R, const __grid_constant__ HardQueue hq) {
+               const int64_t B, const __grid_constant__ FRoles R, const __grid_constant__ HardQueue hq,
+               const __grid_constant__ KSeq Q) {
     extern __shared__ __align__(16) double fused_smem[];
     double chain[SMEM ? 1 : kScratchDoubles];
     const Scratch scr = SMEM ? Scratch{fused_smem + threadIdx.x, NT} : Scratch{chain, 1};
     for (int64_t inst = (int64_t)blockIdx.x * NT + threadIdx.x; inst < B; inst += (int64_t)gridDim.x * NT) {
         // record memory is indexed by instance (capacity >= B): only the queue slot needs an atomic
         double *rec = hq.rec ? hq.rec + (size_t)inst * hq.rec_doubles : nullptr;
-        const bool hard = fused_instance<KD, HAS_BASE>(P, Mdl, R, io, inst, scr, rec, nullptr);
+        const bool hard = fused_instance<KD, HAS_BASE, SEQ>(P, Mdl, R, io, inst, scr, rec, nullptr, SEQ ? &Q : nullptr);
         if (hard) {
             const int slot = atomicAdd(hq.count, 1);
             hq.inst[slot] = inst;

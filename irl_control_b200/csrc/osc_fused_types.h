@@ -34,6 +34,19 @@ struct FIo {
     double *ctrl, *u_all;
     uint8_t *status;
     double *ee_xyz, *ee_quat;
+    // action-sequence mode (irlosc_step_sequence): episode state, see irlosc_sequence_io
+    const double *wp_xyz, *wp_quat;
+    int32_t *seq_action, *seq_entered, *seq_timer;
+    double *seq_err, *seq_mv0, *seq_tgt_xyz, *seq_tgt_quat;
+};
+struct KAction {
+    int32_t type, grip_steps;
+    double kp, max_error, min_speed, max_speed, gripper_force;
+};
+struct KSeq {
+    int32_t n_actions, active_dev, gripper_slot, pad_;
+    double passive_quat[4];
+    KAction act[IRLOSC_MAX_ACTIONS];
 };
 // Instances that need the eigen path: one record each, finished by osc_fused_fixup.
 struct HardQueue {

@@ -315,6 +315,46 @@ class BatchedOSC:
             _native.check(self.lib.irlosc_step_fused_host(self._handle, B, C.byref(io)))
         return out
 
+    def step_sequence(self, state: Dict, seq, seq_state: Dict, out: Optional[Dict] = None, want_u_all: bool = False,
+                      want_status: bool = True) -> Dict:
+        """One control step of B episodes of `seq` (`sequence.ActionSequence`): the state machine of
+        examples/insertion_task.py:190-204,279-297 runs per instance inside the fused step.  `state`
+        holds q, dq (+ optional max_vel, ft_raw); the targets live in `seq_state` (updated in place)."""
+        import torch
+        q = state["q"]
+        B = int(q.shape[0])
+        st2 = dict(state, target_xyz=seq_state["target_xyz"], target_quat=seq_state["target_quat"])
+
+        def ok(name, t):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device == q.device):
+                raise ValueError("state['%s'] must be a contiguous float64 CUDA tensor on %s" % (name, q.device))
+        self._fused_check(st2, B, ok)
+        out = {} if out is None else out
+        if "ctrl" not in out:
+            out["ctrl"] = torch.empty(B, self.n_ctrl, dtype=torch.float64, device=q.device)
+        if want_u_all and "u_all" not in out:
+            out["u_all"] = torch.empty(B, self.n, dtype=torch.float64, device=q.device)
+        if want_status and "status" not in out:
+            out["status"] = torch.empty(B, dtype=torch.uint8, device=q.device)
+        io = _native.FusedIo()
+        for name in self._FUSED_FIELDS:
+            t = st2.get(name)
+            setattr(io, name, t.data_ptr() if t is not None else None)
+        for name in ("ctrl", "u_all", "status"):
+            setattr(io, name, out[name].data_ptr() if name in out else None)
+        sio = _native.SequenceIo()
+        for name in ("wp_xyz", "wp_quat", "action", "entered", "timer", "err", "max_vel0", "target_xyz", "target_quat"):
+            t = seq_state[name]
+            want = torch.int32 if name in ("action", "entered", "timer") else torch.float64
+            if not (t.is_cuda and t.dtype == want and t.is_contiguous() and t.shape[0] == B):
+                raise ValueError("seq_state['%s'] must be a contiguous %s CUDA tensor with leading axis %d" % (name, want, B))
+            setattr(sio, name, t.data_ptr())
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        with torch.cuda.device(q.device):
+            _native.check(self.lib.irlosc_step_sequence(self._handle, B, C.byref(io), C.byref(seq.c_struct),
+                                                        C.byref(sio), C.c_void_p(stream)))
+        return out
+
     def calc_error(self, ee_xyz, ee_quat, target_xyz, target_quat):
         """Batched `OSC.calc_error` (osc.py:101-118) on CUDA tensors -> (B, D, 6)."""
         import torch

@@ -1,0 +1,70 @@
+"""TEST INFRASTRUCTURE ONLY - CPU restatement of the caller loop of the reference's insertion demo.
+
+Follows ir-lab/irl_control `examples/insertion_task.py` statement by statement:
+    run_sequence            312-317
+    go_to_waypoint          279-297
+    grip                    190-204   (the wall-clock timer is counted in control steps here)
+    send_forces             146-179   (gripper override, error update)
+    set_waypoint_targets    206-268   (passive arm: current EE xyz + DEFAULT_EE_QUAT)
+The simulator is replaced by a pose stream: `poses[t]` is the state the t-th `generate` call sees,
+`poses[t + 1]` the state after its `sim.step()`.
+
+Parity unpinned: the example itself cannot run here (it needs mujoco_py, an MjViewer and the
+scene meshes), so this restatement is anchored on the source lines above only.
+"""
+import numpy as np
+
+from . import osc_numpy
+
+
+class _Stop(Exception):
+    pass
+
+
+def run_sequence(actions, wp_xyz, wp_quat, poses, active_dev, passive_quat, max_vel0, n_ticks):
+    """actions: list of dicts with the defaults applied (kp, max_error, min_speed_xyz, max_speed_xyz,
+    gripper_force, grip_steps); wp_xyz / wp_quat [A, .]: what set_waypoint_targets computes for the
+    active arm per action; poses: dict of arrays indexed by tick - active_xyz, active_quat,
+    passive_xyz; active_dev: device dict of the layout (for calc_error).
+    Returns one record per generate() call."""
+    rec = []
+    tick = [0]
+    targets = {"active_xyz": np.zeros(3), "active_quat": np.array([1.0, 0, 0, 0]),      # Target() (utils.py:10-15)
+               "passive_xyz": np.zeros(3), "passive_quat": np.array([1.0, 0, 0, 0])}
+    state = {"max_vel0": float(max_vel0), "err": 0.0}
+
+    def calc_error_norm():
+        t = tick[0]
+        return float(np.linalg.norm(osc_numpy.calc_error(active_dev, poses["active_xyz"][t], poses["active_quat"][t],
+                                                         targets["active_xyz"], targets["active_quat"])))
+
+    def generate_and_send(a, gripper_force):
+        # controller.generate(self.targets) sees the state of tick t; send_forces steps the simulator
+        rec.append(dict(tick=tick[0], action=a, err=state["err"], max_vel0=state["max_vel0"],
+                        gripper_force=float(gripper_force) if gripper_force else 0.0,
+                        **{k: np.array(v, dtype=np.float64) for k, v in targets.items()}))
+        tick[0] += 1
+        if tick[0] >= n_ticks:
+            raise _Stop
+        state["err"] = calc_error_norm()                      # insertion_task.py:169-179
+
+    try:
+        for a, p in enumerate(actions):
+            if p["action"] == "WP":
+                # set_waypoint_targets (206-268)
+                targets["passive_xyz"] = np.array(poses["passive_xyz"][tick[0]], dtype=np.float64)
+                targets["passive_quat"] = np.array(passive_quat, dtype=np.float64)
+                targets["active_xyz"] = np.array(wp_xyz[a], dtype=np.float64)
+                targets["active_quat"] = np.array(wp_quat[a], dtype=np.float64)
+                state["err"] = np.inf                         # 289
+                while state["err"] > p["max_error"]:          # 290
+                    state["max_vel0"] = max(p["min_speed_xyz"], min(p["max_speed_xyz"], p["kp"] * state["err"]))
+                    generate_and_send(a, p["gripper_force"])
+            else:
+                for _ in range(p["grip_steps"]):              # while self.timer_running (201)
+                    generate_and_send(a, p["gripper_force"])
+        while True:                                           # sequence finished: the batch keeps holding
+            generate_and_send(len(actions), 0.0)
+    except _Stop:
+        pass
+    return rec

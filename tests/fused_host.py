@@ -103,3 +103,28 @@ def run_stream(layout, state, debug=False, strides=None):
     out["n_chunks"] = int(nch.value)
     out.update(dbg)
     return out
+
+
+def sequence_step(layout, model, seq, inp, seq_state):
+    """One `irlosc_step_sequence` on the CPU (numpy arrays; seq_state is updated in place)."""
+    lib = load()
+    lib.sequence_host_step.restype = C.c_int64
+    lib.sequence_host_step.argtypes = [C.POINTER(_native.Params), C.POINTER(_native.Model), C.c_int64,
+                                       C.POINTER(_native.FusedIo), C.POINTER(_native.Sequence), C.POINTER(_native.SequenceIo)]
+    B = int(inp["q"].shape[0])
+    keep = {k_: np.ascontiguousarray(v, dtype=np.float64) for k_, v in inp.items()}
+    out = {"ctrl": np.zeros((B, layout.n_ctrl)), "u_all": np.zeros((B, layout.n)), "status": np.zeros(B, dtype=np.uint8),
+           "ee_xyz": np.zeros((B, layout.D, 3)), "ee_quat": np.zeros((B, layout.D, 4))}
+    io = _native.FusedIo()
+    for name in ("q", "dq", "target_vel", "max_vel", "ft_raw"):
+        setattr(io, name, keep[name].ctypes.data if name in keep else None)
+    for name in out:
+        setattr(io, name, out[name].ctypes.data)
+    sio = _native.SequenceIo()
+    for name in ("wp_xyz", "wp_quat", "action", "entered", "timer", "err", "max_vel0", "target_xyz", "target_quat"):
+        setattr(sio, name, seq_state[name].ctypes.data)
+    params = layout.to_c_params()
+    rc = lib.sequence_host_step(C.byref(params), C.byref(model), B, C.byref(io), C.byref(seq.c_struct), C.byref(sio))
+    if rc < 0:
+        raise RuntimeError(lib.fused_host_error().decode())
+    return out

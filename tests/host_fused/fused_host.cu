@@ -76,7 +76,8 @@ static int host_eigen_solve(const double *A0, const double *g, bool force_pinv, 
 }
 
 template <int KD, bool HB>
-static int64_t run(const KParams &P, const KModel &M, const FRoles &R, const FIo &io, int64_t B, const Debug *dbg0) {
+static int64_t run(const KParams &P, const KModel &M, const FRoles &R, const FIo &io, int64_t B, const Debug *dbg0,
+                   const KSeq *Q = nullptr) {
     using RC = Rec<KD, HB>;
     constexpr int K = RC::K;
     std::vector<double> scratch(kScratchDoubles), rec(RC::SIZE);
@@ -94,7 +95,8 @@ static int64_t run(const KParams &P, const KModel &M, const FRoles &R, const FIo
             dp = &d;
         }
         const Scratch scr{scratch.data(), 1};
-        const bool hard = fused_instance<KD, HB>(P, M, R, io, i, scr, rec.data(), dp);
+        const bool hard = Q ? fused_instance<KD, HB, true>(P, M, R, io, i, scr, rec.data(), dp, Q)
+                            : fused_instance<KD, HB, false>(P, M, R, io, i, scr, rec.data(), dp);
         if (hard) {
             ++n_hard;
             double w[K];
@@ -124,12 +126,42 @@ extern "C" int64_t fused_host_run(const irlosc_params *params, const irlosc_mode
     k.q = io->q; k.dq = io->dq; k.target_xyz = io->target_xyz; k.target_quat = io->target_quat;
     k.target_vel = io->target_vel; k.max_vel = io->max_vel; k.ft_raw = io->ft_raw;
     k.ctrl = io->ctrl; k.u_all = io->u_all; k.status = io->status; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    k.wp_xyz = k.wp_quat = nullptr;
+    k.seq_action = k.seq_entered = k.seq_timer = nullptr;
+    k.seq_err = k.seq_mv0 = k.seq_tgt_xyz = k.seq_tgt_quat = nullptr;
     Debug d{dbg_A, dbg_g, dbg_uv, dbg_bias, dbg_dx, dbg_J};
     const Debug *dp = (dbg_A || dbg_uv || dbg_J) ? &d : nullptr;
     if (kd == 3 && hb) return run<3, true>(P, M, R, k, B, dp);
     if (kd == 3 && !hb) return run<3, false>(P, M, R, k, B, dp);
     if (kd == 6 && hb) return run<6, true>(P, M, R, k, B, dp);
     return run<6, false>(P, M, R, k, B, dp);
+}
+
+// One control step of an action sequence (irlosc_step_sequence) on the CPU.
+extern "C" int64_t sequence_host_step(const irlosc_params *params, const irlosc_model *model, int64_t B,
+                                      const irlosc_fused_io *io, const irlosc_sequence *seq,
+                                      const irlosc_sequence_io *sio) {
+    KParams P;
+    if (build_kparams(*params, P) != IRLOSC_OK) return -1;
+    FRoles R;
+    int kd = 0;
+    bool hb = false;
+    if (!fused_roles(P, R, kd, hb)) { irlosc::fail(1, "not the DualUR5 topology"); return -1; }
+    KModel M;
+    if (build_kmodel(P, *model, M) != IRLOSC_OK) return -1;
+    KSeq Q;
+    if (build_kseq(P, R, *seq, Q) != IRLOSC_OK) return -1;
+    FIo k;
+    k.q = io->q; k.dq = io->dq; k.target_xyz = sio->target_xyz; k.target_quat = sio->target_quat;
+    k.target_vel = io->target_vel; k.max_vel = io->max_vel; k.ft_raw = io->ft_raw;
+    k.ctrl = io->ctrl; k.u_all = io->u_all; k.status = io->status; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    k.wp_xyz = sio->wp_xyz; k.wp_quat = sio->wp_quat;
+    k.seq_action = sio->action; k.seq_entered = sio->entered; k.seq_timer = sio->timer;
+    k.seq_err = sio->err; k.seq_mv0 = sio->max_vel0; k.seq_tgt_xyz = sio->target_xyz; k.seq_tgt_quat = sio->target_quat;
+    if (kd == 3 && hb) return run<3, true>(P, M, R, k, B, nullptr, &Q);
+    if (kd == 3 && !hb) return run<3, false>(P, M, R, k, B, nullptr, &Q);
+    if (kd == 6 && hb) return run<6, true>(P, M, R, k, B, nullptr, &Q);
+    return run<6, false>(P, M, R, k, B, nullptr, &Q);
 }
 
 // ------------------------------------------------------------------ streaming step (state given)
