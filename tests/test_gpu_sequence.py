@@ -46,12 +46,15 @@ def test_sequence_on_gpu_matches_reference_loop_and_fused_step():
             mv2[:, seq.active_device, 0] = st["max_vel0"]
             ref = eng.step_fused({"q": qd[t].contiguous(), "dq": dqd[t].contiguous(), "max_vel": mv2,
                                   "target_xyz": st["target_xyz"], "target_quat": st["target_quat"]}, want_u_all=True)
-            assert torch.equal(out["u_all"], ref["u_all"])
+            # (another template instantiation, and the active arm is processed first: equal up to rounding)
+            scale = ref["u_all"].abs().amax(dim=1, keepdim=True)
+            assert ((out["u_all"] - ref["u_all"]).abs() / scale).max().item() < 1e-9
             gf = torch.tensor([p["gripper_force"] for p in seq.params] + [0.0], dtype=torch.float64, device=dev)[st["action"].long()]
             want = ref["ctrl"].clone()
             sel = gf != 0
             want[sel, seq.gripper_slot] = gf[sel]
-            assert torch.equal(out["ctrl"], want)
+            assert ((out["ctrl"] - want).abs() / scale).max().item() < 1e-9
+            assert torch.equal(out["ctrl"][sel, seq.gripper_slot], gf[sel])
             recs.append({k: st[k][:n_chk].cpu().numpy().copy() for k in ("action", "err", "max_vel0", "target_xyz", "target_quat")})
         d = layout.as_dict()["devices"][ia]
         for i in range(n_chk):
