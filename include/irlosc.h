@@ -238,6 +238,20 @@ typedef struct irlosc_sequence_io {
     double *target_quat;      /* [B][D][4] in/out                                                              */
 } irlosc_sequence_io;
 
+/* Waypoint cycling of the gain_test demo (examples/gain_test.py:134-162): every arm walks its own
+ * list of xyz waypoints; after each generate the distance |EE_XYZ - target| is compared with a
+ * threshold and the arm's waypoint index advances (wrapping) when it is below. */
+typedef struct irlosc_waypoints_io {
+    const double *wps;        /* [B][D][W][3] waypoint lists per target device (rows of devices that are not arms are ignored) */
+    int32_t W;                /* allocated waypoints per device                                                */
+    int32_t n_wp[IRLOSC_MAX_DEVICES]; /* used waypoints per device (right_wps.shape[0] / left_wps.shape[0])      */
+    int32_t reserved_;
+    double threshold;         /* threshold_ee = 0.1                                  (gain_test.py:121)        */
+    int32_t *wp_idx;          /* [B][D] in/out: right_wp_idx / left_wp_idx                                     */
+    double *target_xyz;       /* [B][D][3] in/out: targets[...].xyz, used instead of irlosc_fused_io.target_xyz */
+    double *target_quat;      /* [B][D][4] in: Target() default [1,0,0,0] unless the caller changed it         */
+} irlosc_waypoints_io;
+
 typedef struct irlosc_handle irlosc_handle;
 
 /* Thread-local, human-readable description of the last failure on this thread. */
@@ -278,6 +292,9 @@ int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irlosc_fused_i
  * io->target_xyz / target_quat are ignored (the targets live in sio). */
 int32_t irlosc_step_sequence(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_device, const irlosc_sequence *seq,
                              const irlosc_sequence_io *sio_device, void *cuda_stream);
+/* One control step of B gain_test-style episodes: waypoint cycling + fused step in one kernel. */
+int32_t irlosc_step_waypoints(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_device,
+                              const irlosc_waypoints_io *wio_device, void *cuda_stream);
 
 /* Replaces: OSC.calc_error (osc.py:101-118), also called by insertion_task.py:173-179.
  * err[B][D][6] (unmasked), device pointers, asynchronous. */

@@ -139,8 +139,13 @@ class SequenceIo(C.Structure):
                 ("target_xyz", C.c_void_p), ("target_quat", C.c_void_p)]
 
 
+class WaypointsIo(C.Structure):
+    _fields_ = [("wps", C.c_void_p), ("W", C.c_int32), ("n_wp", C.c_int32 * MAX_DEVICES), ("reserved_", C.c_int32),
+                ("threshold", C.c_double), ("wp_idx", C.c_void_p), ("target_xyz", C.c_void_p), ("target_quat", C.c_void_p)]
+
+
 EXPORTS = [
-    "irlosc_set_model", "irlosc_step_fused", "irlosc_step_fused_host", "irlosc_step_sequence",
+    "irlosc_set_model", "irlosc_step_fused", "irlosc_step_fused_host", "irlosc_step_sequence", "irlosc_step_waypoints",
     "irlosc_last_error", "irlosc_abi_version", "irlosc_create", "irlosc_destroy",
     "irlosc_num_task_rows", "irlosc_num_ctrl", "irlosc_step", "irlosc_step_host",
     "irlosc_calc_error", "irlosc_host_alloc", "irlosc_host_free", "irlosc_set_kernel", "irlosc_set_sm_margin",
@@ -191,6 +196,8 @@ def load() -> C.CDLL:
     lib.irlosc_step_sequence.restype = C.c_int32
     lib.irlosc_step_sequence.argtypes = [C.c_void_p, C.c_int64, C.POINTER(FusedIo), C.POINTER(Sequence),
                                          C.POINTER(SequenceIo), C.c_void_p]
+    lib.irlosc_step_waypoints.restype = C.c_int32
+    lib.irlosc_step_waypoints.argtypes = [C.c_void_p, C.c_int64, C.POINTER(FusedIo), C.POINTER(WaypointsIo), C.c_void_p]
     lib.irlosc_calc_error.restype = C.c_int32
     lib.irlosc_calc_error.argtypes = [C.c_void_p, C.c_int64] + [C.c_void_p] * 5 + [C.c_void_p]
     lib.irlosc_host_alloc.restype = C.c_int32

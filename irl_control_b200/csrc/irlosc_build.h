@@ -231,6 +231,24 @@ inline int32_t build_kseq(const KParams &P, const fused::FRoles &R, const irlosc
     return IRLOSC_OK;
 }
 
+inline int32_t build_kseq_waypoints(const KParams &P, const fused::FRoles &R, const irlosc_waypoints_io &u, fused::KSeq &Q) {
+    memset(&Q, 0, sizeof Q);
+    if (!u.wps || !u.wp_idx || !u.target_xyz || !u.target_quat) return fail(IRLOSC_ERR_INVALID, "every array of irlosc_waypoints_io is required");
+    if (u.W < 1) return fail(IRLOSC_ERR_INVALID, "W=%d", u.W);
+    Q.mode = 1;
+    Q.active_dev = R.dev_arm[0];
+    Q.gripper_slot = -1;
+    Q.W = u.W;
+    Q.threshold = u.threshold;
+    for (int a = 0; a < 2; ++a) {
+        const int d = R.dev_arm[a];
+        if (u.n_wp[d] < 1 || u.n_wp[d] > u.W) return fail(IRLOSC_ERR_INVALID, "n_wp[%d]=%d outside 1..W=%d", d, u.n_wp[d], u.W);
+    }
+    for (int d = 0; d < IRLOSC_MAX_DEVICES; ++d) Q.n_wp[d] = u.n_wp[d];
+    (void)P;
+    return IRLOSC_OK;
+}
+
 // Copy plan of the streaming step (osc_stream.cuh): which doubles of an instance's arrays go to which
 // stage entry of which group, as 8-entry chunks with per-lane byte offsets.  Works for every M / J
 // layout and stride of irlosc_io because a chunk carries its array's base pointer and stride.

@@ -91,6 +91,8 @@ int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
     k.wp_xyz = k.wp_quat = nullptr;
     k.seq_action = k.seq_entered = k.seq_timer = nullptr;
     k.seq_err = k.seq_mv0 = k.seq_tgt_xyz = k.seq_tgt_quat = nullptr;
+    k.wps = nullptr;
+    k.wp_idx = nullptr;
     return IRLOSC_OK;
 }
 
@@ -300,6 +302,26 @@ extern "C" int32_t irlosc_step_sequence(irlosc_handle *h, int64_t B, const irlos
     k.wp_xyz = sio->wp_xyz; k.wp_quat = sio->wp_quat;
     k.seq_action = sio->action; k.seq_entered = sio->entered; k.seq_timer = sio->timer;
     k.seq_err = sio->err; k.seq_mv0 = sio->max_vel0; k.seq_tgt_xyz = sio->target_xyz; k.seq_tgt_quat = sio->target_quat;
+    return launch_fused(h, B, k, (cudaStream_t)cuda_stream, &Q);
+}
+
+extern "C" int32_t irlosc_step_waypoints(irlosc_handle *h, int64_t B, const irlosc_fused_io *io,
+                                         const irlosc_waypoints_io *wio, void *cuda_stream) {
+    if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
+    if (!h->has_model) return fail(IRLOSC_ERR_INVALID, "irlosc_set_model has not been called");
+    if (!io || !wio) return fail(IRLOSC_ERR_INVALID, "null argument");
+    if (B < 0) return fail(IRLOSC_ERR_INVALID, "B=%lld is negative", (long long)B);
+    if (B == 0) return IRLOSC_OK;
+    KSeq Q;
+    int32_t rc = build_kseq_waypoints(h->kp, h->fr, *wio, Q);
+    if (rc != IRLOSC_OK) return rc;
+    irlosc_fused_io io2 = *io;
+    io2.target_xyz = wio->target_xyz;
+    io2.target_quat = wio->target_quat;
+    FIo k;
+    rc = check_fio(h, &io2, k);
+    if (rc != IRLOSC_OK) return rc;
+    k.wps = wio->wps; k.wp_idx = wio->wp_idx; k.seq_tgt_xyz = wio->target_xyz; k.seq_tgt_quat = wio->target_quat;
     return launch_fused(h, B, k, (cudaStream_t)cuda_stream, &Q);
 }
 

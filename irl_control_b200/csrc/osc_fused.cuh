@@ -345,7 +345,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 #pragma unroll 1
     for (int it = 0; it < 2; ++it) {
         int arm = it;
-        if (SEQ) {
+        if (SEQ && Q->mode == 0) {
             const int act_arm = (R.dev_arm[0] == Q->active_dev) ? 0 : 1;
             arm = it == 0 ? act_arm : 1 - act_arm;
         }
@@ -398,7 +398,17 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
             mat3_mul(Bc.R, F.R, Re);
             double ee_q[4], mv0 = -1.0;
             mat_to_quat(Re, ee_q);
-            if (SEQ) {
+            if (SEQ && Q->mode == 1) {
+                // gain_test.py:138-158: target = wps[idx]; after generate, |EE_XYZ - target| < threshold -> next
+                // waypoint (wrapping).  The comparison uses the state this step is computed from.
+                int idx = io.wp_idx[inst * D + dev];
+                const double *wp = io.wps + (((size_t)inst * D + dev) * Q->W + idx) * 3;
+                double *tx = io.seq_tgt_xyz + (inst * D + dev) * 3;
+                double e2 = 0.0;
+                for (int i = 0; i < 3; ++i) { tx[i] = wp[i]; const double dlt = ee_p[i] - wp[i]; e2 = fma(dlt, dlt, e2); }
+                if (sqrt(e2) < Q->threshold) idx = (idx < Q->n_wp[dev] - 1) ? idx + 1 : 0;
+                io.wp_idx[inst * D + dev] = idx;
+            } else if (SEQ) {
                 if (dev == Q->active_dev) {
                     seq = seq_advance(*Q, P.dev[dev], io, inst, D, ee_p, ee_q);
                     mv0 = io.seq_mv0[inst];

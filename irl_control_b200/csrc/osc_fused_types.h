@@ -38,13 +38,19 @@ struct FIo {
     const double *wp_xyz, *wp_quat;
     int32_t *seq_action, *seq_entered, *seq_timer;
     double *seq_err, *seq_mv0, *seq_tgt_xyz, *seq_tgt_quat;
+    // waypoint-cycling mode (irlosc_step_waypoints), see irlosc_waypoints_io
+    const double *wps;
+    int32_t *wp_idx;
 };
 struct KAction {
     int32_t type, grip_steps;
     double kp, max_error, min_speed, max_speed, gripper_force;
 };
 struct KSeq {
-    int32_t n_actions, active_dev, gripper_slot, pad_;
+    int32_t n_actions, active_dev, gripper_slot;
+    int32_t mode;                      // 0 action sequence (insertion_task.py), 1 waypoint cycling (gain_test.py)
+    int32_t W, n_wp[IRLOSC_MAX_DEVICES], pad_;
+    double threshold;
     double passive_quat[4];
     KAction act[IRLOSC_MAX_ACTIONS];
 };

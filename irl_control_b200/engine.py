@@ -355,6 +355,51 @@ class BatchedOSC:
                                                         C.byref(sio), C.c_void_p(stream)))
         return out
 
+    def step_waypoints(self, state: Dict, wp_state: Dict, threshold: float = 0.1, out: Optional[Dict] = None,
+                       want_u_all: bool = False, want_status: bool = True) -> Dict:
+        """One control step of B gain_test-style episodes (examples/gain_test.py:134-162): every arm steers to
+        `wp_state["wps"][b, d, wp_idx[b, d]]` and moves on to its next waypoint (wrapping) once
+        `|EE_XYZ - target| < threshold`.  `wp_state`: wps [B, D, W, 3] float64, n_wp (D ints), wp_idx [B, D] int32,
+        target_xyz [B, D, 3], target_quat [B, D, 4] (updated in place)."""
+        import torch
+        q = state["q"]
+        B = int(q.shape[0])
+        st2 = dict(state, target_xyz=wp_state["target_xyz"], target_quat=wp_state["target_quat"])
+
+        def ok(name, t):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device == q.device):
+                raise ValueError("state['%s'] must be a contiguous float64 CUDA tensor on %s" % (name, q.device))
+        self._fused_check(st2, B, ok)
+        wps, idx = wp_state["wps"], wp_state["wp_idx"]
+        if not (wps.is_cuda and wps.dtype == torch.float64 and wps.is_contiguous() and wps.dim() == 4 and
+                tuple(wps.shape[:2]) == (B, self.D) and wps.shape[3] == 3):
+            raise ValueError("wp_state['wps'] must be a contiguous float64 CUDA tensor [B, D, W, 3]")
+        if not (idx.is_cuda and idx.dtype == torch.int32 and idx.is_contiguous() and tuple(idx.shape) == (B, self.D)):
+            raise ValueError("wp_state['wp_idx'] must be a contiguous int32 CUDA tensor [B, D]")
+        out = {} if out is None else out
+        if "ctrl" not in out:
+            out["ctrl"] = torch.empty(B, self.n_ctrl, dtype=torch.float64, device=q.device)
+        if want_u_all and "u_all" not in out:
+            out["u_all"] = torch.empty(B, self.n, dtype=torch.float64, device=q.device)
+        if want_status and "status" not in out:
+            out["status"] = torch.empty(B, dtype=torch.uint8, device=q.device)
+        io = _native.FusedIo()
+        for name in self._FUSED_FIELDS:
+            t = st2.get(name)
+            setattr(io, name, t.data_ptr() if t is not None else None)
+        for name in ("ctrl", "u_all", "status"):
+            setattr(io, name, out[name].data_ptr() if name in out else None)
+        wio = _native.WaypointsIo()
+        wio.wps, wio.W, wio.threshold = wps.data_ptr(), int(wps.shape[2]), float(threshold)
+        for d, n in enumerate(wp_state["n_wp"]):
+            wio.n_wp[d] = int(n)
+        wio.wp_idx = idx.data_ptr()
+        wio.target_xyz, wio.target_quat = wp_state["target_xyz"].data_ptr(), wp_state["target_quat"].data_ptr()
+        stream = torch.cuda.current_stream(q.device).cuda_stream
+        with torch.cuda.device(q.device):
+            _native.check(self.lib.irlosc_step_waypoints(self._handle, B, C.byref(io), C.byref(wio), C.c_void_p(stream)))
+        return out
+
     def calc_error(self, ee_xyz, ee_quat, target_xyz, target_quat):
         """Batched `OSC.calc_error` (osc.py:101-118) on CUDA tensors -> (B, D, 6)."""
         import torch

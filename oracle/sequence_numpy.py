@@ -68,3 +68,16 @@ def run_sequence(actions, wp_xyz, wp_quat, poses, active_dev, passive_quat, max_
     except _Stop:
         pass
     return rec
+
+
+def run_waypoint_cycle(wps, ee_xyz, threshold, n_ticks):
+    """examples/gain_test.py:134-162 for ONE arm: `wps [W, 3]` its waypoint list, `ee_xyz[t]` the EE position
+    the t-th generate() sees.  Returns (target, wp_idx before the update) per tick."""
+    idx, rec = 0, []
+    for t in range(n_ticks):
+        target = np.array(wps[idx], dtype=np.float64)            # targets[...].set_xyz(wps[idx])       (138-139)
+        rec.append((target, idx))                                # controller.generate(targets)         (143)
+        err = np.linalg.norm(ee_xyz[t] - target)                 # self.errors[...]                     (151-152)
+        if err < threshold:                                      # (153-162)
+            idx = idx + 1 if idx < len(wps) - 1 else 0
+    return rec

@@ -128,3 +128,30 @@ def sequence_step(layout, model, seq, inp, seq_state):
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
     return out
+
+
+def waypoints_step(layout, model, inp, wp_state, threshold=0.1):
+    """One `irlosc_step_waypoints` on the CPU (numpy arrays; wp_state is updated in place)."""
+    lib = load()
+    lib.waypoints_host_step.restype = C.c_int64
+    lib.waypoints_host_step.argtypes = [C.POINTER(_native.Params), C.POINTER(_native.Model), C.c_int64,
+                                        C.POINTER(_native.FusedIo), C.POINTER(_native.WaypointsIo)]
+    B = int(inp["q"].shape[0])
+    keep = {k_: np.ascontiguousarray(v, dtype=np.float64) for k_, v in inp.items()}
+    out = {"ctrl": np.zeros((B, layout.n_ctrl)), "u_all": np.zeros((B, layout.n)), "status": np.zeros(B, dtype=np.uint8)}
+    io = _native.FusedIo()
+    for name in ("q", "dq", "target_vel", "max_vel", "ft_raw"):
+        setattr(io, name, keep[name].ctypes.data if name in keep else None)
+    for name in out:
+        setattr(io, name, out[name].ctypes.data)
+    wio = _native.WaypointsIo()
+    wio.wps, wio.W, wio.threshold = wp_state["wps"].ctypes.data, int(wp_state["wps"].shape[2]), float(threshold)
+    for d, n in enumerate(wp_state["n_wp"]):
+        wio.n_wp[d] = int(n)
+    wio.wp_idx = wp_state["wp_idx"].ctypes.data
+    wio.target_xyz, wio.target_quat = wp_state["target_xyz"].ctypes.data, wp_state["target_quat"].ctypes.data
+    params = layout.to_c_params()
+    rc = lib.waypoints_host_step(C.byref(params), C.byref(model), B, C.byref(io), C.byref(wio))
+    if rc < 0:
+        raise RuntimeError(lib.fused_host_error().decode())
+    return out

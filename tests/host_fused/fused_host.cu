@@ -129,6 +129,7 @@ extern "C" int64_t fused_host_run(const irlosc_params *params, const irlosc_mode
     k.wp_xyz = k.wp_quat = nullptr;
     k.seq_action = k.seq_entered = k.seq_timer = nullptr;
     k.seq_err = k.seq_mv0 = k.seq_tgt_xyz = k.seq_tgt_quat = nullptr;
+    k.wps = nullptr; k.wp_idx = nullptr;
     Debug d{dbg_A, dbg_g, dbg_uv, dbg_bias, dbg_dx, dbg_J};
     const Debug *dp = (dbg_A || dbg_uv || dbg_J) ? &d : nullptr;
     if (kd == 3 && hb) return run<3, true>(P, M, R, k, B, dp);
@@ -158,6 +159,7 @@ extern "C" int64_t sequence_host_step(const irlosc_params *params, const irlosc_
     k.wp_xyz = sio->wp_xyz; k.wp_quat = sio->wp_quat;
     k.seq_action = sio->action; k.seq_entered = sio->entered; k.seq_timer = sio->timer;
     k.seq_err = sio->err; k.seq_mv0 = sio->max_vel0; k.seq_tgt_xyz = sio->target_xyz; k.seq_tgt_quat = sio->target_quat;
+    k.wps = nullptr; k.wp_idx = nullptr;
     if (kd == 3 && hb) return run<3, true>(P, M, R, k, B, nullptr, &Q);
     if (kd == 3 && !hb) return run<3, false>(P, M, R, k, B, nullptr, &Q);
     if (kd == 6 && hb) return run<6, true>(P, M, R, k, B, nullptr, &Q);
@@ -256,4 +258,29 @@ extern "C" int64_t stream_host_run(const irlosc_params *params, int64_t B, const
     if (kd == 3 && !hb) return run_stream<3, false>(P, R, plan, out, B, dp);
     if (kd == 6 && hb) return run_stream<6, true>(P, R, plan, out, B, dp);
     return run_stream<6, false>(P, R, plan, out, B, dp);
+}
+
+// One control step of gain_test-style waypoint cycling (irlosc_step_waypoints) on the CPU.
+extern "C" int64_t waypoints_host_step(const irlosc_params *params, const irlosc_model *model, int64_t B,
+                                       const irlosc_fused_io *io, const irlosc_waypoints_io *wio) {
+    KParams P;
+    if (build_kparams(*params, P) != IRLOSC_OK) return -1;
+    FRoles R;
+    int kd = 0;
+    bool hb = false;
+    if (!fused_roles(P, R, kd, hb)) { irlosc::fail(1, "not the DualUR5 topology"); return -1; }
+    KModel M;
+    if (build_kmodel(P, *model, M) != IRLOSC_OK) return -1;
+    KSeq Q;
+    if (build_kseq_waypoints(P, R, *wio, Q) != IRLOSC_OK) return -1;
+    FIo k;
+    memset(&k, 0, sizeof k);
+    k.q = io->q; k.dq = io->dq; k.target_xyz = wio->target_xyz; k.target_quat = wio->target_quat;
+    k.target_vel = io->target_vel; k.max_vel = io->max_vel; k.ft_raw = io->ft_raw;
+    k.ctrl = io->ctrl; k.u_all = io->u_all; k.status = io->status; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    k.wps = wio->wps; k.wp_idx = wio->wp_idx; k.seq_tgt_xyz = wio->target_xyz; k.seq_tgt_quat = wio->target_quat;
+    if (kd == 3 && hb) return run<3, true>(P, M, R, k, B, nullptr, &Q);
+    if (kd == 3 && !hb) return run<3, false>(P, M, R, k, B, nullptr, &Q);
+    if (kd == 6 && hb) return run<6, true>(P, M, R, k, B, nullptr, &Q);
+    return run<6, false>(P, M, R, k, B, nullptr, &Q);
 }

@@ -72,3 +72,46 @@ def test_sequence_on_gpu_matches_reference_loop_and_fused_step():
         # the unreachable episodes are still inside the first waypoint, at the saturated speed schedule
         a_all = st["action"].cpu().numpy()
         assert (a_all[n_chk:] == 0).all()
+
+
+def test_waypoint_cycling_on_gpu_matches_the_gain_test_loop():
+    import torch
+    from irl_control_b200.engine import BatchedOSC
+    from irl_control_b200.synthetic import scenario_model
+    from oracle import sequence_numpy
+    B, T, W, n_chk = 2048, 50, 4, 6
+    dev = "cuda:0"
+    layout, model = scenario_model("gain_test")
+    names = [d.name for d in layout.devices]
+    assert names == ["ur5right", "ur5left", "base"]
+    eng = BatchedOSC(layout, device=0)
+    eng.set_model(model)
+    q, dq = _trajectory(B, T, seed=31)
+    poses = _poses(layout, q[:, :n_chk])
+    D = layout.D
+    n_wp = [4, 3, 1]
+    rng = np.random.default_rng(2)
+    wps = rng.uniform(-0.5, 0.5, size=(B, D, W, 3)) + np.array([0.3, 0.0, 0.9])
+    for d, ts in {0: [5, 11, 12, 30], 1: [3, 20, 33]}.items():
+        for w, t in enumerate(ts):
+            wps[:n_chk, d, w] = poses[names[d]][0][t]
+    st = {"wps": torch.from_numpy(wps).to(dev), "n_wp": n_wp, "wp_idx": torch.zeros(B, D, dtype=torch.int32, device=dev),
+          "target_xyz": torch.zeros(B, D, 3, dtype=torch.float64, device=dev),
+          "target_quat": torch.tensor([1.0, 0, 0, 0], dtype=torch.float64, device=dev).expand(B, D, 4).contiguous()}
+    mv = torch.tensor([list(d.max_vel) for d in layout.devices], dtype=torch.float64, device=dev)[None].expand(B, -1, -1).contiguous()
+    qd, dqd = torch.from_numpy(q).to(dev), torch.from_numpy(dq).to(dev)
+    got = []
+    for t in range(T):
+        before = st["wp_idx"][:n_chk].cpu().numpy().copy()
+        out = eng.step_waypoints({"q": qd[t].contiguous(), "dq": dqd[t].contiguous(), "max_vel": mv}, st, threshold=0.1, want_u_all=True)
+        ref = eng.step_fused({"q": qd[t].contiguous(), "dq": dqd[t].contiguous(), "max_vel": mv,
+                              "target_xyz": st["target_xyz"], "target_quat": st["target_quat"]}, want_u_all=True)
+        scale = ref["u_all"].abs().amax(dim=1, keepdim=True)
+        assert ((out["u_all"] - ref["u_all"]).abs() / scale).max().item() < 1e-9
+        got.append((st["target_xyz"][:n_chk].cpu().numpy().copy(), before))
+    for i in range(n_chk):
+        for d in (0, 1):
+            ref = sequence_numpy.run_waypoint_cycle(wps[i, d, :n_wp[d]], poses[names[d]][0][:, i], 0.1, T)
+            for t in range(T):
+                assert got[t][1][i, d] == ref[t][1], (i, d, t)
+                assert np.array_equal(got[t][0][i, d], ref[t][0])

@@ -28,7 +28,8 @@ def test_struct_sizes_match_header(native_lib, tmp_path):
                    'sizeof(irlosc_device_params), sizeof(irlosc_params), sizeof(irlosc_io));'
                    'printf("%zu %zu %zu %zu\\n", sizeof(irlosc_joint_model), sizeof(irlosc_frame_model), '
                    'sizeof(irlosc_model), sizeof(irlosc_fused_io));'
-                   'printf("%zu %zu %zu\\n", sizeof(irlosc_action), sizeof(irlosc_sequence), sizeof(irlosc_sequence_io));'
+                   'printf("%zu %zu %zu %zu\\n", sizeof(irlosc_action), sizeof(irlosc_sequence), sizeof(irlosc_sequence_io), '
+                   'sizeof(irlosc_waypoints_io));'
                    'return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
@@ -36,7 +37,7 @@ def test_struct_sizes_match_header(native_lib, tmp_path):
     assert [int(x) for x in out] == [C.sizeof(_native.DeviceParams), C.sizeof(_native.Params), C.sizeof(_native.Io),
                                      C.sizeof(_native.JointModel), C.sizeof(_native.FrameModel),
                                      C.sizeof(_native.Model), C.sizeof(_native.FusedIo), C.sizeof(_native.Action),
-                                     C.sizeof(_native.Sequence), C.sizeof(_native.SequenceIo)]
+                                     C.sizeof(_native.Sequence), C.sizeof(_native.SequenceIo), C.sizeof(_native.WaypointsIo)]
 
 
 def test_library_is_sm100a_only(native_lib):

