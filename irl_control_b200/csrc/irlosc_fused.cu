@@ -34,35 +34,52 @@ struct FusedEntry {
 template <int KD, bool HB, int NT, bool SMEM>
 FusedEntry entry(int variant, const char *name) {
     const void *seq = nullptr;
-    if constexpr (NT == 256 && SMEM) seq = (const void *)osc_step_fused<KD, HB, NT, SMEM, true>;
+    if constexpr (SMEM && (NT == 256 || NT == 224)) seq = (const void *)osc_step_fused<KD, HB, NT, SMEM, true>;
     return FusedEntry{KD, HB, variant, NT, SMEM ? (size_t)kScratchDoubles * NT * sizeof(double) : 0,
                       (const void *)osc_step_fused<KD, HB, NT, SMEM>, (const void *)osc_tail_fixup<KD, HB>,
                       Rec<KD, HB>::SIZE, name, seq};
 }
 
+// Variant 0 is the default and exists with 8 and with 7 warps per CTA (one CTA per SM): a thread owns an
+// instance, so a batch is ceil(B / 32 / (SMs * warps)) passes, and with 148 SMs the headline batch of
+// 65 536 is 1.73 passes at 8 warps but 1.98 at 7.  launch_fused picks the cheaper of the two for B
+// (measured pass times: 8 warps 92.5 us, 7 warps 82.5 us; profiles/r01_fused_variants_final.jsonl).
 const FusedEntry *fused_table(int *count) {
     static const FusedEntry t[] = {
         entry<3, true, 256, true>(0, "osc_step_fused<kd3,base,t256,smem>"),
         entry<6, false, 256, true>(0, "osc_step_fused<kd6,t256,smem>"),
         entry<6, true, 256, true>(0, "osc_step_fused<kd6,base,t256,smem>"),
         entry<3, false, 256, true>(0, "osc_step_fused<kd3,t256,smem>"),
+        entry<3, true, 224, true>(0, "osc_step_fused<kd3,base,t224,smem>"),
+        entry<6, false, 224, true>(0, "osc_step_fused<kd6,t224,smem>"),
+        entry<6, true, 224, true>(0, "osc_step_fused<kd6,base,t224,smem>"),
+        entry<3, false, 224, true>(0, "osc_step_fused<kd3,t224,smem>"),
         entry<3, true, 256, false>(1, "osc_step_fused<kd3,base,t256,local>"),
         entry<6, false, 256, false>(1, "osc_step_fused<kd6,t256,local>"),
         entry<3, true, 384, false>(2, "osc_step_fused<kd3,base,t384,local>"),
-        entry<6, false, 384, false>(2, "osc_step_fused<kd6,t384,local>"),
         entry<3, true, 192, true>(3, "osc_step_fused<kd3,base,t192,smem>"),
         entry<3, true, 128, false>(4, "osc_step_fused<kd3,base,t128,local>"),
+        entry<3, true, 224, false>(6, "osc_step_fused<kd3,base,t224,local>"),
     };
     *count = (int)(sizeof t / sizeof t[0]);
     return t;
 }
 
-const FusedEntry *fused_find(int kd, bool has_base, int variant = 0) {
+const FusedEntry *fused_find(int kd, bool has_base, int variant = 0, int threads = 0) {
     int cnt = 0;
     const FusedEntry *t = fused_table(&cnt);
     for (int i = 0; i < cnt; ++i)
-        if (t[i].kd == kd && t[i].has_base == has_base && t[i].variant == variant) return &t[i];
+        if (t[i].kd == kd && t[i].has_base == has_base && t[i].variant == variant && (threads == 0 || t[i].threads == threads))
+            return &t[i];
     return nullptr;
+}
+
+// 8 or 7 warps per CTA for a batch of B (see fused_table)
+int fused_threads_for(int64_t B, int sms) {
+    const int64_t tiles = (B + 31) / 32;
+    const double p8 = (double)((tiles + (int64_t)sms * 8 - 1) / ((int64_t)sms * 8)) * 92.5;
+    const double p7 = (double)((tiles + (int64_t)sms * 7 - 1) / ((int64_t)sms * 7)) * 82.5;
+    return p7 < p8 ? 224 : 256;
 }
 
 int32_t ensure_queue(irlosc_handle *h, int q, int64_t B, int rec_doubles) {
@@ -98,7 +115,11 @@ int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
 
 int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st, const KSeq *seq = nullptr) {
     const int variant = (h->kernel_choice >= 2 && h->kernel_choice < 9) ? h->kernel_choice - 2 : 0;
-    const FusedEntry *e = fused_find(h->fused_kd, h->fused_base, variant);
+    const int sms0 = std::max(1, h->sm_count - h->sm_margin);
+    int want_threads = variant == 0 ? fused_threads_for(B, sms0) : 0;
+    if (const char *t = getenv("IRLOSC_FUSED_THREADS")) want_threads = atoi(t);                         // experiments only
+    const FusedEntry *e = fused_find(h->fused_kd, h->fused_base, variant, want_threads);
+    if (!e) e = fused_find(h->fused_kd, h->fused_base, variant);
     if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d variant=%d", h->fused_kd, (int)h->fused_base, variant);
     int32_t rc = ensure_queue(h, 0, B, e->rec_doubles);
     if (rc != IRLOSC_OK) return rc;
@@ -203,6 +224,19 @@ int32_t irlosc::stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaSt
     const int warp_bytes = 2 * stage_bytes + ((32 * h->kp.n_ctrl * 8 + 15) & ~15);
     const size_t head = (sizeof(stream::Plan) + 15) & ~size_t(15);
     int warps = (int)std::min<size_t>(e->max_threads / 32, (kSmemLimit - head) / warp_bytes);
+    {   // a warp owns 32 instances: pick the warp count whose number of passes over the batch is cheapest
+        // (pass times measured at 4 / 6 / 7 / 8 warps, profiles/r01_stream_vs_tree.log)
+        static const double pass_us[9] = {0, 40, 42, 44, 45.5, 47, 55, 66.5, 79};
+        const int64_t tiles_ = (B + 31) / 32;
+        const int sms_ = std::max(1, h->sm_count - h->sm_margin);
+        int best = warps;
+        double best_t = 1e300;
+        for (int w = std::min(warps, 8); w >= 4; --w) {
+            const double t_ = (double)((tiles_ + (int64_t)sms_ * w - 1) / ((int64_t)sms_ * w)) * pass_us[w];
+            if (t_ < best_t - 1e-9) { best_t = t_; best = w; }
+        }
+        warps = best;
+    }
     if (const char *w = getenv("IRLOSC_STREAM_WARPS")) warps = std::max(1, std::min(warps, atoi(w)));   // experiments only
     if (warps < 1) return fail(IRLOSC_ERR_INVALID, "streaming kernel: a stage does not fit in shared memory");
     const size_t smem = head + (size_t)warps * warp_bytes;
