@@ -121,3 +121,40 @@ def test_reduced_model_lumps_welded_bodies():
     assert abs(sum(model.joint[j].mass for j in range(25)) - moving) < 1e-12     # origin_base (100 kg) is welded to the world
     assert [model.ee[d].joint for d in range(3)] == [6, 18, 0]
     assert [model.ft[d].joint for d in range(3)] == [6, 18, -1]
+
+
+def test_mujoco_binding_view_reduces_to_the_same_model():
+    """`mujoco_adapter.MjModelView` on a stand-in that carries the arrays of `mujoco.MjModel`
+    (mujoco itself is absent): the reduced model equals the one built from the mujoco_py-shaped model."""
+    import ctypes as C
+    from types import SimpleNamespace
+    from irl_control_b200.mujoco_adapter import MjModelView, joint_state, scatter_ctrl
+    from irl_control_b200.rigid_model import reduce_model
+    app, _o, names, layout = build_scenario("admit_test")
+    robot = app.get_robot("DualUR5")
+    m = app.sim.model
+    nb = m.n_robot_bodies
+    mass, ipos, iquat, inertia = np.zeros(nb), np.zeros((nb, 3)), np.tile([1.0, 0, 0, 0], (nb, 1)), np.zeros((nb, 3))
+    for b, it in enumerate(m.body_inertial[:nb]):
+        if it is not None:
+            ipos[b], iquat[b], mass[b], inertia[b] = it
+    mj = SimpleNamespace(nbody=nb, body_parentid=m.body_parentid[:nb], body_pos=m.body_pos[:nb], body_quat=m.body_quat[:nb],
+                         body_jntadr=m.body_jntadr[:nb], body_jntnum=m.body_jntnum[:nb], jnt_bodyid=m.jnt_bodyid,
+                         jnt_axis=m.jnt_axis, jnt_pos=m.jnt_pos, jnt_qposadr=np.arange(25), jnt_dofadr=np.arange(25),
+                         site_bodyid=m.site_bodyid, site_pos=m.site_pos, site_quat=m.site_quat,
+                         body_mass=mass, body_ipos=ipos, body_iquat=iquat, body_inertia=inertia)
+    ids = {"body": m.body_name2id, "site": m.site_name2id}
+    view = MjModelView(mj, name2id=lambda kind, name: ids[kind](name))
+    ee = [d.ee_body for d in layout.devices]
+    ft = ["ft_frame_" + d.name for d in layout.devices]
+    a = reduce_model(view, robot.joint_ids_all, ee, ft)
+    b = model_for_layout(m, robot.joint_ids_all, layout)
+    assert bytes(a) == bytes(b)
+    assert "ft_frame_ur5right" in view.site_names and "nope" not in view.site_names
+    data = SimpleNamespace(qpos=np.arange(40.0), qvel=-np.arange(37.0), ctrl=np.zeros(15))
+    q, dq = joint_state(data, view, robot.joint_ids_all)
+    assert np.array_equal(q, np.arange(25.0)) and np.array_equal(dq, -np.arange(25.0))
+    row = np.arange(1.0, layout.n_ctrl + 1)
+    scatter_ctrl(data.ctrl, layout, row)
+    for sl, dl in zip(layout.ctrl_slices, layout.devices):
+        assert np.array_equal(data.ctrl[list(dl.ctrl_idxs)], row[sl])
