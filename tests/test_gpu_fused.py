@@ -135,3 +135,21 @@ def test_fused_requires_model_and_topology():
     model.joint[3].parent = 0
     with pytest.raises(_native.OscError, match="parent"):
         eng.set_model(model)
+
+
+def test_fused_size_independent_properties_at_full_batch():
+    """B = 65 536: determinism, instance-permutation equivariance, split invariance (the launch picks a
+    different warp count for the half batch), and the action-free sequence of two steps is stateless."""
+    torch = _torch()
+    layout, eng, st, fin = _setup("gain_test", 65536, seed=2)
+    a = {k: v.clone() for k, v in eng.step_fused(fin, want_u_all=True).items()}
+    b = eng.step_fused(fin, want_u_all=True)
+    assert torch.equal(a["ctrl"], b["ctrl"]) and torch.equal(a["status"], b["status"])
+    perm = torch.randperm(65536, device="cuda:0", generator=torch.Generator(device="cuda:0").manual_seed(3))
+    c = eng.step_fused({k: v[perm].contiguous() for k, v in fin.items()}, want_u_all=True)
+    assert torch.equal(c["ctrl"], a["ctrl"][perm]) and torch.equal(c["u_all"], a["u_all"][perm])
+    d = eng.step_fused({k: v[30000:].contiguous() for k, v in fin.items()})
+    assert torch.equal(d["ctrl"], a["ctrl"][30000:])
+    cols = [j for dl in layout.devices for j in dl.actuator_trnids]
+    assert torch.equal(a["ctrl"], a["u_all"][:, cols])            # packing (osc.py:203-208)
+    assert torch.isfinite(a["ctrl"]).all()
