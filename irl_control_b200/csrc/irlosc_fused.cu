@@ -113,7 +113,7 @@ int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
     return IRLOSC_OK;
 }
 
-int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st, const KSeq *seq = nullptr) {
+int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st, const KSeq *seq = nullptr, int queue = 0) {
     const int variant = (h->kernel_choice >= 2 && h->kernel_choice < 9) ? h->kernel_choice - 2 : 0;
     const int sms0 = std::max(1, h->sm_count - h->sm_margin);
     int want_threads = variant == 0 ? fused_threads_for(B, sms0) : 0;
@@ -121,9 +121,9 @@ int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st,
     const FusedEntry *e = fused_find(h->fused_kd, h->fused_base, variant, want_threads);
     if (!e) e = fused_find(h->fused_kd, h->fused_base, variant);
     if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d variant=%d", h->fused_kd, (int)h->fused_base, variant);
-    int32_t rc = ensure_queue(h, 0, B, e->rec_doubles);
+    int32_t rc = ensure_queue(h, queue, B, e->rec_doubles);
     if (rc != IRLOSC_OK) return rc;
-    HardBuffers &hb = h->hard[0];
+    HardBuffers &hb = h->hard[queue];
     CUDA_TRY(cudaMemsetAsync(hb.count, 0, sizeof(int), st));
     HardQueue hq{hb.count, (int)std::min<int64_t>(hb.cap, INT32_MAX), e->rec_doubles, hb.rec, hb.inst};
     const int sms = std::max(1, h->sm_count - h->sm_margin);
@@ -375,10 +375,9 @@ extern "C" int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irl
     struct In { const double *src; size_t per; } ins[7] = {
         {hk.q, n}, {hk.dq, n}, {hk.target_xyz, 3 * D}, {hk.target_quat, 4 * D},
         {hk.target_vel, 6 * D}, {hk.max_vel, 2 * D}, {hk.ft_raw, 6 * D}};
-    // The queue of eigen-path instances is per launch, so chunks are serialised on the kernel side by
-    // using ONE compute stream; copies of the next chunk overlap through the per-stage streams.
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(4 * h->host_chunk, B));
-    cudaEvent_t done[kPipeDepth] = {nullptr};
+    // Chunks rotate over kPipeDepth stages, each with its own stream, staging buffers and queue of
+    // eigen-path instances, so the H2D copy of chunk i + 1 overlaps kernel and D2H copy of chunk i.
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(2 * h->host_chunk, B));
     int turn = 0;
     int32_t result = IRLOSC_OK;
     for (int64_t b0 = 0; b0 < B && result == IRLOSC_OK; b0 += chunk, ++turn) {
@@ -408,15 +407,8 @@ extern "C" int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irl
         dk.status = hk.status ? (uint8_t *)S.buf[10] : nullptr;
         dk.ee_xyz = hk.ee_xyz ? (double *)S.buf[11] : nullptr;
         dk.ee_quat = hk.ee_quat ? (double *)S.buf[12] : nullptr;
-        // the shared queue: wait for the previous chunk's kernels before this chunk's start
-        if (turn > 0) {
-            cudaEvent_t prev = done[(turn - 1) % kPipeDepth];
-            CUDA_TRY(cudaStreamWaitEvent(S.stream, prev, 0));
-        }
-        result = launch_fused(h, nb, dk, S.stream);
+        result = launch_fused(h, nb, dk, S.stream, nullptr, 1 + turn % kPipeDepth);
         if (result != IRLOSC_OK) break;
-        if (!done[turn % kPipeDepth]) CUDA_TRY(cudaEventCreateWithFlags(&done[turn % kPipeDepth], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(done[turn % kPipeDepth], S.stream));
         CUDA_TRY(cudaMemcpyAsync(hk.ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
                                  cudaMemcpyDeviceToHost, S.stream));
         if (hk.u_all)
@@ -433,7 +425,6 @@ extern "C" int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irl
     for (int s = 0; s < kPipeDepth; ++s) {
         cudaError_t e = cudaStreamSynchronize(h->fstage[s].stream);
         if (e != cudaSuccess && result == IRLOSC_OK) result = fail(IRLOSC_ERR_CUDA, "stream sync: %s", cudaGetErrorString(e));
-        if (done[s]) cudaEventDestroy(done[s]);
     }
     return result;
 }
