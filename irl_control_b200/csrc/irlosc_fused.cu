@@ -377,7 +377,7 @@ extern "C" int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irl
         {hk.target_vel, 6 * D}, {hk.max_vel, 2 * D}, {hk.ft_raw, 6 * D}};
     // Chunks rotate over kPipeDepth stages, each with its own stream, staging buffers and queue of
     // eigen-path instances, so the H2D copy of chunk i + 1 overlaps kernel and D2H copy of chunk i.
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(2 * h->host_chunk, B));
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(4 * h->host_chunk, B));   // 2 x measured slower (per-chunk call overhead)
     int turn = 0;
     int32_t result = IRLOSC_OK;
     for (int64_t b0 = 0; b0 < B && result == IRLOSC_OK; b0 += chunk, ++turn) {
