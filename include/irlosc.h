@@ -46,8 +46,6 @@ extern "C" {
 #define IRLOSC_ST_VEL_BRANCH 0x08   /* >=1 device took the non-zero target-velocity branch (osc.py:175-177) */
 #define IRLOSC_ST_DX_RANGE 0x10     /* that branch indexed dx out of range: the reference raises IndexError
                                        (robot.py:52-55 vs osc.py:150,176); outputs are NaN               */
-#define IRLOSC_ST_DEFLATED 0x40     /* pinv branch that cuts exactly one eigenvalue, resolved inside the step kernel by
-                                       deflation (rigorous eigenvalue bounds) instead of the eigen-decomposition          */
 #define IRLOSC_ST_SPARSITY 0x20     /* check_topology was set and M / J had a non-zero where the declared
                                        kinematic tree says zero; outputs are NaN                         */
 

@@ -23,7 +23,6 @@ ST_EIGEN = 0x04
 ST_VEL_BRANCH = 0x08
 ST_DX_RANGE = 0x10
 ST_SPARSITY = 0x20
-ST_DEFLATED = 0x40
 
 M_DENSE, M_PACKED = 0, 1
 J_ROWS, J_FULL6 = 0, 1

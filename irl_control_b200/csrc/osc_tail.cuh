@@ -55,148 +55,6 @@ IRLOSC_HD void put_joint(const FRoles &R, double *u_all_row, double *ctrl_row, i
 }
 
 
-// In-thread resolution of the pinv branch (osc.py:52-55) for an instance the cheap certificate left open.
-// numpy's pinv(A, rcond) keeps an eigenvalue iff it is > rcond * lambda_max.  With rigorous two-sided bounds
-//   L <= lambda_max <= U    (repeated squaring of A / tr A: tr(B^(2^m))^(1/2^m) is within K^(1/2^m) of lambda_max)
-// three outcomes are certain without an eigen-decomposition:
-//   1  1 / tr(A^-1) > rcond U            : nothing is cut, pinv = inverse (w from the LDL^T stands);
-//   2  the smallest Rayleigh quotient (3 inverse iterations on the LDL^T at hand, so lambda_min <= rho) is
-//      <= rcond L, and the deflated matrix A' = A + U x x^T has 1 / tr(A'^-1) > rcond U.  Eigenvalues
-//      interlace (lambda_2(A) >= lambda_1(A')), so exactly one eigenvalue is cut:
-//      w = A'^-1 (g - x (x . g));
-//   0  anything else (borderline within the bounds, two or more small eigenvalues, a failed pivot): left to
-//      the eigen fix-up kernel.
-// Runs on local arrays with rolled loops: it is the rare path of one lane, code size matters more than speed.
-template <int K>
-IRLOSC_HD int resolve_pinv(double (*Af)[K], double (*Lf)[K], const double *dinv, const double *g, double tr_inv, double *w) {
-    constexpr int MS = 6;                        // squarings at most: bounds within K^(1/64) (4 % for K = 13)
-    double tr = 0.0;
-    for (int i = 0; i < K; ++i) tr += Af[i][i];
-    if (!(tr > 0.0) || !(tr_inv > 0.0)) return 0;
-    auto solve = [&](double (*Lm)[K], const double *dv, double *x) {      // x <- (L D L^T)^-1 x
-        for (int i = 0; i < K; ++i) {
-            double z = x[i];
-            for (int j = 0; j < i; ++j) z = fma(-Lm[i][j], x[j], z);
-            x[i] = z;
-        }
-        for (int i = 0; i < K; ++i) x[i] *= dv[i];
-        for (int i = K - 1; i >= 0; --i) {
-            double z = x[i];
-            for (int j = i + 1; j < K; ++j) z = fma(-Lm[j][i], x[j], z);
-            x[i] = z;
-        }
-    };
-    // ---- smallest eigenpair: inverse iteration with the factors at hand.  It contracts by
-    // lambda_min / lambda_2 per step, which the classification does not bound away from 1: iterate until the
-    // extrapolated error of x is at rounding level (or do without outcome 2).
-    double x[K], xp[K];
-    for (int i = 0; i < K; ++i) x[i] = xp[i] = 1.0 + 0.1 * i;        // a component along every axis
-    bool converged = false;
-    double d_prev = HUGE_VAL;
-    for (int it = 0; it < 64 && !converged; ++it) {
-        solve(Lf, dinv, x);
-        double n2 = 0.0, dot = 0.0;
-        for (int i = 0; i < K; ++i) { n2 = fma(x[i], x[i], n2); dot = fma(x[i], xp[i], dot); }
-        if (!(n2 > 0.0) || !(n2 < HUGE_VAL)) break;
-        const double in = (dot < 0.0 ? -1.0 : 1.0) / sqrt(n2);
-        double d2 = 0.0;
-        for (int i = 0; i < K; ++i) {
-            x[i] *= in;
-            const double dlt = x[i] - xp[i];
-            d2 = fma(dlt, dlt, d2);
-            xp[i] = x[i];
-        }
-        const double d = sqrt(d2);
-        if (it >= 2) {
-            const double r = d / d_prev;                              // observed contraction
-            converged = (d == 0.0) || (r < 0.97 && d * r / (1.0 - r) < 1e-13);
-        }
-        d_prev = d;
-    }
-    double rho = HUGE_VAL;                                            // Rayleigh quotient: lambda_min <= rho
-    if (converged) {
-        rho = 0.0;
-        for (int i = 0; i < K; ++i) {
-            double acc = 0.0;
-            for (int j = 0; j < K; ++j) acc = fma(Af[i][j], x[j], acc);
-            rho = fma(x[i], acc, rho);
-        }
-    }
-    // ---- bounds on lambda_max, refined one squaring at a time until the instance is classified
-    double Bm[K][K], Cm[K][K], dv2[K], sm[MS];
-    {
-        const double itr = 1.0 / tr;
-        for (int i = 0; i < K; ++i)
-            for (int j = 0; j < K; ++j) Bm[i][j] = Af[i][j] * itr;
-    }
-    bool deflated = false;
-    double tr2 = 0.0;
-    for (int m = 0; m <= MS; ++m) {
-        if (m > 0) {                             // B <- B^2 / tr(B^2): traces stay 1
-            double t = 0.0;
-            for (int i = 0; i < K; ++i)
-                for (int j = 0; j <= i; ++j) {
-                    double acc = 0.0;
-                    for (int l = 0; l < K; ++l) acc = fma(Bm[i][l], Bm[l][j], acc);
-                    Cm[i][j] = acc;
-                    if (i == j) t += acc;
-                }
-            if (!(t > 0.0)) return 0;
-            sm[m - 1] = t;
-            const double it = 1.0 / t;
-            for (int i = 0; i < K; ++i)
-                for (int j = 0; j <= i; ++j) { Bm[i][j] = Cm[i][j] * it; Bm[j][i] = Bm[i][j]; }
-        }
-        double up = 1.0, lo = 1.0 / K;           // lambda_max(B_m) in [1 / K, 1] (PSD, trace 1)
-        for (int j = m - 1; j >= 0; --j) { up = sqrt(sm[j] * up); lo = sqrt(sm[j] * lo); }
-        const double c_hi = kPinvRcond * tr * up * (1.0 + 1e-12), c_lo = kPinvRcond * tr * lo * (1.0 - 1e-12);
-        if (1.0 > c_hi * tr_inv) return 1;       // every eigenvalue is above the cutoff
-        if (rho <= c_lo) {                       // the smallest one is below it
-            if (!deflated) {                     // factor A' = A + tr(A) x x^T once
-                deflated = true;
-                for (int i = 0; i < K; ++i)
-                    for (int j = 0; j <= i; ++j) Cm[i][j] = fma(tr * x[i], x[j], Af[i][j]);
-                for (int p = 0; p < K; ++p) {
-                    const double d = Cm[p][p];
-                    if (!(d > 0.0)) return 0;
-                    const double inv = 1.0 / d;
-                    dv2[p] = inv;
-                    for (int i = p + 1; i < K; ++i) {
-                        const double l = Cm[i][p] * inv;
-                        for (int j = p + 1; j <= i; ++j) Cm[i][j] = fma(-l, Cm[j][p], Cm[i][j]);
-                    }
-                    for (int i = p + 1; i < K; ++i) Cm[i][p] *= inv;
-                }
-                for (int j = 0; j < K; ++j) {    // tr(A'^-1) = sum_p dv2_p |row p of L^-1|^2
-                    double col[K];
-                    col[j] = 1.0;
-                    double acc = dv2[j];
-                    for (int i = j + 1; i < K; ++i) {
-                        double z = -Cm[i][j];
-                        for (int l = j + 1; l < i; ++l) z = fma(-Cm[i][l], col[l], z);
-                        col[i] = z;
-                        acc = fma(z * z, dv2[i], acc);
-                    }
-                    tr2 += acc;
-                }
-                // (Cm is needed again below: the squaring must not overwrite it)
-                for (int i = 0; i < K; ++i)
-                    for (int j = 0; j <= i; ++j) Af[j][i] = Cm[i][j];        // park the factors in Af's upper part
-            }
-            if (1.0 > c_hi * tr2) {              // and every other one is above it: cut exactly that one
-                for (int i = 0; i < K; ++i)
-                    for (int j = 0; j < i; ++j) Cm[i][j] = Af[j][i];
-                double xg = 0.0;
-                for (int i = 0; i < K; ++i) xg = fma(x[i], g[i], xg);
-                for (int i = 0; i < K; ++i) w[i] = fma(-xg, x[i], g[i]);
-                solve(Cm, dv2, w);
-                return 2;
-            }
-        }
-    }
-    return 0;
-}
-
 template <int KD, bool HAS_BASE>
 IRLOSC_HD bool osc_tail(const KParams &P, const FRoles &R, const double *target_vel, unsigned vel_zero, int flags,
                         bool m_ok, const double (*akA)[KD * (KD + 1) / 2], const double *j0, const double *jst,
@@ -312,9 +170,9 @@ IRLOSC_HD bool osc_tail(const KParams &P, const FRoles &R, const double *target_
     // so ||A||_F tr(A^-1) < 1e5 certifies that nothing is cut.  tr(A^-1) = sum_p dinv_p |row p of L^-1|^2.
     const bool small_det = !(fabs(detinv) <= 1.0 / kDetThreshold);
     bool certified = true;
-    double tr_inv = 0.0;
     if (small_det && !a_bad) {
         // X = L^-1 (unit lower triangular), column by column
+        double tr_inv = 0.0;
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             double x[K];
@@ -332,32 +190,8 @@ IRLOSC_HD bool osc_tail(const KParams &P, const FRoles &R, const double *target_
         }
         certified = (fro2 * tr_inv * tr_inv < (1.0 / kPinvRcond) * (1.0 / kPinvRcond));
     }
-    bool hard = !poison && (a_bad || (small_det && !certified));
+    const bool hard = !poison && (a_bad || (small_det && !certified));
     if (small_det && !a_bad) flags |= IRLOSC_ST_PINV;
-    if (hard && !a_bad) {                           // rare: copy to local arrays, resolve without an eigen-decomposition
-        double Af[K][K], Lf[K][K], wl[K], gl[K], dl[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) {
-            const double ji = j0c[i] * inv0;
-            gl[i] = gc[i];
-            dl[i] = dinv[i];
-            wl[i] = w[i];
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                const double v = fma(ji, j0c[j], blk(i, j));
-                Af[i][j] = v;
-                Af[j][i] = v;
-                Lf[i][j] = a[i * (i + 1) / 2 + j];
-            }
-        }
-        const int how = resolve_pinv<K>(Af, Lf, dl, gl, tr_inv, wl);
-        if (how != 0) hard = false;
-        if (how == 2) {
-            flags |= IRLOSC_ST_DEFLATED;
-#pragma unroll
-            for (int i = 0; i < K; ++i) w[i] = wl[i];
-        }
-    }
 
     // ------------------------------------------------------------ joint-space assembly + packing
     if (hard && hard_rec != nullptr) {              // record in canonical row order (w comes back canonical)

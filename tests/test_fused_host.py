@@ -75,10 +75,7 @@ def test_fused_step_matches_the_oracle(scenario, B):
     want = np.concatenate([ref["u_all"][:, list(d.actuator_trnids)] for d in layout.devices], axis=1)
     assert _rel(out["ctrl"], want).max() < REL_TOL
     if scenario in ("admit_test", "insertion", "worst_case"):
-        from irl_control_b200 import _native
-        # both ways out of the pinv branch are exercised: in-thread deflation and the eigen fix-up path
-        assert ((out["status"] & _native.ST_DEFLATED) != 0).any()
-        assert scenario != "worst_case" or out["n_hard"] > 0
+        assert out["n_hard"] > 0          # the eigen fix-up path is exercised
 
 
 def test_velocity_tracking_branch_and_index_error_flag():
