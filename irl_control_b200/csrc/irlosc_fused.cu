@@ -82,6 +82,12 @@ int fused_threads_for(int64_t B, int sms) {
     return p7 < p8 ? 224 : 256;
 }
 
+// experimental fix-up path (osc_fixup_coop.cuh), off unless IRLOSC_FIXUP_COOP=1
+int fixup_coop() {
+    static const int v = [] { const char *e = getenv("IRLOSC_FIXUP_COOP"); return e ? atoi(e) : 0; }();
+    return v;
+}
+
 int32_t ensure_queue(irlosc_handle *h, int q, int64_t B, int rec_doubles) {
     HardBuffers &hb = h->hard[q];
     if (!hb.count) CUDA_TRY(cudaMalloc(&hb.count, sizeof(int)));
@@ -142,7 +148,8 @@ int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st,
     TailOut tout;
     memset(&tout, 0, sizeof tout);
     tout.u_all = k.u_all; tout.ctrl = k.ctrl; tout.status = k.status;
-    void *fargs[] = {(void *)&h->kp, (void *)&tout, (void *)&h->fr, (void *)&hq};
+    const int coop = fixup_coop();
+    void *fargs[] = {(void *)&h->kp, (void *)&tout, (void *)&h->fr, (void *)&hq, (void *)&coop};
     err = cudaLaunchKernel(e->fixup, dim3(fgrid), dim3(128), fargs, 0, st);
     if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fix-up kernel launch: %s", cudaGetErrorString(err));
     h->launches += 2;
@@ -264,7 +271,8 @@ int32_t irlosc::stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaSt
     tout.n_gather = io.n_gather; tout.gather_offset = io.gather_offset; tout.ctrl_mc = io.ctrl_mc;
     for (int g = 0; g < io.n_gather; ++g) tout.ctrl_gather[g] = io.ctrl_gather[g];
     const int fgrid = (int)std::min<int64_t>((B + 3) / 4, (int64_t)sms * 4);
-    void *fargs[] = {(void *)&h->kp, (void *)&tout, (void *)&R, (void *)&hq};
+    const int coop = fixup_coop();
+    void *fargs[] = {(void *)&h->kp, (void *)&tout, (void *)&R, (void *)&hq, (void *)&coop};
     err = cudaLaunchKernel(e->fixup, dim3(fgrid), dim3(128), fargs, 0, st);
     if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fix-up kernel launch: %s", cudaGetErrorString(err));
     h->launches += 2;

@@ -285,6 +285,7 @@ struct TailOut {
 
 #if defined(__CUDACC__) && !defined(IRLOSC_FUSED_NO_KERNELS)
 #include "osc_eigen.cuh"
+#include "osc_fixup_coop.cuh"
 
 namespace irlosc {
 namespace fused {
@@ -294,7 +295,7 @@ namespace fused {
 template <int KD, bool HAS_BASE>
 __global__ void __launch_bounds__(128, 1)
 osc_tail_fixup(const __grid_constant__ KParams P, const __grid_constant__ TailOut out, const __grid_constant__ FRoles R,
-               const __grid_constant__ HardQueue hq) {
+               const __grid_constant__ HardQueue hq, const int coop) {
     using RC = Rec<KD, HAS_BASE>;
     constexpr int K = RC::K;
     struct WarpSmem {
@@ -303,6 +304,7 @@ osc_tail_fixup(const __grid_constant__ KParams P, const __grid_constant__ TailOu
         int flags;
     };
     __shared__ WarpSmem sm[4];
+    __shared__ CoopSmem<K> csm[4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     WarpSmem &S = sm[warp];
     const int n_hard = *hq.count;
@@ -314,7 +316,21 @@ osc_tail_fixup(const __grid_constant__ KParams P, const __grid_constant__ TailOu
         if (lane == 0) S.flags = 0;
         __syncwarp();
         const bool a_bad = rec[RC::ABAD] != 0.0;
-        tiled::eigen_solve<K>(S.As, S.Vs, S.g, S.w, S.cbuf, S.sbuf, !a_bad, lane, &S.flags);
+        int how = 0;
+        if (coop && !a_bad) {                    // experimental: bounds + deflation instead of the Jacobi sweeps
+            CoopSmem<K> &CS = csm[warp];
+            for (int e = lane; e < K * K; e += 32) CS.A[e / K][e % K] = S.As[e / K][e % K];
+            if (lane < K) CS.g[lane] = S.g[lane];
+            __syncwarp();
+            CoopDevEx ex{lane};
+            how = coop_resolve_pinv<K>(CS, ex);
+            if (how != 0) {
+                if (lane < K) S.w[lane] = CS.w[lane];
+                if (lane == 0) S.flags = IRLOSC_ST_PINV | (how == 2 ? IRLOSC_ST_EIGEN : 0);
+            }
+            __syncwarp();
+        }
+        if (how == 0) tiled::eigen_solve<K>(S.As, S.Vs, S.g, S.w, S.cbuf, S.sbuf, !a_bad, lane, &S.flags);
         __syncwarp();
         double *ctrl_row = out.ctrl + inst * P.n_ctrl;
         fixup_finish<KD, HAS_BASE>(R, out.u_all ? out.u_all + inst * kN : nullptr, ctrl_row, rec, S.w, lane, 32);

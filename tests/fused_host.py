@@ -19,7 +19,8 @@ _lib = None
 def build():
     deps = [SRC, os.path.join(os.path.dirname(HERE), "include", "irlosc.h")] + [
         os.path.join(CSRC, f) for f in ("osc_fused.cuh", "osc_fused_types.h", "irlosc_device.cuh", "osc_tail.cuh",
-                                        "osc_stream.cuh", "irlosc_build.h", "irlosc_internal.h")]
+                                        "osc_stream.cuh", "osc_fixup_coop.cuh", "osc_sequence.cuh", "irlosc_build.h",
+                                        "irlosc_internal.h")]
     if os.path.isfile(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in deps):
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -155,3 +156,15 @@ def waypoints_step(layout, model, inp, wp_state, threshold=0.1):
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
     return out
+
+
+def coop_resolve(A, g):
+    """osc_fixup_coop.cuh on the CPU (lanes emulated): returns (how, w)."""
+    lib = load()
+    lib.coop_host_resolve.restype = C.c_int
+    lib.coop_host_resolve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    g = np.ascontiguousarray(g, dtype=np.float64)
+    w = np.zeros(A.shape[0])
+    how = lib.coop_host_resolve(A.shape[0], A.ctypes.data, g.ctypes.data, w.ctypes.data)
+    return how, w

@@ -12,6 +12,7 @@
 #include "../../irl_control_b200/csrc/irlosc_build.h"
 #include "../../irl_control_b200/csrc/osc_fused.cuh"
 #include "../../irl_control_b200/csrc/osc_stream.cuh"
+#include "../../irl_control_b200/csrc/osc_fixup_coop.cuh"
 
 static std::string g_err;
 int32_t irlosc::fail(int32_t rc, const char *fmt, ...) {
@@ -283,4 +284,26 @@ extern "C" int64_t waypoints_host_step(const irlosc_params *params, const irlosc
     if (kd == 3 && !hb) return run<3, false>(P, M, R, k, B, nullptr, &Q);
     if (kd == 6 && hb) return run<6, true>(P, M, R, k, B, nullptr, &Q);
     return run<6, false>(P, M, R, k, B, nullptr, &Q);
+}
+
+// Warp-cooperative pinv resolution (osc_fixup_coop.cuh) with the 32 lanes emulated phase by phase.
+template <int K>
+static int coop_run(const double *A, const double *g, double *w) {
+    static CoopSmem<K> S;
+    for (int i = 0; i < K; ++i) {
+        for (int j = 0; j < K; ++j) S.A[i][j] = A[i * K + j];
+        S.g[i] = g[i];
+    }
+    CoopHostEx ex;
+    const int how = coop_resolve_pinv<K>(S, ex);
+    for (int i = 0; i < K; ++i) w[i] = S.w[i];
+    return how;
+}
+
+extern "C" int coop_host_resolve(int K, const double *A, const double *g, double *w) {
+    if (K == 6) return coop_run<6>(A, g, w);
+    if (K == 7) return coop_run<7>(A, g, w);
+    if (K == 12) return coop_run<12>(A, g, w);
+    if (K == 13) return coop_run<13>(A, g, w);
+    return -1;
 }

@@ -158,3 +158,36 @@ def test_mujoco_binding_view_reduces_to_the_same_model():
     scatter_ctrl(data.ctrl, layout, row)
     for sl, dl in zip(layout.ctrl_slices, layout.devices):
         assert np.array_equal(data.ctrl[list(dl.ctrl_idxs)], row[sl])
+
+
+def test_cooperative_pinv_resolution_matches_numpy():
+    """osc_fixup_coop.cuh (experimental fix-up path, lanes emulated on the CPU): whenever it decides, the
+    decision equals numpy's pinv(rcond=1e-5) truncation and the solution agrees; it may only abstain."""
+    rng = np.random.default_rng(4)
+    decided = np.zeros(3, int)
+    for K in (7, 12, 13):
+        for trial in range(120):
+            Q, _ = np.linalg.qr(rng.normal(size=(K, K)))
+            lam = 10.0 ** rng.uniform(-2, 1, size=K)
+            kind = trial % 4
+            if kind == 1:
+                lam[0] = lam.max() * 10.0 ** rng.uniform(-9, -5.5)          # one eigenvalue clearly cut
+            elif kind == 2:
+                lam[0] = lam.max() * 10.0 ** rng.uniform(-5.2, -4.8)        # around the cutoff
+            elif kind == 3:
+                lam[:2] = lam.max() * 10.0 ** rng.uniform(-9, -6, size=2)   # two cut: must abstain
+            A = (Q * lam) @ Q.T
+            A = 0.5 * (A + A.T)
+            g = rng.normal(size=K)
+            how, w = fused_host.coop_resolve(A, g)
+            decided[how] += 1
+            ev = np.linalg.eigvalsh(A)
+            n_cut = int((ev <= 1e-5 * ev[-1]).sum())
+            if how == 0:
+                continue
+            assert (how == 1 and n_cut == 0) or (how == 2 and n_cut == 1), (K, trial, how, n_cut)
+            ref = np.linalg.pinv(A, rcond=1e-5, hermitian=True) @ g
+            assert np.abs(w - ref).max() <= 1e-8 * np.abs(ref).max(), (K, trial, how)
+            if kind == 3:
+                raise AssertionError("two eigenvalues below the cutoff must not be decided")
+    assert decided[1] > 80 and decided[2] > 60                                # it does decide most of the time
