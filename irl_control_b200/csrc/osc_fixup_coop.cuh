@@ -29,7 +29,7 @@ struct CoopSmem {
     double L[K][K + 1];      // factors (strict lower part, unit diagonal implied)
     double Y[K][K + 1];      // inverse
     double B[K][K + 1], C[K][K + 1];
-    double dinv[K], g[K], x[K], xn[K], t[K], w[K], w1[K];
+    double dinv[K], g[K], x[K], xn[K], t[K], w[K];
     int fail;
 };
 
@@ -106,15 +106,53 @@ IRLOSC_HD int coop_resolve_pinv(CoopSmem<K> &S, EX &ex) {
     double tr = 0.0, tr_inv = 0.0;
     for (int i = 0; i < K; ++i) { tr += S.A[i][i]; tr_inv += S.Y[i][i]; }
     if (!(tr > 0.0) || !(tr_inv > 0.0)) return 0;
-    ex.par([&](int lane) {                                      // w1 = A^-1 g (outcome 1)
-        if (lane < K) {
-            double acc = 0.0;
-            for (int j = 0; j < K; ++j) acc = fma(S.Y[lane][j], S.g[j], acc);
-            S.w1[lane] = acc;
-            S.x[lane] = 1.0 + 0.1 * lane;
-        }
+    // ---- bounds on lambda_max, one squaring at a time; outcome 1 needs nothing else
+    double sm[MS];
+    const double itr = 1.0 / tr;
+    ex.par([&](int lane) {
+        for (int e = lane; e < K * K; e += 32) S.C[e / K][e % K] = S.A[e / K][e % K] * itr;      // B_m lives in C
     });
-    // ---- smallest eigenpair by inverse iteration (x <- A^-1 x), until the extrapolated error is at rounding level
+    double c_hi = 0.0, c_lo = 0.0;
+    for (int m = 0; m <= MS; ++m) {
+        if (m > 0) {                                            // C <- C^2 / tr(C^2) via the scratch B
+            ex.par([&](int lane) {
+                for (int e = lane; e < K * K; e += 32) {
+                    const int i = e / K, j = e % K;
+                    double acc = 0.0;
+                    for (int l = 0; l < K; ++l) acc = fma(S.C[i][l], S.C[l][j], acc);
+                    S.B[i][j] = acc;
+                }
+            });
+            double t = 0.0;
+            for (int i = 0; i < K; ++i) t += S.B[i][i];
+            if (!(t > 0.0)) return 0;
+            sm[m - 1] = t;
+            const double it2 = 1.0 / t;
+            ex.par([&](int lane) {
+                for (int e = lane; e < K * K; e += 32) S.C[e / K][e % K] = S.B[e / K][e % K] * it2;
+            });
+        }
+        double up = 1.0, lo = 1.0 / K;                          // lambda_max(B_m) in [1 / K, 1] (PSD, trace 1)
+        for (int j = m - 1; j >= 0; --j) { up = sqrt(sm[j] * up); lo = sqrt(sm[j] * lo); }
+        c_hi = kPinvRcond * tr * up * (1.0 + 1e-12);
+        c_lo = kPinvRcond * tr * lo * (1.0 - 1e-12);
+        if (1.0 > c_hi * tr_inv) {                              // outcome 1: w = A^-1 g
+            ex.par([&](int lane) {
+                if (lane < K) {
+                    double acc = 0.0;
+                    for (int j = 0; j < K; ++j) acc = fma(S.Y[lane][j], S.g[j], acc);
+                    S.w[lane] = acc;
+                }
+            });
+            return 1;
+        }
+    }
+    // ---- not certified with the tightest bounds: smallest eigenpair by inverse iteration (x <- A^-1 x),
+    //      until the extrapolated error of x is at rounding level (the contraction lambda_min / lambda_2 is
+    //      not bounded away from 1 by the classification)
+    ex.par([&](int lane) {
+        if (lane < K) S.x[lane] = 1.0 + 0.1 * lane;
+    });
     bool converged = false;
     double d_prev = HUGE_VAL;
     for (int it = 0; it < 64 && !converged; ++it) {
@@ -141,86 +179,42 @@ IRLOSC_HD int coop_resolve_pinv(CoopSmem<K> &S, EX &ex) {
         }
         d_prev = d;
     }
-    double rho = HUGE_VAL;                                      // lambda_min <= rho
-    if (converged) {
-        ex.par([&](int lane) {
-            if (lane < K) {
-                double acc = 0.0;
-                for (int j = 0; j < K; ++j) acc = fma(S.A[lane][j], S.x[j], acc);
-                S.t[lane] = acc;
-            }
-        });
-        rho = 0.0;
-        for (int i = 0; i < K; ++i) rho = fma(S.x[i], S.t[i], rho);
-    }
-    // ---- bounds on lambda_max, one squaring at a time; classification
-    double sm[MS];
-    const double itr = 1.0 / tr;
+    if (!converged) return 0;
     ex.par([&](int lane) {
-        for (int e = lane; e < K * K; e += 32) S.C[e / K][e % K] = S.A[e / K][e % K] * itr;      // B_m lives in C
+        if (lane < K) {
+            double acc = 0.0;
+            for (int j = 0; j < K; ++j) acc = fma(S.A[lane][j], S.x[j], acc);
+            S.t[lane] = acc;
+        }
     });
-    bool deflated = false;
+    double rho = 0.0;                                           // Rayleigh quotient: lambda_min <= rho
+    for (int i = 0; i < K; ++i) rho = fma(S.x[i], S.t[i], rho);
+    if (!(rho <= c_lo)) return 0;
+    // ---- A' = A + tr(A) x x^T: every other eigenvalue must be above the cutoff
+    ex.par([&](int lane) {
+        for (int e = lane; e < K * K; e += 32) {
+            const int i = e / K, j = e % K;
+            S.B[i][j] = fma(tr * S.x[i], S.x[j], S.A[i][j]);
+        }
+    });
+    if (!coop_factor<K>(S, ex)) return 0;
+    coop_inverse<K>(S, ex);
     double tr2 = 0.0;
-    for (int m = 0; m <= MS; ++m) {
-        if (m > 0) {                                            // C <- C^2 / tr(C^2) via the scratch B
-            ex.par([&](int lane) {
-                for (int e = lane; e < K * K; e += 32) {
-                    const int i = e / K, j = e % K;
-                    double acc = 0.0;
-                    for (int l = 0; l < K; ++l) acc = fma(S.C[i][l], S.C[l][j], acc);
-                    S.B[i][j] = acc;
-                }
-            });
-            double t = 0.0;
-            for (int i = 0; i < K; ++i) t += S.B[i][i];
-            if (!(t > 0.0)) return 0;
-            sm[m - 1] = t;
-            const double it2 = 1.0 / t;
-            ex.par([&](int lane) {
-                for (int e = lane; e < K * K; e += 32) S.C[e / K][e % K] = S.B[e / K][e % K] * it2;
-            });
+    for (int i = 0; i < K; ++i) tr2 += S.Y[i][i];
+    if (!(tr2 > 0.0) || !(1.0 > c_hi * tr2)) return 0;
+    double xg = 0.0;                                            // outcome 2: w = A'^-1 (g - x (x . g))
+    for (int i = 0; i < K; ++i) xg = fma(S.x[i], S.g[i], xg);
+    ex.par([&](int lane) {
+        if (lane < K) S.t[lane] = fma(-xg, S.x[lane], S.g[lane]);
+    });
+    ex.par([&](int lane) {
+        if (lane < K) {
+            double acc = 0.0;
+            for (int j = 0; j < K; ++j) acc = fma(S.Y[lane][j], S.t[j], acc);
+            S.w[lane] = acc;
         }
-        double up = 1.0, lo = 1.0 / K;
-        for (int j = m - 1; j >= 0; --j) { up = sqrt(sm[j] * up); lo = sqrt(sm[j] * lo); }
-        const double c_hi = kPinvRcond * tr * up * (1.0 + 1e-12), c_lo = kPinvRcond * tr * lo * (1.0 - 1e-12);
-        if (1.0 > c_hi * tr_inv) {                              // outcome 1
-            ex.par([&](int lane) {
-                if (lane < K) S.w[lane] = S.w1[lane];
-            });
-            return 1;
-        }
-        if (rho <= c_lo) {
-            if (!deflated) {                                    // A' = A + tr(A) x x^T: factor and invert once
-                deflated = true;
-                ex.par([&](int lane) {
-                    for (int e = lane; e < K * K; e += 32) {
-                        const int i = e / K, j = e % K;
-                        S.B[i][j] = fma(tr * S.x[i], S.x[j], S.A[i][j]);
-                    }
-                });
-                if (!coop_factor<K>(S, ex)) return 0;
-                coop_inverse<K>(S, ex);
-                for (int i = 0; i < K; ++i) tr2 += S.Y[i][i];
-                if (!(tr2 > 0.0)) return 0;
-            }
-            if (1.0 > c_hi * tr2) {                             // outcome 2
-                double xg = 0.0;
-                for (int i = 0; i < K; ++i) xg = fma(S.x[i], S.g[i], xg);
-                ex.par([&](int lane) {
-                    if (lane < K) S.t[lane] = fma(-xg, S.x[lane], S.g[lane]);
-                });
-                ex.par([&](int lane) {
-                    if (lane < K) {
-                        double acc = 0.0;
-                        for (int j = 0; j < K; ++j) acc = fma(S.Y[lane][j], S.t[j], acc);
-                        S.w[lane] = acc;
-                    }
-                });
-                return 2;
-            }
-        }
-    }
-    return 0;
+    });
+    return 2;
 }
 
 }  // namespace fused
