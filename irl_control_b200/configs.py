@@ -83,4 +83,24 @@ SCENE_FREE_OBJECTS = {
     "gain_test_scene.xml": 0,        # gain_test_scene.xml:5-6
     "admit_test_scene.xml": 2,       # admit_test_scene.xml:14-15
     "insertion_task_scene.xml": 4,   # insertion_task_scene.xml:10-13
+    "iros2022.xml": 2,               # iros2022.xml:8-9 (quad bracket + quad pegs)
 }
+
+# `device_config` block of action_sequence_configs/iros2022_task.yaml:1-4.  The reference ships the
+# file but no code reads it (no example loads iros2022_task.yaml; `control_type` appears nowhere in
+# its Python), so "joint" vs "task" has no defined behaviour to reproduce: `device_cfgs()` pairs
+# devices with controllers in the listed order - which is also the target order - and
+# `control_type` is carried along unread, as in the reference.
+IROS2022_DEVICE_CONFIG = {
+    "devices": ["base", "ur5left", "ur5right"],
+    "controllers": ["osc0", "osc2", "osc2"],
+    "control_type": ["joint", "task", "task"],
+}
+
+
+def device_cfgs(device_config):
+    """[(device name, controller config name)] in the order a `device_config` block lists them."""
+    devs, ctrls = device_config["devices"], device_config["controllers"]
+    if len(devs) != len(ctrls):
+        raise ValueError("device_config: %d devices but %d controllers" % (len(devs), len(ctrls)))
+    return list(zip(devs, ctrls))

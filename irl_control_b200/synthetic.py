@@ -22,7 +22,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-from .configs import robot_config
+from .configs import IROS2022_DEVICE_CONFIG, device_cfgs, robot_config
 from .dual_ur5 import DualUR5Model, dynamics, sample_joint_states
 from .layout import OscLayout
 
@@ -43,6 +43,11 @@ SCENARIOS: Dict[str, Dict] = {
     "worst_case": dict(config="default_xyz_abg.yaml+start_body", scene="gain_test_scene.xml",
                        device_cfgs=[("base", "osc0"), ("ur5right", "osc2"), ("ur5left", "osc2")],
                        targets=["ur5right", "ur5left", "base"], admittance=False),
+    # robot_configs/iros2022.yaml (osc0 = osc2 = kp 200 / kv 20 / ko 75, base max_vel [0, 2],
+    # arms [2, 5], start_body set) with the devices, controllers and order of iros2022_task.yaml:1-4
+    "iros2022": dict(config="iros2022.yaml", scene="iros2022.xml",
+                     device_cfgs=device_cfgs(IROS2022_DEVICE_CONFIG),
+                     targets=list(IROS2022_DEVICE_CONFIG["devices"]), admittance=False),
 }
 
 

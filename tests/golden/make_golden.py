@@ -118,8 +118,17 @@ def singular_pose(st, layout):
         st["target_xyz"][:, d] = st["ee_xyz"][:, d] + delta
 
 
+def iros2022_cases():
+    """iros2022.yaml gains / max_vel with the device order of iros2022_task.yaml:1-4."""
+    run_case("iros2022_s8", "iros2022", 24, 8)
+    run_case("iros2022_vel_s9", "iros2022", 12, 9, mutate=vel_all_nonzero)
+
+
 if __name__ == "__main__":
     assert ref_harness.reference_available(), "needs /root/reference"
+    if "--only-iros2022" in sys.argv:          # added after the first eight files were committed
+        iros2022_cases()
+        sys.exit(0)
     run_case("gain_test_s0", "gain_test", 24, 0)
     run_case("admit_test_s1", "admit_test", 24, 1)
     run_case("insertion_s2", "insertion", 24, 2, insertion_schedule=True)
@@ -128,3 +137,4 @@ if __name__ == "__main__":
     run_case("worst_case_vel_s5", "worst_case", 12, 5, mutate=vel_all_nonzero)
     run_case("insertion_vel_s6", "insertion", 8, 6, mutate=vel_all_nonzero)
     run_case("admit_singular_s7", "admit_test", 16, 7, mutate=singular_pose)
+    iros2022_cases()

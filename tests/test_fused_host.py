@@ -45,7 +45,7 @@ def _rel(got, want):
     return (np.abs(got - want) / scale).max(axis=1)
 
 
-@pytest.mark.parametrize("scenario", ["gain_test", "admit_test", "insertion", "worst_case"])
+@pytest.mark.parametrize("scenario", ["gain_test", "admit_test", "insertion", "worst_case", "iros2022"])
 def test_provider_quantities_match_the_rigid_body_model(scenario):
     layout, model, st, inp = _case(scenario, 96, seed=11)
     out = fused_host.run(layout, model, inp, debug=True)
@@ -62,7 +62,8 @@ def test_provider_quantities_match_the_rigid_body_model(scenario):
     assert np.abs(out["ee_quat"] * sgn - eq).max() < 1e-13
 
 
-@pytest.mark.parametrize("scenario,B", [("gain_test", 512), ("admit_test", 512), ("insertion", 512), ("worst_case", 256)])
+@pytest.mark.parametrize("scenario,B", [("gain_test", 512), ("admit_test", 512), ("insertion", 512), ("worst_case", 256),
+                                        ("iros2022", 256)])
 def test_fused_step_matches_the_oracle(scenario, B):
     layout, model, st, inp = _case(scenario, B, seed=3)
     out = fused_host.run(layout, model, inp)
@@ -74,7 +75,7 @@ def test_fused_step_matches_the_oracle(scenario, B):
     # packing (osc.py:203-208)
     want = np.concatenate([ref["u_all"][:, list(d.actuator_trnids)] for d in layout.devices], axis=1)
     assert _rel(out["ctrl"], want).max() < REL_TOL
-    if scenario in ("admit_test", "insertion", "worst_case"):
+    if scenario in ("admit_test", "insertion", "worst_case", "iros2022"):
         assert out["n_hard"] > 0          # the eigen fix-up path is exercised
 
 

@@ -41,7 +41,8 @@ def test_scene_free_objects_keep_robot_ids():
 
 
 def test_layout_rows_and_dx_idx_order():
-    for name, k, n_ctrl in (("gain_test", 7, 15), ("admit_test", 12, 14), ("insertion", 12, 14), ("worst_case", 13, 15)):
+    for name, k, n_ctrl in (("gain_test", 7, 15), ("admit_test", 12, 14), ("insertion", 12, 14), ("worst_case", 13, 15),
+                            ("iros2022", 13, 15)):
         _, _, targets, L = build_scenario(name)
         assert (L.k, L.n_ctrl, L.D) == (k, n_ctrl, len(targets))
     _, _, _, L = build_scenario("gain_test")

@@ -1,0 +1,65 @@
+"""CPU: the streaming step (`csrc/osc_stream.cuh` copy plan + per-instance elimination, `osc_tail.cuh`)
+compiled for the host (tests/host_fused, test infrastructure) against the reference's golden outputs.
+
+Same assertions as `tests/test_gpu_parity.py::test_streaming_kernel_matches_reference_golden`, so the
+arithmetic, the gather plan of every `M` / `J` layout and the status flags of the default kernel of the
+6-row configurations (admit_test, insertion, k = 13, iros2022) are checked without a GPU; what only the
+GPU suite sees is the cp.async staging and the fix-up kernel's warp code.
+"""
+import numpy as np
+import pytest
+
+import fused_host
+from conftest import GOLDEN_CASES, GOLDEN_CASES_F4, load_golden
+from irl_control_b200 import _native
+from irl_control_b200.layout import DeviceLayout, OscLayout
+
+REL_TOL = 1e-6
+DUAL_UR5_PARENT = (-1, 0, 1, 2, 3, 4, 5, 6, 7, 6, 6, 10, 6, 0, 13, 14, 15, 16, 17, 18, 19, 18, 18, 22, 18)
+EE_JOINT = {"base": 0, "ur5right": 6, "ur5left": 18}
+
+
+def _layout(ld):
+    devs = tuple(DeviceLayout(name=d["name"], ctrlr_dof=tuple(d["ctrlr_dof"]), joint_ids_all=tuple(d["joint_ids_all"]),
+                              actuator_trnids=tuple(d["actuator_trnids"]), ctrl_idxs=tuple(d["ctrl_idxs"]),
+                              dx_idx=tuple(d["dx_idx"]), has_max_vel=d["has_max_vel"], max_vel=tuple(d["max_vel"]),
+                              kp=d["kp"], kv=d["kv"], ko=d["ko"], k=tuple(d["k"]), d=tuple(d["d"]),
+                              ee_joint=EE_JOINT[d["name"]]) for d in ld["devices"])
+    return OscLayout(n=ld["n"], devices=devs, use_g=ld["use_g"], admittance=ld["admittance"],
+                     nullspace_kv=ld["nullspace_kv"], joint_parent=DUAL_UR5_PARENT, check_topology=False)
+
+
+def _state(g, layout, packed_M, full6_J):
+    rows = [(d, c) for d, dl in enumerate(layout.devices) for c in range(6) if dl.ctrlr_dof[c]]
+    st = {k: np.array(g[k]) for k in ("M", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat", "max_vel")}
+    st["J"] = np.array(g["J6"]) if full6_J else np.stack([g["J6"][:, d, c] for d, c in rows], 1)
+    if packed_M:
+        n = layout.n
+        il = np.tril_indices(n)
+        st["M"] = np.ascontiguousarray(st["M"][:, il[0], il[1]])
+    if layout.admittance:
+        st["ft_xmat"], st["ft_raw"] = np.array(g["ft_xmat"]), np.array(g["ft_raw"])
+    if np.any(g["target_vel"] != 0):
+        st["target_vel"] = np.array(g["target_vel"])
+    return st
+
+
+@pytest.mark.parametrize("packed_M,full6_J", [(False, False), (True, True), (True, False)])
+@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4)
+def test_host_build_of_the_streaming_step_matches_reference_golden(case, packed_M, full6_J):
+    g, ld = load_golden(case)
+    layout = _layout(ld)
+    out = fused_host.run_stream(layout, _state(g, layout, packed_M, full6_J))
+    ctrl, u_all, status = out["ctrl"], out["u_all"], out["status"]
+    bad = np.array(g["index_error"])
+    assert np.all((status[bad] & _native.ST_DX_RANGE) != 0) and np.all(np.isnan(ctrl[bad]))
+    ok = ~bad
+    if ok.any():
+        assert np.array_equal((status[ok] & _native.ST_PINV) != 0, g["pinv"][ok])
+        assert not np.any(status[ok] & (_native.ST_M_NOT_PD | _native.ST_DX_RANGE | _native.ST_SPARSITY))
+        scale = np.abs(g["u_all"][ok]).max(axis=1)
+        e_u = np.abs(u_all[ok] - g["u_all"][ok]).max(axis=1) / scale
+        e_c = np.abs(ctrl[ok] - g["ctrl"][ok]).max(axis=1) / scale
+        assert e_u.max() < REL_TOL and e_c.max() < REL_TOL, (case, e_u.max(), e_c.max())
+        vel = (np.asarray(g["target_vel"]) != 0).all(axis=-1).any(axis=-1)
+        assert np.array_equal((status[ok] & _native.ST_VEL_BRANCH) != 0, vel[ok])
