@@ -123,7 +123,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gain_test")
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU")
-    ap.add_argument("--m-layout", default="packed", choices=["packed", "dense"])
+    ap.add_argument("--m-layout", default="packed", choices=["packed", "dense", "qM"],
+                    help="packed lower triangle (the SURVEY 8d record, default), dense n x n, or MuJoCo's sparse qM "
+                         "(IRLOSC_M_QM: 155 instead of 325 doubles; the roofline still counts the SURVEY record)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")
     ap.add_argument("--sm-margin", type=int, default=-1,
                     help="SMs left free for the gather when --gpus > 1 (-1: 0 for the fused gather, 8 for NCCL)")
@@ -183,7 +185,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     st = synth_batch(layout, B, seed=1000 * rank, device=dev)
-    kin = kernel_inputs(st, layout, packed_M=(args.m_layout == "packed"))
+    kin = kernel_inputs(st, layout, packed_M=(args.m_layout == "packed"), qM=(args.m_layout == "qM"))
     in_bytes = sum(v.numel() * v.element_size() for v in kin.values())
     config["l2_policy"] = "inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (in_bytes / 1e6)
     eng = BatchedOSC(layout, device=local_rank)
@@ -439,7 +441,7 @@ def main():
         traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": kernel_name, "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_step": abytes, "peak_source": peak_src}
+                "algorithmic_bytes_per_step": abytes, "input_bytes_per_step": in_bytes // B, "peak_source": peak_src}
     cb = None
     if world == 1 and not args.no_cpu_baseline:
         nsample = (os.cpu_count() or 1) * 192

@@ -52,6 +52,12 @@ extern "C" {
 /* layouts of the inertia / Jacobian inputs */
 #define IRLOSC_M_DENSE 0        /* [B][ldm rows used: n][ldm]  row-major n x n block, row stride ldm   */
 #define IRLOSC_M_PACKED 1       /* [B][n(n+1)/2] lower triangle, row-major: (i,j<=i) at i(i+1)/2+j     */
+#define IRLOSC_M_QM 2           /* [B][m_stride >= nM] MuJoCo's own sparse inertia, mjData.qM - what robot.py:69
+                                   hands to mj_fullM: dof i owns M[i][i], M[i][parent(i)], M[i][parent(parent(i))],
+                                   ... down to its root, stored from dof_Madr[i] = sum of depth(r) for r < i
+                                   (depth counts i itself).  Needs has_topology (joint_parent = dof_parentid of the
+                                   robot's dofs, which must be the scene's first n dofs); nM = sum of depths (155
+                                   for the DualUR5), m_stride = the scene's nM.  Read by the streaming kernel only */
 #define IRLOSC_J_ROWS 0         /* [B][k][ldj]   only the controlled rows, target order (osc.py:136-138) */
 #define IRLOSC_J_FULL6 1        /* [B][D][6][ldj] full [jacp;jacr] per target device (device.py:125-130);
                                    rows with ctrlr_dof == 0 are never read                              */
@@ -104,9 +110,9 @@ typedef struct irlosc_params {
  */
 typedef struct irlosc_io {
     const double *M;          /* RobotState.M (robot.py:68-72)                                        */
-    int32_t m_layout;         /* IRLOSC_M_DENSE | IRLOSC_M_PACKED                                      */
+    int32_t m_layout;         /* IRLOSC_M_DENSE | IRLOSC_M_PACKED | IRLOSC_M_QM                        */
     int32_t ldm;              /* dense: row stride in doubles (>= n; scene nv if the block is a view)  */
-    int64_t m_stride;         /* doubles between instances; 0 = tight (ldm*n dense, n(n+1)/2 packed)   */
+    int64_t m_stride;         /* doubles between instances; 0 = tight (ldm*n dense, n(n+1)/2 packed, nM qM) */
     const double *J;          /* RobotState.J stacked for the targets                                  */
     int32_t j_layout;         /* IRLOSC_J_ROWS | IRLOSC_J_FULL6                                        */
     int32_t ldj;              /* row stride in doubles (>= n)                                          */

@@ -24,7 +24,7 @@ ST_VEL_BRANCH = 0x08
 ST_DX_RANGE = 0x10
 ST_SPARSITY = 0x20
 
-M_DENSE, M_PACKED = 0, 1
+M_DENSE, M_PACKED, M_QM = 0, 1, 2
 J_ROWS, J_FULL6 = 0, 1
 
 KERNEL_AUTO, KERNEL_GENERIC, KERNEL_TILED = 0, 1, 2

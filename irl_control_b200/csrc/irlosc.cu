@@ -102,17 +102,8 @@ static int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k) {
     if (P.use_g && !io->bias) return fail(IRLOSC_ERR_INVALID, "use_g is set but bias is null");
     if (P.admittance && (!io->ft_xmat || !io->ft_raw))
         return fail(IRLOSC_ERR_INVALID, "admittance is set but ft_xmat / ft_raw is null");
-    k.M = io->M; k.m_layout = io->m_layout;
-    if (io->m_layout == IRLOSC_M_DENSE) {
-        k.ldm = io->ldm ? io->ldm : P.n;
-        if (k.ldm < P.n) return fail(IRLOSC_ERR_INVALID, "ldm=%d < n=%d", k.ldm, P.n);
-        k.m_stride = io->m_stride ? io->m_stride : (int64_t)k.ldm * P.n;
-    } else if (io->m_layout == IRLOSC_M_PACKED) {
-        k.ldm = 0;
-        k.m_stride = io->m_stride ? io->m_stride : (int64_t)P.n * (P.n + 1) / 2;
-    } else {
-        return fail(IRLOSC_ERR_INVALID, "unknown m_layout %d", io->m_layout);
-    }
+    const int32_t mrc = resolve_m_layout(P, *io, k);
+    if (mrc != IRLOSC_OK) return mrc;
     k.J = io->J; k.j_layout = io->j_layout;
     k.ldj = io->ldj ? io->ldj : P.n;
     if (k.ldj < P.n) return fail(IRLOSC_ERR_INVALID, "ldj=%d < n=%d", k.ldj, P.n);
@@ -143,6 +134,12 @@ constexpr int kKernelStream = 9;
 static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st, int queue = 0) {
     if (B == 0) return IRLOSC_OK;
     const bool stream_ok = stream_supported(h, k);
+    if (k.m_layout == IRLOSC_M_QM) {          // only the streaming kernel's copy plan addresses MuJoCo's sparse qM
+        if (!stream_ok || (h->kernel_choice != 0 && h->kernel_choice != kKernelStream))
+            return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM is read by the streaming kernel only: declare the DualUR5 topology, "
+                                            "leave check_topology off and keep the kernel selector at 0 or 9");
+        return stream_launch(h, B, k, st, queue);
+    }
     if (h->kernel_choice == kKernelStream) {
         if (!stream_ok) return fail(IRLOSC_ERR_INVALID, "streaming kernel requested but the DualUR5 topology is not declared (or check_topology is set)");
         return stream_launch(h, B, k, st, queue);

@@ -249,6 +249,53 @@ inline int32_t build_kseq_waypoints(const KParams &P, const fused::FRoles &R, co
     return IRLOSC_OK;
 }
 
+// MuJoCo's sparse inertia `qM` (mjData.qM, the array robot.py:69 hands to mj_fullM; IRLOSC_M_QM): dof i owns
+// the entries M[i][i], M[i][parent(i)], M[i][parent(parent(i))], ... down to its root, stored from
+// dof_Madr[i], and dof_Madr[i + 1] = dof_Madr[i] + depth(i) (mj_fullM walks exactly this: `adr = dof_Madr[i];
+// for (j = i; j >= 0; j = dof_parentid[j]) dst[i][j] = dst[j][i] = qM[adr++]`).  Callers have checked that
+// every parent precedes its child.
+inline int qm_depth(const KParams &P, int i) {
+    int d = 0;
+    for (int j = i; j >= 0; j = P.joint_parent[j]) ++d;
+    return d;
+}
+inline int qm_size(const KParams &P) {
+    int s = 0;
+    for (int i = 0; i < P.n; ++i) s += qm_depth(P, i);
+    return s;
+}
+inline int qm_offset(const KParams &P, int i, int j) {       // -1 unless j is i or one of its ancestors
+    int adr = 0;
+    for (int r = 0; r < i; ++r) adr += qm_depth(P, r);
+    for (int a = i; a >= 0; a = P.joint_parent[a], ++adr)
+        if (a == j) return adr;
+    return -1;
+}
+
+// M part of irlosc_io -> KIo: layout, leading dimension and instance stride with their defaults.
+inline int32_t resolve_m_layout(const KParams &P, const irlosc_io &io, KIo &k) {
+    k.M = io.M; k.m_layout = io.m_layout;
+    if (io.m_layout == IRLOSC_M_DENSE) {
+        k.ldm = io.ldm ? io.ldm : P.n;
+        if (k.ldm < P.n) return fail(IRLOSC_ERR_INVALID, "ldm=%d < n=%d", k.ldm, P.n);
+        k.m_stride = io.m_stride ? io.m_stride : (int64_t)k.ldm * P.n;
+    } else if (io.m_layout == IRLOSC_M_PACKED) {
+        k.ldm = 0;
+        k.m_stride = io.m_stride ? io.m_stride : (int64_t)P.n * (P.n + 1) / 2;
+    } else if (io.m_layout == IRLOSC_M_QM) {
+        if (!P.has_topology) return fail(IRLOSC_ERR_INVALID, "m_layout IRLOSC_M_QM needs has_topology (joint_parent = dof_parentid)");
+        for (int j = 0; j < P.n; ++j)
+            if (P.joint_parent[j] >= j) return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM: joint_parent[%d]=%d does not precede it", j, P.joint_parent[j]);
+        const int nm = qm_size(P);
+        k.ldm = 0;
+        k.m_stride = io.m_stride ? io.m_stride : (int64_t)nm;
+        if (k.m_stride < nm) return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM: m_stride=%lld < nM=%d", (long long)k.m_stride, nm);
+    } else {
+        return fail(IRLOSC_ERR_INVALID, "unknown m_layout %d", io.m_layout);
+    }
+    return IRLOSC_OK;
+}
+
 // Copy plan of the streaming step (osc_stream.cuh): which doubles of an instance's arrays go to which
 // stage entry of which group, as 8-entry chunks with per-lane byte offsets.  Works for every M / J
 // layout and stride of irlosc_io because a chunk carries its array's base pointer and stride.
@@ -258,8 +305,13 @@ inline int32_t build_stream_plan(const KParams &P, const KIo &io, const fused::F
     struct Item { const void *base; int64_t stride; int64_t off; int dst; };
     std::vector<Item> groups[kGroups];
     const int n = P.n, D = P.D;
-    auto M_at = [&](int i, int j) -> Item {        // i >= j
-        const int64_t e = io.m_layout == IRLOSC_M_PACKED ? (int64_t)i * (i + 1) / 2 + j : (int64_t)i * io.ldm + j;
+    bool qm_miss = false;
+    auto M_at = [&](int i, int j) -> Item {        // i >= j, and j is i or an ancestor of i (the tree's non-zeros)
+        int64_t e = io.m_layout == IRLOSC_M_PACKED ? (int64_t)i * (i + 1) / 2 + j : (int64_t)i * io.ldm + j;
+        if (io.m_layout == IRLOSC_M_QM) {
+            e = qm_offset(P, i, j);
+            if (e < 0) { qm_miss = true; e = 0; }
+        }
         return Item{io.M, io.m_stride * 8, e * 8, 0};
     };
     auto J_at = [&](int row, int j) -> Item {
@@ -313,6 +365,7 @@ inline int32_t build_stream_plan(const KParams &P, const KIo &io, const fused::F
         max_entries = std::max(max_entries, kd * 7 + 6);
         device_block(g0 + 4, R.dev_arm[arm], 0);
     }
+    if (qm_miss) return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM: the plan asked for an entry outside the kinematic tree");
     memset(&plan, 0, sizeof plan);
     plan.has_mvel = io.max_vel != nullptr;
     const int trash = max_entries;

@@ -25,7 +25,7 @@ from typing import Dict, Optional
 import numpy as np
 
 from . import _native
-from .layout import OscLayout
+from .layout import OscLayout, qm_size
 
 _OPTIONAL = ("bias", "target_vel", "max_vel", "ft_xmat", "ft_raw")
 _FIELDS = ("M", "J", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat",
@@ -93,8 +93,28 @@ class BatchedOSC:
     def _infer_layouts(self, state):
         M, J = state["M"], state["J"]
         m_layout = _native.M_DENSE if len(M.shape) == 3 else _native.M_PACKED
+        if state.get("_qM"):
+            m_layout = _native.M_QM
         j_layout = _native.J_FULL6 if len(J.shape) == 4 else _native.J_ROWS
         return m_layout, j_layout
+
+    def _accept_qM(self, state, shapes_out=None):
+        """`state["qM"]` ([B, nM of the scene], MuJoCo's sparse `mjData.qM` - the array the reference expands
+        with `mj_fullM`, robot.py:69) may stand in for `state["M"]` (IRLOSC_M_QM)."""
+        if "qM" not in state:
+            return state
+        if "M" in state:
+            raise ValueError("give either state['M'] or state['qM'], not both")
+        qM = state["qM"]
+        nM = qm_size(self.layout.joint_parent) if self.layout.joint_parent is not None else None
+        if nM is None:
+            raise ValueError("state['qM'] needs a layout with the kinematic tree (joint_parent)")
+        if len(qM.shape) != 2 or int(qM.shape[1]) < nM:
+            raise ValueError("state['qM'] has shape %s, expected (B, >= %d)" % (tuple(qM.shape), nM))
+        state = {k: v for k, v in state.items() if k != "qM"}
+        state["M"] = qM
+        state["_qM"] = True
+        return state
 
     def _check(self, state, B, shapes, is_ok):
         for name in _FIELDS:
@@ -135,13 +155,17 @@ class BatchedOSC:
                   instead of once per peer (`irlosc_io.ctrl_multicast`).
         """
         import torch
+        state = self._accept_qM(state)
         M = state["M"]
         if not M.is_cuda:
             raise ValueError("BatchedOSC.step expects CUDA tensors; use step_host for host arrays")
         B = int(M.shape[0])
         m_layout, j_layout = self._infer_layouts(state)
         shapes = self._shapes(B, m_layout, j_layout)
-        strides = strides or {}
+        strides = dict(strides or {})
+        if m_layout == _native.M_QM:
+            shapes["M"] = tuple(M.shape)
+            strides["m_stride"] = int(M.shape[1])
         if "ldm" in strides:
             shapes["M"] = tuple(M.shape)            # a view: the caller vouches for ldm / m_stride
         if "ldj" in strides:
@@ -185,10 +209,13 @@ class BatchedOSC:
     def step_host(self, state: Dict, out: Optional[Dict] = None, want_u_all: bool = False,
                   want_status: bool = True) -> Dict:
         """Same step with HOST numpy arrays (float64, C-contiguous); blocks until results are valid."""
+        state = self._accept_qM(state)
         M = state["M"]
         B = int(M.shape[0])
         m_layout, j_layout = self._infer_layouts(state)
         shapes = self._shapes(B, m_layout, j_layout)
+        if m_layout == _native.M_QM:
+            shapes["M"] = tuple(M.shape)
 
         def ok(name, a):
             if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
@@ -203,6 +230,8 @@ class BatchedOSC:
             out["status"] = np.empty((B,), dtype=np.uint8)
         io = _native.Io()
         io.m_layout, io.j_layout = m_layout, j_layout
+        if m_layout == _native.M_QM:
+            io.m_stride = int(M.shape[1])
         for name in _FIELDS:
             a = state.get(name)
             setattr(io, name, a.ctypes.data if a is not None else None)

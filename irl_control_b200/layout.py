@@ -10,7 +10,7 @@ description.  It is handed to the CUDA library as `irlosc_params`
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -187,3 +187,25 @@ def compile_layout(robot, device_configs: Dict[str, Dict], target_names: Sequenc
         nullspace_kv=None if nullspace_config is None else float(nullspace_config['kv']),
         joint_parent=joint_parents(robot.sim.model, robot.joint_ids_all),
         check_topology=bool(check_topology))
+
+
+# ---------------------------------------------------------------- MuJoCo's sparse inertia (IRLOSC_M_QM)
+def qm_index(joint_parent: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+    """(rows, cols) of the entries of `mjData.qM` in storage order for a dof tree given by `dof_parentid`:
+    dof i owns M[i, i], M[i, parent(i)], M[i, parent(parent(i))], ... down to its root, dofs in order
+    (the walk of `mj_fullM`, which robot.py:69 calls).  `M[:, rows, cols]` is the robot's part of qM."""
+    rows, cols = [], []
+    for i in range(len(joint_parent)):
+        j = i
+        while j >= 0:
+            if joint_parent[j] >= j:
+                raise ValueError("joint_parent[%d]=%d does not precede it" % (j, joint_parent[j]))
+            rows.append(i)
+            cols.append(j)
+            j = joint_parent[j]
+    return np.asarray(rows, dtype=np.int64), np.asarray(cols, dtype=np.int64)
+
+
+def qm_size(joint_parent: Sequence[int]) -> int:
+    """nM of the tree: 155 for the DualUR5's 25 dofs."""
+    return int(len(qm_index(joint_parent)[0]))

@@ -173,15 +173,29 @@ def scenario_model(name: str):
     return layout, model_for_layout(app.sim.model, robot.joint_ids_all, layout)
 
 
+def sparse_qM(M: torch.Tensor, joint_parent: Sequence[int], pad: int = 0) -> torch.Tensor:
+    """(B, n, n) -> (B, nM + pad): the entries MuJoCo keeps in `mjData.qM` (IRLOSC_M_QM); `pad` extra doubles
+    per instance stand for the free bodies' entries that follow the robot's in a scene."""
+    from .layout import qm_index
+    rows, cols = qm_index(joint_parent)
+    q = M[:, torch.as_tensor(rows, device=M.device), torch.as_tensor(cols, device=M.device)]
+    if pad:
+        q = torch.cat([q, torch.full((M.shape[0], pad), float("nan"), dtype=M.dtype, device=M.device)], 1)
+    return q.contiguous()
+
+
 def kernel_inputs(st: Dict[str, torch.Tensor], layout: OscLayout, packed_M: bool = False,
-                  full6_J: bool = False, with_vel: bool = False) -> Dict[str, torch.Tensor]:
+                  full6_J: bool = False, with_vel: bool = False, qM: bool = False) -> Dict[str, torch.Tensor]:
     """Select the fields `BatchedOSC.step` consumes from a `synth_batch` dict."""
     keep = {
-        "M": pack_lower(st["M"]) if packed_M else st["M"],
         "J": st["J6"] if full6_J else st["J"],
         "dq": st["dq"], "ee_xyz": st["ee_xyz"], "ee_quat": st["ee_quat"],
         "target_xyz": st["target_xyz"], "target_quat": st["target_quat"],
     }
+    if qM:
+        keep["qM"] = sparse_qM(st["M"], layout.joint_parent)
+    else:
+        keep["M"] = pack_lower(st["M"]) if packed_M else st["M"]
     if layout.use_g:
         keep["bias"] = st["bias"]
     if "max_vel" in st:

@@ -197,3 +197,21 @@ def osc_batch(layout: Dict, batch: Dict[str, np.ndarray], idx=None) -> Dict[str,
         "det": np.array([o["det"] for o in outs]),
         "vel_branch": np.stack([o["vel_branch"] for o in outs]),
     }
+
+
+def full_from_qM(qM, dof_parentid):
+    """Dense n x n inertia from MuJoCo's sparse `qM`: restatement of `mj_fullM`, which the reference calls at
+    robot.py:69 (`mujoco_py.cymj._mj_fullM(model, M_vec, sim.data.qM)`).  MuJoCo is a third-party dependency
+    absent from /root/reference and from this image (parity unpinned); published algorithm (MuJoCo 2.x
+    engine_util_misc.c): `adr = dof_Madr[i]; for (j = i; j >= 0; j = dof_parentid[j]) dst[i][j] = dst[j][i] =
+    qM[adr++]`, with dof_Madr the running sum of the dofs' depths."""
+    n = len(dof_parentid)
+    M = np.zeros((n, n))
+    adr = 0
+    for i in range(n):
+        j = i
+        while j >= 0:
+            M[i, j] = M[j, i] = qM[adr]
+            adr += 1
+            j = dof_parentid[j]
+    return M

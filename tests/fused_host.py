@@ -80,7 +80,13 @@ def run_stream(layout, state, debug=False, strides=None):
     n, D, k, nc = layout.n, layout.D, layout.k, layout.n_ctrl
     out = {"ctrl": np.zeros((B, nc)), "u_all": np.zeros((B, n)), "status": np.zeros(B, dtype=np.uint8)}
     io = _native.Io()
-    io.m_layout = _native.M_DENSE if keep["M"].ndim == 3 else _native.M_PACKED
+    if "qM" in keep:                       # MuJoCo's sparse inertia (IRLOSC_M_QM), [B][>= nM]
+        keep["M"] = keep.pop("qM")
+        io.m_layout = _native.M_QM
+        strides = dict(strides or {})
+        strides.setdefault("m_stride", int(keep["M"].shape[1]))
+    else:
+        io.m_layout = _native.M_DENSE if keep["M"].ndim == 3 else _native.M_PACKED
     io.j_layout = _native.J_FULL6 if keep["J"].ndim == 4 else _native.J_ROWS
     for name in ("M", "J", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat", "target_vel", "max_vel",
                  "ft_xmat", "ft_raw"):

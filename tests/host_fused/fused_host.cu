@@ -241,9 +241,7 @@ extern "C" int64_t stream_host_run(const irlosc_params *params, int64_t B, const
     if (!fused_roles(P, R, kd, hb)) { irlosc::fail(1, "not the DualUR5 topology"); return -1; }
     KIo k;
     memset(&k, 0, sizeof k);
-    k.M = io->M; k.m_layout = io->m_layout;
-    if (io->m_layout == IRLOSC_M_DENSE) { k.ldm = io->ldm ? io->ldm : P.n; k.m_stride = io->m_stride ? io->m_stride : (int64_t)k.ldm * P.n; }
-    else { k.ldm = 0; k.m_stride = io->m_stride ? io->m_stride : (int64_t)P.n * (P.n + 1) / 2; }
+    if (resolve_m_layout(P, *io, k) != IRLOSC_OK) return -1;
     k.J = io->J; k.j_layout = io->j_layout; k.ldj = io->ldj ? io->ldj : P.n;
     k.j_stride = io->j_stride ? io->j_stride : (io->j_layout == IRLOSC_J_ROWS ? (int64_t)k.ldj * P.k : (int64_t)k.ldj * 6 * P.D);
     k.dq = io->dq; k.bias = io->bias; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;

@@ -1,0 +1,80 @@
+"""GPU: IRLOSC_M_QM - the step fed with MuJoCo's sparse inertia `mjData.qM` (the array robot.py:69 expands
+with mj_fullM) instead of a dense / packed `M`.
+
+Written after round 1's GPU budget was spent.  The copy plan and the arithmetic are checked in the CPU suite on
+the host build of the streaming step (tests/test_stream_host.py); this file is the layout's first run on a GPU
+and is collected last for that reason.
+"""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, GOLDEN_CASES_F4, load_golden
+from test_gpu_parity import REL_TOL, _golden_state, _layout_from_dict, _rel_err, _torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _with_qM(st, layout, pad):
+    from irl_control_b200.synthetic import sparse_qM
+    st = dict(st)
+    st["qM"] = sparse_qM(st.pop("M"), layout.joint_parent, pad=pad)
+    return st
+
+
+@pytest.mark.parametrize("full6_J,pad", [(False, 0), (True, 42)])
+@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4)
+def test_streaming_kernel_reads_sparse_qM(case, full6_J, pad):
+    torch = _torch()
+    from irl_control_b200 import _native
+    from irl_control_b200.engine import BatchedOSC
+    g, ld = load_golden(case)
+    layout = _layout_from_dict(ld, topology=True, check=False)
+    eng = BatchedOSC(layout, device=0)
+    dense_state = _golden_state(g, layout, torch, False, full6_J)
+    eng.set_kernel(9)
+    dense = eng.step(dense_state, want_u_all=True)
+    eng.set_kernel(0)                                   # auto must route qM to the streaming kernel
+    out = eng.step(_with_qM(dense_state, layout, pad), want_u_all=True)
+    torch.cuda.synchronize()
+    assert eng.last_kernel.startswith("osc_step_stream"), eng.last_kernel
+    ok = ~np.array(g["index_error"])
+    u, u_dense = out["u_all"].cpu().numpy(), dense["u_all"].cpu().numpy()
+    assert np.array_equal(out["status"].cpu().numpy(), dense["status"].cpu().numpy())
+    assert np.array_equal(u[ok], u_dense[ok])           # same entries, same arithmetic
+    if ok.any():
+        assert _rel_err(u[ok], g["u_all"][ok]).max() < REL_TOL
+        e_c = np.abs(out["ctrl"].cpu().numpy()[ok] - g["ctrl"][ok]).max(axis=1) / np.abs(g["u_all"][ok]).max(axis=1)
+        assert e_c.max() < REL_TOL
+        assert np.array_equal((out["status"].cpu().numpy()[ok] & _native.ST_PINV) != 0, g["pinv"][ok])
+
+
+def test_qM_full_batch_host_buffers_and_refusals():
+    """B = 65 536 gain_test: qM run == packed-M run bit for bit (device and host-buffer entry points); kernels
+    that cannot address qM refuse it instead of misreading it."""
+    torch = _torch()
+    from irl_control_b200 import _native
+    from irl_control_b200.engine import BatchedOSC
+    from irl_control_b200.synthetic import kernel_inputs, scenario_layout, synth_batch
+    layout = scenario_layout("gain_test")
+    B = 65536
+    st = synth_batch(layout, B, seed=77, device="cuda:0")
+    eng = BatchedOSC(layout, device=0)
+    eng.set_kernel(9)
+    a = eng.step(kernel_inputs(st, layout, packed_M=True), want_u_all=True)
+    eng.set_kernel(0)
+    qin = kernel_inputs(st, layout, qM=True)
+    assert tuple(qin["qM"].shape) == (B, 155)
+    b = eng.step(qin, want_u_all=True)
+    torch.cuda.synchronize()
+    assert torch.equal(a["u_all"], b["u_all"]) and torch.equal(a["ctrl"], b["ctrl"]) and torch.equal(a["status"], b["status"])
+    n = 3000
+    host = {k: v[:n].cpu().numpy() for k, v in qin.items()}
+    h = eng.step_host(host, want_u_all=True)
+    assert np.array_equal(h["u_all"], b["u_all"][:n].cpu().numpy())
+    for which in (1, 2):
+        eng.set_kernel(which)
+        with pytest.raises(_native.OscError):
+            eng.step(qin)
+    eng.set_kernel(0)
+    with pytest.raises(ValueError):
+        eng.step(dict(qin, M=st["M"]))

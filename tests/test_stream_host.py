@@ -12,7 +12,8 @@ import pytest
 import fused_host
 from conftest import GOLDEN_CASES, GOLDEN_CASES_F4, load_golden
 from irl_control_b200 import _native
-from irl_control_b200.layout import DeviceLayout, OscLayout
+from irl_control_b200.layout import DeviceLayout, OscLayout, qm_index, qm_size
+from oracle import osc_numpy
 
 REL_TOL = 1e-6
 DUAL_UR5_PARENT = (-1, 0, 1, 2, 3, 4, 5, 6, 7, 6, 6, 10, 6, 0, 13, 14, 15, 16, 17, 18, 19, 18, 18, 22, 18)
@@ -29,11 +30,15 @@ def _layout(ld):
                      nullspace_kv=ld["nullspace_kv"], joint_parent=DUAL_UR5_PARENT, check_topology=False)
 
 
-def _state(g, layout, packed_M, full6_J):
+def _state(g, layout, packed_M, full6_J, qM_pad=None):
     rows = [(d, c) for d, dl in enumerate(layout.devices) for c in range(6) if dl.ctrlr_dof[c]]
     st = {k: np.array(g[k]) for k in ("M", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat", "max_vel")}
     st["J"] = np.array(g["J6"]) if full6_J else np.stack([g["J6"][:, d, c] for d, c in rows], 1)
-    if packed_M:
+    if qM_pad is not None:
+        rows, cols = qm_index(layout.joint_parent)
+        q = st.pop("M")[:, rows, cols]
+        st["qM"] = np.ascontiguousarray(np.concatenate([q, np.full((q.shape[0], qM_pad), np.nan)], 1))
+    elif packed_M:
         n = layout.n
         il = np.tril_indices(n)
         st["M"] = np.ascontiguousarray(st["M"][:, il[0], il[1]])
@@ -63,3 +68,54 @@ def test_host_build_of_the_streaming_step_matches_reference_golden(case, packed_
         assert e_u.max() < REL_TOL and e_c.max() < REL_TOL, (case, e_u.max(), e_c.max())
         vel = (np.asarray(g["target_vel"]) != 0).all(axis=-1).any(axis=-1)
         assert np.array_equal((status[ok] & _native.ST_VEL_BRANCH) != 0, vel[ok])
+
+
+def test_qm_index_is_the_mj_fullM_walk():
+    """`layout.qm_index` (product) and `oracle.full_from_qM` (restatement of mj_fullM, robot.py:69) are inverse
+    to each other on the DualUR5 tree; nM = 155 (155 of 325 lower entries are structural)."""
+    g, ld = load_golden("gain_test_s0")
+    rows, cols = qm_index(DUAL_UR5_PARENT)
+    assert qm_size(DUAL_UR5_PARENT) == 155 and len(rows) == 155
+    assert (rows[0], cols[0]) == (0, 0) and list(zip(rows[1:3], cols[1:3])) == [(1, 1), (1, 0)]
+    for i in range(4):
+        M = np.array(g["M"][i])
+        back = osc_numpy.full_from_qM(M[rows, cols], DUAL_UR5_PARENT)
+        assert np.array_equal(back, M)          # every entry outside the walk is an exact zero of the tree
+
+
+@pytest.mark.parametrize("full6_J,pad", [(False, 0), (True, 42)])
+@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4)
+def test_host_build_of_the_streaming_step_reads_mujoco_sparse_qM(case, full6_J, pad):
+    """IRLOSC_M_QM: the step fed with what `sim.data.qM` holds (robot.py:69 expands it with mj_fullM) - tight,
+    and padded like a scene whose free bodies add entries after the robot's - reproduces the goldens."""
+    g, ld = load_golden(case)
+    layout = _layout(ld)
+    dense = fused_host.run_stream(layout, _state(g, layout, False, full6_J))
+    out = fused_host.run_stream(layout, _state(g, layout, False, full6_J, qM_pad=pad))
+    ok = ~np.array(g["index_error"])
+    assert np.array_equal(out["status"], dense["status"])
+    # same entries, same arithmetic: bit-identical to the dense-M run
+    assert np.array_equal(out["u_all"][ok], dense["u_all"][ok]) and np.array_equal(out["ctrl"][ok], dense["ctrl"][ok])
+    if ok.any():
+        scale = np.abs(g["u_all"][ok]).max(axis=1)
+        assert (np.abs(out["u_all"][ok] - g["u_all"][ok]).max(axis=1) / scale).max() < REL_TOL
+        assert (np.abs(out["ctrl"][ok] - g["ctrl"][ok]).max(axis=1) / scale).max() < REL_TOL
+    assert out["n_chunks"] <= dense["n_chunks"]
+
+
+def test_engine_accepts_qM_in_place_of_M():
+    """Host-side handling of `state["qM"]` (no GPU: the object is built without `irlosc_create`)."""
+    from irl_control_b200.engine import BatchedOSC
+    _, ld = load_golden("gain_test_s0")
+    eng = BatchedOSC.__new__(BatchedOSC)
+    eng._handle = None
+    eng.layout = _layout(ld)
+    J = np.zeros((4, 7, 25))
+    st = eng._accept_qM({"qM": np.zeros((4, 155 + 21)), "J": J})
+    assert "qM" not in st and st["M"].shape == (4, 176)
+    assert eng._infer_layouts(st) == (_native.M_QM, _native.J_ROWS)
+    assert eng._infer_layouts({"M": np.zeros((4, 325)), "J": J}) == (_native.M_PACKED, _native.J_ROWS)
+    with pytest.raises(ValueError):
+        eng._accept_qM({"qM": np.zeros((4, 154)), "J": J})
+    with pytest.raises(ValueError):
+        eng._accept_qM({"qM": np.zeros((4, 155)), "M": np.zeros((4, 325)), "J": J})
