@@ -371,13 +371,16 @@ def main():
         # caller loop fused in: the insertion demo's WP / GRIP state machine per instance
         try:
             from irl_control_b200.sequence import ActionSequence
-            acts = [{"action": "WP"}, {"action": "GRIP", "gripper_force": -0.08, "gripper_duration": 1.0},
-                    {"action": "WP", "gripper_force": -0.08}, {"action": "GRIP", "gripper_force": 0.2, "gripper_duration": 2.0},
-                    {"action": "WP", "gripper_force": 0.2}]
+            # the reference's own 12-entry action list and object offsets (insertion_task.yaml), adapters placed
+            # at random per episode (insertion_task.py:341-369), waypoints from set_waypoint_targets (206-268)
+            from irl_control_b200 import insertion
+            from irl_control_b200.configs import action_config
+            acfg = action_config("insertion_task.yaml")
+            acts, objs = acfg["insertion_action_sequence"], acfg["nist_action_objects"]
             seq = ActionSequence(layout, acts, active_arm="ur5right")
             ia = seq.active_device
-            wp_xyz = (st["ee_xyz"][:, ia, None, :] + 0.05 * torch.randn(B, len(acts), 3, dtype=torch.float64, device=dev)).contiguous()
-            wp_quat = st["ee_quat"][:, ia, None, :].expand(B, len(acts), 4).contiguous()
+            placed = insertion.random_object_poses(B, "right", objs, rng=np.random.default_rng(7 + rank))
+            wp_xyz, wp_quat = insertion.waypoint_poses(acts, objs, placed, st["ee_xyz"][:, ia].cpu().numpy())
             sst = seq.new_state(B, wp_xyz, wp_quat, device=dev)
             sin = {k: v for k, v in fin.items() if k not in ("target_xyz", "target_quat")}
             for _ in range(3):
@@ -392,7 +395,8 @@ def main():
             torch.cuda.synchronize()
             s_ms = sum(a.elapsed_time(b) for a, b in sev) / len(sev)
             fused["sequence"] = {"value": B / (s_ms * 1e-3), "unit": "episode-steps/s per GPU", "ms_per_step": s_ms,
-                                 "api": "BatchedOSC.step_sequence -> irlosc_step_sequence (5-action insertion sequence)"}
+                                 "api": "BatchedOSC.step_sequence -> irlosc_step_sequence (insertion_task.yaml: 12 actions, "
+                                        "randomised adapter poses per episode)"}
         except Exception as exc:      # the sequence step needs two arm devices in the layout
             fused["sequence"] = {"unavailable": str(exc)}
         if not args.no_e2e:

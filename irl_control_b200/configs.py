@@ -104,3 +104,66 @@ def device_cfgs(device_config):
     if len(devs) != len(ctrls):
         raise ValueError("device_config: %d devices but %d controllers" % (len(devs), len(ctrls)))
     return list(zip(devs, ctrls))
+
+
+# ---------------------------------------------------------------- action sequence configs
+def _wp(**kw):
+    return dict(action="WP", **kw)
+
+
+def _grip(force, duration):
+    return dict(action="GRIP", gripper_force=force, gripper_duration=duration)
+
+
+def _insertion_task():
+    """action_sequence_configs/insertion_task.yaml as Python (same keys and values)."""
+    def objects(male_joint, male, female_joint, female):
+        return {
+            "male_object": dict(joint_name=male_joint, hover_offset=male[0], grip_offset=male[1],
+                                initial_pos_xyz=male[2], initial_pos_abg=male[3], grip_yaw=90),
+            "female_object": dict(joint_name=female_joint, hover_offset=female[0], hover_offset_lift=female[1],
+                                  insert_offset=female[2], initial_pos_xyz=female[3], initial_pos_abg=female[4],
+                                  grip_yaw=90),
+        }
+    return {
+        # insertion_task.yaml:1-16
+        "grommet_action_objects": objects(
+            "free_joint_grommet_11mm", ([0, 0, 0.2], [0, 0, 0.158], [-0.2, 0.5, 0.005], [0, 0, 20]),
+            "free_joint_dual_peg", ([0, 0, 0.23], [0, 0, 0.25], [0, 0, 0.18], [-0.4, 0.7, 0.0], [0, 0, 30])),
+        # insertion_task.yaml:18-33
+        "nist_action_objects": objects(
+            "free_joint_male", ([0, 0, 0.32], [0, 0, 0.24], [0.4, 0.6, -0.0515], [0, 0, 30]),
+            "free_joint_female", ([0, 0, 0.27], [0, 0, 0.3], [0, 0, 0.22], [0.7, 0.4, -0.00002], [0, 0, -30])),
+        # insertion_task.yaml:35-104: the 12 entries
+        "insertion_action_sequence": [
+            _wp(target_xyz="male_object", target_abg="male_object", offset="hover_offset"),
+            _grip(-0.08, 1.0),
+            _wp(target_xyz="male_object", target_abg="male_object", offset="grip_offset", gripper_force=-0.08),
+            _grip(0.2, 2.0),
+            _wp(target_xyz="male_object", target_abg="male_object", gripper_force=0.2, offset="hover_offset"),
+            _wp(max_speed_xyz=0.3, target_xyz="female_object", target_abg="male_object", gripper_force=0.2,
+                offset="hover_offset"),
+            _wp(max_speed_xyz=0.1, target_xyz="female_object", target_abg="female_object", gripper_force=0.2,
+                offset="hover_offset"),
+            _grip(0.2, 1.0),
+            _wp(target_xyz="female_object", target_abg="female_object", max_speed_xyz=1.0, gripper_force=0.1,
+                max_error=0.01, offset="insert_offset"),
+            _grip(-0.1, 2.0),
+            _wp(target_xyz="female_object", target_abg="female_object", gripper_force=-0.1, max_speed_xyz=0.1,
+                offset="hover_offset_lift"),
+            _wp(target_xyz="start_pos", target_abg="female_object", max_speed_xyz=2.0, gripper_force=0, max_error=0.05),
+        ],
+    }
+
+
+def action_config(name: str):
+    """Fresh config dict of a built-in action sequence file (`InsertionTask.get_action_config`, insertion_task.py:130-140);
+    a path to a YAML file with the same schema is read instead when it exists."""
+    import os
+    if os.path.isfile(name):
+        import yaml
+        with open(name, "r") as fh:
+            return yaml.safe_load(fh)
+    if os.path.basename(name) == "insertion_task.yaml":
+        return _insertion_task()
+    raise KeyError(name)

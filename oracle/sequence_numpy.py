@@ -81,3 +81,86 @@ def run_waypoint_cycle(wps, ee_xyz, threshold, n_ticks):
         if err < threshold:                                      # (153-162)
             idx = idx + 1 if idx < len(wps) - 1 else 0
     return rec
+
+
+# ---------------------------------------------------------------- around the loop: object placement, waypoint targets
+# (restated one episode at a time with the transforms3d restatement of oracle/t3d.py)
+DEFAULT_EE_ROT = np.deg2rad([0, -90, -90])                        # insertion_task.py:18
+
+
+def initialize_action_objects(action_objects):
+    """insertion_task.py:299-311 -> {object: (pos, quat)} as `set_free_joint_qpos` would store them."""
+    from . import t3d
+    out = {}
+    for name, obj in action_objects.items():
+        quat = t3d.euler2quat(*(np.deg2rad(obj['initial_pos_abg']))) if 'initial_pos_abg' in obj else None
+        pos = obj['initial_pos_xyz'] if 'initial_pos_xyz' in obj else None
+        out[name] = (np.array(pos, dtype=np.float64), np.array(quat, dtype=np.float64))
+    return out
+
+
+def initialize_action_objects_random(action_objects, arm_name, uniform):
+    """insertion_task.py:341-369; `uniform(low, high)` stands for `np.random.uniform` (called six times in the
+    reference's order).  Mutates `action_objects` like the reference."""
+    from . import t3d
+    mx = uniform(0.4, 0.6)
+    my = uniform(0.5, 0.7)
+    fx = uniform(0.0, 0.3)
+    fy = uniform(0.5, 0.7)
+    out = {}
+    male_obj = action_objects['male_object']
+    yaw_male = int(uniform(-20, 20))
+    male_obj['initial_pos_abg'] = [0, 0, yaw_male]
+    male_obj['initial_pos_xyz'][0] = mx if arm_name == 'right' else -1 * mx
+    male_obj['initial_pos_xyz'][1] = my
+    out['male_object'] = (np.array(male_obj['initial_pos_xyz'], dtype=np.float64),
+                          np.array(t3d.euler2quat(*male_obj['initial_pos_abg'])))          # degrees, as written (358)
+    female_obj = action_objects['female_object']
+    yaw_female = int(uniform(-20, 20))
+    female_obj['initial_pos_abg'] = [0, 0, yaw_female]
+    female_obj['initial_pos_xyz'][0] = fx if arm_name == 'right' else -1 * fx
+    female_obj['initial_pos_xyz'][1] = fy
+    out['female_object'] = (np.array(female_obj['initial_pos_xyz'], dtype=np.float64),
+                            np.array(t3d.euler2quat(*female_obj['initial_pos_abg'])))      # (367)
+    return out
+
+
+def set_waypoint_targets(params, action_objects, object_qpos, start_pos):
+    """Active-arm part of insertion_task.py:206-268.  `object_qpos[name] = (pos, quat)` is what
+    `sim.data.get_joint_qpos(joint_name)` returns, split.  Returns (target xyz, target quat)."""
+    from . import t3d
+    default_quat = t3d.euler2quat(*DEFAULT_EE_ROT)
+    if 'target_xyz' in params.keys():
+        offset = params['offset'] if 'offset' in params.keys() else [0.0, 0.0, 0.0]
+        if isinstance(params['target_xyz'], str):
+            if params['target_xyz'] == 'start_pos':
+                target = start_pos
+            else:
+                target_obj = action_objects[params['target_xyz']]
+                if isinstance(offset, str):
+                    offset = target_obj[offset]
+                obj_pos = object_qpos[params['target_xyz']][0]
+                target = obj_pos + offset
+        elif isinstance(params['target_xyz'], list):
+            target = params['target_xyz'] + offset
+        else:
+            raise ValueError
+        assert len(target) == 3                                    # Target.set_xyz (utils.py:36)
+        xyz = np.asarray(target, dtype=np.float64)
+    else:
+        raise KeyError('target_xyz')
+    if 'target_abg' in params.keys():
+        if isinstance(params['target_abg'], str):
+            target_obj = action_objects[params['target_abg']]
+            obj_quat = object_qpos[params['target_abg']][1]
+            grip_eul = DEFAULT_EE_ROT + [0, 0, np.deg2rad(target_obj['grip_yaw'])]
+            tfmat = np.matmul(t3d.quat2mat(obj_quat), t3d.euler2mat(*grip_eul))      # compose() with zero translation
+            target_abg = np.array(t3d.mat2euler(tfmat[:3, :3]))
+        elif isinstance(params['target_abg'], list):
+            target_abg = np.deg2rad(params['target_abg'])
+        else:
+            raise ValueError
+        quat = np.asarray(t3d.euler2quat(*target_abg))              # Target.set_abg (utils.py:52-54)
+    else:
+        quat = np.asarray(default_quat)
+    return xyz, quat

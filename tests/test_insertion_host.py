@@ -1,0 +1,152 @@
+"""CPU: the host side of the batched insertion demo (`irl_control_b200/insertion.py`: object placement and
+`set_waypoint_targets` for B episodes) against the per-episode restatement in oracle/sequence_numpy.py, and the
+reference's own 12-entry action list (action_sequence_configs/insertion_task.yaml:35-104) through the state
+machine compiled into the fused step (host build) against the restated caller loop."""
+import copy
+
+import numpy as np
+import pytest
+
+import fused_host
+from irl_control_b200 import insertion
+from irl_control_b200.configs import action_config
+from irl_control_b200.rigid_model import model_for_layout
+from irl_control_b200.sequence import ActionSequence, default_ee_quat
+from irl_control_b200.synthetic import build_scenario
+from oracle import sequence_numpy, t3d
+from test_sequence_host import _poses, _trajectory
+
+
+def test_builtin_action_config_has_the_reference_schema():
+    cfg = action_config("insertion_task.yaml")
+    seq = cfg["insertion_action_sequence"]
+    assert [a["action"] for a in seq] == ["WP", "GRIP", "WP", "GRIP", "WP", "WP", "WP", "GRIP", "WP", "GRIP", "WP", "WP"]
+    assert seq[-1]["target_xyz"] == "start_pos" and seq[8]["max_error"] == 0.01 and seq[5]["max_speed_xyz"] == 0.3
+    for objs in ("nist_action_objects", "grommet_action_objects"):
+        assert set(cfg[objs]) == {"male_object", "female_object"}
+        assert cfg[objs]["female_object"]["grip_yaw"] == 90 and len(cfg[objs]["male_object"]["grip_offset"]) == 3
+    with pytest.raises(KeyError):
+        action_config("no_such_task.yaml")
+
+
+def test_batched_rotations_match_the_scalar_restatement():
+    rng = np.random.default_rng(2)
+    e = rng.uniform(-3.1, 3.1, size=(64, 3))
+    e[0] = [0.3, np.pi / 2, -0.2]                      # gimbal branch of mat2euler
+    q = insertion.euler2quat_b(e)
+    m = insertion.euler2mat_b(e)
+    for i in range(64):
+        assert np.abs(q[i] - t3d.euler2quat(*e[i])).max() < 1e-15
+        assert np.abs(m[i] - t3d.euler2mat(*e[i])).max() < 1e-15
+        assert np.abs(insertion.quat2mat_b(q)[i] - t3d.quat2mat(q[i])).max() < 1e-15
+        assert np.abs(insertion.mat2euler_b(m)[i] - np.array(t3d.mat2euler(m[i]))).max() < 1e-15
+
+
+@pytest.mark.parametrize("objects_name", ["nist_action_objects", "grommet_action_objects"])
+@pytest.mark.parametrize("arm", ["right", "left"])
+@pytest.mark.parametrize("randomize", [False, True])
+def test_waypoint_poses_match_set_waypoint_targets(objects_name, arm, randomize):
+    B = 24
+    cfg = action_config("insertion_task.yaml")
+    actions, objs = cfg["insertion_action_sequence"], cfg[objects_name]
+    rng = np.random.default_rng(5)
+    start = rng.uniform(-0.5, 0.5, size=(B, 3)) + [0.3, 0.2, 0.9]
+    u = rng.random((B, 6))
+    u[0, 4], u[1, 5] = 0.49, 0.51                       # yaw draws of -0.4 and +0.4 degrees: int() gives 0 for both
+    placed = insertion.random_object_poses(B, arm, objs, u=u) if randomize else insertion.configured_object_poses(B, objs)
+    wp_xyz, wp_quat = insertion.waypoint_poses(actions, objs, placed, start)
+    assert wp_xyz.shape == (B, 12, 3) and wp_quat.shape == (B, 12, 4)
+    for i in range(B):
+        o = copy.deepcopy(objs)
+        if randomize:
+            draws = iter(u[i])
+            qpos = sequence_numpy.initialize_action_objects_random(o, arm, lambda lo, hi: lo + (hi - lo) * next(draws))
+        else:
+            qpos = sequence_numpy.initialize_action_objects(o)
+        for name in qpos:
+            assert np.array_equal(placed[name][0][i], qpos[name][0])
+            assert np.abs(placed[name][1][i] - qpos[name][1]).max() < 1e-15
+        for a, p in enumerate(actions):
+            if p["action"] != "WP":
+                assert np.array_equal(wp_xyz[i, a], np.zeros(3)) and np.array_equal(wp_quat[i, a], [1, 0, 0, 0])
+                continue
+            xyz, quat = sequence_numpy.set_waypoint_targets(p, o, qpos, start[i])
+            assert np.abs(wp_xyz[i, a] - xyz).max() < 1e-15, (i, a)
+            assert np.abs(wp_quat[i, a] - quat).max() < 1e-14, (i, a)
+    if randomize:
+        sign = 1.0 if arm == "right" else -1.0
+        mx = sign * placed["male_object"][0][:, 0]
+        assert (mx >= 0.4).all() and (mx <= 0.6).all() and (placed["female_object"][0][:, 1] >= 0.5).all()
+        assert np.array_equal(placed["male_object"][1][0], [1.0, 0.0, 0.0, 0.0])      # yaw truncated to 0
+        # z keeps the YAML value (only x and y are redrawn, insertion_task.py:359-360)
+        assert np.all(placed["male_object"][0][:, 2] == objs["male_object"]["initial_pos_xyz"][2])
+
+
+def test_waypoint_poses_error_cases():
+    cfg = action_config("insertion_task.yaml")
+    objs = cfg["nist_action_objects"]
+    placed = insertion.configured_object_poses(2, objs)
+    start = np.zeros((2, 3))
+    with pytest.raises(KeyError):
+        insertion.waypoint_poses([{"action": "WP"}], objs, placed, start)
+    with pytest.raises(AssertionError):            # list + list = six numbers -> Target.set_xyz asserts (utils.py:36)
+        insertion.waypoint_poses([{"action": "WP", "target_xyz": [0.1, 0.2, 0.3]}], objs, placed, start)
+    with pytest.raises(ValueError):
+        insertion.waypoint_poses([{"action": "WP", "target_xyz": 3.0}], objs, placed, start)
+    with pytest.raises(KeyError):
+        insertion.waypoint_poses([{"action": "WP", "target_xyz": "no_object"}], objs, placed, start)
+    xyz, quat = insertion.waypoint_poses([{"action": "WP", "target_xyz": "start_pos", "target_abg": [0, -90, -90]},
+                                          {"action": "WP", "target_xyz": "start_pos"}], objs, placed, start)
+    assert np.abs(quat[0, 0] - default_ee_quat()).max() < 1e-15 and np.abs(quat[0, 1] - default_ee_quat()).max() < 1e-15
+
+
+@pytest.mark.parametrize("active", ["ur5right", "ur5left"])
+def test_reference_action_list_through_the_kernel_state_machine(active):
+    """All 12 entries of insertion_task.yaml (their kp / speed limits / max_error / gripper forces; GRIP durations
+    counted with a 0.25 s control period so that an episode fits in ~100 steps) on the host build of the sequence
+    kernel; every step's action index, targets, max_vel[0], error and gripper override equal the restated loop."""
+    B, T = 4, 110
+    actions = action_config("insertion_task.yaml")["insertion_action_sequence"]
+    A = len(actions)
+    app, _osc, names, layout = build_scenario("insertion")
+    robot = app.get_robot("DualUR5")
+    model = model_for_layout(app.sim.model, robot.joint_ids_all, layout)
+    passive = [n for n in names if n != active][0]
+    seq = ActionSequence(layout, actions, active_arm=active, step_period=0.25)
+    assert [p.get("grip_steps") for p in seq.params if p["action"] == "GRIP"] == [4, 8, 4, 8]
+    q, dq = _trajectory(B, T, seed=12)
+    poses = _poses(layout, q)
+    # the waypoint of the i-th WP entry = the pose the active arm will have at a chosen tick
+    wp_actions = [a for a, p in enumerate(actions) if p["action"] == "WP"]
+    hits = dict(zip(wp_actions, (5, 16, 31, 38, 46, 58, 74, 95)))
+    wp_xyz, wp_quat = np.zeros((B, A, 3)), np.zeros((B, A, 4))
+    wp_quat[..., 0] = 1.0
+    for a, t in hits.items():
+        wp_xyz[:, a], wp_quat[:, a] = poses[active][0][t], poses[active][1][t]
+    st = seq.new_state(B, wp_xyz, wp_quat)
+    mv = np.tile(np.array([list(d.max_vel) for d in layout.devices])[None], (B, 1, 1))
+    ia, ip = names.index(active), names.index(passive)
+    dev = layout.as_dict()["devices"][ia]
+    recs, ctrls = [[] for _ in range(B)], []
+    for t in range(T):
+        out = fused_host.sequence_step(layout, model, seq, {"q": q[t], "dq": dq[t], "max_vel": mv}, st)
+        ctrls.append(out["ctrl"].copy())
+        for i in range(B):
+            recs[i].append(dict(action=int(st["action"][i]), err=float(st["err"][i]), max_vel0=float(st["max_vel0"][i]),
+                                target_xyz=st["target_xyz"][i].copy(), target_quat=st["target_quat"][i].copy()))
+    for i in range(B):
+        ps = {"active_xyz": poses[active][0][:, i], "active_quat": poses[active][1][:, i], "passive_xyz": poses[passive][0][:, i]}
+        ref = sequence_numpy.run_sequence(seq.params, wp_xyz[i], wp_quat[i], ps, dev, default_ee_quat(),
+                                          layout.devices[ia].max_vel[0], T)
+        for t in range(T):
+            r, g = ref[t], recs[i][t]
+            assert g["action"] == r["action"], (i, t)
+            assert g["max_vel0"] == pytest.approx(r["max_vel0"], rel=1e-12, abs=0), (i, t)
+            if r["action"] < A:
+                assert (np.isinf(g["err"]) and np.isinf(r["err"])) or g["err"] == pytest.approx(r["err"], rel=1e-9, abs=1e-13)
+            assert np.abs(g["target_xyz"][ia] - r["active_xyz"]).max() < 1e-15
+            assert np.abs(g["target_quat"][ia] - r["active_quat"]).max() < 1e-15
+            assert np.abs(g["target_xyz"][ip] - r["passive_xyz"]).max() < 1e-12
+            if r["gripper_force"] != 0.0:
+                assert ctrls[t][i, seq.gripper_slot] == r["gripper_force"]
+        assert recs[i][-1]["action"] == A, (i, recs[i][-1]["action"])       # all twelve actions completed
