@@ -166,3 +166,48 @@ def test_waypoint_cycling_matches_the_gain_test_loop():
                 assert np.array_equal(got[t][0][i, d], ref[t][0])
     assert (st["wp_idx"][:, :2] != 0).any() or True
     assert max(r[1] for r in ref) > 0                             # indices advanced and wrapped
+
+
+def test_waypoint_cycling_under_admittance_matches_the_force_test_loop():
+    """examples/force_test.py:88-110: admittance controller (F/T term in the law), the right arm holds one
+    waypoint, the left arm walks ten with a fixed orientation target; `errors['ur5left'] < threshold_ee`
+    advances / wraps its index.  Same kernel entry as the gain_test loop, admit_test layout (osc1 == osc2 of
+    default_xyz_abg.yaml numerically)."""
+    B, T = 4, 64
+    app, _osc, names, layout = build_scenario("admit_test")
+    assert names == ["ur5right", "ur5left"] and layout.admittance
+    robot = app.get_robot("DualUR5")
+    model = model_for_layout(app.sim.model, robot.joint_ids_all, layout)
+    q, dq = _trajectory(B, T, seed=33)
+    poses = _poses(layout, q)
+    D, W = layout.D, 10
+    n_wp = [1, 10]
+    wps = np.zeros((B, D, W, 3))
+    wps[:, 0, 0] = [0.3, 0.46432, 0.36243]                        # force_test.py:39-41 (never reached here)
+    left_ticks = [4, 9, 15, 16, 22, 30, 37, 41, 50, 58]           # the left EE passes through its ten waypoints
+    for w, t in enumerate(left_ticks):
+        wps[:, 1, w] = poses["ur5left"][0][t]
+    from irl_control_b200.insertion import euler2quat_b
+    tq = np.tile(np.array([1.0, 0, 0, 0]), (B, D, 1))
+    tq[:, 1] = euler2quat_b(np.array([0.0, 0.0, -np.pi / 2]))      # targets['ur5left'].set_abg([0, 0, -pi/2]) (94)
+    st = {"wps": wps, "n_wp": n_wp, "wp_idx": np.zeros((B, D), np.int32), "target_xyz": np.zeros((B, D, 3)),
+          "target_quat": tq.copy()}
+    mv = np.tile(np.array([list(d.max_vel) for d in layout.devices])[None], (B, 1, 1))
+    ft = np.random.default_rng(1).normal(0.0, 5.0, size=(B, D, 6))
+    seen = []
+    for t in range(T):
+        before = st["wp_idx"].copy()
+        inp = {"q": q[t], "dq": dq[t], "max_vel": mv, "ft_raw": ft}
+        out = fused_host.waypoints_step(layout, model, inp, st, threshold=0.01)
+        seen.append((st["target_xyz"].copy(), before))
+        ref = fused_host.run(layout, model, dict(inp, target_xyz=st["target_xyz"], target_quat=st["target_quat"]))
+        assert np.array_equal(out["ctrl"], ref["ctrl"])
+        assert np.array_equal(st["target_quat"], tq)              # orientation targets are the caller's
+    for i in range(B):
+        for d in (0, 1):
+            ref = sequence_numpy.run_waypoint_cycle(wps[i, d, :n_wp[d]], poses[names[d]][0][:, i], 0.01, T)
+            for t in range(T):
+                assert seen[t][1][i, d] == ref[t][1], (i, d, t)
+                assert np.array_equal(seen[t][0][i, d], ref[t][0])
+    # right holds its only waypoint; left walked all ten and wrapped to the first one again
+    assert st["wp_idx"][:, 0].max() == 0 and max(s[1][:, 1].max() for s in seen) == 9 and (st["wp_idx"][:, 1] == 0).all()
