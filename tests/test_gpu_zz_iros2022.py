@@ -23,7 +23,10 @@ def test_cuda_matches_reference_golden_iros2022(case, packed_M, full6_J, kernel,
     from irl_control_b200 import _native
     from irl_control_b200.engine import BatchedOSC
     g, ld = load_golden(case)
-    layout = _layout_from_dict(ld, topology=topology, check=topology)
+    if kernel == 2 and full6_J:
+        pytest.skip("the tree-sparse kernel stages the row-stacked Jacobian layout only")
+    # check_topology makes the kernels that read every entry eligible only, so not with the streaming kernel
+    layout = _layout_from_dict(ld, topology=topology, check=(topology and kernel == 2))
     eng = BatchedOSC(layout, device=0)
     eng.set_kernel(kernel)
     out = eng.step(_golden_state(g, layout, torch, packed_M, full6_J), want_u_all=True)
