@@ -42,6 +42,40 @@ def algorithmic_bytes(layout, per_instance_max_vel=True):
     return 8 * words
 
 
+def side_legs():
+    """tools/side_legs.py in child processes (isolated from this one's CUDA context, bounded by a timeout): paths
+    written after the round's GPU budget was spent, each checked before it is timed.  Nothing from here enters
+    `value`, `e2e` or `roofline`."""
+    tool = os.path.join(ROOT, "tools", "side_legs.py")
+    runs = [("default", ["--legs", "qm,qm_admit,iros2022,sequence,coop"], {"IRLOSC_FIXUP_COOP": "0"}, 200),
+            ("fixup_coop", ["--legs", "coop"], {"IRLOSC_FIXUP_COOP": "1"}, 90)]
+    out = {}
+    for name, extra, env_add, limit in runs:
+        env = dict(os.environ, **env_add)
+        rec = {"legs": []}
+        try:
+            proc = subprocess.Popen([sys.executable, tool, "--steps", "10", "--warmup", "3"] + extra, env=env,
+                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            try:
+                so, se = proc.communicate(timeout=limit)
+            except subprocess.TimeoutExpired:
+                proc.kill()
+                so, se = proc.communicate()
+                rec["timeout_s"] = limit
+            for ln in so.splitlines():
+                try:
+                    rec["legs"].append(json.loads(ln))
+                except ValueError:
+                    pass
+            if proc.returncode not in (0, None):
+                rec["returncode"] = proc.returncode
+                rec["stderr_tail"] = se[-400:]
+        except Exception as exc:
+            rec["error"] = "%s: %s" % (type(exc).__name__, exc)
+        out[name] = rec
+    return out
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -135,6 +169,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fused", action="store_true", help="skip the fused state-provider measurement (SURVEY 8 f1)")
+    ap.add_argument("--no-side-legs", action="store_true",
+                    help="skip tools/side_legs.py (N = 1 only: checked side measurements of paths without a GPU run of "
+                         "their own yet, in a child process; use this flag under ncu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -452,10 +489,15 @@ def main():
         sub = {k: v[:nsample] for k, v in st.items()}
         cb = cpu_baseline(layout, oracle_inputs(sub, layout))
     config["gather"] = gather_mode
+    side = None
+    if world == 1 and not args.no_side_legs:
+        side = side_legs()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb, "fused_state": fused}
+    if side is not None:
+        line["side_legs"] = side
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
