@@ -90,3 +90,23 @@ def scatter_ctrl(ctrl, layout, ctrl_row) -> None:
     """`sim.data.ctrl[force_idx] = force` for every target device (gain_test.py:146-147) from one packed row."""
     for sl, dl in zip(layout.ctrl_slices, layout.devices):
         ctrl[list(dl.ctrl_idxs)] = np.asarray(ctrl_row)[sl]
+
+
+def sparse_inertia(m, data, layout) -> np.ndarray:
+    """`MjData.qM` as `state["qM"]` (IRLOSC_M_QM) - the array robot.py:69 expands with `mj_fullM` - after checking
+    that the addressing the kernel derives from `layout.joint_parent` is the model's own: the robot's n dofs are
+    the scene's first n, `dof_parentid` agrees, `dof_Madr` is the running sum of the dofs' depths.  Returns the
+    scene's whole qM (length nM); the kernel reads the leading robot part, `m_stride = nM`."""
+    from .layout import qm_index
+    n = layout.n
+    parent = np.asarray(m.dof_parentid)[:n]
+    if layout.joint_parent is None or list(parent) != list(layout.joint_parent):
+        raise ValueError("the model's dof_parentid[:%d] is not the layout's kinematic tree" % n)
+    rows, _ = qm_index(layout.joint_parent)
+    madr = np.searchsorted(rows, np.arange(n))              # first entry of every dof
+    if list(np.asarray(m.dof_Madr)[:n]) != list(madr):
+        raise ValueError("the model's dof_Madr[:%d] is not the running sum of the tree's depths" % n)
+    qM = np.asarray(data.qM, dtype=np.float64)
+    if qM.shape[0] < len(rows):
+        raise ValueError("qM has %d entries, the robot alone needs %d" % (qM.shape[0], len(rows)))
+    return qM

@@ -119,3 +119,30 @@ def test_engine_accepts_qM_in_place_of_M():
         eng._accept_qM({"qM": np.zeros((4, 154)), "J": J})
     with pytest.raises(ValueError):
         eng._accept_qM({"qM": np.zeros((4, 155)), "M": np.zeros((4, 325)), "J": J})
+
+
+def test_adapter_checks_the_models_qM_addressing():
+    """`mujoco_adapter.sparse_inertia` on a stand-in carrying MjModel's `dof_parentid` / `dof_Madr`."""
+    from types import SimpleNamespace
+    from irl_control_b200.mujoco_adapter import sparse_inertia
+    _, ld = load_golden("gain_test_s0")
+    layout = _layout(ld)
+    free = [-1, 25, 26, 27, 28, 29]                        # one free body after the robot: dofs 25..30
+    parent = list(DUAL_UR5_PARENT) + free
+    depth = []
+    for i in range(len(parent)):
+        d, j = 0, i
+        while j >= 0:
+            d, j = d + 1, parent[j]
+        depth.append(d)
+    madr = np.concatenate([[0], np.cumsum(depth)[:-1]])
+    m = SimpleNamespace(dof_parentid=np.array(parent), dof_Madr=madr)
+    data = SimpleNamespace(qM=np.arange(float(sum(depth))))
+    assert sum(depth) == 155 + 21
+    assert sparse_inertia(m, data, layout).shape == (176,)
+    with pytest.raises(ValueError):                         # robot not first in the scene
+        sparse_inertia(SimpleNamespace(dof_parentid=np.array(free + parent[:25]), dof_Madr=madr), data, layout)
+    with pytest.raises(ValueError):
+        sparse_inertia(SimpleNamespace(dof_parentid=np.array(parent), dof_Madr=madr + 1), data, layout)
+    with pytest.raises(ValueError):
+        sparse_inertia(m, SimpleNamespace(qM=np.zeros(100)), layout)
