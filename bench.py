@@ -47,8 +47,8 @@ def side_legs():
     written after the round's GPU budget was spent, each checked before it is timed.  Nothing from here enters
     `value`, `e2e` or `roofline`."""
     tool = os.path.join(ROOT, "tools", "side_legs.py")
-    runs = [("default", ["--legs", "qm,qm_admit,iros2022,sequence,coop"], {"IRLOSC_FIXUP_COOP": "0"}, 200),
-            ("fixup_coop", ["--legs", "coop"], {"IRLOSC_FIXUP_COOP": "1"}, 90)]
+    runs = [("default", ["--legs", "qm,qm_admit,iros2022,sequence,coop"], {"IRLOSC_FIXUP_COOP": "0"}, 120),
+            ("fixup_coop", ["--legs", "coop"], {"IRLOSC_FIXUP_COOP": "1"}, 60)]
     out = {}
     for name, extra, env_add, limit in runs:
         env = dict(os.environ, **env_add)
