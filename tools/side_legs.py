@@ -25,6 +25,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+DEV = "cuda:0"          # tests/test_side_legs_mock.py runs the legs' host logic with "cpu" and a stand-in engine
 
 
 def emit(name, **kw):
@@ -56,7 +57,7 @@ def leg_qm(torch, np, scenario, B, steps, warmup, name, with_e2e):
     from irl_control_b200.engine import BatchedOSC, pinned_empty
     from irl_control_b200.synthetic import kernel_inputs, scenario_layout, synth_batch
     layout = scenario_layout(scenario)
-    st = synth_batch(layout, B, seed=4242, device="cuda:0")
+    st = synth_batch(layout, B, seed=4242, device=DEV)
     eng = BatchedOSC(layout, device=0)
     eng.set_kernel(9)
     pin, qin = kernel_inputs(st, layout, packed_M=True), kernel_inputs(st, layout, qM=True)
@@ -72,7 +73,7 @@ def leg_qm(torch, np, scenario, B, steps, warmup, name, with_e2e):
         emit(name, **res)
         return
     out = {"ctrl": torch.empty_like(a["ctrl"])}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     res["packed"] = time_steps(torch, lambda: eng.step(pin, out=out, want_status=False), steps, warmup, flush)
     res["qM"] = time_steps(torch, lambda: eng.step(qin, out=out, want_status=False), steps, warmup, flush)
     res["l2_policy"] = "256 MB flush write before every timed step"
@@ -106,7 +107,7 @@ def leg_iros2022(torch, np, B, steps, warmup):
     from irl_control_b200.synthetic import fused_inputs, kernel_inputs, oracle_inputs, scenario_model, synth_batch
     from oracle import osc_numpy
     layout, model = scenario_model("iros2022")
-    st = synth_batch(layout, B, seed=31, device="cuda:0")
+    st = synth_batch(layout, B, seed=31, device=DEV)
     eng = BatchedOSC(layout, device=0)
     kin = kernel_inputs(st, layout, packed_M=True)
     o = eng.step(kin, want_u_all=True)
@@ -126,7 +127,7 @@ def leg_iros2022(torch, np, B, steps, warmup):
     res["fused_max_rel_err_vs_oracle"] = rel_err(np, f["u_all"].cpu().numpy()[idx][agree], ref["u_all"][agree])
     res["fused_kernel"] = eng.last_kernel
     out = {"ctrl": torch.empty_like(o["ctrl"])}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     res["step"] = time_steps(torch, lambda: eng.step(kin, out=out, want_status=False), steps, warmup, flush)
     res["step_fused"] = time_steps(torch, lambda: eng.step_fused(fin, out=out, want_status=False), steps, warmup, flush)
     emit("iros2022", **res)
@@ -139,7 +140,7 @@ def leg_sequence(torch, np, B, steps, warmup):
     from irl_control_b200.sequence import ActionSequence
     from irl_control_b200.synthetic import fused_inputs, scenario_model, synth_batch
     layout, model = scenario_model("insertion")
-    st = synth_batch(layout, B, seed=77, device="cuda:0", insertion_schedule=True)
+    st = synth_batch(layout, B, seed=77, device=DEV, insertion_schedule=True)
     eng = BatchedOSC(layout, device=0)
     eng.set_model(model)
     cfg = action_config("insertion_task.yaml")
@@ -148,15 +149,15 @@ def leg_sequence(torch, np, B, steps, warmup):
     ia = seq.active_device
     placed = insertion.random_object_poses(B, "right", objs, rng=np.random.default_rng(11))
     wp_xyz, wp_quat = insertion.waypoint_poses(acts, objs, placed, st["ee_xyz"][:, ia].cpu().numpy())
-    sst = seq.new_state(B, wp_xyz, wp_quat, device="cuda:0")
+    sst = seq.new_state(B, wp_xyz, wp_quat, device=DEV)
     fin = fused_inputs(st, layout)
     sin = {k: v for k, v in fin.items() if k not in ("target_xyz", "target_quat")}
-    out = {"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device="cuda:0")}
+    out = {"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=DEV)}
     eng.step_sequence(sin, seq, sst, out=out)
     torch.cuda.synchronize()
     # first step: every episode is in action 0 and its active-arm target is the first waypoint
     ok = bool((sst["action"] == 0).all().item()) and bool(torch.equal(sst["target_xyz"][:, ia].cpu(), torch.from_numpy(wp_xyz[:, 0])))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     t = time_steps(torch, lambda: eng.step_sequence(sin, seq, sst, out=out, want_status=False), steps, warmup, flush)
     emit("sequence", workload="insertion layout, insertion_task.yaml (12 actions), randomised adapters", batch=B,
          first_step_state_ok=ok, finite=bool(torch.isfinite(out["ctrl"]).all().item()), step=t,
@@ -168,10 +169,10 @@ def leg_coop(torch, np, B, steps, warmup):
     from irl_control_b200.synthetic import fused_inputs, oracle_inputs, scenario_model, synth_batch
     from oracle import osc_numpy
     res = {"IRLOSC_FIXUP_COOP": os.environ.get("IRLOSC_FIXUP_COOP", "0"), "batch": B}
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda:0")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
     for scenario in ("gain_test", "admit_test"):
         layout, model = scenario_model(scenario)
-        st = synth_batch(layout, B, seed=5, device="cuda:0")
+        st = synth_batch(layout, B, seed=5, device=DEV)
         eng = BatchedOSC(layout, device=0)
         eng.set_model(model)
         fin = fused_inputs(st, layout)
