@@ -13,10 +13,12 @@ this image; its call sites on the path are
 Published algorithm (transforms3d 0.4.x): quaternions are (w, x, y, z);
 `quat2euler(q) = mat2euler(quat2mat(q))`; `mat2euler` for 'sxyz' uses
 cy = hypot(M00, M10) with the 4*eps gimbal switch; `euler2quat` is the
-half-angle product in static x, y, z order.  PARITY UNPINNED: the package
-source is unavailable here, so these five functions are anchored only on
-mathematical identities (tests/test_oracle.py: round trips, composition with
-rotation matrices) - not on transforms3d outputs.
+half-angle product in static x, y, z order.  PARITY UNPINNED against
+transforms3d itself: the package is unavailable here, so these functions are
+anchored on mathematical identities (tests/test_oracle.py: round trips,
+composition with rotation matrices) and on scipy's independent `Rotation`
+implementation with extrinsic "xyz" axes (same convention) - not on
+transforms3d outputs.
 """
 import math
 

@@ -103,3 +103,37 @@ def test_host_rotations_equal_oracle_rotations():
         assert R.quat2euler(q) == t3d.quat2euler(q)
         assert np.array_equal(R.qmult(q, e.tolist() + [1.0]), np.array(t3d.qmult(q, e.tolist() + [1.0])))
         assert np.array_equal(R.normalized_vector(q), t3d.normalized_vector(q))
+
+
+def test_t3d_restatement_agrees_with_scipy_rotations():
+    """Independent third-party anchor for the transforms3d restatement (transforms3d itself is absent):
+    scipy's `Rotation` with extrinsic axes 'xyz' is the same static-frame x-y-z convention transforms3d calls
+    'sxyz' (its default); scipy quaternions are scalar-last."""
+    Rotation = pytest.importorskip("scipy.spatial.transform").Rotation
+    rng = np.random.default_rng(7)
+    for _ in range(200):
+        e = rng.uniform([-np.pi, -np.pi / 2 + 1e-3, -np.pi], [np.pi, np.pi / 2 - 1e-3, np.pi])
+        r = Rotation.from_euler("xyz", e)
+        x, y, z, w = r.as_quat()
+        q = t3d.euler2quat(*e)
+        sgn = 1.0 if q[0] * w >= 0 else -1.0                         # q and -q are the same rotation
+        assert np.abs(q - sgn * np.array([w, x, y, z])).max() < 1e-14
+        assert np.abs(t3d.quat2mat(q) - r.as_matrix()).max() < 1e-14
+        assert np.abs(t3d.euler2mat(*e) - r.as_matrix()).max() < 1e-14
+        assert np.allclose(t3d.quat2euler(q), r.as_euler("xyz"), atol=1e-12)
+        # Hamilton product order: qmult(a, b) is "b then a" as rotations
+        e2 = rng.uniform(-1.0, 1.0, 3)
+        r2 = Rotation.from_euler("xyz", e2)
+        qa = t3d.qmult(q, t3d.euler2quat(*e2))
+        assert np.abs(t3d.quat2mat(qa) - (r * r2).as_matrix()).max() < 1e-14
+        assert np.abs(np.asarray(t3d.qconjugate(q)) - np.array([q[0], -q[1], -q[2], -q[3]])).max() == 0.0
+    # the pose error of osc.py:115-117 as a whole: euler(conj(q_d * conj(q_ee)))
+    for _ in range(50):
+        qd, qe = rng.normal(size=4), rng.normal(size=4)
+        qe /= np.linalg.norm(qe)
+        rd = Rotation.from_quat(np.roll(qd / np.linalg.norm(qd), -1))
+        re_ = Rotation.from_quat(np.roll(qe, -1))
+        want = (rd * re_.inv()).inv().as_euler("xyz")
+        q_r = t3d.qmult(t3d.normalized_vector(qd), t3d.qconjugate(qe))
+        got = np.array(t3d.quat2euler(t3d.qconjugate(q_r)))
+        assert np.allclose(got, want, atol=1e-11)
