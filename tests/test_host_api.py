@@ -154,3 +154,41 @@ def test_topology_is_derived_from_the_model_tree():
         for j in range(25):
             if j not in anc[dl.ee_joint]:
                 assert (J[:, d, :, j] == 0).all()
+
+
+def test_bias_forces_satisfy_the_lagrangian_form():
+    """Independent derivation of `qfrc_bias` (what osc.py:191 reads): the recursive Newton-Euler result of
+    `dual_ur5.dynamics` must equal the Euler-Lagrange expression built from the inertia matrix and the potential
+    energy alone, c_i = sum_jk (dM_ij/dq_k - 1/2 dM_jk/dq_i) dq_j dq_k + dV/dq_i, with the derivatives taken by
+    central differences of M(q) and V(q) = -sum_b m_b g . com_b(q)."""
+    import torch
+    from irl_control_b200.dual_ur5 import GRAVITY
+    m = DualUR5Model()
+    qs, dqs = sample_joint_states(2, 9)
+    n, h = 25, 1e-5
+    g = np.asarray(GRAVITY)
+
+    def M_and_V(qb):
+        qt = torch.from_numpy(qb)
+        d = dynamics(m, qt, torch.zeros_like(qt))
+        V = np.zeros(qb.shape[0])
+        for b in range(1, m.n_robot_bodies):
+            it = m.body_inertial[b]
+            if it is None:
+                continue
+            ipos, _iquat, mass, _diag = it
+            com = d.xpos[:, b].numpy() + (d.xmat[:, b].numpy() @ np.asarray(ipos))
+            V -= mass * (com @ g)
+        return d.M.numpy(), V
+
+    for q0, dq0 in zip(qs, dqs):
+        qb = np.repeat(q0[None], 2 * n, 0)
+        for k in range(n):
+            qb[2 * k, k] += h
+            qb[2 * k + 1, k] -= h
+        Mb, Vb = M_and_V(qb)
+        dM = (Mb[0::2] - Mb[1::2]) / (2 * h)                      # dM[k][i][j] = dM_ij / dq_k
+        dV = (Vb[0::2] - Vb[1::2]) / (2 * h)
+        c = np.einsum("kij,j,k->i", dM, dq0, dq0) - 0.5 * np.einsum("ijk,j,k->i", dM, dq0, dq0) + dV
+        bias = dynamics(m, torch.from_numpy(q0[None]), torch.from_numpy(dq0[None])).bias.numpy()[0]
+        assert np.abs(bias - c).max() < 1e-6 * max(1.0, np.abs(bias).max()), np.abs(bias - c).max()
