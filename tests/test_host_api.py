@@ -1,4 +1,6 @@
 """CPU: the host mirror of the reference API (index maps, error behaviour, layout flattening)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -192,3 +194,16 @@ def test_bias_forces_satisfy_the_lagrangian_form():
         c = np.einsum("kij,j,k->i", dM, dq0, dq0) - 0.5 * np.einsum("ijk,j,k->i", dM, dq0, dq0) + dV
         bias = dynamics(m, torch.from_numpy(q0[None]), torch.from_numpy(dq0[None])).bias.numpy()[0]
         assert np.abs(bias - c).max() < 1e-6 * max(1.0, np.abs(bias).max()), np.abs(bias - c).max()
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isfile("/root/reference/irl_control/scenes/dual_ur5.xml"), reason="needs /root/reference")
+def test_model_table_is_what_the_extractor_reads_from_the_reference_scene():
+    """`dual_ur5_model.py` (travels with the repo) == a fresh extraction from the reference's dual_ur5.xml."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "extract_dual_ur5.py"),
+                          "/root/reference/irl_control/scenes/dual_ur5.xml"], capture_output=True, text=True, check=True).stdout
+    with open(os.path.join(root, "irl_control_b200", "dual_ur5_model.py")) as fh:
+        assert out.strip() == fh.read().strip()
