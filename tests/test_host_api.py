@@ -207,3 +207,20 @@ def test_model_table_is_what_the_extractor_reads_from_the_reference_scene():
                           "/root/reference/irl_control/scenes/dual_ur5.xml"], capture_output=True, text=True, check=True).stdout
     with open(os.path.join(root, "irl_control_b200", "dual_ur5_model.py")) as fh:
         assert out.strip() == fh.read().strip()
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isdir("/root/reference/irl_control/robot_configs"), reason="needs /root/reference")
+def test_builtin_configs_equal_the_reference_yaml_files():
+    """The Python copies in configs.py (they travel to the GPU box) carry the reference's YAML values."""
+    import yaml
+    from irl_control_b200 import configs
+    ref = "/root/reference/irl_control"
+    for name in ("default_xyz.yaml", "default_xyz_abg.yaml", "iros2022.yaml"):
+        with open(os.path.join(ref, "robot_configs", name)) as fh:
+            want = yaml.safe_load(fh)
+        assert configs.robot_config(name) == want, name
+    with open(os.path.join(ref, "action_sequence_configs", "insertion_task.yaml")) as fh:
+        assert configs.action_config("insertion_task.yaml") == yaml.safe_load(fh)
+    with open(os.path.join(ref, "action_sequence_configs", "iros2022_task.yaml")) as fh:
+        assert configs.IROS2022_DEVICE_CONFIG == yaml.safe_load(fh)["device_config"]
