@@ -23,7 +23,9 @@ from . import _native
 
 # examples/insertion_task.py:82-103 get_default_action_ctrl_params
 WP_DEFAULTS = {"kp": 6.0, "max_error": 0.0018, "gripper_force": 0.0, "min_speed_xyz": 0.1, "max_speed_xyz": 3.0}
-GRIP_DEFAULTS = {"gripper_force": -0.08, "gripper_duration": 1.0}
+# the reference spells the second key 'gripper_duation' (insertion_task.py:101), so a GRIP entry without its own
+# `gripper_duration` raises KeyError there (196) - and here
+GRIP_DEFAULTS = {"gripper_force": -0.08, "gripper_duation": 1.0}
 # examples/insertion_task.py:18-20: euler2quat(*deg2rad([0, -90, -90])), static xyz
 DEFAULT_EE_ROT = np.deg2rad([0.0, -90.0, -90.0])
 

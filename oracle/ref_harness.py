@@ -262,3 +262,248 @@ class ReferenceRunner:
         t.set_xyz(np.array(tgt_xyz, dtype=np.float64))
         t.set_quat(np.array(tgt_quat, dtype=np.float64))
         return self.osc.calc_error(t, self.robot.get_device(name))
+
+
+# ---------------------------------------------------------------- the insertion demo's caller loop, unmodified
+def import_insertion_task():
+    """`irl_control.examples.insertion_task` (unmodified) with stubs for what it imports beyond the OSC path:
+    `mujoco_py.mjviewer.MjViewer` (never constructed here) and `transforms3d.affines.compose`."""
+    import_reference()
+    from . import t3d
+    mjp = sys.modules["mujoco_py"]
+    if "mujoco_py.mjviewer" not in sys.modules:
+        mv = types.ModuleType("mujoco_py.mjviewer")
+        mv.MjViewer = object
+        mjp.mjviewer = mv
+        sys.modules["mujoco_py.mjviewer"] = mv
+    if "transforms3d.affines" not in sys.modules:
+        af = types.ModuleType("transforms3d.affines")
+
+        def compose(T, R, Z, S=None):                 # transforms3d.affines.compose without shear
+            A = np.eye(4)
+            A[:3, :3] = np.asarray(R) @ np.diag(np.asarray(Z, dtype=np.float64))
+            A[:3, 3] = T
+            return A
+
+        af.compose = compose
+        sys.modules["transforms3d"].affines = af
+        sys.modules["transforms3d.affines"] = af
+    # insertion_task.py:19 evaluates `quat2euler(..., 'rxyz')` once at import for a constant nothing reads
+    # (DEFAULT_EE_ORIENTATION); the restatement covers the default 'sxyz' axes only, so that single call gets NaNs
+    eu = sys.modules["transforms3d.euler"]
+    plain = eu.quat2euler
+    eu.quat2euler = lambda q, axes='sxyz': plain(q) if axes == 'sxyz' else (float("nan"),) * 3
+    try:
+        import irl_control.examples.insertion_task as mod
+    finally:
+        eu.quat2euler = plain
+    return mod
+
+
+class SequenceStop(Exception):
+    pass
+
+
+def drive_reference_sequence(actions, action_objects, object_qpos, poses, active, ctrlr_dof, max_vel0, n_ticks,
+                             step_period):
+    """Runs the reference's own `run_sequence` / `go_to_waypoint` / `grip` / `send_forces` /
+    `set_waypoint_targets` (insertion_task.py, unmodified methods) on a pose stream instead of a simulator.
+
+    object_qpos[joint_name] = 7-vector (what `sim.data.get_joint_qpos` returns); poses: active_xyz / active_quat /
+    passive_xyz indexed by tick; GRIP durations are turned into step budgets of round(duration / step_period)
+    (the reference waits on a wall-clock timer thread).  Returns one record per `controller.generate` call."""
+    mod = import_insertion_task()
+    Device, Robot, OSC, Target, DeviceState, RobotState = import_reference()
+    passive = "ur5left" if active == "ur5right" else "ur5right"
+    tick = [0]
+    rec = []
+
+    class FakeDevice:
+        def __init__(self, name, is_active):
+            self.name, self._active = name, is_active
+            self.max_vel = [float(max_vel0), 5.0]
+            self.ctrlr_dof_xyz, self.ctrlr_dof_abg = list(ctrlr_dof[:3]), list(ctrlr_dof[3:])
+
+        def get_state(self, which):
+            t = tick[0]
+            if which == DeviceState.EE_XYZ:
+                return np.array(poses["active_xyz"][t] if self._active else poses["passive_xyz"][t], dtype=np.float64)
+            if which == DeviceState.EE_QUAT:
+                assert self._active
+                return np.array(poses["active_quat"][t], dtype=np.float64)
+            raise KeyError(which)
+
+    devs = {active: FakeDevice(active, True), passive: FakeDevice(passive, False)}
+
+    class FakeData:
+        ctrl = np.zeros(15)
+
+        @staticmethod
+        def get_joint_qpos(name):
+            return np.array(object_qpos[name], dtype=np.float64)
+
+    class FakeSim:
+        data = FakeData()
+
+        @staticmethod
+        def step():
+            tick[0] += 1
+            if tick[0] >= n_ticks:
+                raise SequenceStop
+
+    class FakeController:
+        @staticmethod
+        def generate(targets):
+            rec.append(dict(tick=tick[0], action=task._cur, err=float(task.errors.get(active, 0.0)),
+                            max_vel0=float(devs[active].max_vel[0]),
+                            active_xyz=np.array(targets[active].get_xyz(), dtype=np.float64),
+                            active_quat=np.array(targets[active].get_quat(), dtype=np.float64),
+                            passive_xyz=np.array(targets[passive].get_xyz(), dtype=np.float64),
+                            passive_quat=np.array(targets[passive].get_quat(), dtype=np.float64)))
+            return [np.arange(1, 8)], [np.zeros(7)]
+
+        @staticmethod
+        def calc_error(target, device):
+            return OSC.calc_error(None, target, device)           # the reference's own method (uses no self state)
+
+    class Driven(mod.InsertionTask):
+        def __init__(self):                                         # the real one needs a simulator and a viewer
+            pass
+
+        def sleep_for(self, sleep_time):                           # the timer thread's body: replaced by a step budget
+            pass
+
+        @property
+        def timer_running(self):
+            if self._budget > 0:
+                self._budget -= 1
+                return True
+            return False
+
+        def go_to_waypoint(self, params):
+            self._cur += 1
+            return super().go_to_waypoint(params)
+
+        def grip(self, params):
+            self._cur += 1
+            self._budget = int(round(float(params['gripper_duration']) / step_period))
+            return super().grip(params)
+
+        def send_forces(self, forces, gripper_force=None, update_errors=None, render=True):
+            rec[-1]["gripper_force"] = float(gripper_force) if gripper_force else 0.0
+            return super().send_forces(forces, gripper_force=gripper_force, update_errors=update_errors, render=render)
+
+    task = Driven()
+    task._cur, task._budget = -1, 0
+    task.ur5right, task.ur5left = devs["ur5right"], devs["ur5left"]
+    task.set_active_arm("right" if active == "ur5right" else "left")
+    task.sim = FakeSim()
+    task.viewer = types.SimpleNamespace(render=lambda: None)
+    task.controller = FakeController()
+    task.robot = types.SimpleNamespace(get_device=lambda name: devs[name])
+    task.errors = {}
+    task.action_objects = action_objects
+    task.action_map = task.get_action_map()
+    task.DEFAULT_PARAMS = dict((a, task.get_default_action_ctrl_params(a)) for a in mod.Action)
+    task.targets = {active: Target(), passive: Target()}
+    try:
+        task.run_sequence(actions)
+    except SequenceStop:
+        pass
+    return rec
+
+
+def reference_object_placement(action_objects, arm_name=None, seed=None):
+    """The reference's `initialize_action_objects` (arm_name None) or `initialize_action_objects_random`
+    (insertion_task.py:299-311, 341-369), unmodified, with `set_free_joint_qpos` captured instead of written into a
+    simulator.  Returns {joint_name: (pos, quat)} and, for the random variant, the six numbers `np.random.uniform`
+    produced (same seed replayed in the reference's call order)."""
+    mod = import_insertion_task()
+    placed = {}
+
+    class Driven(mod.InsertionTask):
+        def __init__(self):
+            pass
+
+        def set_free_joint_qpos(self, free_joint_name, quat=None, pos=None):
+            placed[free_joint_name] = (np.array(pos, dtype=np.float64), np.array(quat, dtype=np.float64))
+
+    task = Driven()
+    task.action_objects = action_objects
+    if arm_name is None:
+        task.initialize_action_objects()
+        return placed, None
+    np.random.seed(seed)
+    task.initialize_action_objects_random(arm_name)
+    np.random.seed(seed)
+    draws = [np.random.uniform(lo, hi) for lo, hi in ((0.4, 0.6), (0.5, 0.7), (0.0, 0.3), (0.5, 0.7), (-20, 20), (-20, 20))]
+    return placed, draws
+
+
+def drive_reference_gain_test(right_wps, left_wps, ee_right, ee_left, n_ticks):
+    """The reference's `GainTest.run('gain_test', ...)` (examples/gain_test.py:98-172, unmodified) on a pose stream:
+    `ee_right[t]` / `ee_left[t]` are the EE positions the t-th loop iteration sees.  The demo timer becomes a
+    budget of n_ticks iterations.  Returns (right target, left target, right index, left index) per `generate`."""
+    import_insertion_task()                                      # registers the mjviewer stub
+    Device, Robot, OSC, Target, DeviceState, RobotState = import_reference()
+    mjp = sys.modules["mujoco_py"]
+    if not hasattr(mjp, "GlfwContext"):
+        mjp.GlfwContext = object
+    import irl_control.examples.gain_test as mod
+    tick = [0]
+    rec = []
+    right_wps, left_wps = np.asarray(right_wps, dtype=np.float64), np.asarray(left_wps, dtype=np.float64)
+
+    class FakeDevice:
+        def __init__(self, stream):
+            self._stream = stream
+
+        def get_state(self, which):
+            assert which == DeviceState.EE_XYZ
+            return np.array(self._stream[tick[0]], dtype=np.float64)
+
+    devs = {"ur5right": FakeDevice(ee_right), "ur5left": FakeDevice(ee_left)}
+
+    def index_of(wps, xyz):
+        return int(np.argmin(np.abs(wps - np.asarray(xyz)).sum(axis=1)))
+
+    class FakeController:
+        @staticmethod
+        def generate(targets):
+            r, l = np.array(targets["ur5right"].get_xyz()), np.array(targets["ur5left"].get_xyz())
+            rec.append((r, l, index_of(right_wps, r), index_of(left_wps, l)))
+            return [np.arange(1, 8)], [np.zeros(7)]
+
+    class FakeData:
+        ctrl = np.zeros(15)
+
+        @staticmethod
+        def set_mocap_pos(name, pos):
+            pass
+
+    class Driven(mod.GainTest):
+        def __init__(self):
+            self._budget = n_ticks
+
+        def sleep_for(self, sleep_time):
+            pass
+
+        @property
+        def timer_running(self):
+            if self._budget > 0:
+                self._budget -= 1
+                return True
+            return False
+
+        def gen_waypoint_path(self):
+            return right_wps, left_wps
+
+    task = Driven()
+    task.robot = types.SimpleNamespace(get_device=lambda name: devs[name], stop=lambda: None)
+    task.robot_data_thread = types.SimpleNamespace(join=lambda: None)
+    task.controller = FakeController()
+    task.errors = {}
+    task.viewer = types.SimpleNamespace(render=lambda: None)
+    task.sim = types.SimpleNamespace(data=FakeData(), step=lambda: tick.__setitem__(0, tick[0] + 1))
+    task.run("gain_test", 10)
+    return rec

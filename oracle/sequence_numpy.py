@@ -9,8 +9,12 @@ Follows ir-lab/irl_control `examples/insertion_task.py` statement by statement:
 The simulator is replaced by a pose stream: `poses[t]` is the state the t-th `generate` call sees,
 `poses[t + 1]` the state after its `sim.step()`.
 
-Parity unpinned: the example itself cannot run here (it needs mujoco_py, an MjViewer and the
-scene meshes), so this restatement is anchored on the source lines above only.
+Pinned against the reference itself: the example as a program cannot run here (mujoco_py, an MjViewer, the
+scene meshes), but its methods can - `oracle/ref_harness.drive_reference_sequence` /
+`drive_reference_gain_test` / `reference_object_placement` call the UNMODIFIED `run_sequence`, `go_to_waypoint`,
+`grip`, `send_forces`, `set_waypoint_targets`, `initialize_action_objects[_random]` and `GainTest.run` on a
+subclass whose simulator, viewer and wall-clock timer are stand-ins, and the tests compare this restatement with
+them tick by tick (tests/test_insertion_host.py, tests/test_sequence_host.py; build container only).
 """
 import numpy as np
 

@@ -150,3 +150,106 @@ def test_reference_action_list_through_the_kernel_state_machine(active):
             if r["gripper_force"] != 0.0:
                 assert ctrls[t][i, seq.gripper_slot] == r["gripper_force"]
         assert recs[i][-1]["action"] == A, (i, recs[i][-1]["action"])       # all twelve actions completed
+
+
+# ---------------------------------------------------------------- pinned against the UNMODIFIED reference loop
+from oracle import ref_harness  # noqa: E402
+
+
+def _stream_through(wp_xyz, wp_quat, wp_actions, T, seed):
+    """Pose stream of the active arm that passes exactly through the given waypoints at increasing ticks (linear
+    approach in between, orientation switching a few ticks before the hit) + a wandering passive arm."""
+    rng = np.random.default_rng(seed)
+    # leave room for the GRIP budgets between consecutive waypoints
+    hits = np.array([8 + 14 * i + int(rng.integers(0, 4)) for i in range(len(wp_actions))])
+    assert hits[-1] < T - 2
+    xyz = np.zeros((T, 3))
+    quat = np.zeros((T, 4))
+    prev_t, prev = 0, wp_xyz[wp_actions[0]] + rng.normal(0, 0.3, 3)
+    for a, t in zip(wp_actions, hits):
+        for s in range(prev_t + (1 if prev_t else 0), t + 1):       # (the previous hit tick keeps its exact pose)
+            w = (s - prev_t) / max(1, t - prev_t)
+            xyz[s] = (1 - w) * prev + w * wp_xyz[a]
+            q = wp_quat[a] + (0.2 * (1 - w)) * rng.normal(size=4)          # noisy until the hit itself
+            quat[s] = q / np.linalg.norm(q)
+        quat[t] = wp_quat[a]
+        prev_t, prev = t, wp_xyz[a]
+    xyz[prev_t:], quat[prev_t:] = prev, quat[prev_t]
+    passive = np.cumsum(rng.normal(0, 0.01, size=(T, 3)), axis=0) + [-0.4, 0.3, 0.8]
+    return {"active_xyz": xyz, "active_quat": quat, "passive_xyz": passive}
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="needs /root/reference")
+@pytest.mark.parametrize("active,objects_name", [("ur5right", "nist_action_objects"), ("ur5left", "grommet_action_objects")])
+def test_restated_loop_and_waypoint_poses_match_the_unmodified_reference(active, objects_name):
+    """The reference's own `run_sequence`, `go_to_waypoint`, `grip`, `send_forces`, `set_waypoint_targets`
+    (insertion_task.py, methods called unmodified on a subclass whose simulator, viewer and timer are stand-ins)
+    against (1) `insertion.waypoint_poses` - the product's batched set_waypoint_targets - and (2) the restated loop
+    `oracle/sequence_numpy.run_sequence` that the kernel's state machine is checked with."""
+    T, dt = 140, 0.25
+    cfg = action_config("insertion_task.yaml")
+    actions, objs = cfg["insertion_action_sequence"], cfg[objects_name]
+    _app, _osc, names, layout = build_scenario("insertion")
+    ia = names.index(active)
+    placed = insertion.random_object_poses(1, "right" if active == "ur5right" else "left", objs,
+                                           rng=np.random.default_rng(4))
+    qpos = {objs[k]["joint_name"]: np.concatenate([placed[k][0][0], placed[k][1][0]]) for k in objs}
+    wp_actions = [a for a, p in enumerate(actions) if p["action"] == "WP"]
+    # start_pos is read from the stream's first tick by both sides; it only matters for the last action, whose
+    # waypoint the stream must hit, so fix it first
+    start = np.array([0.35, 0.1, 0.85])
+    wp_xyz, wp_quat = insertion.waypoint_poses(actions, objs, placed, start[None])
+    poses = _stream_through(wp_xyz[0], wp_quat[0], wp_actions, T, seed=1)
+    poses["active_xyz"][0] = start
+    seq = ActionSequence(layout, actions, active_arm=active, step_period=dt)
+    dev = layout.as_dict()["devices"][ia]
+    ref = ref_harness.drive_reference_sequence(copy.deepcopy(actions), copy.deepcopy(objs), qpos, poses, active,
+                                               dev["ctrlr_dof"], layout.devices[ia].max_vel[0], T, dt)
+    mine = sequence_numpy.run_sequence(seq.params, wp_xyz[0], wp_quat[0], poses, dev, default_ee_quat(),
+                                       layout.devices[ia].max_vel[0], T)
+    # the reference program ends with its sequence; the restated loop keeps holding (action == len) until T
+    done = [r for r in mine if r["action"] < len(actions)]
+    assert len(ref) == len(done) and len(done) < T, (len(ref), len(done))
+    for r, g in zip(ref, mine):
+        assert r["tick"] == g["tick"] and r["action"] == g["action"], (r["tick"], r["action"], g["action"])
+        assert (np.isinf(r["err"]) and np.isinf(g["err"])) or r["err"] == pytest.approx(g["err"], rel=1e-12, abs=1e-15)
+        assert r["max_vel0"] == pytest.approx(g["max_vel0"], rel=1e-12, abs=0)
+        assert r["gripper_force"] == g["gripper_force"]
+        for k in ("active_xyz", "active_quat", "passive_xyz", "passive_quat"):
+            assert np.abs(r[k] - g[k]).max() < 1e-14, (r["tick"], k)
+    assert max(r["action"] for r in ref) == len(actions) - 1        # the stream drove the reference through all 12
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="needs /root/reference")
+@pytest.mark.parametrize("objects_name", ["nist_action_objects", "grommet_action_objects"])
+def test_object_placement_matches_the_unmodified_reference(objects_name):
+    """`insertion.configured_object_poses` / `random_object_poses` against the reference's own
+    `initialize_action_objects` / `initialize_action_objects_random` (seeded `np.random`, same draws)."""
+    objs = action_config("insertion_task.yaml")[objects_name]
+    ref, _ = ref_harness.reference_object_placement(copy.deepcopy(objs))
+    mine = insertion.configured_object_poses(1, objs)
+    for name, obj in objs.items():
+        assert np.abs(mine[name][0][0] - ref[obj["joint_name"]][0]).max() == 0.0
+        assert np.abs(mine[name][1][0] - ref[obj["joint_name"]][1]).max() < 1e-15
+    lo = np.array([0.4, 0.5, 0.0, 0.5, -20.0, -20.0])
+    hi = np.array([0.6, 0.7, 0.3, 0.7, 20.0, 20.0])
+    for arm in ("right", "left"):
+        for seed in range(12):
+            ref, draws = ref_harness.reference_object_placement(copy.deepcopy(objs), arm, seed)
+            u = ((np.array(draws) - lo) / (hi - lo))[None]
+            mine = insertion.random_object_poses(1, arm, objs, u=u)
+            for name, obj in objs.items():
+                assert np.abs(mine[name][0][0] - ref[obj["joint_name"]][0]).max() < 1e-15, (arm, seed, name)
+                assert np.abs(mine[name][1][0] - ref[obj["joint_name"]][1]).max() < 1e-14, (arm, seed, name)
+
+
+def test_grip_without_duration_raises_like_the_reference():
+    """insertion_task.py:101 spells the default 'gripper_duation', so `params['gripper_duration']` (196) raises
+    KeyError for a GRIP entry that does not carry its own duration."""
+    _app, _osc, _names, layout = build_scenario("insertion")
+    with pytest.raises(KeyError):
+        ActionSequence(layout, [{"action": "GRIP", "gripper_force": 0.1}], active_arm="ur5right")
+    seq = ActionSequence(layout, [{"action": "GRIP", "gripper_duration": 0.5}], active_arm="ur5right", step_period=0.1)
+    assert seq.params[0]["gripper_force"] == -0.08 and seq.params[0]["grip_steps"] == 5

@@ -211,3 +211,31 @@ def test_waypoint_cycling_under_admittance_matches_the_force_test_loop():
                 assert np.array_equal(seen[t][0][i, d], ref[t][0])
     # right holds its only waypoint; left walked all ten and wrapped to the first one again
     assert st["wp_idx"][:, 0].max() == 0 and max(s[1][:, 1].max() for s in seen) == 9 and (st["wp_idx"][:, 1] == 0).all()
+
+
+from oracle import ref_harness  # noqa: E402
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="needs /root/reference")
+def test_restated_waypoint_cycle_matches_the_unmodified_gain_test_loop():
+    """`oracle/sequence_numpy.run_waypoint_cycle` (what `irlosc_step_waypoints` is checked with) against the
+    reference's own `GainTest.run` loop driven on the same EE position streams."""
+    T = 80
+    rng = np.random.default_rng(6)
+    rw = rng.uniform(-0.5, 0.5, size=(4, 3))
+    lw = rng.uniform(-0.5, 0.5, size=(3, 3))
+    streams = {}
+    for name, wps in (("r", rw), ("l", lw)):
+        s = np.cumsum(rng.normal(0, 0.03, size=(T + 1, 3)), axis=0)
+        for t in rng.choice(np.arange(2, T), size=14, replace=False):        # visits: some hit the current waypoint
+            s[t] = wps[rng.integers(0, len(wps))] + rng.normal(0, 0.02, 3)
+        streams[name] = s
+    ref = ref_harness.drive_reference_gain_test(rw, lw, streams["r"], streams["l"], T)
+    assert len(ref) == T
+    mine_r = sequence_numpy.run_waypoint_cycle(rw, streams["r"], 0.1, T)
+    mine_l = sequence_numpy.run_waypoint_cycle(lw, streams["l"], 0.1, T)
+    for t in range(T):
+        assert np.array_equal(ref[t][0], mine_r[t][0]) and ref[t][2] == mine_r[t][1], t
+        assert np.array_equal(ref[t][1], mine_l[t][0]) and ref[t][3] == mine_l[t][1], t
+    assert max(r[2] for r in ref) > 0 and max(r[3] for r in ref) > 0          # both lists advanced
