@@ -124,8 +124,70 @@ def iros2022_cases():
     run_case("iros2022_vel_s9", "iros2022", 12, 9, mutate=vel_all_nonzero)
 
 
+def caller_loop_goldens():
+    """The reference's caller loops (examples/insertion_task.py, examples/gain_test.py), their own unmodified methods
+    driven on pose streams through oracle/ref_harness: one record per `controller.generate` call."""
+    import copy
+    sys.path.insert(0, os.path.dirname(HERE))
+    from test_insertion_host import _stream_through
+    from irl_control_b200 import insertion
+    from irl_control_b200.configs import action_config
+    T, dt = 140, 0.25
+    cfg = action_config("insertion_task.yaml")
+    actions = cfg["insertion_action_sequence"]
+    _, _, names, layout = build_scenario("insertion")
+    for active, objects_name, seed in (("ur5right", "nist_action_objects", 21), ("ur5left", "grommet_action_objects", 22)):
+        objs = cfg[objects_name]
+        arm = "right" if active == "ur5right" else "left"
+        ref_placed, draws = ref_harness.reference_object_placement(copy.deepcopy(objs), arm, seed)
+        qpos = {jn: np.concatenate([p, q]) for jn, (p, q) in ref_placed.items()}
+        placed = {k: (qpos[objs[k]["joint_name"]][None, :3], qpos[objs[k]["joint_name"]][None, 3:]) for k in objs}
+        start = np.array([0.35 if arm == "right" else -0.35, 0.1, 0.85])
+        wp_xyz, wp_quat = insertion.waypoint_poses(actions, objs, placed, start[None])     # only shapes the stream
+        wp_actions = [a for a, p in enumerate(actions) if p["action"] == "WP"]
+        poses = _stream_through(wp_xyz[0], wp_quat[0], wp_actions, T, seed=seed)
+        poses["active_xyz"][0] = start
+        ia = names.index(active)
+        dof = layout.as_dict()["devices"][ia]["ctrlr_dof"]
+        mv0 = layout.devices[ia].max_vel[0]
+        rec = ref_harness.drive_reference_sequence(copy.deepcopy(actions), copy.deepcopy(objs), qpos, poses, active,
+                                                   dof, mv0, T, dt)
+        assert max(r["action"] for r in rec) == len(actions) - 1
+        out = {k: np.stack([np.asarray(r[k], dtype=np.float64) for r in rec]) for k in
+               ("tick", "action", "err", "max_vel0", "gripper_force", "active_xyz", "active_quat", "passive_xyz", "passive_quat")}
+        out.update({"pose_" + k: v for k, v in poses.items()})
+        out.update(draws=np.array(draws), male_qpos=qpos[objs["male_object"]["joint_name"]],
+                   female_qpos=qpos[objs["female_object"]["joint_name"]], start_pos=start, step_period=np.array(dt),
+                   n_ticks=np.array(T), max_vel0_initial=np.array(mv0), active=np.array(active),
+                   objects_name=np.array(objects_name), arm=np.array(arm))
+        path = os.path.join(HERE, "sequence_%s.npz" % active)
+        np.savez_compressed(path, **out)
+        print("%-28s %3d generate() calls through %d actions -> %s" % ("sequence_" + active, len(rec), len(actions),
+                                                                       os.path.relpath(path, ROOT)))
+    # gain_test waypoint cycling (gain_test.py:134-162)
+    T = 80
+    rng = np.random.default_rng(6)
+    rw, lw = rng.uniform(-0.5, 0.5, size=(4, 3)), rng.uniform(-0.5, 0.5, size=(3, 3))
+    streams = {}
+    for name, wps in (("r", rw), ("l", lw)):
+        s = np.cumsum(rng.normal(0, 0.03, size=(T + 1, 3)), axis=0)
+        for t in rng.choice(np.arange(2, T), size=14, replace=False):
+            s[t] = wps[rng.integers(0, len(wps))] + rng.normal(0, 0.02, 3)
+        streams[name] = s
+    rec = ref_harness.drive_reference_gain_test(rw, lw, streams["r"], streams["l"], T)
+    path = os.path.join(HERE, "waypoint_cycle.npz")
+    np.savez_compressed(path, right_wps=rw, left_wps=lw, ee_right=streams["r"], ee_left=streams["l"],
+                        right_target=np.stack([r[0] for r in rec]), left_target=np.stack([r[1] for r in rec]),
+                        right_idx=np.array([r[2] for r in rec]), left_idx=np.array([r[3] for r in rec]),
+                        threshold=np.array(0.1))
+    print("%-28s %3d generate() calls -> %s" % ("waypoint_cycle", len(rec), os.path.relpath(path, ROOT)))
+
+
 if __name__ == "__main__":
     assert ref_harness.reference_available(), "needs /root/reference"
+    if "--only-caller-loops" in sys.argv:      # added after the OSC.generate files were committed
+        caller_loop_goldens()
+        sys.exit(0)
     if "--only-iros2022" in sys.argv:          # added after the first eight files were committed
         iros2022_cases()
         sys.exit(0)
@@ -138,3 +200,4 @@ if __name__ == "__main__":
     run_case("insertion_vel_s6", "insertion", 8, 6, mutate=vel_all_nonzero)
     run_case("admit_singular_s7", "admit_test", 16, 7, mutate=singular_pose)
     iros2022_cases()
+    caller_loop_goldens()

@@ -3,6 +3,7 @@
 reference's own 12-entry action list (action_sequence_configs/insertion_task.yaml:35-104) through the state
 machine compiled into the fused step (host build) against the restated caller loop."""
 import copy
+import os
 
 import numpy as np
 import pytest
@@ -253,3 +254,37 @@ def test_grip_without_duration_raises_like_the_reference():
         ActionSequence(layout, [{"action": "GRIP", "gripper_force": 0.1}], active_arm="ur5right")
     seq = ActionSequence(layout, [{"action": "GRIP", "gripper_duration": 0.5}], active_arm="ur5right", step_period=0.1)
     assert seq.params[0]["gripper_force"] == -0.08 and seq.params[0]["grip_steps"] == 5
+
+
+@pytest.mark.parametrize("active", ["ur5right", "ur5left"])
+def test_caller_loop_golden_from_the_reference(active):
+    """tests/golden/sequence_<arm>.npz: records of the reference's own insertion loop (generated by
+    tests/golden/make_golden.py --only-caller-loops from the unmodified methods).  Checked here without the reference:
+    the product's object placement and waypoint poses, and the restated loop the kernel is compared with."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sequence_%s.npz" % active))
+    cfg = action_config("insertion_task.yaml")
+    actions, objs = cfg["insertion_action_sequence"], cfg[str(g["objects_name"])]
+    lo = np.array([0.4, 0.5, 0.0, 0.5, -20.0, -20.0])
+    hi = np.array([0.6, 0.7, 0.3, 0.7, 20.0, 20.0])
+    placed = insertion.random_object_poses(1, str(g["arm"]), objs, u=((g["draws"] - lo) / (hi - lo))[None])
+    for name, key in (("male_object", "male_qpos"), ("female_object", "female_qpos")):
+        assert np.abs(placed[name][0][0] - g[key][:3]).max() < 1e-15 and np.abs(placed[name][1][0] - g[key][3:]).max() < 1e-14
+    wp_xyz, wp_quat = insertion.waypoint_poses(actions, objs, placed, g["start_pos"][None])
+    _app, _osc, names, layout = build_scenario("insertion")
+    ia = names.index(active)
+    seq = ActionSequence(layout, actions, active_arm=active, step_period=float(g["step_period"]))
+    poses = {k: g["pose_" + k] for k in ("active_xyz", "active_quat", "passive_xyz")}
+    T = int(g["n_ticks"])
+    mine = sequence_numpy.run_sequence(seq.params, wp_xyz[0], wp_quat[0], poses, layout.as_dict()["devices"][ia],
+                                       default_ee_quat(), float(g["max_vel0_initial"]), T)
+    n = len(g["tick"])
+    assert n < T and [r["action"] for r in mine[n:]] == [len(actions)] * (len(mine) - n)
+    for t in range(n):
+        r = mine[t]
+        assert r["tick"] == int(g["tick"][t]) and r["action"] == int(g["action"][t]), t
+        assert (np.isinf(r["err"]) and np.isinf(g["err"][t])) or r["err"] == pytest.approx(float(g["err"][t]), rel=1e-12, abs=1e-15)
+        assert r["max_vel0"] == pytest.approx(float(g["max_vel0"][t]), rel=1e-12, abs=0)
+        assert r["gripper_force"] == float(g["gripper_force"][t])
+        for k in ("active_xyz", "active_quat", "passive_xyz", "passive_quat"):
+            assert np.abs(r[k] - g[k][t]).max() < 1e-14, (t, k)
+    assert int(g["action"].max()) == len(actions) - 1

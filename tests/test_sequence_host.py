@@ -239,3 +239,15 @@ def test_restated_waypoint_cycle_matches_the_unmodified_gain_test_loop():
         assert np.array_equal(ref[t][0], mine_r[t][0]) and ref[t][2] == mine_r[t][1], t
         assert np.array_equal(ref[t][1], mine_l[t][0]) and ref[t][3] == mine_l[t][1], t
     assert max(r[2] for r in ref) > 0 and max(r[3] for r in ref) > 0          # both lists advanced
+
+
+def test_waypoint_cycle_golden_from_the_reference():
+    """tests/golden/waypoint_cycle.npz: the reference's own `GainTest.run` loop on recorded EE streams."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "waypoint_cycle.npz"))
+    T = len(g["right_idx"])
+    for side in ("right", "left"):
+        mine = sequence_numpy.run_waypoint_cycle(g[side + "_wps"], g["ee_" + side], float(g["threshold"]), T)
+        for t in range(T):
+            assert np.array_equal(mine[t][0], g[side + "_target"][t]) and mine[t][1] == int(g[side + "_idx"][t]), (side, t)
+        assert g[side + "_idx"].max() > 0
