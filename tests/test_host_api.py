@@ -224,3 +224,37 @@ def test_builtin_configs_equal_the_reference_yaml_files():
         assert configs.action_config("insertion_task.yaml") == yaml.safe_load(fh)
     with open(os.path.join(ref, "action_sequence_configs", "iros2022_task.yaml")) as fh:
         assert configs.IROS2022_DEVICE_CONFIG == yaml.safe_load(fh)["device_config"]
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not os.path.isfile("/root/reference/irl_control/osc.py"), reason="needs /root/reference")
+@pytest.mark.parametrize("scenario", sorted(SCENARIOS))
+def test_host_classes_resolve_the_same_maps_as_the_reference_classes(scenario):
+    """`Device` / `Robot` / `OSC` of this package next to the reference's own classes constructed on the same model
+    and YAML: index maps, DoF masks, Jacobian row numbering, gains after the constructor's precompute."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden
+    runner = make_golden.reference_runner(scenario)
+    app, osc, targets, layout = build_scenario(scenario)
+    robot = app.get_robot("DualUR5")
+    assert robot.num_joints_total == runner.robot.num_joints_total
+    assert list(robot.joint_ids_all) == list(runner.robot.joint_ids_all)
+    for name, ref_dev in runner.robot.sub_devices_dict.items():
+        dev = robot.get_device(name)
+        for attr in ("joint_ids", "joint_ids_all", "ctrl_idxs", "actuator_trnids", "ctrlr_dof", "ctrlr_dof_xyz",
+                     "ctrlr_dof_abg", "max_vel", "start_angles"):
+            assert list(np.ravel(getattr(dev, attr))) == list(np.ravel(getattr(ref_dev, attr))), (name, attr)
+    # Jacobian row numbering (robot.py:52-55) as seen through the layout's dx_idx
+    from irl_control_b200.synthetic import synth_batch
+    st = {k: v.numpy()[0] for k, v in synth_batch(layout, 1, seed=3).items()}
+    runner.run(st, st["target_xyz"], st["target_quat"], max_vel=st["max_vel"])          # loads the instance
+    _Js, J_idxs = runner.robot.get_all_states()[make_golden.ref_harness.import_reference()[5].J]
+    for dl in layout.devices:
+        assert list(dl.dx_idx) == list(J_idxs[dl.name]), dl.name
+    # gains after OSC.__init__'s in-place precompute (osc.py:35-39)
+    for dl in layout.devices:
+        cfg = runner.osc.device_configs[dl.name]
+        assert (dl.kp, dl.kv, dl.ko) == (cfg["kp"], cfg["kv"], cfg["ko"])
+        assert list(dl.k) == list(cfg["k"]) and list(dl.d) == list(cfg["d"])
+    assert layout.nullspace_kv == runner.osc.nullspace_config["kv"]
