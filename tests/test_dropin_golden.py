@@ -39,6 +39,11 @@ class _HostEngine:
 @pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4)
 def test_generate_reproduces_the_reference_goldens(case, monkeypatch):
     monkeypatch.setattr(pkg_osc, "BatchedOSC", _HostEngine)
+    generate_on_golden(case)
+
+
+def generate_on_golden(case):
+    """Shared with tests/test_gpu_zz_dropin.py, which runs it with the real engine (libirlosc.so on the GPU)."""
     g, _ld = load_golden(case)
     sc = SCENARIOS[str(g["scenario"])]
     cfg = configs.robot_config(sc["config"])
