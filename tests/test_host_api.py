@@ -258,3 +258,13 @@ def test_host_classes_resolve_the_same_maps_as_the_reference_classes(scenario):
         assert (dl.kp, dl.kv, dl.ko) == (cfg["kp"], cfg["kv"], cfg["ko"])
         assert list(dl.k) == list(cfg["k"]) and list(dl.d) == list(cfg["d"])
     assert layout.nullspace_kv == runner.osc.nullspace_config["kv"]
+
+
+def test_roofline_bytes_are_the_survey_figures():
+    """`bench.algorithmic_bytes` (the numerator of roofline.achieved) against SURVEY.md 8(d): 4 904 B gain_test,
+    5 864 B admit_test, 5 768 B insertion, 6 104 B for k = 13 (worst case and iros2022)."""
+    import bench
+    want = {"gain_test": 4904, "admit_test": 5864, "insertion": 5768, "worst_case": 6104, "iros2022": 6104}
+    for name, nbytes in want.items():
+        _, _, _, L = build_scenario(name)
+        assert bench.algorithmic_bytes(L) == nbytes, name
