@@ -149,7 +149,7 @@ class OSC:
         """B instances at once; `state` holds CUDA tensors (-> BatchedOSC.step) or numpy
         arrays (-> BatchedOSC.step_host), per-device fields in `target_names` order."""
         engine = self.engine_for(list(target_names))
-        first = state["M"]
+        first = state["M"] if "M" in state else state["qM"]       # qM: MuJoCo's sparse inertia (IRLOSC_M_QM)
         if isinstance(first, np.ndarray):
             return engine.step_host(state, **kw)
         return engine.step(state, **kw)
