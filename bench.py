@@ -48,7 +48,8 @@ def side_legs():
     `value`, `e2e` or `roofline`."""
     tool = os.path.join(ROOT, "tools", "side_legs.py")
     runs = [("default", ["--legs", "qm,qm_admit,iros2022,sequence,coop"], {"IRLOSC_FIXUP_COOP": "0"}, 120),
-            ("fixup_coop", ["--legs", "coop"], {"IRLOSC_FIXUP_COOP": "1"}, 60)]
+            ("fixup_coop", ["--legs", "coop"], {"IRLOSC_FIXUP_COOP": "1"}, 60),
+            ("qm_tree", ["--legs", "qm_tree"], {}, 60)]
     out = {}
     for name, extra, env_add, limit in runs:
         env = dict(os.environ, **env_add)

@@ -134,10 +134,21 @@ constexpr int kKernelStream = 9;
 static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st, int queue = 0) {
     if (B == 0) return IRLOSC_OK;
     const bool stream_ok = stream_supported(h, k);
-    if (k.m_layout == IRLOSC_M_QM) {          // only the streaming kernel's copy plan addresses MuJoCo's sparse qM
-        if (!stream_ok || (h->kernel_choice != 0 && h->kernel_choice != kKernelStream))
-            return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM is read by the streaming kernel only: declare the DualUR5 topology, "
-                                            "leave check_topology off and keep the kernel selector at 0 or 9");
+    if (k.m_layout == IRLOSC_M_QM) {
+        // MuJoCo's sparse qM: addressed by the streaming kernel's copy plan (auto / 9) and, on explicit request only
+        // (selector 2 + v, tight stride), by the tree-sparse kernel's qM instantiations
+        if (h->kernel_choice >= 2 && h->kernel_choice != kKernelStream) {
+            const int v = h->kernel_choice - 2;
+            if (!tiled_supported(h->kp, k, v))
+                return fail(IRLOSC_ERR_INVALID, "no tree-sparse kernel variant %d for IRLOSC_M_QM with this controller / stride", v);
+            cudaError_t e = tiled_launch(h->kp, k, B, h->sm_count - h->sm_margin, st, &h->last_kernel, v);
+            if (e != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "tiled kernel launch: %s", cudaGetErrorString(e));
+            h->launches += 1;
+            return IRLOSC_OK;
+        }
+        if (!stream_ok || h->kernel_choice == 1)
+            return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM needs the declared DualUR5 topology (check_topology off) and "
+                                            "kernel selector 0, 9 or 2 + v");
         return stream_launch(h, B, k, st, queue);
     }
     if (h->kernel_choice == kKernelStream) {

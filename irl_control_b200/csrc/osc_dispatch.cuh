@@ -26,6 +26,7 @@ struct TiledEntry {
     bool has_base;        // tree only
     int warps, slots;     // tree only: warps per CTA, input slots per CTA
     int slot_fixed, priv; // tree only: bytes of the fixed slot part / per-warp scratch
+    bool qm = false;      // tree only: M arrives as MuJoCo's sparse qM (IRLOSC_M_QM, tight stride 155)
 };
 
 template <int N, int K, int D, int G, bool PACKED, int MINB>
@@ -45,14 +46,14 @@ inline TiledEntry rows_entry(int variant, const char *name) {
 constexpr size_t kTreeSmemLimit = 227 * 1024;
 constexpr int kTreeHeader = 64;
 
-template <int KD, bool HAS_BASE, bool PACKED, int W, int NS, int GW = 1>
+template <int KD, bool HAS_BASE, bool PACKED, int W, int NS, int GW = 1, bool QM = false>
 inline TiledEntry tree_entry(int variant, const char *name) {
-    using SLT = tree::TreeSlot<KD, HAS_BASE, PACKED>;
+    using SLT = tree::TreeSlot<KD, HAS_BASE, PACKED, QM>;
     using PVT = tree::TreePriv<KD, HAS_BASE>;
     return TiledEntry{1, tree::kN, SLT::K, SLT::D, PACKED, variant, 1,
-                      (const void *)tree::osc_step_tree<KD, HAS_BASE, PACKED, W, NS, GW>,
+                      (const void *)tree::osc_step_tree<KD, HAS_BASE, PACKED, W, NS, GW, QM>,
                       kTreeSmemLimit, name, KD, HAS_BASE, W, NS,
-                      (int)(sizeof(SLT) - 16), (int)((sizeof(PVT) + 15) & ~size_t(15))};
+                      (int)(sizeof(SLT) - 16), (int)((sizeof(PVT) + 15) & ~size_t(15)), QM};
 }
 
 inline const TiledEntry *tiled_table(int *count) {
@@ -68,6 +69,14 @@ inline const TiledEntry *tiled_table(int *count) {
         tree_entry<6, true, false, 3, 2, 1>(0, "osc_step_tree<kd6,base,dense,w3,s2,g1>"),
         tree_entry<3, true, true, 6, 3, 3>(3, "osc_step_tree<kd3,base,packed,w6,s3,g3>"),
         tree_entry<3, true, true, 4, 4, 1>(4, "osc_step_tree<kd3,base,packed,w4,s4,g1>"),
+        // ---- tree-sparse on MuJoCo's sparse qM (IRLOSC_M_QM; explicit kernel selection only, not yet run on a GPU):
+        //      a slot is 27 KB instead of 38 KB, so a fourth slot and an eighth warp fit
+        tree_entry<3, true, true, 8, 4, 1, true>(0, "osc_step_tree<kd3,base,qM,w8,s4,g1>"),
+        tree_entry<3, true, true, 7, 3, 1, true>(0, "osc_step_tree<kd3,base,qM,w7,s3,g1>"),
+        tree_entry<3, true, true, 7, 4, 1, true>(3, "osc_step_tree<kd3,base,qM,w7,s4,g1>"),
+        tree_entry<3, true, true, 8, 3, 1, true>(4, "osc_step_tree<kd3,base,qM,w8,s3,g1>"),
+        tree_entry<6, false, true, 4, 2, 1, true>(0, "osc_step_tree<kd6,qM,w4,s2,g1>"),
+        tree_entry<6, true, true, 4, 2, 1, true>(0, "osc_step_tree<kd6,base,qM,w4,s2,g1>"),
         // ---- dense: default without topology (variant 1 when a topology is declared), all DualUR5 shapes;
         //      variant 2 keeps the column/scratch kernel of the headline shape for A/B runs
         rows_entry<25, 7, 3, 8, true, 2>(1, "osc_step_rows<n25,k7,D3,G8,packed>"),
@@ -122,8 +131,10 @@ inline bool tree_roles(const KParams &P, tree::Roles &R, int &kd, bool &has_base
 inline const TiledEntry *tiled_find(const KParams &P, const KIo &io, int variant, tree::Roles *roles_out) {
     auto al16 = [](const void *p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     if (io.j_layout != IRLOSC_J_ROWS || io.ldj != P.n || io.j_stride != (int64_t)P.n * P.k) return nullptr;
-    const bool packed = io.m_layout == IRLOSC_M_PACKED;
-    if (packed && io.m_stride != (int64_t)P.n * (P.n + 1) / 2) return nullptr;
+    const bool qm = io.m_layout == IRLOSC_M_QM;
+    const bool packed = io.m_layout == IRLOSC_M_PACKED || qm;       // qM entries are registered with packed = true
+    if (qm && io.m_stride != tree::kQmSize) return nullptr;        // a tile's qM block must be one contiguous bulk copy
+    if (!qm && packed && io.m_stride != (int64_t)P.n * (P.n + 1) / 2) return nullptr;
     if (!packed && (io.ldm != P.n || io.m_stride != (int64_t)P.n * P.n)) return nullptr;
     if (!(al16(io.M) && al16(io.J) && al16(io.dq) && al16(io.bias) && al16(io.ee_xyz) && al16(io.ee_quat) &&
           al16(io.target_xyz) && al16(io.target_quat) && al16(io.target_vel) && al16(io.max_vel) &&
@@ -138,7 +149,7 @@ inline const TiledEntry *tiled_find(const KParams &P, const KIo &io, int variant
     int cnt = 0;
     const TiledEntry *t = tiled_table(&cnt);
     for (int i = 0; i < cnt; ++i) {
-        if (t[i].packed != packed || t[i].variant != want) continue;
+        if (t[i].packed != packed || t[i].qm != qm || t[i].variant != want) continue;
         if (t[i].kind == 1) {
             if (!(tree_ok && t[i].kd == kd && t[i].has_base == has_base)) continue;
             // shared-memory plan: optional per-instance arrays go to the slot tail

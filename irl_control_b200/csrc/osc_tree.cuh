@@ -76,12 +76,25 @@ struct Roles {            // which target device plays which part (indices into 
 };
 
 // Fixed part of an input slot; the optional per-instance arrays follow in a tail.
-template <int KD, bool HAS_BASE, bool PACKED>
+// MuJoCo's sparse inertia qM (IRLOSC_M_QM) of the DualUR5 tree: dof i owns M[i][i], M[i][parent], ... down to the
+// stand joint, stored from kQmAdr(i); 155 doubles in all.  Arm a's chain rows start at kQmArm(a), its gripper rows
+// 27 doubles later (depths 2..7 of the six arm joints).
+constexpr int kQmSize = 155;
+__host__ __device__ constexpr int qm_adr(int i) {
+    constexpr int parent[kN] = {-1, 0, 1, 2, 3, 4, 5, 6, 7, 6, 6, 10, 6, 0, 13, 14, 15, 16, 17, 18, 19, 18, 18, 22, 18};
+    int adr = 0;
+    for (int r = 0; r < i; ++r)
+        for (int j = r; j >= 0; j = parent[j]) ++adr;
+    return adr;
+}
+static_assert(qm_adr(1) == 1 && qm_adr(7) == 28 && qm_adr(13) == 78 && qm_adr(24) + 8 == kQmSize, "qM addressing");
+
+template <int KD, bool HAS_BASE, bool PACKED, bool QM = false>
 struct TreeSlot {
     static constexpr int N = kN, WI = kWI;
     static constexpr int D = 2 + (HAS_BASE ? 1 : 0);
     static constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
-    static constexpr int MSZ = PACKED ? N * (N + 1) / 2 : N * N;
+    static constexpr int MSZ = QM ? kQmSize : (PACKED ? N * (N + 1) / 2 : N * N);
     alignas(16) double M[WI * MSZ];
     alignas(16) double J[WI * K * N];
     alignas(16) double dq[WI * N];
@@ -134,10 +147,10 @@ __device__ __forceinline__ void mbar_arrive(void *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tiled::smem_u32(bar)) : "memory");
 }
 
-template <int KD, bool HAS_BASE, bool PACKED, int W, int NS, int GW>
+template <int KD, bool HAS_BASE, bool PACKED, int W, int NS, int GW, bool QM = false>
 __global__ void __launch_bounds__(W * 32, 1)
 osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
-    using SLT = TreeSlot<KD, HAS_BASE, PACKED>;
+    using SLT = TreeSlot<KD, HAS_BASE, PACKED, QM>;
     using PVT = TreePriv<KD, HAS_BASE>;
     constexpr int N = kN, WI = kWI, G = kG, D = SLT::D, K = SLT::K, MSZ = SLT::MSZ;
     constexpr unsigned FULL = 0xffffffffu;
@@ -202,7 +215,7 @@ osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
         if (has_mvel) copy_rows(SL.tail + R.opt_mvel, io.max_vel, 2 * D, i0, valid);
         if (adm) { copy_rows(SL.tail + R.opt_ftx, io.ft_xmat, 9 * D, i0, valid); copy_rows(SL.tail + R.opt_ftr, io.ft_raw, 6 * D, i0, valid); }
         for (int s = valid; s < WI; ++s) {       // padded instances: keep the arithmetic finite
-            for (int i = lane; i < N; i += 32) SL.M[s * MSZ + (PACKED ? i * (i + 1) / 2 + i : i * N + i)] = 1.0;
+            for (int i = lane; i < N; i += 32) SL.M[s * MSZ + (QM ? qm_adr(i) : PACKED ? i * (i + 1) / 2 + i : i * N + i)] = 1.0;
             for (int dd = lane; dd < D; dd += 32) { SL.ee_quat[(s * D + dd) * 4] = 1.0; SL.t_quat[(s * D + dd) * 4] = 1.0; }
         }
     };
@@ -273,7 +286,7 @@ osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
         // optional verification of the declared sparsity (irlosc_params.check_topology)
         bool sparse_bad = false;
         if (P.check_topology) {
-            for (int i = 0; i < N; ++i) {
+            for (int i = 0; i < (QM ? 0 : N); ++i) {       // qM holds the tree's entries only: nothing to verify in M
                 const uint32_t anc = dual_ur5_anc(i);
                 for (int j = l; j < (PACKED ? i + 1 : N); j += G) {
                     const bool related = (j <= i) ? ((anc >> j) & 1u) : ((dual_ur5_anc(j) >> i) & 1u);
@@ -300,13 +313,15 @@ osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
             c[0] = (l == 0) ? m00 : 0.0;                      // M[0][0] enters once (right arm, h = 0)
             uvC[0] = c[0] * dqc[0];
         }
+        const int qa = arm ? qm_adr(13) : qm_adr(1);          // qM: first entry of this arm's chain rows
         sfor<1, 7>([&](auto ic) {
             constexpr int i = decltype(ic)::value;
-            const int ro = rowoff(jb + i - 1);
+            const int ro = QM ? qa + (i - 1) * (i + 2) / 2 : rowoff(jb + i - 1);
             sfor<0, i + 1>([&](auto jc) {
                 constexpr int j = decltype(jc)::value;
                 double v = 0.0;                               // the h = 1 copy accumulates updates only
-                if (h == 0) v = Ms[ro + ccol(j)];
+                // qM row of arm joint i: [itself, arm joints i-1 .. 1, stand]
+                if (h == 0) v = QM ? Ms[ro + (j == 0 ? i : i - j)] : Ms[ro + ccol(j)];
                 c[i * (i + 1) / 2 + j] = v;
                 uvC[i] = fma(v, dqc[j], uvC[i]);
                 if constexpr (j != i) uvC[j] = fma(v, dqc[i], uvC[j]);
@@ -317,19 +332,21 @@ osc_step_tree(const KParams P, const KIo io, const int64_t B, const Roles R) {
         sfor<0, 3>([&](auto rc) {
             constexpr int r = decltype(rc)::value;
             const int gj = gb + r;
-            const int ro = rowoff(gj);
+            // qM rows of a gripper half: [gb, arm 6..1, stand] (8), [gb+1, gb, arm 6..1, stand] (9), [gb+2, arm 6..1, stand] (8)
+            constexpr int qs = (r == 1) ? 1 : 0;
+            const int ro = QM ? qa + 27 + 25 * h + (r == 0 ? 0 : r == 1 ? 8 : 17) : rowoff(gj);
             dqg[r] = dqs[gj];
-            dg[r] = Ms[ro + gj];
+            dg[r] = QM ? Ms[ro] : Ms[ro + gj];
             uvg[r] = dg[r] * dqg[r];
             sfor<0, 7>([&](auto ic) {
                 constexpr int i = decltype(ic)::value;
-                const double v = Ms[ro + ccol(i)];
+                const double v = QM ? Ms[ro + (i == 0 ? 7 + qs : 7 + qs - i)] : Ms[ro + ccol(i)];
                 rg[r][i] = v;
                 uvg[r] = fma(v, dqc[i], uvg[r]);
                 uvC[i] = fma(v, dqg[r], uvC[i]);
             });
         });
-        const double e10 = Ms[rowoff(gb + 1) + gb];           // M[gb+1][gb]
+        const double e10 = QM ? Ms[qa + 27 + 25 * h + 8 + 1] : Ms[rowoff(gb + 1) + gb];           // M[gb+1][gb]
         uvg[1] = fma(e10, dqg[0], uvg[1]);
         uvg[0] = fma(e10, dqg[1], uvg[0]);
         sfor<0, 3>([&](auto rc) { PV.uv[grp][gb + decltype(rc)::value] = uvg[decltype(rc)::value]; });

@@ -108,3 +108,9 @@ def test_iros2022_sequence_and_coop_legs(legs, capsys):
     r = _run(capsys, lambda: legs.leg_coop(torch, np, 128, 2, 1))
     for sc in ("gain_test", "admit_test"):
         assert r[sc]["max_rel_err_vs_oracle"] < 1e-6 and r[sc]["branch_agreement"] == 1.0
+
+
+def test_qm_tree_leg(legs, capsys):
+    import torch
+    r = _run(capsys, lambda: legs.leg_qm_tree(torch, np, 64, 2, 1))
+    assert r["bit_identical_to_packed_B1003"] and r["bit_identical_to_packed_B64"] and "host build" in r

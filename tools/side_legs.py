@@ -14,6 +14,8 @@ Legs (`--legs a,b,...`):
   qm_admit  the same kernel comparison on the admit_test layout (k = 12)
   iros2022  SURVEY 8 (f4) layout: parity against the oracle on a strided subset, kernel times
   sequence  the reference's 12-entry insertion action list, randomised adapters, B = 16 384
+  qm_tree   the tree-sparse kernel's qM instantiations (explicit kernel selection; never run on a GPU before - bench.py
+            gives this leg a child process of its own)
   coop      fused gain_test step with IRLOSC_FIXUP_COOP=1 (run by bench.py as a second child with that
             environment variable): parity against the oracle + step time
 """
@@ -99,6 +101,42 @@ def leg_qm(torch, np, scenario, B, steps, warmup, name, with_e2e):
                          "d2h_bytes_per_step": int(host_out["ctrl"].nbytes),
                          "api": "BatchedOSC.step_host({'qM': ...}) -> irlosc_step_host, IRLOSC_M_QM"}
     emit(name, **res)
+
+
+def leg_qm_tree(torch, np, B, steps, warmup):
+    """Tree-sparse kernel staging qM (osc_step_tree<..., qM>, explicit selection only): first run on a GPU.  Equality
+    with the packed-M tree kernel on a full and on a ragged batch, then the variants' kernel times."""
+    from irl_control_b200.engine import BatchedOSC
+    from irl_control_b200.synthetic import kernel_inputs, scenario_layout, synth_batch
+    layout = scenario_layout("gain_test")
+    eng = BatchedOSC(layout, device=0)
+    eng.set_kernel(2)
+    res = {"workload": "gain_test", "batch": B}
+    for nb in (1003, B):
+        st = synth_batch(layout, nb, seed=99, device=DEV)
+        pin, qin = kernel_inputs(st, layout, packed_M=True), kernel_inputs(st, layout, qM=True)
+        a = eng.step(pin, want_u_all=True)
+        name_p = eng.last_kernel
+        b = eng.step(qin, want_u_all=True)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(a["u_all"], b["u_all"]) and torch.equal(a["ctrl"], b["ctrl"]) and torch.equal(a["status"], b["status"]))
+        res["bit_identical_to_packed_B%d" % nb] = same
+        if not same:
+            res["max_rel_diff_B%d" % nb] = rel_err(np, b["u_all"].cpu().numpy(), a["u_all"].cpu().numpy())
+            emit("qm_tree", **res)
+            return
+    out = {"ctrl": torch.empty_like(a["ctrl"])}
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+    res[name_p] = time_steps(torch, lambda: eng.step(pin, out=out, want_status=False), steps, warmup, flush)
+    for which in (2, 5, 6):                                   # qM table variants 0 (w8 s4, else w7 s3), 3 (w7 s4), 4 (w8 s3)
+        try:
+            eng.set_kernel(which)
+            eng.step(qin, out=out, want_status=False)
+            nm = eng.last_kernel
+            res[nm] = time_steps(torch, lambda: eng.step(qin, out=out, want_status=False), steps, warmup, flush)
+        except Exception as exc:
+            res["selector_%d" % which] = "%s: %s" % (type(exc).__name__, exc)
+    emit("qm_tree", **res)
 
 
 def leg_iros2022(torch, np, B, steps, warmup):
@@ -208,6 +246,7 @@ def main():
         "iros2022": lambda: leg_iros2022(torch, np, args.batch, args.steps, args.warmup),
         "sequence": lambda: leg_sequence(torch, np, min(args.batch, 16384), args.steps, args.warmup),
         "coop": lambda: leg_coop(torch, np, args.batch, args.steps, args.warmup),
+        "qm_tree": lambda: leg_qm_tree(torch, np, args.batch, args.steps, args.warmup),
     }
     for leg in args.legs.split(","):
         try:
