@@ -19,6 +19,10 @@ for B in 65536 262144; do
       > gpurun_out/stream_${L}_B${B}.json 2>> gpurun_out/bench_first.err
   done
 done
+for K in 2 5 6; do      # tree-sparse kernel on qM: table variants 0 (w8 s4), 3 (w7 s4), 4 (w8 s3); packed default = --kernel 0
+  python bench.py --kernel $K --m-layout qM --no-side-legs --no-fused --no-cpu-baseline --no-e2e \
+    > gpurun_out/tree_qM_k${K}.json 2>> gpurun_out/bench_first.err
+done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_first.csv \
   python bench.py --steps 4 --warmup 3 --no-side-legs --no-cpu-baseline > gpurun_out/ncu_bench_first.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:osc_step_stream -s 3 -c 1 \
