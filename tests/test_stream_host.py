@@ -146,3 +146,30 @@ def test_adapter_checks_the_models_qM_addressing():
         sparse_inertia(SimpleNamespace(dof_parentid=np.array(parent), dof_Madr=madr + 1), data, layout)
     with pytest.raises(ValueError):
         sparse_inertia(m, SimpleNamespace(qM=np.zeros(100)), layout)
+
+
+def test_tree_kernel_qM_offsets_are_the_mj_fullM_walk():
+    """The tree-sparse kernel's qM instantiations (csrc/osc_tree.cuh) address the record as per-lane base +
+    compile-time offsets; the same expressions, evaluated here, must hit the slots `layout.qm_index` assigns."""
+    rows, cols = qm_index(DUAL_UR5_PARENT)
+    off = {(int(r), int(c)): k for k, (r, c) in enumerate(zip(rows, cols))}
+    adr = {}
+    for k, r in enumerate(rows):
+        adr.setdefault(int(r), k)
+    assert (adr[1], adr[7], adr[13], adr[24] + 8) == (1, 28, 78, 155)          # the kernel's static_assert
+    for arm in (0, 1):
+        jb, qa = 1 + 12 * arm, (adr[13] if arm else adr[1])
+        ccol = lambda i: 0 if i == 0 else jb + i - 1                           # noqa: E731
+        for i in range(1, 7):                                                  # arm chain rows
+            ro = qa + (i - 1) * (i + 2) // 2
+            for j in range(i + 1):
+                assert ro + (i if j == 0 else i - j) == off[(jb + i - 1, ccol(j))]
+        for h in (0, 1):                                                       # gripper halves
+            gb = jb + 6 + 3 * h
+            for r in range(3):
+                qs = 1 if r == 1 else 0
+                ro = qa + 27 + 25 * h + (0, 8, 17)[r]
+                assert ro == off[(gb + r, gb + r)]
+                for i in range(7):
+                    assert ro + 7 + qs - i == off[(gb + r, ccol(i))]
+            assert qa + 27 + 25 * h + 9 == off[(gb + 1, gb)]
