@@ -81,6 +81,18 @@ def leg_qm(torch, np, scenario, B, steps, warmup, name, with_e2e):
     res["l2_policy"] = "256 MB flush write before every timed step"
     res["steps_per_s"] = {k: B / (res[k]["ms_median"] * 1e-3) for k in ("packed", "qM")}
     if with_e2e:
+        # launch knobs the library reads per launch (experiments only): warps per CTA and the cp.async L2 hint
+        sweep = {}
+        for lay, inp in (("packed", pin), ("qM", qin)):
+            for warps in (6, 7, 8):
+                for mode in (0, 1):
+                    os.environ["IRLOSC_STREAM_WARPS"], os.environ["IRLOSC_STREAM_MODE"] = str(warps), str(mode)
+                    t = time_steps(torch, lambda: eng.step(inp, out=out, want_status=False), max(3, steps // 2), 2, flush)
+                    sweep["%s_w%d_mode%d" % (lay, warps, mode)] = t["ms_median"]
+        os.environ.pop("IRLOSC_STREAM_WARPS", None)
+        os.environ.pop("IRLOSC_STREAM_MODE", None)
+        res["stream_knob_sweep_ms"] = sweep
+    if with_e2e:
         host_in = {}
         for k, v in qin.items():
             buf = pinned_empty(tuple(v.shape))
