@@ -49,7 +49,7 @@ def side_legs():
     tool = os.path.join(ROOT, "tools", "side_legs.py")
     runs = [("default", ["--legs", "qm,qm_admit,iros2022,sequence,coop"], {"IRLOSC_FIXUP_COOP": "0"}, 120),
             ("fixup_coop", ["--legs", "coop"], {"IRLOSC_FIXUP_COOP": "1"}, 60),
-            ("qm_tree", ["--legs", "qm_tree"], {}, 60)]
+            ("qm_tree", ["--legs", "qm_tree,fp64_peak"], {}, 75)]
     out = {}
     for name, extra, env_add, limit in runs:
         env = dict(os.environ, **env_add)

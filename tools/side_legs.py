@@ -16,6 +16,7 @@ Legs (`--legs a,b,...`):
   sequence  the reference's 12-entry insertion action list, randomised adapters, B = 16 384
   qm_tree   the tree-sparse kernel's qM instantiations (explicit kernel selection; never run on a GPU before - bench.py
             gives this leg a child process of its own)
+  fp64_peak cuBLAS DGEMM rate of the box (the FP64 reference point SURVEY 8d asks for)
   coop      fused gain_test step with IRLOSC_FIXUP_COOP=1 (run by bench.py as a second child with that
             environment variable): parity against the oracle + step time
 """
@@ -214,6 +215,18 @@ def leg_sequence(torch, np, B, steps, warmup):
          episode_steps_per_s=B / (t["ms_median"] * 1e-3))
 
 
+def leg_fp64_peak(torch, np):
+    """FP64 rate of the box (not in MEASURED_PEAKS.json): cuBLAS DGEMM 8192^3 through torch, best of 5 -
+    the denominator for the FP64-pipe share the fused kernel is quoted against."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=DEV)
+    b = torch.randn(n, n, dtype=torch.float64, device=DEV)
+    c = torch.empty_like(a)
+    t = time_steps(torch, lambda: torch.matmul(a, b, out=c), 5, 2)
+    emit("fp64_peak", how="torch.matmul float64 %d^3 (cuBLAS DGEMM), CUDA events, best of 5" % n,
+         tflops=2.0 * n ** 3 / (t["ms_min"] * 1e-3) / 1e12, ms_min=t["ms_min"])
+
+
 def leg_coop(torch, np, B, steps, warmup):
     from irl_control_b200.engine import BatchedOSC
     from irl_control_b200.synthetic import fused_inputs, oracle_inputs, scenario_model, synth_batch
@@ -259,6 +272,7 @@ def main():
         "sequence": lambda: leg_sequence(torch, np, min(args.batch, 16384), args.steps, args.warmup),
         "coop": lambda: leg_coop(torch, np, args.batch, args.steps, args.warmup),
         "qm_tree": lambda: leg_qm_tree(torch, np, args.batch, args.steps, args.warmup),
+        "fp64_peak": lambda: leg_fp64_peak(torch, np),
     }
     for leg in args.legs.split(","):
         try:
