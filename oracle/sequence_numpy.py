@@ -93,78 +93,70 @@ DEFAULT_EE_ROT = np.deg2rad([0, -90, -90])                        # insertion_ta
 
 
 def initialize_action_objects(action_objects):
-    """insertion_task.py:299-311 -> {object: (pos, quat)} as `set_free_joint_qpos` would store them."""
+    """Configured placement (insertion_task.py:299-311): YAML position, YAML Euler angles in degrees -> radians ->
+    quaternion.  Returns {object: (pos, quat)} - what `set_free_joint_qpos` would store."""
     from . import t3d
-    out = {}
-    for name, obj in action_objects.items():
-        quat = t3d.euler2quat(*(np.deg2rad(obj['initial_pos_abg']))) if 'initial_pos_abg' in obj else None
-        pos = obj['initial_pos_xyz'] if 'initial_pos_xyz' in obj else None
-        out[name] = (np.array(pos, dtype=np.float64), np.array(quat, dtype=np.float64))
-    return out
+    placed = {}
+    for name, spec in action_objects.items():
+        angles = np.deg2rad(spec['initial_pos_abg'])
+        placed[name] = (np.array(spec['initial_pos_xyz'], dtype=np.float64), np.array(t3d.euler2quat(*angles)))
+    return placed
 
 
 def initialize_action_objects_random(action_objects, arm_name, uniform):
-    """insertion_task.py:341-369; `uniform(low, high)` stands for `np.random.uniform` (called six times in the
-    reference's order).  Mutates `action_objects` like the reference."""
+    """Randomised placement (insertion_task.py:341-369).  `uniform(low, high)` stands for `np.random.uniform`; the
+    reference draws, in this order: male x, male y, female x, female y, male yaw, female yaw.  x is mirrored for the
+    left arm, z stays as configured, the yaw is cut to an integer and - unlike the configured placement - handed to
+    euler2quat WITHOUT a degree conversion (358, 367).  `action_objects` is updated in place like the reference's."""
     from . import t3d
-    mx = uniform(0.4, 0.6)
-    my = uniform(0.5, 0.7)
-    fx = uniform(0.0, 0.3)
-    fy = uniform(0.5, 0.7)
-    out = {}
-    male_obj = action_objects['male_object']
-    yaw_male = int(uniform(-20, 20))
-    male_obj['initial_pos_abg'] = [0, 0, yaw_male]
-    male_obj['initial_pos_xyz'][0] = mx if arm_name == 'right' else -1 * mx
-    male_obj['initial_pos_xyz'][1] = my
-    out['male_object'] = (np.array(male_obj['initial_pos_xyz'], dtype=np.float64),
-                          np.array(t3d.euler2quat(*male_obj['initial_pos_abg'])))          # degrees, as written (358)
-    female_obj = action_objects['female_object']
-    yaw_female = int(uniform(-20, 20))
-    female_obj['initial_pos_abg'] = [0, 0, yaw_female]
-    female_obj['initial_pos_xyz'][0] = fx if arm_name == 'right' else -1 * fx
-    female_obj['initial_pos_xyz'][1] = fy
-    out['female_object'] = (np.array(female_obj['initial_pos_xyz'], dtype=np.float64),
-                            np.array(t3d.euler2quat(*female_obj['initial_pos_abg'])))      # (367)
-    return out
+    xy = {"male_object": (uniform(0.4, 0.6), uniform(0.5, 0.7))}
+    xy["female_object"] = (uniform(0.0, 0.3), uniform(0.5, 0.7))
+    side = 1.0 if arm_name == 'right' else -1.0
+    placed = {}
+    for name in ("male_object", "female_object"):
+        spec = action_objects[name]
+        spec['initial_pos_abg'] = [0, 0, int(uniform(-20, 20))]
+        spec['initial_pos_xyz'][0] = side * xy[name][0]
+        spec['initial_pos_xyz'][1] = xy[name][1]
+        placed[name] = (np.array(spec['initial_pos_xyz'], dtype=np.float64),
+                        np.array(t3d.euler2quat(*spec['initial_pos_abg'])))
+    return placed
 
 
 def set_waypoint_targets(params, action_objects, object_qpos, start_pos):
-    """Active-arm part of insertion_task.py:206-268.  `object_qpos[name] = (pos, quat)` is what
-    `sim.data.get_joint_qpos(joint_name)` returns, split.  Returns (target xyz, target quat)."""
+    """Active-arm target of one WP action (insertion_task.py:217-270).  `object_qpos[name] = (pos, quat)`: the free
+    joint's qpos as the simulator reports it when the waypoint starts.  Returns (xyz, quat).
+
+    Position: `start_pos`, or an object's position plus an offset that is either a 3-list or the NAME of one of that
+    object's offset attributes; a literal list target is concatenated with the offset list by the reference's `+`
+    and then rejected by `Target.set_xyz` (len != 3).  Orientation: none -> DEFAULT_EE_QUAT; a list -> degrees;
+    an object name -> R(object) . R(DEFAULT_EE_ROT + [0, 0, grip_yaw]) -> static-xyz Euler angles -> quaternion."""
     from . import t3d
-    default_quat = t3d.euler2quat(*DEFAULT_EE_ROT)
-    if 'target_xyz' in params.keys():
-        offset = params['offset'] if 'offset' in params.keys() else [0.0, 0.0, 0.0]
-        if isinstance(params['target_xyz'], str):
-            if params['target_xyz'] == 'start_pos':
-                target = start_pos
-            else:
-                target_obj = action_objects[params['target_xyz']]
-                if isinstance(offset, str):
-                    offset = target_obj[offset]
-                obj_pos = object_qpos[params['target_xyz']][0]
-                target = obj_pos + offset
-        elif isinstance(params['target_xyz'], list):
-            target = params['target_xyz'] + offset
-        else:
-            raise ValueError
-        assert len(target) == 3                                    # Target.set_xyz (utils.py:36)
-        xyz = np.asarray(target, dtype=np.float64)
-    else:
+    if 'target_xyz' not in params:
         raise KeyError('target_xyz')
-    if 'target_abg' in params.keys():
-        if isinstance(params['target_abg'], str):
-            target_obj = action_objects[params['target_abg']]
-            obj_quat = object_qpos[params['target_abg']][1]
-            grip_eul = DEFAULT_EE_ROT + [0, 0, np.deg2rad(target_obj['grip_yaw'])]
-            tfmat = np.matmul(t3d.quat2mat(obj_quat), t3d.euler2mat(*grip_eul))      # compose() with zero translation
-            target_abg = np.array(t3d.mat2euler(tfmat[:3, :3]))
-        elif isinstance(params['target_abg'], list):
-            target_abg = np.deg2rad(params['target_abg'])
+    where, shift = params['target_xyz'], params.get('offset', [0.0, 0.0, 0.0])
+    if isinstance(where, str):
+        if where == 'start_pos':
+            xyz = np.asarray(start_pos, dtype=np.float64)
         else:
-            raise ValueError
-        quat = np.asarray(t3d.euler2quat(*target_abg))              # Target.set_abg (utils.py:52-54)
+            if isinstance(shift, str):
+                shift = action_objects[where][shift]
+            xyz = np.asarray(object_qpos[where][0], dtype=np.float64) + np.asarray(shift, dtype=np.float64)
+    elif isinstance(where, list):
+        joined = where + shift                                     # list concatenation, as in the reference
+        assert len(joined) == 3                                    # Target.set_xyz (utils.py:36)
+        xyz = np.asarray(joined, dtype=np.float64)
     else:
-        quat = np.asarray(default_quat)
-    return xyz, quat
+        raise ValueError
+    facing = params.get('target_abg')
+    if facing is None:
+        return xyz, np.asarray(t3d.euler2quat(*DEFAULT_EE_ROT))
+    if isinstance(facing, str):
+        yaw = np.deg2rad(action_objects[facing]['grip_yaw'])
+        rot = t3d.quat2mat(object_qpos[facing][1]) @ t3d.euler2mat(*(DEFAULT_EE_ROT + [0, 0, yaw]))
+        abg = np.array(t3d.mat2euler(rot))
+    elif isinstance(facing, list):
+        abg = np.deg2rad(facing)
+    else:
+        raise ValueError
+    return xyz, np.asarray(t3d.euler2quat(*abg))                  # Target.set_abg (utils.py:52-54)
