@@ -13,75 +13,64 @@ from .rotations import euler2quat, quat2euler
 
 
 class Target:
-    """Set-point of one device: position xyz, orientation as a w-x-y-z quaternion,
-    and their target velocities (utils.py:5-67)."""
+    """Set-point of one device: position xyz, orientation as a w-x-y-z quaternion, and their target
+    velocities.  Public surface of the reference's class (utils.py:5-67): `get_* / set_*` for `xyz`, `xyz_vel`,
+    `quat`, `quat_vel` (stored) and `abg`, `abg_vel` (static-xyz Euler view of the quaternions), plus
+    `set_all_quat` / `set_all_abg`.  Setters check the length and keep the caller's array (no copy), like the
+    reference's; the accessor methods are generated below from the two tables."""
+
+    _STORED = {"xyz": 3, "xyz_vel": 3, "quat": 4, "quat_vel": 4}
+    _EULER_VIEW = {"abg": "quat", "abg_vel": "quat_vel"}
 
     def __init__(self, xyz_abg=None, xyz_abg_vel=None):
         pose = np.zeros(6) if xyz_abg is None else np.asarray(xyz_abg, dtype=np.float64)
         rate = np.zeros(6) if xyz_abg_vel is None else np.asarray(xyz_abg_vel, dtype=np.float64)
         assert len(pose) == 6 and len(rate) == 6
-        self._xyz = pose[:3].copy()
-        self._xyz_vel = rate[:3].copy()
-        self._quat = euler2quat(*pose[3:])
-        self._quat_vel = euler2quat(*rate[3:])
-
-    # ---- getters ----
-    def get_xyz(self):
-        return self._xyz
-
-    def get_xyz_vel(self):
-        return self._xyz_vel
-
-    def get_quat(self):
-        return self._quat
-
-    def get_quat_vel(self):
-        return np.asarray(self._quat_vel)
-
-    def get_abg(self):
-        return np.asarray(quat2euler(self._quat))
-
-    def get_abg_vel(self):
-        return np.asarray(quat2euler(self._quat_vel))
-
-    # ---- setters ----
-    def set_xyz(self, xyz):
-        assert len(xyz) == 3
-        self._xyz = np.asarray(xyz)
-
-    def set_xyz_vel(self, xyz_vel):
-        assert len(xyz_vel) == 3
-        self._xyz_vel = np.asarray(xyz_vel)
-
-    def set_quat(self, quat):
-        assert len(quat) == 4
-        self._quat = np.asarray(quat)
-
-    def set_quat_vel(self, quat_vel):
-        assert len(quat_vel) == 4
-        self._quat_vel = np.asarray(quat_vel)
-
-    def set_abg(self, abg):
-        assert len(abg) == 3
-        self._quat = np.asarray(euler2quat(*abg))
-
-    def set_abg_vel(self, abg_vel):
-        assert len(abg_vel) == 3
-        self._quat_vel = np.asarray(euler2quat(*abg_vel))
+        self._v = {"xyz": pose[:3].copy(), "xyz_vel": rate[:3].copy(),
+                   "quat": euler2quat(*pose[3:]), "quat_vel": euler2quat(*rate[3:])}
 
     def set_all_quat(self, xyz, quat):
         assert len(xyz) == 3 and len(quat) == 4
-        self.set_xyz(xyz)
-        self.set_quat(quat)
+        self._v["xyz"], self._v["quat"] = np.asarray(xyz), np.asarray(quat)
 
     def set_all_abg(self, xyz, abg):
         assert len(xyz) == 3 and len(abg) == 3
-        self.set_xyz(xyz)
-        self.set_abg(abg)
+        self._v["xyz"], self._v["quat"] = np.asarray(xyz), np.asarray(euler2quat(*abg))
 
     def velocity6(self) -> np.ndarray:
         """[xyz_vel, abg_vel] exactly as `generate` assembles it (osc.py:172)."""
         return np.hstack([self.get_xyz_vel(), self.get_abg_vel()]).astype(np.float64)
+
+
+def _stored_accessors(field, size):
+    def getter(self):
+        return self._v[field]
+
+    def setter(self, value):
+        assert len(value) == size
+        self._v[field] = np.asarray(value)
+    return getter, setter
+
+
+def _euler_accessors(quat_field):
+    def getter(self):
+        return np.asarray(quat2euler(self._v[quat_field]))
+
+    def setter(self, angles):
+        assert len(angles) == 3
+        self._v[quat_field] = np.asarray(euler2quat(*angles))
+    return getter, setter
+
+
+for _field, _size in Target._STORED.items():
+    _g, _s = _stored_accessors(_field, _size)
+    setattr(Target, "get_" + _field, _g)
+    setattr(Target, "set_" + _field, _s)
+for _field, _quat_field in Target._EULER_VIEW.items():
+    _g, _s = _euler_accessors(_quat_field)
+    setattr(Target, "get_" + _field, _g)
+    setattr(Target, "set_" + _field, _s)
+del _field, _size, _quat_field, _g, _s
 
 
 class ControllerConfig:
