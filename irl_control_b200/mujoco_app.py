@@ -53,25 +53,25 @@ class MujocoApp:
         self.devices = np.array(loose + robots, dtype=object)
 
     def sleep_for(self, sleep_time: float):
+        """Blocking timer other threads poll through `timer_running` (mujoco_app.py:37-41); not re-entrant."""
         assert self.timer_running == False  # noqa: E712 (same contract as the reference)
         self.timer_running = True
-        time.sleep(sleep_time)
-        self.timer_running = False
+        try:
+            time.sleep(sleep_time)
+        finally:
+            self.timer_running = False
 
     def get_robot(self, robot_name: str) -> Robot:
-        for item in self.devices:
-            if type(item) == Robot and item.name == robot_name:
-                return item
+        """The `Robot` with that name, or None (mujoco_app.py:43-47)."""
+        return next((item for item in self.devices if type(item) == Robot and item.name == robot_name), None)
 
     def get_controller_config(self, name: str) -> Dict:
-        for entry in self.config['controller_configs']:
-            if entry['name'] == name:
-                return entry
+        """The `controller_configs` entry with that name - the YAML dict itself, not a copy - or None."""
+        return next((entry for entry in self.config['controller_configs'] if entry['name'] == name), None)
 
     def set_free_joint_qpos(self, free_joint_name, quat=None, pos=None):
-        jnt_id = self.sim.model.joint_name2id(free_joint_name)
-        offset = self.sim.model.jnt_qposadr[jnt_id]
-        if quat is not None:
-            self.sim.data.qpos[offset + 3:offset + 7] = quat
-        if pos is not None:
-            self.sim.data.qpos[offset:offset + 3] = pos
+        """Write a free joint's pose into `sim.data.qpos` (layout: x y z, then w x y z; mujoco_app.py:55-63)."""
+        start = self.sim.model.jnt_qposadr[self.sim.model.joint_name2id(free_joint_name)]
+        for value, lo, hi in ((pos, 0, 3), (quat, 3, 7)):
+            if value is not None:
+                self.sim.data.qpos[start + lo:start + hi] = value

@@ -268,3 +268,28 @@ def test_roofline_bytes_are_the_survey_figures():
     for name, nbytes in want.items():
         _, _, _, L = build_scenario(name)
         assert bench.algorithmic_bytes(L) == nbytes, name
+
+
+def test_mujoco_app_helpers():
+    """`get_robot`, `get_controller_config`, `set_free_joint_qpos`, `sleep_for` (mujoco_app.py:37-63)."""
+    import threading
+    import time
+    app = pkg.MujocoApp("default_xyz_abg.yaml+start_body", "insertion_task_scene.xml")
+    assert app.get_robot("DualUR5").name == "DualUR5" and app.get_robot("nope") is None
+    cfg = app.get_controller_config("osc1")
+    assert cfg["kv"] == 50 and cfg is app.get_controller_config("osc1") and app.get_controller_config("zzz") is None
+    m = app.sim.model
+    name = m.joint_id2name(25)                                    # first free joint after the robot's 25 hinges
+    off = m.jnt_qposadr[m.joint_name2id(name)]
+    app.set_free_joint_qpos(name, quat=[0.5, 0.5, 0.5, 0.5], pos=[1, 2, 3])
+    assert list(app.sim.data.qpos[off:off + 7]) == [1, 2, 3, 0.5, 0.5, 0.5, 0.5]
+    app.set_free_joint_qpos(name, pos=[4, 5, 6])
+    assert list(app.sim.data.qpos[off:off + 7]) == [4, 5, 6, 0.5, 0.5, 0.5, 0.5]
+    th = threading.Thread(target=app.sleep_for, args=(0.2,))
+    th.start()
+    time.sleep(0.05)
+    assert app.timer_running
+    with pytest.raises(AssertionError):                           # not re-entrant (mujoco_app.py:38)
+        app.sleep_for(0.01)
+    th.join()
+    assert not app.timer_running
