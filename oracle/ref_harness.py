@@ -223,7 +223,9 @@ class ReferenceRunner:
                 t.set_abg_vel(np.array(tgt_vel[i][3:], dtype=np.float64))
             targets[name] = t
             if max_vel is not None:
-                self.robot.get_device(name).max_vel = [float(max_vel[i][0]), float(max_vel[i][1])]
+                # NaN in the first slot stands for `device.max_vel = None` (osc.py:163: the un-limited gain branch)
+                self.robot.get_device(name).max_vel = (None if np.isnan(max_vel[i][0]) else
+                                                       [float(max_vel[i][0]), float(max_vel[i][1])])
         calls = {"pinv": 0}
         real_pinv = np.linalg.pinv
 

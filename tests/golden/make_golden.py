@@ -43,8 +43,13 @@ def reference_runner(scenario: str):
                                        use_g=True, admittance=sc["admittance"])
 
 
-def run_case(name, scenario, B, seed, mutate=None, insertion_schedule=False):
+def run_case(name, scenario, B, seed, mutate=None, insertion_schedule=False, no_max_vel=()):
+    """no_max_vel: device names whose `max_vel` is cleared to None before generate (osc.py:163-168)."""
+    import dataclasses
     _, _, targets, layout = build_scenario(scenario)
+    if no_max_vel:
+        layout = dataclasses.replace(layout, devices=tuple(
+            dataclasses.replace(d, has_max_vel=False) if d.name in no_max_vel else d for d in layout.devices))
     st = synth_batch(layout, B, seed=seed, insertion_schedule=insertion_schedule)
     st = {k: v.numpy() for k, v in st.items()}
     st["target_vel"] = np.zeros((B, layout.D, 6))
@@ -61,8 +66,12 @@ def run_case(name, scenario, B, seed, mutate=None, insertion_schedule=False):
     for i in range(B):
         inst = {k: v[i] for k, v in st.items()}
         tv = st["target_vel"][i] if np.any(st["target_vel"][i] != 0) else None
+        mv = np.array(st["max_vel"][i], dtype=np.float64)
+        for d, dl in enumerate(layout.devices):
+            if dl.name in no_max_vel:
+                mv[d] = np.nan                      # ReferenceRunner.run: device.max_vel = None
         try:
-            r = runner.run(inst, st["target_xyz"][i], st["target_quat"][i], tgt_vel=tv, max_vel=st["max_vel"][i])
+            r = runner.run(inst, st["target_xyz"][i], st["target_quat"][i], tgt_vel=tv, max_vel=mv)
             ctrl.append(np.concatenate(r["forces"]))
             u_all.append(r["u_all"])
             pinv.append(r["pinv"])
@@ -116,6 +125,12 @@ def singular_pose(st, layout):
         st["ee_xyz"][:, d] = dyn.xpos[:, b].numpy()
         st["ee_quat"][:, d] = dyn.xquat[:, b].numpy()
         st["target_xyz"][:, d] = st["ee_xyz"][:, d] + delta
+
+
+def no_max_vel_cases():
+    """osc.py:163-168, the branch no shipped YAML takes: `device.max_vel is None` -> gains x stiffness, no limiter."""
+    run_case("gain_test_nomaxvel_s10", "gain_test", 12, 10, no_max_vel=("ur5left", "base"))
+    run_case("admit_nomaxvel_s11", "admit_test", 12, 11, no_max_vel=("ur5right",))
 
 
 def iros2022_cases():
@@ -188,6 +203,9 @@ if __name__ == "__main__":
     if "--only-caller-loops" in sys.argv:      # added after the OSC.generate files were committed
         caller_loop_goldens()
         sys.exit(0)
+    if "--only-no-max-vel" in sys.argv:
+        no_max_vel_cases()
+        sys.exit(0)
     if "--only-iros2022" in sys.argv:          # added after the first eight files were committed
         iros2022_cases()
         sys.exit(0)
@@ -200,4 +218,5 @@ if __name__ == "__main__":
     run_case("insertion_vel_s6", "insertion", 8, 6, mutate=vel_all_nonzero)
     run_case("admit_singular_s7", "admit_test", 16, 7, mutate=singular_pose)
     iros2022_cases()
+    no_max_vel_cases()
     caller_loop_goldens()

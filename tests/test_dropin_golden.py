@@ -44,7 +44,7 @@ def test_generate_reproduces_the_reference_goldens(case, monkeypatch):
 
 def generate_on_golden(case):
     """Shared with tests/test_gpu_zz_dropin.py, which runs it with the real engine (libirlosc.so on the GPU)."""
-    g, _ld = load_golden(case)
+    g, ld = load_golden(case)
     sc = SCENARIOS[str(g["scenario"])]
     cfg = configs.robot_config(sc["config"])
     model = DualUR5Model(n_free_objects=configs.SCENE_FREE_OBJECTS[sc["scene"]])
@@ -70,7 +70,8 @@ def generate_on_golden(case):
                 t.set_xyz_vel(tv[:3])
                 t.set_abg_vel(tv[3:])
             targets[nm] = t
-            robot.get_device(nm).max_vel = [float(g["max_vel"][i][d][0]), float(g["max_vel"][i][d][1])]
+            robot.get_device(nm).max_vel = ([float(g["max_vel"][i][d][0]), float(g["max_vel"][i][d][1])]
+                                            if ld["devices"][d]["has_max_vel"] else None)
         if g["index_error"][i]:
             with pytest.raises(IndexError):          # what the reference raised for this instance
                 osc.generate(targets)

@@ -121,3 +121,29 @@ def test_target_velocity_branch_and_index_error_like_the_reference(monkeypatch):
         runner.osc.generate({nm: ref_Target(np.zeros(6), vel) for nm in names})
     with pytest.raises(IndexError):
         osc.generate({nm: pkg.Target(np.zeros(6), vel) for nm in names})
+
+
+def test_max_vel_none_takes_the_unsaturated_gain_branch_like_the_reference(monkeypatch):
+    """`device.max_vel = None` (a caller may clear it; osc.py:163-168): the pose error is multiplied by the task-space
+    gains and the stiffness without the velocity limiter - also after a generate() with the limiter has already run."""
+    runner, osc, names, layout = _both("gain_test", monkeypatch)
+    ref_Target = ref_harness.import_reference()[3]
+    st = {k: v.numpy() for k, v in synth_batch(layout, 2, seed=15).items()}
+    robot = osc.robot
+    for i, cleared in ((0, ()), (1, ("ur5left",)), (1, ("ur5left", "base"))):
+        runner.run({k: v[i] for k, v in st.items()}, st["target_xyz"][i], st["target_quat"][i], max_vel=st["max_vel"][i])
+        mine, theirs = {}, {}
+        for d, nm in enumerate(names):
+            for cls, bag in ((pkg.Target, mine), (ref_Target, theirs)):
+                t = cls()
+                t.set_xyz(st["target_xyz"][i][d])
+                t.set_quat(st["target_quat"][i][d])
+                bag[nm] = t
+            mv = None if nm in cleared else [float(st["max_vel"][i][d][0]), float(st["max_vel"][i][d][1])]
+            robot.get_device(nm).max_vel = mv
+            runner.robot.get_device(nm).max_vel = mv
+        ridx, rforces = runner.osc.generate(theirs)
+        idxs, forces = osc.generate(mine)
+        scale = max(np.abs(f).max() for f in rforces)
+        for d in range(len(names)):
+            assert np.abs(forces[d] - rforces[d]).max() < 1e-6 * scale, (cleared, names[d])

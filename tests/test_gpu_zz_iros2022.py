@@ -1,6 +1,9 @@
 """GPU: SURVEY 8 (f4) - the iros2022 configuration (robot_configs/iros2022.yaml gains and max_vel, devices and
 order of action_sequence_configs/iros2022_task.yaml:1-4: base, ur5left, ur5right; k = 13) through the C ABI.
 
+The same parametrised test also runs the other late goldens of `GOLDEN_CASES_F4`: `device.max_vel = None` on some
+devices (osc.py:163-168, the un-limited gain branch; layouts with `has_max_vel` False).
+
 Written after round 1's GPU budget was spent: the goldens (reference outputs) and the host build of the
 default kernel are checked in the CPU suite (tests/test_oracle.py, tests/test_stream_host.py,
 tests/test_fused_host.py); this file is their first run on a GPU, kept apart from tests/test_gpu_parity.py
