@@ -36,7 +36,9 @@ GOLDEN_CASES = ["gain_test_s0", "admit_test_s1", "insertion_s2", "worst_case_s3"
 # build of the streaming step); their GPU run is tests/test_gpu_zz_iros2022.py
 GOLDEN_CASES_F4 = ["iros2022_s8", "iros2022_vel_s9",
                    # osc.py:163-168 with `device.max_vel = None` on some devices (layout: has_max_vel False)
-                   "gain_test_nomaxvel_s10", "admit_nomaxvel_s11"]
+                   "gain_test_nomaxvel_s10", "admit_nomaxvel_s11",
+                   # constructor options no example uses: use_g=False (osc.py:190), nullspace_config=None (osc.py:195)
+                   "gain_test_no_g_s12", "admit_no_nullspace_s13", "worst_case_bare_s14"]
 
 
 def golden_oracle_batch(g):

@@ -34,19 +34,23 @@ from irl_control_b200.configs import SCENE_FREE_OBJECTS  # noqa: E402
 from oracle import ref_harness  # noqa: E402
 
 
-def reference_runner(scenario: str):
+def reference_runner(scenario: str, use_g: bool = True, nullspace: bool = True):
     sc = SCENARIOS[scenario]
     yaml_name = sc["config"].replace("+start_body", "")
     cfg = ref_harness.load_reference_yaml(yaml_name, inject_start_body=True)
     model = DualUR5Model(n_free_objects=SCENE_FREE_OBJECTS[sc["scene"]])
-    return ref_harness.ReferenceRunner(model, cfg, sc["device_cfgs"], sc["targets"], "nullspace",
-                                       use_g=True, admittance=sc["admittance"])
+    return ref_harness.ReferenceRunner(model, cfg, sc["device_cfgs"], sc["targets"], "nullspace" if nullspace else None,
+                                       use_g=use_g, admittance=sc["admittance"])
 
 
-def run_case(name, scenario, B, seed, mutate=None, insertion_schedule=False, no_max_vel=()):
-    """no_max_vel: device names whose `max_vel` is cleared to None before generate (osc.py:163-168)."""
+def run_case(name, scenario, B, seed, mutate=None, insertion_schedule=False, no_max_vel=(), use_g=True,
+             nullspace=True):
+    """no_max_vel: device names whose `max_vel` is cleared to None before generate (osc.py:163-168);
+    use_g / nullspace: the OSC constructor's `use_g` flag and `nullspace_config=None` (osc.py:19,190,195)."""
     import dataclasses
     _, _, targets, layout = build_scenario(scenario)
+    if not use_g or not nullspace:
+        layout = dataclasses.replace(layout, use_g=use_g, nullspace_kv=layout.nullspace_kv if nullspace else None)
     if no_max_vel:
         layout = dataclasses.replace(layout, devices=tuple(
             dataclasses.replace(d, has_max_vel=False) if d.name in no_max_vel else d for d in layout.devices))
@@ -55,7 +59,7 @@ def run_case(name, scenario, B, seed, mutate=None, insertion_schedule=False, no_
     st["target_vel"] = np.zeros((B, layout.D, 6))
     if mutate is not None:
         mutate(st, layout)
-    runner = reference_runner(scenario)
+    runner = reference_runner(scenario, use_g=use_g, nullspace=nullspace)
     # the host layer's index maps must be the reference's own
     for dl in layout.devices:
         ref_dev = runner.robot.get_device(dl.name)
@@ -131,6 +135,10 @@ def no_max_vel_cases():
     """osc.py:163-168, the branch no shipped YAML takes: `device.max_vel is None` -> gains x stiffness, no limiter."""
     run_case("gain_test_nomaxvel_s10", "gain_test", 12, 10, no_max_vel=("ur5left", "base"))
     run_case("admit_nomaxvel_s11", "admit_test", 12, 11, no_max_vel=("ur5right",))
+    # constructor options no example uses: OSC(..., use_g=False) and OSC(..., nullspace_config=None)
+    run_case("gain_test_no_g_s12", "gain_test", 12, 12, use_g=False)
+    run_case("admit_no_nullspace_s13", "admit_test", 12, 13, nullspace=False)
+    run_case("worst_case_bare_s14", "worst_case", 12, 14, use_g=False, nullspace=False)
 
 
 def iros2022_cases():

@@ -52,8 +52,9 @@ def generate_on_golden(case):
     devices = [pkg.Device(d, model, sim, True) for d in cfg["devices"]]
     robot = pkg.Robot([devices[i] for i in cfg["robots"][0]["device_ids"]], "DualUR5", sim, True)
     by_name = {c["name"]: c for c in cfg["controller_configs"]}
-    osc = pkg.OSC(robot, sim, [(dev, dict(by_name[c])) for dev, c in sc["device_cfgs"]], dict(by_name["nullspace"]),
-                  admittance=sc["admittance"])
+    osc = pkg.OSC(robot, sim, [(dev, dict(by_name[c])) for dev, c in sc["device_cfgs"]],
+                  dict(by_name["nullspace"]) if ld["nullspace_kv"] is not None else None,
+                  use_g=ld["use_g"], admittance=sc["admittance"])
     names = list(sc["targets"])
     B = g["dq"].shape[0]
     keys = ("M", "J6", "dq", "bias", "ee_xyz", "ee_quat", "ft_xmat", "ft_raw")
