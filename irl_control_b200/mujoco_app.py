@@ -22,8 +22,9 @@ from .sim import SyntheticSim
 
 class MujocoApp:
     def __init__(self, robot_config_file: str = None, scene_file: str = None, use_sim: bool = True,
-                 sim_factory: Optional[Callable[[str], object]] = None):
-        self.config = self._load_config(robot_config_file)
+                 sim_factory: Optional[Callable[[str], object]] = None, config_override: Optional[Dict] = None):
+        # config_override: an already loaded config dict (same schema) instead of a file / built-in name
+        self.config = config_override if config_override is not None else self._load_config(robot_config_file)
         if sim_factory is not None:
             self.sim = sim_factory(scene_file)
         else:

@@ -43,6 +43,13 @@ SCENARIOS: Dict[str, Dict] = {
     "worst_case": dict(config="default_xyz_abg.yaml+start_body", scene="gain_test_scene.xml",
                        device_cfgs=[("base", "osc0"), ("ur5right", "osc2"), ("ur5left", "osc2")],
                        targets=["ur5right", "ur5left", "base"], admittance=False),
+    # a user-edited YAML: DoF masks no shipped config has (right arm xyz + b, g; left arm xyz + a) -> 5 + 4 + 1 rows.
+    # No specialised kernel serves unequal arm row counts: this is the generic kernel's case.
+    "mixed_dof": dict(config="default_xyz_abg.yaml+start_body", scene="gain_test_scene.xml",
+                      device_cfgs=[("base", "osc0"), ("ur5right", "osc2"), ("ur5left", "osc2")],
+                      targets=["ur5right", "ur5left", "base"], admittance=False,
+                      config_patch={"ur5right": {"ctrlr_dof_abg": [False, True, True]},
+                                    "ur5left": {"ctrlr_dof_abg": [True, False, False]}}),
     # robot_configs/iros2022.yaml (osc0 = osc2 = kp 200 / kv 20 / ko 75, base max_vel [0, 2],
     # arms [2, 5], start_body set) with the devices, controllers and order of iros2022_task.yaml:1-4
     "iros2022": dict(config="iros2022.yaml", scene="iros2022.xml",
@@ -51,12 +58,20 @@ SCENARIOS: Dict[str, Dict] = {
 }
 
 
+def patched_config(sc: Dict) -> Dict:
+    """The scenario's robot config with its optional per-device `config_patch` applied (a user-edited YAML)."""
+    cfg = robot_config(sc["config"])
+    for dev in cfg["devices"]:
+        dev.update(sc.get("config_patch", {}).get(dev["name"], {}))
+    return cfg
+
+
 def build_scenario(name: str):
     """(app, osc, target_names, layout) for a named scenario, built through the host API."""
     from .mujoco_app import MujocoApp
     from .osc import OSC
     sc = SCENARIOS[name]
-    app = MujocoApp(sc["config"], sc["scene"])
+    app = MujocoApp(sc["config"], sc["scene"], config_override=patched_config(sc) if "config_patch" in sc else None)
     robot = app.get_robot("DualUR5")
     cfgs = [(dev, app.get_controller_config(cfg)) for dev, cfg in sc["device_cfgs"]]
     osc = OSC(robot, app.sim, cfgs, app.get_controller_config("nullspace"), admittance=sc["admittance"])

@@ -41,6 +41,11 @@ GOLDEN_CASES_F4 = ["iros2022_s8", "iros2022_vel_s9",
                    "gain_test_no_g_s12", "admit_no_nullspace_s13", "worst_case_bare_s14"]
 
 
+# DoF masks no shipped YAML has (5 + 4 + 1 task rows): no specialised kernel and no host build serves them - oracle
+# on the CPU, the generic kernel on the GPU (tests/test_gpu_zz_mixed_dof.py)
+GOLDEN_CASES_GENERIC = ["mixed_dof_s15", "mixed_dof_vel_s16"]
+
+
 def golden_oracle_batch(g):
     """Golden arrays in the oracle's field names."""
     return dict(M=g["M"], J=g["J6"], dq=g["dq"], bias=g["bias"], ee_xyz=g["ee_xyz"], ee_quat=g["ee_quat"],

@@ -38,6 +38,8 @@ def reference_runner(scenario: str, use_g: bool = True, nullspace: bool = True):
     sc = SCENARIOS[scenario]
     yaml_name = sc["config"].replace("+start_body", "")
     cfg = ref_harness.load_reference_yaml(yaml_name, inject_start_body=True)
+    for dev in cfg["devices"]:                          # a scenario may stand for a user-edited YAML
+        dev.update(sc.get("config_patch", {}).get(dev["name"], {}))
     model = DualUR5Model(n_free_objects=SCENE_FREE_OBJECTS[sc["scene"]])
     return ref_harness.ReferenceRunner(model, cfg, sc["device_cfgs"], sc["targets"], "nullspace" if nullspace else None,
                                        use_g=use_g, admittance=sc["admittance"])
@@ -139,6 +141,9 @@ def no_max_vel_cases():
     run_case("gain_test_no_g_s12", "gain_test", 12, 12, use_g=False)
     run_case("admit_no_nullspace_s13", "admit_test", 12, 13, nullspace=False)
     run_case("worst_case_bare_s14", "worst_case", 12, 14, use_g=False, nullspace=False)
+    # DoF masks no shipped YAML has (5 + 4 + 1 rows): the generic kernel's case
+    run_case("mixed_dof_s15", "mixed_dof", 12, 15)
+    run_case("mixed_dof_vel_s16", "mixed_dof", 8, 16, mutate=vel_all_nonzero)
 
 
 def iros2022_cases():

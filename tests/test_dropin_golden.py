@@ -15,7 +15,7 @@ import irl_control_b200.osc as pkg_osc
 from conftest import GOLDEN_CASES, GOLDEN_CASES_F4, load_golden
 from irl_control_b200 import configs
 from irl_control_b200.dual_ur5 import DualUR5Model
-from irl_control_b200.synthetic import SCENARIOS
+from irl_control_b200.synthetic import SCENARIOS, patched_config
 from oracle.ref_harness import FakeSim
 
 
@@ -46,7 +46,7 @@ def generate_on_golden(case):
     """Shared with tests/test_gpu_zz_dropin.py, which runs it with the real engine (libirlosc.so on the GPU)."""
     g, ld = load_golden(case)
     sc = SCENARIOS[str(g["scenario"])]
-    cfg = configs.robot_config(sc["config"])
+    cfg = patched_config(sc)
     model = DualUR5Model(n_free_objects=configs.SCENE_FREE_OBJECTS[sc["scene"]])
     sim = _Sim(model)
     devices = [pkg.Device(d, model, sim, True) for d in cfg["devices"]]
