@@ -42,7 +42,7 @@ GOLDEN_CASES_F4 = ["iros2022_s8", "iros2022_vel_s9",
 
 
 # DoF masks no shipped YAML has (5 + 4 + 1 task rows): no specialised kernel and no host build serves them - oracle
-# on the CPU, the generic kernel on the GPU (tests/test_gpu_zz_mixed_dof.py)
+# on the CPU, the generic kernel on the GPU (tests/test_gpu_zzz_mixed_dof.py)
 GOLDEN_CASES_GENERIC = ["mixed_dof_s15", "mixed_dof_vel_s16"]
 
 
