@@ -5,13 +5,13 @@ runs it on the CPU with the host build of the kernel; written after round 1's GP
 """
 import pytest
 
-from conftest import GOLDEN_CASES, GOLDEN_CASES_F4, GOLDEN_CASES_GENERIC
+from conftest import GOLDEN_CASES, GOLDEN_CASES_F4
 from test_dropin_golden import generate_on_golden
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4 + GOLDEN_CASES_GENERIC)
+@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4)
 def test_generate_on_the_gpu_reproduces_the_reference_goldens(case):
     import torch
     assert torch.cuda.is_available()

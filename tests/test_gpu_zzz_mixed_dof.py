@@ -34,3 +34,11 @@ def test_generic_kernel_serves_unshipped_dof_masks(case, packed_M, full6_J, kern
     assert e_u.max() < REL_TOL and e_c.max() < REL_TOL
     vel = (np.asarray(g["target_vel"]) != 0).all(axis=-1).any(axis=-1)
     assert np.array_equal((status & _native.ST_VEL_BRANCH) != 0, vel)
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES_GENERIC)
+def test_generate_through_the_host_classes_with_unshipped_dof_masks(case):
+    """Same goldens through `Device / Robot / OSC.generate` (tests/test_dropin_golden.py's body, real engine)."""
+    _torch()
+    from test_dropin_golden import generate_on_golden
+    generate_on_golden(case)
