@@ -149,16 +149,23 @@ static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream
         if (!stream_ok || h->kernel_choice == 1)
             return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM needs the declared DualUR5 topology (check_topology off) and "
                                             "kernel selector 0, 9 or 2 + v");
-        return stream_launch(h, B, k, st, queue);
+        const int32_t rc = stream_launch(h, B, k, st, queue);
+        return rc == kErrPlanTooLarge ? IRLOSC_ERR_INVALID : rc;
     }
     if (h->kernel_choice == kKernelStream) {
         if (!stream_ok) return fail(IRLOSC_ERR_INVALID, "streaming kernel requested but the DualUR5 topology is not declared (or check_topology is set)");
-        return stream_launch(h, B, k, st, queue);
+        const int32_t rc = stream_launch(h, B, k, st, queue);
+        return rc == kErrPlanTooLarge ? IRLOSC_ERR_INVALID : rc;
     }
     bool use_tiled = false;
     const int variant = h->kernel_choice >= 2 ? h->kernel_choice - 2 : 0;
     if (h->kernel_choice != 1) use_tiled = tiled_supported(h->kp, k, variant);
-    if (h->kernel_choice == 0 && stream_ok && (stream_preferred(h) || !use_tiled)) return stream_launch(h, B, k, st, queue);
+    if (h->kernel_choice == 0 && stream_ok && (stream_preferred(h) || !use_tiled)) {
+        const int32_t rc = stream_launch(h, B, k, st, queue);
+        if (rc != kErrPlanTooLarge) return rc;
+        // this configuration's copy plan does not fit (three 6-row devices with admittance): the kernels below stage
+        // whole records instead
+    }
     if (h->kernel_choice >= 2 && !use_tiled)
         return fail(IRLOSC_ERR_INVALID, "tiled kernel requested but this shape/layout is not supported (n=%d k=%d)", h->kp.n, h->kp.k);
     if (use_tiled) {

@@ -379,7 +379,7 @@ inline int32_t build_stream_plan(const KParams &P, const KIo &io, const fused::F
         });
         size_t at = 0;
         while (at < v.size()) {
-            if (nc >= kMaxChunks) return fail(IRLOSC_ERR_INVALID, "stream plan needs more than %d chunks", kMaxChunks);
+            if (nc >= kMaxChunks) return fail(kErrPlanTooLarge, "stream plan needs more than %d chunks", kMaxChunks);
             Chunk &c = plan.ch[nc++];
             c.base = (uint64_t)(uintptr_t)v[at].base;
             c.stride = (int32_t)v[at].stride;

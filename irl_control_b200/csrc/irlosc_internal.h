@@ -8,6 +8,11 @@
 
 namespace irlosc {
 
+// internal (never returned through the C ABI): the streaming kernel's copy plan of this configuration needs more than
+// stream::kMaxChunks chunks (three 6-row devices with admittance) - auto dispatch then takes a record-staging kernel
+constexpr int32_t kErrPlanTooLarge = 100;
+
+
 constexpr int kPipeDepth = 3;   // chunks in flight in the *_host entry points
 
 struct Staging {

@@ -43,6 +43,11 @@ SCENARIOS: Dict[str, Dict] = {
     "worst_case": dict(config="default_xyz_abg.yaml+start_body", scene="gain_test_scene.xml",
                        device_cfgs=[("base", "osc0"), ("ur5right", "osc2"), ("ur5left", "osc2")],
                        targets=["ur5right", "ur5left", "base"], admittance=False),
+    # admittance=True with the base among the targets (no example does): the base has no F/T sensor, its wrench is
+    # identically zero (device.py:150-170), the arms' wrenches enter as in admit_test
+    "worst_case_admit": dict(config="default_xyz_abg.yaml+start_body", scene="gain_test_scene.xml",
+                             device_cfgs=[("base", "osc0"), ("ur5right", "osc2"), ("ur5left", "osc2")],
+                             targets=["ur5right", "ur5left", "base"], admittance=True),
     # a user-edited YAML: DoF masks no shipped config has (right arm xyz + b, g; left arm xyz + a) -> 5 + 4 + 1 rows.
     # No specialised kernel serves unequal arm row counts: this is the generic kernel's case.
     "mixed_dof": dict(config="default_xyz_abg.yaml+start_body", scene="gain_test_scene.xml",

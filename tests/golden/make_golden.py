@@ -144,6 +144,15 @@ def no_max_vel_cases():
     # DoF masks no shipped YAML has (5 + 4 + 1 rows): the generic kernel's case
     run_case("mixed_dof_s15", "mixed_dof", 12, 15)
     run_case("mixed_dof_vel_s16", "mixed_dof", 8, 16, mutate=vel_all_nonzero)
+    # admittance with the base among the targets
+    run_case("worst_case_admit_s17", "worst_case_admit", 12, 17, mutate=base_without_sensor)
+
+
+def base_without_sensor(st, layout):
+    """The base has no F/T sensor: what the state pull hands over for it is a zero wrench in an identity frame."""
+    d = [dl.name for dl in layout.devices].index("base")
+    st["ft_raw"][:, d] = 0.0
+    st["ft_xmat"][:, d] = np.eye(3).reshape(-1)
 
 
 def iros2022_cases():

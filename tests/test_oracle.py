@@ -5,11 +5,11 @@ import math
 import numpy as np
 import pytest
 
-from conftest import GOLDEN_CASES, GOLDEN_CASES_F4, GOLDEN_CASES_GENERIC, golden_oracle_batch, load_golden
+from conftest import GOLDEN_CASES, GOLDEN_CASES_F4, GOLDEN_CASES_FALLBACK, GOLDEN_CASES_GENERIC, golden_oracle_batch, load_golden
 from oracle import osc_numpy, t3d, ref_harness
 
 
-@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4 + GOLDEN_CASES_GENERIC)
+@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4 + GOLDEN_CASES_GENERIC + GOLDEN_CASES_FALLBACK)
 def test_oracle_matches_reference_golden(case):
     g, layout = load_golden(case)
     batch = golden_oracle_batch(g)

@@ -173,3 +173,14 @@ def test_tree_kernel_qM_offsets_are_the_mj_fullM_walk():
                 for i in range(7):
                     assert ro + 7 + qs - i == off[(gb + r, ccol(i))]
             assert qa + 27 + 25 * h + 9 == off[(gb + 1, gb)]
+
+
+def test_copy_plan_limit_is_reported_for_three_devices_with_admittance():
+    """admittance=True with the base among the targets needs 74 copy-plan chunks, the streaming kernel holds 72: the
+    plan builder says so (auto dispatch in `irlosc_step` then takes a record-staging kernel,
+    tests/test_gpu_zzz_mixed_dof.py)."""
+    from conftest import GOLDEN_CASES_FALLBACK
+    g, ld = load_golden(GOLDEN_CASES_FALLBACK[0])
+    layout = _layout(ld)
+    with pytest.raises(RuntimeError, match="more than 72 chunks"):
+        fused_host.run_stream(layout, _state(g, layout, True, False))
