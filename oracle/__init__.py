@@ -15,11 +15,20 @@ osc_numpy.py    clean-room float64 numpy restatement of the reference control
 t3d.py          restatement of the five `transforms3d` functions the path
                 calls (third-party, unpinned in `requirements.in:3`, absent
                 from /root/reference and from this image).
+sequence_numpy.py  restatement of the caller loops around `generate`:
+                `examples/insertion_task.py` (run_sequence, go_to_waypoint,
+                grip, send_forces, set_waypoint_targets, object placement)
+                and the waypoint cycling of `examples/gain_test.py:134-162`.
 ref_harness.py  drives the UNMODIFIED reference sources from /root/reference
                 through stub `mujoco_py` / `transforms3d` modules and a fake
-                `sim`; only usable where /root/reference exists (this
-                container).  Used to pin osc_numpy.py and to generate
-                `tests/golden/*.npz`.
+                `sim`: `OSC.generate` (ReferenceRunner), the insertion demo's
+                own methods and `GainTest.run` on pose streams
+                (drive_reference_sequence, drive_reference_gain_test,
+                reference_object_placement).  Its reference-driving parts only
+                work where /root/reference exists (this container); `FakeSim`
+                alone is plain numpy and is also used by
+                tests/test_dropin_golden.py.  Used to pin the restatements
+                and to generate `tests/golden/*.npz`.
 
 Parity pinning
 --------------
@@ -28,9 +37,12 @@ The reference ships no golden vectors, KATs or fixtures for this path
 therefore pinned against outputs of the reference itself run here:
 `tests/golden/make_golden.py` calls the real `OSC.generate` via
 ref_harness.py and stores inputs + outputs; `tests/test_oracle.py` checks
-osc_numpy.py against those vectors.  The one boundary that cannot be pinned
+osc_numpy.py against those vectors (18 files: `OSC.generate` on every
+shipped configuration plus the branches no shipped YAML takes, and the
+caller loops).  The one boundary that cannot be pinned
 is `transforms3d` (not installed anywhere reachable): t3d.py is written from
 the published algorithm of transforms3d 0.4.x ('sxyz' static-frame Euler
-convention, w-x-y-z quaternions) - "parity unpinned" for those five
-functions only; DESIGN.md repeats this.
+convention, w-x-y-z quaternions) and cross-checked against scipy's
+independent `Rotation` implementation - "parity unpinned" against
+transforms3d itself for those functions only; DESIGN.md repeats this.
 """
