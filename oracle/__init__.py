@@ -37,8 +37,8 @@ The reference ships no golden vectors, KATs or fixtures for this path
 therefore pinned against outputs of the reference itself run here:
 `tests/golden/make_golden.py` calls the real `OSC.generate` via
 ref_harness.py and stores inputs + outputs; `tests/test_oracle.py` checks
-osc_numpy.py against those vectors (18 files: `OSC.generate` on every
-shipped configuration plus the branches no shipped YAML takes, and the
+osc_numpy.py against those vectors (21 files: 18 of `OSC.generate` - every
+shipped configuration plus the branches no shipped YAML takes - and 3 of the
 caller loops).  The one boundary that cannot be pinned
 is `transforms3d` (not installed anywhere reachable): t3d.py is written from
 the published algorithm of transforms3d 0.4.x ('sxyz' static-frame Euler
