@@ -192,3 +192,29 @@ def test_cooperative_pinv_resolution_matches_numpy():
             if kind == 3:
                 raise AssertionError("two eigenvalues below the cutoff must not be decided")
     assert decided[1] > 80 and decided[2] > 60                                # it does decide most of the time
+
+
+@pytest.mark.parametrize("scenario,use_g,nullspace,no_max_vel", [
+    ("gain_test", False, True, ()), ("admit_test", True, False, ()), ("worst_case", False, False, ()),
+    ("gain_test", True, True, ("ur5left", "base")), ("insertion", True, True, ("ur5right",))])
+def test_fused_step_with_constructor_options_and_cleared_max_vel(scenario, use_g, nullspace, no_max_vel):
+    """The fused step under the options no example uses - `use_g=False` (osc.py:190), `nullspace_config=None`
+    (osc.py:195), `device.max_vel = None` (osc.py:163-168) - against the oracle, whose handling of exactly these
+    options is pinned by the reference goldens `*_no_g_*`, `*_no_nullspace_*`, `*_bare_*`, `*_nomaxvel_*`."""
+    import dataclasses
+    B = 128
+    app, _osc, _names, layout = build_scenario(scenario)
+    layout = dataclasses.replace(
+        layout, use_g=use_g, nullspace_kv=layout.nullspace_kv if nullspace else None,
+        devices=tuple(dataclasses.replace(d, has_max_vel=d.name not in no_max_vel) for d in layout.devices))
+    robot = app.get_robot("DualUR5")
+    model = model_for_layout(app.sim.model, robot.joint_ids_all, layout)
+    st = synth_batch(layout, B, seed=17, insertion_schedule=(scenario == "insertion"))
+    inp = {"q": st["q"].numpy(), "dq": st["dq"].numpy(), "target_xyz": st["target_xyz"].numpy(),
+           "target_quat": st["target_quat"].numpy(), "max_vel": st["max_vel"].numpy()}
+    if layout.admittance:
+        inp["ft_raw"] = st["ft_raw"].numpy()
+    out = fused_host.run(layout, model, inp)
+    ref = osc_numpy.osc_batch(layout.as_dict(), oracle_inputs(st, layout))
+    assert _rel(out["u_all"], ref["u_all"]).max() < REL_TOL
+    assert np.array_equal((out["status"] & 1).astype(bool), np.asarray(ref["pinv"]).astype(bool))
