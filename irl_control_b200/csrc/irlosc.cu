@@ -67,11 +67,6 @@ extern "C" int32_t irlosc_destroy(irlosc_handle *h) {
         if (h->stage[s].stream) cudaStreamDestroy(h->stage[s].stream);
         if (h->fstage[s].stream) cudaStreamDestroy(h->fstage[s].stream);
     }
-    for (int q = 0; q < kQueues; ++q) {
-        if (h->hard[q].count) cudaFree(h->hard[q].count);
-        if (h->hard[q].inst) cudaFree(h->hard[q].inst);
-        if (h->hard[q].rec) cudaFree(h->hard[q].rec);
-    }
     delete h;
     return IRLOSC_OK;
 }
@@ -131,7 +126,7 @@ static int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k) {
 //   check_topology -> the kernels that read every entry.  No topology: dense kernels / generic.
 constexpr int kKernelStream = 9;
 
-static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st, int queue = 0) {
+static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st) {
     if (B == 0) return IRLOSC_OK;
     const bool stream_ok = stream_supported(h, k);
     if (k.m_layout == IRLOSC_M_QM) {
@@ -149,19 +144,19 @@ static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream
         if (!stream_ok || h->kernel_choice == 1)
             return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM needs the declared DualUR5 topology (check_topology off) and "
                                             "kernel selector 0, 9 or 2 + v");
-        const int32_t rc = stream_launch(h, B, k, st, queue);
+        const int32_t rc = stream_launch(h, B, k, st);
         return rc == kErrPlanTooLarge ? IRLOSC_ERR_INVALID : rc;
     }
     if (h->kernel_choice == kKernelStream) {
         if (!stream_ok) return fail(IRLOSC_ERR_INVALID, "streaming kernel requested but the DualUR5 topology is not declared (or check_topology is set)");
-        const int32_t rc = stream_launch(h, B, k, st, queue);
+        const int32_t rc = stream_launch(h, B, k, st);
         return rc == kErrPlanTooLarge ? IRLOSC_ERR_INVALID : rc;
     }
     bool use_tiled = false;
     const int variant = h->kernel_choice >= 2 ? h->kernel_choice - 2 : 0;
     if (h->kernel_choice != 1) use_tiled = tiled_supported(h->kp, k, variant);
     if (h->kernel_choice == 0 && stream_ok && (stream_preferred(h) || !use_tiled)) {
-        const int32_t rc = stream_launch(h, B, k, st, queue);
+        const int32_t rc = stream_launch(h, B, k, st);
         if (rc != kErrPlanTooLarge) return rc;
         // this configuration's copy plan does not fit (three 6-row devices with admittance): the kernels below stage
         // whole records instead
@@ -291,7 +286,7 @@ extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io
         dk.ctrl = (double *)S.buf[12];
         dk.u_all = hk.u_all ? (double *)S.buf[13] : nullptr;
         dk.status = hk.status ? (uint8_t *)S.buf[14] : nullptr;
-        rc = launch_step(h, nb, dk, S.stream, 1 + turn % kPipeDepth);
+        rc = launch_step(h, nb, dk, S.stream);
         if (rc != IRLOSC_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(hk.ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
                                  cudaMemcpyDeviceToHost, S.stream));

@@ -25,8 +25,7 @@ struct FusedEntry {
     int variant;              // 0 = default; others for A/B measurements (irlosc_set_kernel(h, 2 + variant))
     int threads;
     size_t smem;
-    const void *step, *fixup;
-    int rec_doubles;
+    const void *step;
     const char *name;
     const void *step_seq;     // same kernel with the action-sequence state machine compiled in (variant 0 only)
 };
@@ -35,9 +34,9 @@ template <int KD, bool HB, int NT, bool SMEM>
 FusedEntry entry(int variant, const char *name) {
     const void *seq = nullptr;
     if constexpr (SMEM && (NT == 256 || NT == 224)) seq = (const void *)osc_step_fused<KD, HB, NT, SMEM, true>;
-    return FusedEntry{KD, HB, variant, NT, SMEM ? (size_t)kScratchDoubles * NT * sizeof(double) : 0,
-                      (const void *)osc_step_fused<KD, HB, NT, SMEM>, (const void *)osc_tail_fixup<KD, HB>,
-                      Rec<KD, HB>::SIZE, name, seq};
+    // chain scratch (SMEM variants) + one warp-finish scratch per warp
+    const size_t smem = (SMEM ? (size_t)kScratchDoubles * NT * sizeof(double) : 0) + (size_t)(NT / 32) * sizeof(WarpFix<KD, HB>);
+    return FusedEntry{KD, HB, variant, NT, smem, (const void *)osc_step_fused<KD, HB, NT, SMEM>, name, seq};
 }
 
 // Variant 0 is the default and exists with 8 and with 7 warps per CTA (one CTA per SM): a thread owns an
@@ -82,27 +81,6 @@ int fused_threads_for(int64_t B, int sms) {
     return p7 < p8 ? 224 : 256;
 }
 
-// experimental fix-up path (osc_fixup_coop.cuh), off unless IRLOSC_FIXUP_COOP=1
-int fixup_coop() {
-    static const int v = [] { const char *e = getenv("IRLOSC_FIXUP_COOP"); return e ? atoi(e) : 0; }();
-    return v;
-}
-
-int32_t ensure_queue(irlosc_handle *h, int q, int64_t B, int rec_doubles) {
-    HardBuffers &hb = h->hard[q];
-    if (!hb.count) CUDA_TRY(cudaMalloc(&hb.count, sizeof(int)));
-    if (B > hb.cap || rec_doubles != hb.rec_doubles) {
-        if (hb.inst) { CUDA_TRY(cudaFree(hb.inst)); hb.inst = nullptr; }
-        if (hb.rec) { CUDA_TRY(cudaFree(hb.rec)); hb.rec = nullptr; }
-        hb.cap = 0;
-        CUDA_TRY(cudaMalloc(&hb.inst, (size_t)B * sizeof(int64_t)));
-        CUDA_TRY(cudaMalloc(&hb.rec, (size_t)B * rec_doubles * sizeof(double)));
-        hb.cap = B;
-        hb.rec_doubles = rec_doubles;
-    }
-    return IRLOSC_OK;
-}
-
 int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
     if (!io) return fail(IRLOSC_ERR_INVALID, "io is null");
     if (!io->q || !io->dq || !io->target_xyz || !io->target_quat || !io->ctrl)
@@ -119,20 +97,14 @@ int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
     return IRLOSC_OK;
 }
 
-int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st, const KSeq *seq = nullptr, int queue = 0) {
+int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st, const KSeq *seq = nullptr) {
     const int variant = (h->kernel_choice >= 2 && h->kernel_choice < 9) ? h->kernel_choice - 2 : 0;
-    const int sms0 = std::max(1, h->sm_count - h->sm_margin);
-    int want_threads = variant == 0 ? fused_threads_for(B, sms0) : 0;
+    const int sms = std::max(1, h->sm_count - h->sm_margin);
+    int want_threads = variant == 0 ? fused_threads_for(B, sms) : 0;
     if (const char *t = getenv("IRLOSC_FUSED_THREADS")) want_threads = atoi(t);                         // experiments only
     const FusedEntry *e = fused_find(h->fused_kd, h->fused_base, variant, want_threads);
     if (!e) e = fused_find(h->fused_kd, h->fused_base, variant);
     if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d variant=%d", h->fused_kd, (int)h->fused_base, variant);
-    int32_t rc = ensure_queue(h, queue, B, e->rec_doubles);
-    if (rc != IRLOSC_OK) return rc;
-    HardBuffers &hb = h->hard[queue];
-    CUDA_TRY(cudaMemsetAsync(hb.count, 0, sizeof(int), st));
-    HardQueue hq{hb.count, (int)std::min<int64_t>(hb.cap, INT32_MAX), e->rec_doubles, hb.rec, hb.inst};
-    const int sms = std::max(1, h->sm_count - h->sm_margin);
     const int grid = (int)std::min<int64_t>((B + e->threads - 1) / e->threads, (int64_t)sms);
     static const KSeq no_seq = {};
     const void *fn = e->step;
@@ -140,19 +112,10 @@ int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st,
         if (!e->step_seq) return fail(IRLOSC_ERR_INVALID, "the action-sequence step exists for fused variant 0 only");
         fn = e->step_seq;
     }
-    void *args[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr, (void *)&hq,
-                    (void *)(seq ? seq : &no_seq)};
+    void *args[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr, (void *)(seq ? seq : &no_seq)};
     cudaError_t err = cudaLaunchKernel(fn, dim3(grid), dim3(e->threads), args, e->smem, st);
     if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fused kernel launch: %s", cudaGetErrorString(err));
-    const int fgrid = (int)std::min<int64_t>((B + 3) / 4, (int64_t)sms * 4);
-    TailOut tout;
-    memset(&tout, 0, sizeof tout);
-    tout.u_all = k.u_all; tout.ctrl = k.ctrl; tout.status = k.status;
-    const int coop = fixup_coop();
-    void *fargs[] = {(void *)&h->kp, (void *)&tout, (void *)&h->fr, (void *)&hq, (void *)&coop};
-    err = cudaLaunchKernel(e->fixup, dim3(fgrid), dim3(128), fargs, 0, st);
-    if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fix-up kernel launch: %s", cudaGetErrorString(err));
-    h->launches += 2;
+    h->launches += 1;
     h->last_kernel = e->name;
     return IRLOSC_OK;
 }
@@ -162,15 +125,14 @@ struct StreamEntry {
     int kd;
     bool has_base;
     int max_threads;
-    const void *step, *fixup;
-    int rec_doubles;
+    const void *step;
+    int fix_bytes;            // per-warp scratch of the warp finish
     const char *name;
 };
 
 template <int KD, bool HB, int NT>
 StreamEntry sentry(const char *name) {
-    return StreamEntry{KD, HB, NT, (const void *)stream::osc_step_stream<KD, HB, NT>, (const void *)osc_tail_fixup<KD, HB>,
-                       Rec<KD, HB>::SIZE, name};
+    return StreamEntry{KD, HB, NT, (const void *)stream::osc_step_stream<KD, HB, NT>, (int)((sizeof(WarpFix<KD, HB>) + 15) & ~size_t(15)), name};
 }
 
 const StreamEntry *stream_table(int *count) {
@@ -203,7 +165,7 @@ bool irlosc::stream_preferred(const irlosc_handle *h) {
     return fused_roles(h->kp, R, kd, hb) && kd == 6;
 }
 
-int32_t irlosc::stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaStream_t st, int queue) {
+int32_t irlosc::stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaStream_t st) {
     FRoles R;
     int kd = 0;
     bool has_base = false;
@@ -221,14 +183,9 @@ int32_t irlosc::stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaSt
     stream::Plan plan;
     int32_t rc = build_stream_plan(h->kp, io, R, kd, has_base, plan);
     if (rc != IRLOSC_OK) return rc;
-    rc = ensure_queue(h, queue, B, e->rec_doubles);
-    if (rc != IRLOSC_OK) return rc;
-    HardBuffers &hb = h->hard[queue];
-    CUDA_TRY(cudaMemsetAsync(hb.count, 0, sizeof(int), st));
-    HardQueue hq{hb.count, (int)std::min<int64_t>(hb.cap, INT32_MAX), e->rec_doubles, hb.rec, hb.inst};
-    // shared-memory plan: tables, then per warp two stages and the packed ctrl tile
+    // shared-memory plan: tables, then per warp two stages, the packed ctrl tile and the warp-finish scratch
     const int stage_bytes = (plan.stage_entries * stream::kPitch * 8 + 15) & ~15;
-    const int warp_bytes = 2 * stage_bytes + ((32 * h->kp.n_ctrl * 8 + 15) & ~15);
+    const int warp_bytes = 2 * stage_bytes + ((32 * h->kp.n_ctrl * 8 + 15) & ~15) + e->fix_bytes;
     const size_t head = (sizeof(stream::Plan) + 15) & ~size_t(15);
     int warps = (int)std::min<size_t>(e->max_threads / 32, (kSmemLimit - head) / warp_bytes);
     {   // a warp owns 32 instances: pick the warp count whose number of passes over the batch is cheapest
@@ -261,21 +218,11 @@ int32_t irlosc::stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaSt
     const int grid = (int)std::min<int64_t>((n_tiles + warps - 1) / warps, (int64_t)sms);
     int mode = 0;
     if (const char *m = getenv("IRLOSC_STREAM_MODE")) mode = atoi(m);                                   // experiments only
-    void *args[] = {(void *)&h->kp, (void *)&plan, (void *)&out, (void *)&B, (void *)&R, (void *)&hq, (void *)&G,
+    void *args[] = {(void *)&h->kp, (void *)&plan, (void *)&out, (void *)&B, (void *)&R, (void *)&G,
                     (void *)&stage_bytes, (void *)&warp_bytes, (void *)&mode};
     cudaError_t err = cudaLaunchKernel(e->step, dim3(grid), dim3(warps * 32), args, smem, st);
     if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "streaming kernel launch: %s", cudaGetErrorString(err));
-    TailOut tout;
-    memset(&tout, 0, sizeof tout);
-    tout.u_all = io.u_all; tout.ctrl = io.ctrl; tout.status = io.status;
-    tout.n_gather = io.n_gather; tout.gather_offset = io.gather_offset; tout.ctrl_mc = io.ctrl_mc;
-    for (int g = 0; g < io.n_gather; ++g) tout.ctrl_gather[g] = io.ctrl_gather[g];
-    const int fgrid = (int)std::min<int64_t>((B + 3) / 4, (int64_t)sms * 4);
-    const int coop = fixup_coop();
-    void *fargs[] = {(void *)&h->kp, (void *)&tout, (void *)&R, (void *)&hq, (void *)&coop};
-    err = cudaLaunchKernel(e->fixup, dim3(fgrid), dim3(128), fargs, 0, st);
-    if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fix-up kernel launch: %s", cudaGetErrorString(err));
-    h->launches += 2;
+    h->launches += 1;
     h->last_kernel = e->name;
     return IRLOSC_OK;
 }
@@ -415,7 +362,7 @@ extern "C" int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irl
         dk.status = hk.status ? (uint8_t *)S.buf[10] : nullptr;
         dk.ee_xyz = hk.ee_xyz ? (double *)S.buf[11] : nullptr;
         dk.ee_quat = hk.ee_quat ? (double *)S.buf[12] : nullptr;
-        result = launch_fused(h, nb, dk, S.stream, nullptr, 1 + turn % kPipeDepth);
+        result = launch_fused(h, nb, dk, S.stream);
         if (result != IRLOSC_OK) break;
         CUDA_TRY(cudaMemcpyAsync(hk.ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
                                  cudaMemcpyDeviceToHost, S.stream));

@@ -24,26 +24,15 @@ struct Staging {
 int32_t fail(int32_t rc, const char *fmt, ...);
 int32_t ensure_cap(Staging &s, int slot, size_t bytes);
 
-// Queue of instances that need the eigen fix-up kernel (osc_tail.cuh); one per concurrent stream.
-struct HardBuffers {
-    int *count = nullptr;
-    int64_t *inst = nullptr;
-    double *rec = nullptr;
-    int64_t cap = 0;
-    int rec_doubles = 0;
-};
-constexpr int kQueues = kPipeDepth + 1;      // 0: irlosc_step / irlosc_step_fused, 1 + s: host pipeline stage s
-
 }  // namespace irlosc
 
 struct irlosc_handle;
 namespace irlosc {
 // streaming step (irlosc_fused.cu, osc_stream.cuh): serves every layout of the DualUR5 topology;
-// `stream_preferred` says whether it is also the faster choice (6-row arm devices, where the eigen
-// fallback matters and is deferred to a fix-up kernel here).
+// `stream_preferred` says whether it is also the faster choice (6-row arm devices).
 bool stream_supported(const irlosc_handle *h, const KIo &io);
 bool stream_preferred(const irlosc_handle *h);
-int32_t stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaStream_t st, int queue);
+int32_t stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaStream_t st);
 }  // namespace irlosc
 
 #define CUDA_TRY(expr)                                                                        \
@@ -71,6 +60,5 @@ struct irlosc_handle {
     irlosc::fused::FRoles fr;
     int fused_kd = 0;
     bool fused_base = false;
-    irlosc::HardBuffers hard[irlosc::kQueues];
     irlosc::Staging fstage[irlosc::kPipeDepth];
 };

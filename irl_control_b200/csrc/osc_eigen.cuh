@@ -17,10 +17,10 @@ namespace tiled {
 // parallel-order Jacobi.  A round-robin schedule gives K/2 disjoint (p, q) pairs per round, so one
 // round applies K/2 rotations with three passes over the matrix (columns of A and V, rows of A,
 // clean-up) instead of one barrier-separated pass per rotation.
-// A (destroyed) and V have leading dimension K+1; cbuf / sbuf hold >= K doubles each;
+// A (destroyed, leading dimension LDA) and V (K+1); cbuf / sbuf hold >= K doubles each;
 // result w = V f(lambda) V^T g.
-template <int K>
-__device__ void eigen_solve(double (*A)[K + 1], double (*V)[K + 1], const double *g, double *w, double *cbuf,
+template <int K, int LDA = K + 1>
+__device__ void eigen_solve(double (*A)[LDA], double (*V)[K + 1], const double *g, double *w, double *cbuf,
                             double *sbuf, bool force_pinv, int lane, int *flags_out) {
     constexpr int M = (K % 2 == 0) ? K : K + 1;      // players of the round-robin (one dummy when K is odd)
     constexpr int KP = M / 2;                        // pairs per round

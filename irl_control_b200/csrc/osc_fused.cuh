@@ -26,8 +26,8 @@
 // articulated sweep over arm joints 6..1 with the arm's task rows, then the stand joint couples the
 // arms; dense k x k LDL^T solve in registers; the joint-space assembly of osc.py:184-200 in its
 // collapsed form u = c_j (M dq)_j + bias_j - (J^T w)_j.
-// Instances whose task-space inverse needs the eigen-decomposition (pinv with rcond, osc.py:55)
-// are pushed to a queue and finished by a warp-cooperative fix-up kernel (tiled::eigen_solve).
+// The few instances whose task-space solve the thread cannot decide (osc_tail.cuh) are finished by their
+// warp with the cooperative eigen-solver right after the tile, inside this kernel.
 //
 // The per-instance function is __host__ __device__ so that tests/host_fused can run exactly this
 // code on the CPU against the oracle (test infrastructure only; the product never does).
@@ -269,15 +269,14 @@ IRLOSC_HD void device_signal_early(const KParams &P, const FIo &io, int64_t inst
         for (int i = 0; i < 4; ++i) io.ee_quat[(inst * D + d) * 4 + i] = ee_q[i];
 }
 
-// Returns true when the instance was queued for the eigen fix-up (outputs of the chain joints are
-// then written by osc_fused_fixup / fixup_finish).
+// Returns true when the task-space solve must be finished by the warp (state_warp_finish on T rewrites the
+// chain joints).
 template <int KD, bool HAS_BASE, bool SEQ = false>
 IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles &R, const FIo &io, int64_t inst,
-                              const Scratch &scr, double *hard_rec, const Debug *dbg, const KSeq *Q = nullptr) {
+                              const Scratch &scr, TailState<KD, HAS_BASE> &T, const Debug *dbg, const KSeq *Q = nullptr) {
     constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
     constexpr int N = kN;
     constexpr int KT = KD * (KD + 1) / 2;
-    using RC = Rec<KD, HAS_BASE>;
     const int D = P.D;
     const double *q = io.q + inst * N;
     const double *dq = io.dq + inst * N;
@@ -296,10 +295,10 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
         if (!tracking) vel_zero |= 1u << d;
     }
 
-    // what survives the arm loop (dynamic indices -> local memory; kept as small as possible)
-    double akA[2][KT];                  // the arms' diagonal blocks of A = J M^-1 J^T before the stand joint
-    double j0[K], jst[K], dxr[K], g[K]; // stand column of the reduced / original J, dx = J dq, task signal
-    double jarm[2][6][KD], base_arm[2][6];
+    // what survives the arm loop lives in T (dynamic indices -> local memory; kept as small as possible)
+    double (&akA)[2][KT] = T.akA;
+    double (&j0)[K] = T.j0, (&jst)[K] = T.jst, (&dxr)[K] = T.dxr, (&g)[K] = T.g;
+    double (&jarm)[2][6][KD] = T.jarm, (&base_arm)[2][6] = T.base_arm;
 
     // ------------------------------------------------------------ stand joint (world -> joint 0)
     Body S0;
@@ -556,11 +555,15 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
     const double base_st = fma(cu_st, uv_st, gb * b_st);
     if (dbg && dbg->uv) { dbg->uv[0] = uv_st; dbg->bias[0] = b_st; }
 
-    const bool hard = osc_tail<KD, HAS_BASE>(P, R, io.target_vel ? io.target_vel + inst * D * 6 : nullptr, vel_zero, flags,
-                                             m_ok, akA, j0, jst, dxr, g, jarm, base_arm, base_st, inv0,
-                                             io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl,
-                                             io.status ? io.status + inst : nullptr, hard_rec, dbg);
-    // send_forces: `if gripper_force: sim.data.ctrl[gripper_idx] = gripper_force` (insertion_task.py:160-161)
+    T.base_st = base_st;
+    T.inv0 = inv0;
+    T.u_all_row = io.u_all ? io.u_all + inst * N : nullptr;
+    T.ctrl_row = io.ctrl + inst * P.n_ctrl;
+    T.status = io.status ? io.status + inst : nullptr;
+    const bool hard = state_tail<KD, HAS_BASE>(P, R, io.target_vel ? io.target_vel + inst * D * 6 : nullptr, vel_zero, flags,
+                                               m_ok, T, dbg);
+    // send_forces: `if gripper_force: sim.data.ctrl[gripper_idx] = gripper_force` (insertion_task.py:160-161); the
+    // gripper joint is not a chain joint, so a later warp finish does not touch this slot
     if (SEQ && seq.gripper_force != 0.0 && Q->gripper_slot >= 0) io.ctrl[inst * P.n_ctrl + Q->gripper_slot] = seq.gripper_force;
     return hard;
 }
@@ -573,19 +576,21 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 template <int KD, bool HAS_BASE, int NT, bool SMEM, bool SEQ = false>
 __global__ void __launch_bounds__(NT, 1)
 osc_step_fused(const __grid_constant__ KParams P, const __grid_constant__ KModel Mdl, const __grid_constant__ FIo io,
-               const int64_t B, const __grid_constant__ FRoles R, const __grid_constant__ HardQueue hq,
-               const __grid_constant__ KSeq Q) {
+               const int64_t B, const __grid_constant__ FRoles R, const __grid_constant__ KSeq Q) {
     extern __shared__ __align__(16) double fused_smem[];
     double chain[SMEM ? 1 : kScratchDoubles];
     const Scratch scr = SMEM ? Scratch{fused_smem + threadIdx.x, NT} : Scratch{chain, 1};
-    for (int64_t inst = (int64_t)blockIdx.x * NT + threadIdx.x; inst < B; inst += (int64_t)gridDim.x * NT) {
-        // record memory is indexed by instance (capacity >= B): only the queue slot needs an atomic
-        double *rec = hq.rec ? hq.rec + (size_t)inst * hq.rec_doubles : nullptr;
-        const bool hard = fused_instance<KD, HAS_BASE, SEQ>(P, Mdl, R, io, inst, scr, rec, nullptr, SEQ ? &Q : nullptr);
-        if (hard) {
-            const int slot = atomicAdd(hq.count, 1);
-            hq.inst[slot] = inst;
-        }
+    // scratch of the warp-cooperative finish (osc_tail.cuh), one per warp behind the chain scratch
+    WarpFix<KD, HAS_BASE> &wfix = reinterpret_cast<WarpFix<KD, HAS_BASE> *>(fused_smem + (SMEM ? kScratchDoubles * NT : 0))[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count: the finish needs every lane of the warp
+    for (int64_t base = (int64_t)blockIdx.x * NT + (threadIdx.x & ~31); base < B; base += (int64_t)gridDim.x * NT) {
+        const int64_t inst = base + lane;
+        TailState<KD, HAS_BASE> T;
+        bool hard = false;
+        if (inst < B) hard = fused_instance<KD, HAS_BASE, SEQ>(P, Mdl, R, io, inst, scr, T, nullptr, SEQ ? &Q : nullptr);
+        __syncwarp();
+        state_warp_finish<KD, HAS_BASE>(wfix, R, T, hard, lane);
     }
 }
 

@@ -54,14 +54,7 @@ struct KSeq {
     double passive_quat[4];
     KAction act[IRLOSC_MAX_ACTIONS];
 };
-// Instances that need the eigen path: one record each, finished by osc_fused_fixup.
-struct HardQueue {
-    int *count;
-    int capacity;
-    int rec_doubles;
-    double *rec;
-    int64_t *inst;
-};
+// Record a thread hands to its warp when it cannot decide the task-space solve by itself (osc_tail.cuh).
 template <int KD, bool HAS_BASE>
 struct Rec {                       // record layout in doubles
     static constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
@@ -70,7 +63,7 @@ struct Rec {                       // record layout in doubles
     static constexpr int BASE = G + K;             // base[13]: stand, arm0 joints 1..6, arm1 joints 1..6
     static constexpr int JST = BASE + 13;          // J[r][stand], r < K
     static constexpr int JARM = JST + K;           // J[row_arm[a] + cr][arm joint i]: [a][i][cr]
-    static constexpr int ABAD = JARM + 2 * 6 * KD; // 1.0 when the LDL^T pivots failed
+    static constexpr int ABAD = JARM + 2 * 6 * KD; // 0.0: pinv branch known to be taken; 1.0: the eigen-solver decides from its determinant
     static constexpr int SIZE = ABAD + 1;
 };
 

@@ -36,7 +36,6 @@ namespace irlosc {
 namespace stream {
 
 using fused::FRoles;
-using fused::HardQueue;
 using fused::Debug;
 using fused::kN;
 
@@ -249,10 +248,10 @@ IRLOSC_HD bool consume_rows(const RD &rd, const KParams &P, unsigned vel_zero, d
 
 // One instance, all groups available through `group(g)` (returns the reader of group g; on the device
 // this is where the warp waits for the copy and issues the next one).
+// Returns true when the task-space solve must be finished by the warp (state_warp_finish on T).
 template <int KD, bool HAS_BASE, class GROUPS>
 IRLOSC_HD bool stream_instance(const KParams &P, const FRoles &R, const Plan &plan, const Outputs &out, int64_t inst,
-                               GROUPS &group, double *ctrl_row, double *hard_rec, const Debug *dbg) {
-    constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
+                               GROUPS &group, double *ctrl_row, fused::TailState<KD, HAS_BASE> &T, const Debug *dbg) {
     constexpr int KT = KD * (KD + 1) / 2;
     const int D = P.D;
     const double gb = P.use_g ? 1.0 : 0.0;
@@ -268,7 +267,6 @@ IRLOSC_HD bool stream_instance(const KParams &P, const FRoles &R, const Plan &pl
         }
         if (!tracking) vel_zero |= 1u << d;
     }
-    double akA[2][KT], j0[K], jst[K], dxr[K], g[K], jarm[2][6][KD], base_arm[2][6];
     bool m_ok = true;
     double d0 = 0.0, uv_st = 0.0, bias0;
     {   // ---- G0: stand / base device
@@ -276,10 +274,10 @@ IRLOSC_HD bool stream_instance(const KParams &P, const FRoles &R, const Plan &pl
         bias0 = rd(kG0Bias0);
         if (HAS_BASE) {
             const double jb0 = rd(kG0Jbase);
-            j0[R.row_base] = jb0;
-            jst[R.row_base] = jb0;
-            dxr[R.row_base] = jb0;                 // times dq[0], known after the first arm group
-            device_signal_staged(P, R.dev_base, rd, kG0Dev, has_mvel, g);
+            T.j0[R.row_base] = jb0;
+            T.jst[R.row_base] = jb0;
+            T.dxr[R.row_base] = jb0;                 // times dq[0], known after the first arm group
+            device_signal_staged(P, R.dev_base, rd, kG0Dev, has_mvel, T.g);
         }
     }
 #pragma unroll 1
@@ -291,7 +289,7 @@ IRLOSC_HD bool stream_instance(const KParams &P, const FRoles &R, const Plan &pl
             auto rd = group(1 + 5 * arm);
             consume_cc<KD>(rd, arm, S);
         }
-        if (HAS_BASE && arm == 0) dxr[R.row_base] *= S.dqC[0];
+        if (HAS_BASE && arm == 0) T.dxr[R.row_base] *= S.dqC[0];
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             auto rd = group(2 + 5 * arm + half);
@@ -300,26 +298,27 @@ IRLOSC_HD bool stream_instance(const KParams &P, const FRoles &R, const Plan &pl
         double ak[KT], j0r[KD], jstr[KD], dxa[KD], c0, uv0;
         {
             auto rd = group(4 + 5 * arm);
-            m_ok = consume_rows<KD>(rd, P, vel_zero, gb, jb, S, ak, j0r, jstr, dxa, jarm[arm], base_arm[arm], &c0, &uv0, dbg) && m_ok;
+            m_ok = consume_rows<KD>(rd, P, vel_zero, gb, jb, S, ak, j0r, jstr, dxa, T.jarm[arm], T.base_arm[arm], &c0, &uv0, dbg) && m_ok;
         }
         d0 += c0;
         uv_st += uv0;
 #pragma unroll
-        for (int cr = 0; cr < KD; ++cr) { j0[row_a + cr] = j0r[cr]; jst[row_a + cr] = jstr[cr]; dxr[row_a + cr] = dxa[cr]; }
+        for (int cr = 0; cr < KD; ++cr) { T.j0[row_a + cr] = j0r[cr]; T.jst[row_a + cr] = jstr[cr]; T.dxr[row_a + cr] = dxa[cr]; }
 #pragma unroll
-        for (int e = 0; e < KT; ++e) akA[arm][e] = ak[e];
+        for (int e = 0; e < KT; ++e) T.akA[arm][e] = ak[e];
         {
             auto rd = group(5 + 5 * arm);
-            device_signal_staged(P, R.dev_arm[arm], rd, 0, has_mvel, g);
+            device_signal_staged(P, R.dev_arm[arm], rd, 0, has_mvel, T.g);
         }
     }
     m_ok = m_ok && (d0 > 0.0);
-    const double inv0 = fused::rcp64(d0);
-    const double base_st = fma(fused::coef_uv(P, vel_zero, 0), uv_st, gb * bias0);
+    T.inv0 = fused::rcp64(d0);
+    T.base_st = fma(fused::coef_uv(P, vel_zero, 0), uv_st, gb * bias0);
     if (dbg && dbg->uv) dbg->uv[0] = uv_st;
-    return fused::osc_tail<KD, HAS_BASE>(P, R, out.target_vel ? out.target_vel + inst * D * 6 : nullptr, vel_zero, 0, m_ok, akA,
-                                         j0, jst, dxr, g, jarm, base_arm, base_st, inv0, u_all_row, ctrl_row,
-                                         out.status ? out.status + inst : nullptr, hard_rec, dbg);
+    T.u_all_row = u_all_row;
+    T.ctrl_row = ctrl_row;
+    T.status = out.status ? out.status + inst : nullptr;
+    return fused::state_tail<KD, HAS_BASE>(P, R, out.target_vel ? out.target_vel + inst * D * 6 : nullptr, vel_zero, 0, m_ok, T, dbg);
 }
 
 #if defined(__CUDACC__) && !defined(IRLOSC_FUSED_NO_KERNELS)
@@ -345,7 +344,7 @@ struct Gather {       // fused result gather, same contract as KIo
 template <int KD, bool HAS_BASE, int NT>
 __global__ void __launch_bounds__(NT, 1)
 osc_step_stream(const __grid_constant__ KParams P, const __grid_constant__ Plan plan_in, const __grid_constant__ Outputs out,
-                const int64_t B, const __grid_constant__ FRoles R, const __grid_constant__ HardQueue hq,
+                const int64_t B, const __grid_constant__ FRoles R,
                 const __grid_constant__ Gather G, const int stage_bytes, const int warp_bytes, const int mode) {
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -360,6 +359,9 @@ osc_step_stream(const __grid_constant__ KParams P, const __grid_constant__ Plan 
     const int l8 = lane & 7, sub = lane >> 3;
     unsigned char *wbase = smem_raw + ((sizeof(Plan) + 15) & ~size_t(15)) + (size_t)warp * warp_bytes;
     double *ctile = reinterpret_cast<double *>(wbase + 2 * (size_t)stage_bytes);      // [32][n_ctrl]
+    // scratch of the warp-cooperative finish (osc_tail.cuh), behind the packed ctrl tile
+    fused::WarpFix<KD, HAS_BASE> &wfix =
+        *reinterpret_cast<fused::WarpFix<KD, HAS_BASE> *>(wbase + 2 * (size_t)stage_bytes + ((32 * P.n_ctrl * 8 + 15) & ~15));
     const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(wbase);
 
     const int64_t n_tiles = (B + 31) / 32;
@@ -432,14 +434,11 @@ osc_step_stream(const __grid_constant__ KParams P, const __grid_constant__ Plan 
             ++seq_wait;
             return [st](int e) { return st[e * kPitch]; };
         };
-        double *rec = hq.rec ? hq.rec + (size_t)inst_c * hq.rec_doubles : nullptr;
         Outputs o = out;
-        if (!valid) { o.u_all = nullptr; o.status = nullptr; rec = nullptr; }
-        const bool hard = stream_instance<KD, HAS_BASE>(P, R, plan, o, inst_c, group, ctile + lane * P.n_ctrl, rec, nullptr);
-        if (hard && valid) {
-            const int slot = atomicAdd(hq.count, 1);
-            hq.inst[slot] = inst;
-        }
+        if (!valid) { o.u_all = nullptr; o.status = nullptr; }
+        fused::TailState<KD, HAS_BASE> T;
+        const bool hard = stream_instance<KD, HAS_BASE>(P, R, plan, o, inst_c, group, ctile + lane * P.n_ctrl, T, nullptr);
+        fused::state_warp_finish<KD, HAS_BASE>(wfix, R, T, hard && valid, lane);
         __syncwarp();
         // ---- packed ctrl rows of the tile are contiguous in every destination
         const int64_t row0 = tile * 32 * (int64_t)P.n_ctrl;

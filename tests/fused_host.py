@@ -19,7 +19,7 @@ _lib = None
 def build():
     deps = [SRC, os.path.join(os.path.dirname(HERE), "include", "irlosc.h")] + [
         os.path.join(CSRC, f) for f in ("osc_fused.cuh", "osc_fused_types.h", "irlosc_device.cuh", "osc_tail.cuh",
-                                        "osc_stream.cuh", "osc_fixup_coop.cuh", "osc_sequence.cuh", "irlosc_build.h",
+                                        "osc_stream.cuh", "osc_sequence.cuh", "irlosc_build.h",
                                         "irlosc_internal.h")]
     if os.path.isfile(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in deps):
         return LIB
@@ -40,6 +40,8 @@ def load():
         _lib.fused_host_error.restype = C.c_char_p
         _lib.stream_host_run.restype = C.c_int64
         _lib.stream_host_run.argtypes = [C.POINTER(_native.Params), C.c_int64, C.POINTER(_native.Io)] + [C.c_void_p] * 6
+        _lib.host_set_how.restype = None
+        _lib.host_set_how.argtypes = [C.c_void_p]
     return _lib
 
 
@@ -63,10 +65,16 @@ def run(layout, model, inp, debug=False):
                "bias": np.zeros((B, n)), "dx": np.zeros((B, k)), "J": np.zeros((B, k, n))}
         ptrs = [dbg[x].ctypes.data for x in ("A", "g", "uv", "bias", "dx", "J")]
     params = layout.to_c_params()
-    rc = lib.fused_host_run(C.byref(params), C.byref(model), B, C.byref(io), *ptrs)
+    how = np.zeros(B, dtype=np.int32)
+    lib.host_set_how(how.ctypes.data)
+    try:
+        rc = lib.fused_host_run(C.byref(params), C.byref(model), B, C.byref(io), *ptrs)
+    finally:
+        lib.host_set_how(None)
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
     out["n_hard"] = int(rc)
+    out["how"] = how
     out.update(dbg)
     return out
 
@@ -103,10 +111,16 @@ def run_stream(layout, state, debug=False, strides=None):
         ptrs = [dbg[x].ctypes.data for x in ("A", "g", "uv", "dx", "J")]
     params = layout.to_c_params()
     nch = C.c_int32(0)
-    rc = lib.stream_host_run(C.byref(params), B, C.byref(io), *ptrs, C.byref(nch))
+    how = np.zeros(B, dtype=np.int32)
+    lib.host_set_how(how.ctypes.data)
+    try:
+        rc = lib.stream_host_run(C.byref(params), B, C.byref(io), *ptrs, C.byref(nch))
+    finally:
+        lib.host_set_how(None)
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
     out["n_hard"] = int(rc)
+    out["how"] = how
     out["n_chunks"] = int(nch.value)
     out.update(dbg)
     return out
@@ -164,13 +178,5 @@ def waypoints_step(layout, model, inp, wp_state, threshold=0.1):
     return out
 
 
-def coop_resolve(A, g):
-    """osc_fixup_coop.cuh on the CPU (lanes emulated): returns (how, w)."""
-    lib = load()
-    lib.coop_host_resolve.restype = C.c_int
-    lib.coop_host_resolve.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
-    A = np.ascontiguousarray(A, dtype=np.float64)
-    g = np.ascontiguousarray(g, dtype=np.float64)
-    w = np.zeros(A.shape[0])
-    how = lib.coop_host_resolve(A.shape[0], A.ctypes.data, g.ctypes.data, w.ctypes.data)
-    return how, w
+# TailHow bits of csrc/osc_tail.cuh (out["how"])
+HOW_INVERSE, HOW_CUT1, HOW_CUT2, HOW_WARP = 1, 2, 4, 8

@@ -12,7 +12,6 @@
 #include "../../irl_control_b200/csrc/irlosc_build.h"
 #include "../../irl_control_b200/csrc/osc_fused.cuh"
 #include "../../irl_control_b200/csrc/osc_stream.cuh"
-#include "../../irl_control_b200/csrc/osc_fixup_coop.cuh"
 
 static std::string g_err;
 int32_t irlosc::fail(int32_t rc, const char *fmt, ...) {
@@ -28,6 +27,10 @@ int32_t irlosc::ensure_cap(Staging &, int, size_t) { return IRLOSC_OK; }
 
 using namespace irlosc;
 using namespace irlosc::fused;
+
+// optional tap: which path resolved the task-space solve of every instance (TailHow bits), set by the test
+static int *g_how = nullptr;
+extern "C" void host_set_how(int *how) { g_how = how; }
 
 // serial cyclic Jacobi + the truncation rule of tiled::eigen_solve (osc.py:52-55), test-only
 template <int K>
@@ -95,15 +98,22 @@ static int64_t run(const KParams &P, const KModel &M, const FRoles &R, const FIo
             if (d.J) d.J += i * K * kN;
             dp = &d;
         }
+        Debug dh{};
+        if (g_how) {
+            if (!dp) { dp = &dh; }
+            dp->how = g_how + i;
+        }
         const Scratch scr{scratch.data(), 1};
-        const bool hard = Q ? fused_instance<KD, HB, true>(P, M, R, io, i, scr, rec.data(), dp, Q)
-                            : fused_instance<KD, HB, false>(P, M, R, io, i, scr, rec.data(), dp);
+        TailState<KD, HB> T;
+        const bool hard = Q ? fused_instance<KD, HB, true>(P, M, R, io, i, scr, T, dp, Q)
+                            : fused_instance<KD, HB, false>(P, M, R, io, i, scr, T, dp);
         if (hard) {
             ++n_hard;
             double w[K];
+            state_record<KD, HB>(R, T, rec.data());
             const int fl = host_eigen_solve<K>(&rec[RC::A], &rec[RC::G], rec[RC::ABAD] == 0.0, w);
-            fixup_finish<KD, HB>(R, io.u_all ? io.u_all + i * kN : nullptr, io.ctrl + i * P.n_ctrl, rec.data(), w, 0, 1);
-            if (io.status) io.status[i] = (uint8_t)(io.status[i] | fl);
+            fixup_finish<KD, HB>(R, T.u_all_row, T.ctrl_row, rec.data(), w, 0, 1);
+            if (T.status) *T.status = (uint8_t)(*T.status | fl);
         }
     }
     return n_hard;
@@ -131,7 +141,7 @@ extern "C" int64_t fused_host_run(const irlosc_params *params, const irlosc_mode
     k.seq_action = k.seq_entered = k.seq_timer = nullptr;
     k.seq_err = k.seq_mv0 = k.seq_tgt_xyz = k.seq_tgt_quat = nullptr;
     k.wps = nullptr; k.wp_idx = nullptr;
-    Debug d{dbg_A, dbg_g, dbg_uv, dbg_bias, dbg_dx, dbg_J};
+    Debug d{dbg_A, dbg_g, dbg_uv, dbg_bias, dbg_dx, dbg_J, nullptr};
     const Debug *dp = (dbg_A || dbg_uv || dbg_J) ? &d : nullptr;
     if (kd == 3 && hb) return run<3, true>(P, M, R, k, B, dp);
     if (kd == 3 && !hb) return run<3, false>(P, M, R, k, B, dp);
@@ -216,15 +226,22 @@ int64_t run_stream(const KParams &P, const FRoles &R, const stream::Plan &plan, 
             if (d.J) d.J += i * K * kN;
             dp = &d;
         }
+        Debug dh{};
+        if (g_how) {
+            if (!dp) { dp = &dh; }
+            dp->how = g_how + i;
+        }
         HostGroups groups{plan, i, std::vector<double>(plan.stage_entries)};
         double *ctrl_row = out.ctrl + i * P.n_ctrl;
-        const bool hard = stream::stream_instance<KD, HB>(P, R, plan, out, i, groups, ctrl_row, rec.data(), dp);
+        TailState<KD, HB> T;
+        const bool hard = stream::stream_instance<KD, HB>(P, R, plan, out, i, groups, ctrl_row, T, dp);
         if (hard) {
             ++n_hard;
             double w[K];
+            state_record<KD, HB>(R, T, rec.data());
             const int fl = host_eigen_solve<K>(&rec[RC::A], &rec[RC::G], rec[RC::ABAD] == 0.0, w);
-            fixup_finish<KD, HB>(R, out.u_all ? out.u_all + i * kN : nullptr, ctrl_row, rec.data(), w, 0, 1);
-            if (out.status) out.status[i] = (uint8_t)(out.status[i] | fl);
+            fixup_finish<KD, HB>(R, T.u_all_row, T.ctrl_row, rec.data(), w, 0, 1);
+            if (T.status) *T.status = (uint8_t)(*T.status | fl);
         }
     }
     return n_hard;
@@ -251,7 +268,7 @@ extern "C" int64_t stream_host_run(const irlosc_params *params, int64_t B, const
     if (build_stream_plan(P, k, R, kd, hb, plan) != IRLOSC_OK) return -1;
     if (n_chunks) *n_chunks = plan.n_chunks;
     stream::Outputs out{io->u_all, io->ctrl, io->status, io->target_vel};
-    Debug d{dbg_A, dbg_g, dbg_uv, nullptr, dbg_dx, dbg_J};
+    Debug d{dbg_A, dbg_g, dbg_uv, nullptr, dbg_dx, dbg_J, nullptr};
     const Debug *dp = (dbg_A || dbg_uv || dbg_J) ? &d : nullptr;
     if (kd == 3 && hb) return run_stream<3, true>(P, R, plan, out, B, dp);
     if (kd == 3 && !hb) return run_stream<3, false>(P, R, plan, out, B, dp);
@@ -284,24 +301,3 @@ extern "C" int64_t waypoints_host_step(const irlosc_params *params, const irlosc
     return run<6, false>(P, M, R, k, B, nullptr, &Q);
 }
 
-// Warp-cooperative pinv resolution (osc_fixup_coop.cuh) with the 32 lanes emulated phase by phase.
-template <int K>
-static int coop_run(const double *A, const double *g, double *w) {
-    static CoopSmem<K> S;
-    for (int i = 0; i < K; ++i) {
-        for (int j = 0; j < K; ++j) S.A[i][j] = A[i * K + j];
-        S.g[i] = g[i];
-    }
-    CoopHostEx ex;
-    const int how = coop_resolve_pinv<K>(S, ex);
-    for (int i = 0; i < K; ++i) w[i] = S.w[i];
-    return how;
-}
-
-extern "C" int coop_host_resolve(int K, const double *A, const double *g, double *w) {
-    if (K == 6) return coop_run<6>(A, g, w);
-    if (K == 7) return coop_run<7>(A, g, w);
-    if (K == 12) return coop_run<12>(A, g, w);
-    if (K == 13) return coop_run<13>(A, g, w);
-    return -1;
-}

@@ -16,7 +16,8 @@ import pytest
 import fused_host
 from irl_control_b200.dual_ur5 import sample_joint_states
 from irl_control_b200.rigid_model import model_for_layout
-from irl_control_b200.synthetic import build_scenario, oracle_inputs, synth_batch
+from irl_control_b200 import _native
+from irl_control_b200.synthetic import build_scenario, oracle_inputs, scenario_layout, synth_batch
 from oracle import osc_numpy
 
 REL_TOL = 1e-6      # same bar as tests/test_gpu_parity.py (BASELINE.json asks 1e-4)
@@ -76,7 +77,7 @@ def test_fused_step_matches_the_oracle(scenario, B):
     want = np.concatenate([ref["u_all"][:, list(d.actuator_trnids)] for d in layout.devices], axis=1)
     assert _rel(out["ctrl"], want).max() < REL_TOL
     if scenario in ("admit_test", "insertion", "worst_case", "iros2022"):
-        assert out["n_hard"] > 0          # the eigen fix-up path is exercised
+        assert (out["how"] & (fused_host.HOW_CUT1 | fused_host.HOW_CUT2)).any()   # the pinv deflation is exercised
 
 
 def test_velocity_tracking_branch_and_index_error_flag():
@@ -161,37 +162,33 @@ def test_mujoco_binding_view_reduces_to_the_same_model():
         assert np.array_equal(data.ctrl[list(dl.ctrl_idxs)], row[sl])
 
 
-def test_cooperative_pinv_resolution_matches_numpy():
-    """osc_fixup_coop.cuh (experimental fix-up path, lanes emulated on the CPU): whenever it decides, the
-    decision equals numpy's pinv(rcond=1e-5) truncation and the solution agrees; it may only abstain."""
-    rng = np.random.default_rng(4)
-    decided = np.zeros(3, int)
-    for K in (7, 12, 13):
-        for trial in range(120):
-            Q, _ = np.linalg.qr(rng.normal(size=(K, K)))
-            lam = 10.0 ** rng.uniform(-2, 1, size=K)
-            kind = trial % 4
-            if kind == 1:
-                lam[0] = lam.max() * 10.0 ** rng.uniform(-9, -5.5)          # one eigenvalue clearly cut
-            elif kind == 2:
-                lam[0] = lam.max() * 10.0 ** rng.uniform(-5.2, -4.8)        # around the cutoff
-            elif kind == 3:
-                lam[:2] = lam.max() * 10.0 ** rng.uniform(-9, -6, size=2)   # two cut: must abstain
-            A = (Q * lam) @ Q.T
-            A = 0.5 * (A + A.T)
-            g = rng.normal(size=K)
-            how, w = fused_host.coop_resolve(A, g)
-            decided[how] += 1
-            ev = np.linalg.eigvalsh(A)
-            n_cut = int((ev <= 1e-5 * ev[-1]).sum())
-            if how == 0:
-                continue
-            assert (how == 1 and n_cut == 0) or (how == 2 and n_cut == 1), (K, trial, how, n_cut)
-            ref = np.linalg.pinv(A, rcond=1e-5, hermitian=True) @ g
-            assert np.abs(w - ref).max() <= 1e-8 * np.abs(ref).max(), (K, trial, how)
-            if kind == 3:
-                raise AssertionError("two eigenvalues below the cutoff must not be decided")
-    assert decided[1] > 80 and decided[2] > 60                                # it does decide most of the time
+@pytest.mark.parametrize("scenario,B,min_cut1,max_warp", [("gain_test", 2048, 0, 0), ("admit_test", 4096, 30, 2),
+                                                          ("worst_case", 4096, 300, 12)])
+def test_task_space_solve_is_decided_in_the_thread(scenario, B, min_cut1, max_warp):
+    """osc_tail.cuh resolves osc.py:52-55 on the block structure of A in the thread that owns the instance:
+    exact inertia counts decide how many eigenvalues numpy's pinv(rcond=1e-5) cuts, deflation removes them.
+    Against numpy on the same A: every decided instance cuts exactly the eigenvalues numpy cuts, the result
+    matches the oracle, and only a handful are left to the warp-cooperative eigen-solver."""
+    layout = scenario_layout(scenario)
+    st = synth_batch(layout, B, seed=29)
+    state = {k: st[k].numpy() for k in ("M", "J", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat", "max_vel")}
+    if layout.admittance:
+        state["ft_xmat"], state["ft_raw"] = st["ft_xmat"].numpy(), st["ft_raw"].numpy()
+    out = fused_host.run_stream(layout, state)
+    ref = osc_numpy.osc_batch(layout.as_dict(), oracle_inputs(st, layout))
+    assert _rel(out["u_all"], ref["u_all"]).max() < REL_TOL
+    M, J = state["M"], state["J"]
+    A = J @ np.linalg.solve(M, J.transpose(0, 2, 1))
+    ev = np.linalg.eigvalsh(0.5 * (A + A.transpose(0, 2, 1)))
+    small = np.abs(np.linalg.det(A)) < 1e-4
+    n_cut = np.where(small, (ev <= 1e-5 * ev[:, -1:]).sum(1), 0)
+    how = out["how"]
+    decided = how != fused_host.HOW_WARP
+    want = np.select([n_cut == 0, n_cut == 1, n_cut == 2], [fused_host.HOW_INVERSE, fused_host.HOW_CUT1, fused_host.HOW_CUT2], -1)
+    assert np.array_equal(how[decided], want[decided])
+    assert (how == fused_host.HOW_CUT1).sum() >= min_cut1
+    assert (~decided).sum() <= max_warp and out["n_hard"] == (~decided).sum()
+    assert np.array_equal((out["status"] & _native.ST_PINV) != 0, small)
 
 
 @pytest.mark.parametrize("scenario,use_g,nullspace,no_max_vel", [
