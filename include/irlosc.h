@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define IRLOSC_ABI_VERSION 6
+#define IRLOSC_ABI_VERSION 7
 #define IRLOSC_MAX_DEVICES 4   /* target devices per controller (DualUR5: base + 2 arms) */
 #define IRLOSC_MAX_N 32        /* robot DoF, Robot.num_joints_total (robot.py:32); DualUR5: 25 */
 #define IRLOSC_MAX_K 24        /* stacked task rows, sum of ctrlr_dof over targets; DualUR5: <= 13 */
@@ -258,6 +258,49 @@ typedef struct irlosc_waypoints_io {
     double *target_quat;      /* [B][D][4] in: Target() default [1,0,0,0] unless the caller changed it         */
 } irlosc_waypoints_io;
 
+/* ------------------------------------------------------------------------------------------
+ * Batch-interleaved tiles: the native HBM layout of the step.  Instances are grouped in
+ * tiles of 32; inside a tile every scalar of the state is stored for its 32 instances side by side,
+ *     tiles[t][e][l] = entry e of instance 32 t + l,   e < E = irlosc_tile_entries(h),  l < 32,
+ * in the order the elimination consumes them and restricted to the entries the kinematic tree makes non-zero
+ * (the tree contract of has_topology).  What the reference pulls per robot (robot.py:44-72 M, J, dq;
+ * osc.py:191 bias; device.py:93-95,135-170 poses, F/T) is the same information; irlosc_tile_spec lists, for
+ * every entry, where it comes from, and irlosc_pack_tiles converts from the per-variable arrays of irlosc_io.
+ * Instances past B in the last tile are padding (irlosc_pack_tiles repeats the last instance there). */
+#define IRLOSC_TILE 32
+#define IRLOSC_ARR_PAD 0        /* unused slot                                                          */
+#define IRLOSC_ARR_M 1          /* M[i][j], i >= j, j an ancestor of i or i itself     (robot.py:68-72)  */
+#define IRLOSC_ARR_J 2          /* J[task row i][joint j]                             (osc.py:136-138)  */
+#define IRLOSC_ARR_DQ 3         /* dq[i]                                              (robot.py:60-65)  */
+#define IRLOSC_ARR_BIAS 4       /* qfrc_bias[i]; zero when !use_g                     (osc.py:191)      */
+#define IRLOSC_ARR_EE_XYZ 5     /* ee_xyz[target device i][j]                         (device.py:93)    */
+#define IRLOSC_ARR_EE_QUAT 6    /* ee_quat[i][j], w x y z                             (device.py:95)    */
+#define IRLOSC_ARR_T_XYZ 7      /* target_xyz[i][j]                                   (utils.py:17)     */
+#define IRLOSC_ARR_T_QUAT 8     /* target_quat[i][j]                                  (utils.py:23)     */
+#define IRLOSC_ARR_MAX_VEL 9    /* max_vel[i][j]; always present in a tile            (device.py:31)    */
+#define IRLOSC_ARR_FT_XMAT 10   /* ft_xmat[i][j], row-major 3 x 3, admittance only    (device.py:135-143) */
+#define IRLOSC_ARR_FT_RAW 11    /* ft_raw[i][j], admittance only                      (device.py:150-167) */
+
+typedef struct irlosc_tile_entry {
+    int32_t array;            /* IRLOSC_ARR_*                                                         */
+    int32_t i, j;             /* indices as listed above (j = 0 for dq / bias)                        */
+} irlosc_tile_entry;
+
+/* Per-step arrays of the tiled step; DEVICE pointers for irlosc_step_tiles, HOST pointers for
+ * irlosc_step_tiles_host.  Outputs and the fused gather as in irlosc_io. */
+typedef struct irlosc_tiles_io {
+    const double *tiles;      /* [ceil(B / 32)][E][32]                                                 */
+    const double *target_vel; /* [B][D][6] plain array, optional (NULL = all zero, osc.py:172)         */
+    double *u_all;            /* [B][n]      out, optional                                             */
+    double *ctrl;             /* [B][n_ctrl] out                                                       */
+    uint8_t *status;          /* [B]         out, optional                                             */
+    int32_t n_gather;
+    int32_t reserved_;
+    int64_t gather_offset;
+    double *ctrl_gather[IRLOSC_MAX_PEERS];
+    double *ctrl_multicast;
+} irlosc_tiles_io;
+
 typedef struct irlosc_handle irlosc_handle;
 
 /* Thread-local, human-readable description of the last failure on this thread. */
@@ -301,6 +344,24 @@ int32_t irlosc_step_sequence(irlosc_handle *h, int64_t B, const irlosc_fused_io 
 /* One control step of B gain_test-style episodes: waypoint cycling + fused step in one kernel. */
 int32_t irlosc_step_waypoints(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_device,
                               const irlosc_waypoints_io *wio_device, void *cuda_stream);
+
+/* Tile layout of this controller: E = entries per instance (0 when the configuration has no tile layout, i.e. it
+ * is not the DualUR5 tree with two equally masked arm devices [+ the base]); the entry table (returns E, writes at
+ * most `capacity` entries); doubles needed for B instances. */
+int32_t irlosc_tile_entries(const irlosc_handle *h);
+int32_t irlosc_tile_spec(const irlosc_handle *h, irlosc_tile_entry *out, int32_t capacity);
+int64_t irlosc_tiles_doubles(const irlosc_handle *h, int64_t B);
+/* Per-variable arrays (the input part of irlosc_io, any M / J layout) -> tiles.  Device pointers, asynchronous on
+ * `cuda_stream`; the _host form does the same with host pointers on the calling thread (a data-layout helper for
+ * callers that assemble their batch in host memory - no control arithmetic runs on the host). */
+int32_t irlosc_pack_tiles(irlosc_handle *h, int64_t B, const irlosc_io *io_device, double *tiles_device, void *cuda_stream);
+int32_t irlosc_pack_tiles_host(irlosc_handle *h, int64_t B, const irlosc_io *io_host, double *tiles_host);
+/* Replaces: OSC.generate (osc.py:120-210) for B instances stored as tiles in device memory: ONE kernel, the
+ * lane kernel (csrc/osc_lane.cuh).  Asynchronous on `cuda_stream`, never synchronises with the host. */
+int32_t irlosc_step_tiles(irlosc_handle *h, int64_t B, const irlosc_tiles_io *io_device, void *cuda_stream);
+/* Same with HOST buffers (pinned via irlosc_host_alloc): tiles go host -> device in chunks, ctrl / u_all / status
+ * come back, pipelined over internal streams; returns when the outputs are valid. */
+int32_t irlosc_step_tiles_host(irlosc_handle *h, int64_t B, const irlosc_tiles_io *io_host);
 
 /* Replaces: OSC.calc_error (osc.py:101-118), also called by insertion_task.py:173-179.
  * err[B][D][6] (unmasked), device pointers, asynchronous. */

@@ -13,7 +13,7 @@ MAX_DEVICES = 4
 MAX_N = 32
 MAX_K = 24
 MAX_PEERS = 8
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_ACTIONS = 16
 ACT_WP, ACT_GRIP = 0, 1
 
@@ -91,6 +91,25 @@ class Io(C.Structure):
     ]
 
 
+class TileEntry(C.Structure):
+    _fields_ = [("array", C.c_int32), ("i", C.c_int32), ("j", C.c_int32)]
+
+
+class TilesIo(C.Structure):
+    _fields_ = [
+        ("tiles", C.c_void_p), ("target_vel", C.c_void_p),
+        ("u_all", C.c_void_p), ("ctrl", C.c_void_p), ("status", C.c_void_p),
+        ("n_gather", C.c_int32), ("reserved_", C.c_int32), ("gather_offset", C.c_int64),
+        ("ctrl_gather", C.c_void_p * MAX_PEERS),
+        ("ctrl_multicast", C.c_void_p),
+    ]
+
+
+TILE = 32
+(ARR_PAD, ARR_M, ARR_J, ARR_DQ, ARR_BIAS, ARR_EE_XYZ, ARR_EE_QUAT, ARR_T_XYZ, ARR_T_QUAT, ARR_MAX_VEL, ARR_FT_XMAT,
+ ARR_FT_RAW) = range(12)
+
+
 class JointModel(C.Structure):
     _fields_ = [
         ("parent", C.c_int32), ("reserved_", C.c_int32),
@@ -150,6 +169,8 @@ EXPORTS = [
     "irlosc_num_task_rows", "irlosc_num_ctrl", "irlosc_step", "irlosc_step_host",
     "irlosc_calc_error", "irlosc_host_alloc", "irlosc_host_free", "irlosc_set_kernel", "irlosc_set_sm_margin",
     "irlosc_kernel_launches", "irlosc_last_kernel",
+    "irlosc_tile_entries", "irlosc_tile_spec", "irlosc_tiles_doubles", "irlosc_pack_tiles", "irlosc_pack_tiles_host",
+    "irlosc_step_tiles", "irlosc_step_tiles_host",
 ]
 
 _lib: Optional[C.CDLL] = None
@@ -212,6 +233,20 @@ def load() -> C.CDLL:
     lib.irlosc_kernel_launches.argtypes = [C.c_void_p]
     lib.irlosc_last_kernel.restype = C.c_char_p
     lib.irlosc_last_kernel.argtypes = [C.c_void_p]
+    lib.irlosc_tile_entries.restype = C.c_int32
+    lib.irlosc_tile_entries.argtypes = [C.c_void_p]
+    lib.irlosc_tile_spec.restype = C.c_int32
+    lib.irlosc_tile_spec.argtypes = [C.c_void_p, C.POINTER(TileEntry), C.c_int32]
+    lib.irlosc_tiles_doubles.restype = C.c_int64
+    lib.irlosc_tiles_doubles.argtypes = [C.c_void_p, C.c_int64]
+    lib.irlosc_pack_tiles.restype = C.c_int32
+    lib.irlosc_pack_tiles.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Io), C.c_void_p, C.c_void_p]
+    lib.irlosc_pack_tiles_host.restype = C.c_int32
+    lib.irlosc_pack_tiles_host.argtypes = [C.c_void_p, C.c_int64, C.POINTER(Io), C.c_void_p]
+    lib.irlosc_step_tiles.restype = C.c_int32
+    lib.irlosc_step_tiles.argtypes = [C.c_void_p, C.c_int64, C.POINTER(TilesIo), C.c_void_p]
+    lib.irlosc_step_tiles_host.restype = C.c_int32
+    lib.irlosc_step_tiles_host.argtypes = [C.c_void_p, C.c_int64, C.POINTER(TilesIo)]
     if lib.irlosc_abi_version() != ABI_VERSION:
         raise NativeLibraryError("libirlosc ABI %d != binding %d" % (lib.irlosc_abi_version(), ABI_VERSION))
     _lib = lib

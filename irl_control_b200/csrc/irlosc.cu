@@ -67,6 +67,7 @@ extern "C" int32_t irlosc_destroy(irlosc_handle *h) {
         if (h->stage[s].stream) cudaStreamDestroy(h->stage[s].stream);
         if (h->fstage[s].stream) cudaStreamDestroy(h->fstage[s].stream);
     }
+    lane_destroy(h);
     delete h;
     return IRLOSC_OK;
 }
@@ -89,10 +90,11 @@ extern "C" int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which) {
 }
 
 // ------------------------------------------------------------------ step (device pointers)
-static int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k) {
+int32_t irlosc::resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k, bool need_outputs) {
     const KParams &P = h->kp;
     if (!io) return fail(IRLOSC_ERR_INVALID, "io is null");
-    if (!io->M || !io->J || !io->dq || !io->ee_xyz || !io->ee_quat || !io->target_xyz || !io->target_quat || !io->ctrl)
+    if (!io->M || !io->J || !io->dq || !io->ee_xyz || !io->ee_quat || !io->target_xyz || !io->target_quat ||
+        (need_outputs && !io->ctrl))
         return fail(IRLOSC_ERR_INVALID, "a required array (M, J, dq, ee_xyz, ee_quat, target_xyz, target_quat, ctrl) is null");
     if (P.use_g && !io->bias) return fail(IRLOSC_ERR_INVALID, "use_g is set but bias is null");
     if (P.admittance && (!io->ft_xmat || !io->ft_raw))
@@ -183,7 +185,7 @@ extern "C" int32_t irlosc_step(irlosc_handle *h, int64_t B, const irlosc_io *io,
     if (B < 0) return fail(IRLOSC_ERR_INVALID, "B=%lld is negative", (long long)B);
     if (B == 0) return IRLOSC_OK;   // empty batch: nothing to read or write (array pointers may be null)
     KIo k;
-    int32_t rc = resolve_io(h, io, k);
+    int32_t rc = resolve_io(h, io, k, true);
     if (rc != IRLOSC_OK) return rc;
     return launch_step(h, B, k, (cudaStream_t)cuda_stream);
 }
@@ -244,7 +246,7 @@ extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io
     if (B < 0) return fail(IRLOSC_ERR_INVALID, "B is negative");
     if (B == 0) return IRLOSC_OK;
     KIo hk;   // host-pointer view with resolved strides
-    int32_t rc = resolve_io(h, io, hk);
+    int32_t rc = resolve_io(h, io, hk, true);
     if (rc != IRLOSC_OK) return rc;
     if (B == 0) return IRLOSC_OK;
     if (hk.n_gather != 0 || hk.ctrl_mc) return fail(IRLOSC_ERR_INVALID, "the fused gather is only available with irlosc_step (device pointers)");

@@ -33,6 +33,10 @@ namespace irlosc {
 bool stream_supported(const irlosc_handle *h, const KIo &io);
 bool stream_preferred(const irlosc_handle *h);
 int32_t stream_launch(irlosc_handle *h, int64_t B, const KIo &io, cudaStream_t st);
+// tiled step (irlosc_lane.cu, osc_lane.cuh)
+void lane_destroy(irlosc_handle *h);
+// resolves the input part of an irlosc_io (irlosc.cu)
+int32_t resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k, bool need_outputs);
 }  // namespace irlosc
 
 #define CUDA_TRY(expr)                                                                        \
@@ -61,4 +65,5 @@ struct irlosc_handle {
     int fused_kd = 0;
     bool fused_base = false;
     irlosc::Staging fstage[irlosc::kPipeDepth];
+    void *lane_ctx = nullptr;     // tile layout + host pipeline of the tiled step (irlosc_lane.cu), created on first use
 };

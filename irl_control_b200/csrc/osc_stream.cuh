@@ -204,10 +204,10 @@ IRLOSC_HD bool consume_rows(const RD &rd, const KParams &P, unsigned vel_zero, d
             const double v = rd(cr * 7 + i);
             jr[cr][i] = v;
             dx = fma(v, S.dqC[i], dx);
-            if (i > 0) jarm[i - 1][cr] = v;
+            if (jarm != nullptr && i > 0) jarm[i - 1][cr] = v;
         }
         dxr[cr] = dx;
-        jst[cr] = jr[cr][0];
+        if (jst != nullptr) jst[cr] = jr[cr][0];
     }
 #pragma unroll
     for (int i = 1; i < 7; ++i) {
@@ -341,6 +341,35 @@ struct Gather {       // fused result gather, same contract as KIo
     double *ctrl_mc;
 };
 
+// Packed ctrl rows of a 32-instance tile are contiguous in every destination: local array, peer-mapped gathered
+// arrays or the NVSwitch multicast mapping (16-byte vectors when everything is aligned).
+__device__ __forceinline__ void write_ctrl_tile(const double *ctile, double *ctrl, const Gather &G, int n_ctrl, int64_t tile,
+                                                int64_t B, int lane) {
+    const int64_t row0 = tile * 32 * (int64_t)n_ctrl;
+    const int n_valid = (int)((B - tile * 32) < 32 ? (B - tile * 32) : 32);
+    if (n_valid == 32 && G.ctrl_vec) {
+        const double2 *src = reinterpret_cast<const double2 *>(ctile);
+        double2 *dst = reinterpret_cast<double2 *>(ctrl + row0);
+        for (int e = lane; e < 16 * n_ctrl; e += 32) {
+            const double2 v = src[e];
+            dst[e] = v;
+            if (G.ctrl_mc)
+                multimem_st(reinterpret_cast<double2 *>(G.ctrl_mc + G.gather_offset * n_ctrl + row0) + e, v);
+            else
+                for (int gi = 0; gi < G.n_gather; ++gi)
+                    reinterpret_cast<double2 *>(G.ctrl_gather[gi] + G.gather_offset * n_ctrl + row0)[e] = v;
+        }
+    } else {
+        for (int e = lane; e < n_valid * n_ctrl; e += 32) {
+            const double v = ctile[e];
+            ctrl[row0 + e] = v;
+            if (G.ctrl_mc) multimem_st(G.ctrl_mc + G.gather_offset * n_ctrl + row0 + e, v);
+            else
+                for (int gi = 0; gi < G.n_gather; ++gi) G.ctrl_gather[gi][G.gather_offset * n_ctrl + row0 + e] = v;
+        }
+    }
+}
+
 template <int KD, bool HAS_BASE, int NT>
 __global__ void __launch_bounds__(NT, 1)
 osc_step_stream(const __grid_constant__ KParams P, const __grid_constant__ Plan plan_in, const __grid_constant__ Outputs out,
@@ -440,30 +469,7 @@ osc_step_stream(const __grid_constant__ KParams P, const __grid_constant__ Plan 
         const bool hard = stream_instance<KD, HAS_BASE>(P, R, plan, o, inst_c, group, ctile + lane * P.n_ctrl, T, nullptr);
         fused::state_warp_finish<KD, HAS_BASE>(wfix, R, T, hard && valid, lane);
         __syncwarp();
-        // ---- packed ctrl rows of the tile are contiguous in every destination
-        const int64_t row0 = tile * 32 * (int64_t)P.n_ctrl;
-        const int n_valid = (int)((B - tile * 32) < 32 ? (B - tile * 32) : 32);
-        if (n_valid == 32 && G.ctrl_vec) {
-            const double2 *src = reinterpret_cast<const double2 *>(ctile);
-            double2 *dst = reinterpret_cast<double2 *>(out.ctrl + row0);
-            for (int e = lane; e < 16 * P.n_ctrl; e += 32) {
-                const double2 v = src[e];
-                dst[e] = v;
-                if (G.ctrl_mc)
-                    multimem_st(reinterpret_cast<double2 *>(G.ctrl_mc + G.gather_offset * P.n_ctrl + row0) + e, v);
-                else
-                    for (int gi = 0; gi < G.n_gather; ++gi)
-                        reinterpret_cast<double2 *>(G.ctrl_gather[gi] + G.gather_offset * P.n_ctrl + row0)[e] = v;
-            }
-        } else {
-            for (int e = lane; e < n_valid * P.n_ctrl; e += 32) {
-                const double v = ctile[e];
-                out.ctrl[row0 + e] = v;
-                if (G.ctrl_mc) multimem_st(G.ctrl_mc + G.gather_offset * P.n_ctrl + row0 + e, v);
-                else
-                    for (int gi = 0; gi < G.n_gather; ++gi) G.ctrl_gather[gi][G.gather_offset * P.n_ctrl + row0 + e] = v;
-            }
-        }
+        write_ctrl_tile(ctile, out.ctrl, G, P.n_ctrl, tile, B, lane);
         __syncwarp();
     }
     cp_async_wait<0>();

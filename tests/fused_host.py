@@ -19,7 +19,7 @@ _lib = None
 def build():
     deps = [SRC, os.path.join(os.path.dirname(HERE), "include", "irlosc.h")] + [
         os.path.join(CSRC, f) for f in ("osc_fused.cuh", "osc_fused_types.h", "irlosc_device.cuh", "osc_tail.cuh",
-                                        "osc_stream.cuh", "osc_sequence.cuh", "irlosc_build.h",
+                                        "osc_stream.cuh", "osc_lane.cuh", "osc_eigen.cuh", "osc_sequence.cuh", "irlosc_build.h",
                                         "irlosc_internal.h")]
     if os.path.isfile(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in deps):
         return LIB
@@ -175,6 +175,59 @@ def waypoints_step(layout, model, inp, wp_state, threshold=0.1):
     rc = lib.waypoints_host_step(C.byref(params), C.byref(model), B, C.byref(io), C.byref(wio))
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
+    return out
+
+
+class TileEntry(C.Structure):
+    _fields_ = [("array", C.c_int32), ("i", C.c_int32), ("j", C.c_int32)]
+
+
+def lane_spec(layout):
+    """Entry table of the tile layout (csrc/osc_lane.cuh build_tile_spec): (entries [(array, i, j)], gbase)."""
+    lib = load()
+    lib.lane_host_spec.restype = C.c_int32
+    lib.lane_host_spec.argtypes = [C.POINTER(_native.Params), C.POINTER(TileEntry), C.c_int32, C.POINTER(C.c_int32)]
+    params = layout.to_c_params()
+    buf = (TileEntry * 512)()
+    gbase = (C.c_int32 * 12)()
+    E = lib.lane_host_spec(C.byref(params), buf, 512, gbase)
+    return [(buf[e].array, buf[e].i, buf[e].j) for e in range(max(E, 0))], list(gbase)
+
+
+def run_lane(layout, state):
+    """The lane step (osc_lane.cuh) on the CPU: arrays are packed into tiles with the product's pack table, then the
+    kernel's per-instance function reads them.  state: numpy arrays in `BatchedOSC.step` field names."""
+    lib = load()
+    lib.lane_host_run.restype = C.c_int64
+    lib.lane_host_run.argtypes = [C.POINTER(_native.Params), C.c_int64, C.POINTER(_native.Io), C.c_void_p]
+    keep = {k_: np.ascontiguousarray(v, dtype=np.float64) for k_, v in state.items()}
+    B = int(keep["dq"].shape[0])
+    out = {"ctrl": np.zeros((B, layout.n_ctrl)), "u_all": np.zeros((B, layout.n)), "status": np.zeros(B, dtype=np.uint8)}
+    io = _native.Io()
+    if "qM" in keep:
+        keep["M"] = keep.pop("qM")
+        io.m_layout = _native.M_QM
+        io.m_stride = int(keep["M"].shape[1])
+    else:
+        io.m_layout = _native.M_DENSE if keep["M"].ndim == 3 else _native.M_PACKED
+    io.j_layout = _native.J_FULL6 if keep["J"].ndim == 4 else _native.J_ROWS
+    for name in ("M", "J", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat", "target_vel", "max_vel",
+                 "ft_xmat", "ft_raw"):
+        setattr(io, name, keep[name].ctypes.data if name in keep else None)
+    for name in out:
+        setattr(io, name, out[name].ctypes.data)
+    E = len(lane_spec(layout)[0])
+    tiles = np.full(((B + 31) // 32, E, 32), np.nan)
+    params = layout.to_c_params()
+    how = np.zeros(B, dtype=np.int32)
+    lib.host_set_how(how.ctypes.data)
+    try:
+        rc = lib.lane_host_run(C.byref(params), B, C.byref(io), tiles.ctypes.data)
+    finally:
+        lib.host_set_how(None)
+    if rc < 0:
+        raise RuntimeError(lib.fused_host_error().decode())
+    out["n_hard"], out["how"], out["tiles"] = int(rc), how, tiles
     return out
 
 

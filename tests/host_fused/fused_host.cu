@@ -301,3 +301,101 @@ extern "C" int64_t waypoints_host_step(const irlosc_params *params, const irlosc
     return run<6, false>(P, M, R, k, B, nullptr, &Q);
 }
 
+
+// ------------------------------------------------------------------ lane step (state in batch-interleaved tiles)
+// Packs the caller's arrays into tiles with the product's own pack table (osc_lane.cuh: build_tile_spec,
+// build_pack_table, pack_fetch - the functions irlosc_pack_tiles[_host] run) and runs the lane kernel's
+// per-instance function on them.
+#include "../../irl_control_b200/csrc/osc_lane.cuh"
+namespace {
+struct LdHost {
+    double operator()(const double *p) const { return *p; }
+};
+struct TileGroups {
+    const double *tl;          // entry 0 of this lane
+    const int32_t *gbase;
+    struct Reader {
+        const double *p;
+        double operator()(int e) const { return p[(size_t)e * lane::kTile]; }
+    };
+    Reader operator()(int g) const { return Reader{tl + (size_t)gbase[g] * lane::kTile}; }
+};
+
+template <int KD, bool HB>
+int64_t run_lane(const KParams &P, const FRoles &R, const lane::TileSpec &S, const double *tiles, const irlosc_io *io, int64_t B) {
+    using RC = Rec<KD, HB>;
+    constexpr int K = RC::K;
+    std::vector<double> rec(RC::SIZE);
+    int64_t n_hard = 0;
+    for (int64_t i = 0; i < B; ++i) {
+        const double *tl = tiles + (i / lane::kTile) * (int64_t)S.n_entries * lane::kTile + (i % lane::kTile);
+        TileGroups groups{tl, S.gbase};
+        const lane::JTile<KD, HB, LdHost> ja{tl, {S.gbase[4], S.gbase[9]}, S.gbase[0], LdHost{}};
+        lane::LaneState<KD, HB> T;
+        T.u_all_row = io->u_all ? io->u_all + i * kN : nullptr;
+        T.ctrl_row = io->ctrl + i * P.n_ctrl;
+        T.status = io->status ? io->status + i : nullptr;
+        Debug dh{};
+        if (g_how) dh.how = g_how + i;
+        const bool hard = lane::lane_instance<KD, HB>(P, R, io->target_vel ? io->target_vel + i * P.D * 6 : nullptr, groups, ja, T,
+                                                      g_how ? &dh : nullptr);
+        if (hard) {
+            ++n_hard;
+            double w[K];
+            tail_record<KD, HB>(R, T.akA, T.j0, T.g, ja, T.base_arm, T.base_st, T.inv0, T.force_pinv, rec.data());
+            const int fl = host_eigen_solve<K>(&rec[RC::A], &rec[RC::G], rec[RC::ABAD] == 0.0, w);
+            fixup_finish<KD, HB>(R, T.u_all_row, T.ctrl_row, rec.data(), w, 0, 1);
+            if (T.status) *T.status = (uint8_t)(*T.status | fl);
+        }
+    }
+    return n_hard;
+}
+}  // namespace
+
+// Entry table of the tile layout; returns E (0: no tile layout for this controller).
+extern "C" int32_t lane_host_spec(const irlosc_params *params, irlosc_tile_entry *out, int32_t capacity, int32_t *gbase_out) {
+    KParams P;
+    if (build_kparams(*params, P) != IRLOSC_OK) return -1;
+    FRoles R;
+    int kd = 0;
+    bool hb = false;
+    if (!fused_roles(P, R, kd, hb)) return 0;
+    static lane::TileSpec S;
+    if (!lane::build_tile_spec(P, R, kd, hb, S)) return 0;
+    for (int e = 0; out && e < S.n_entries && e < capacity; ++e) out[e] = S.e[e];
+    for (int g = 0; gbase_out && g <= lane::kGroups; ++g) gbase_out[g] = S.gbase[g];
+    return S.n_entries;
+}
+
+// arrays -> tiles (tiles_out: [ceil(B / 32)][E][32]) -> lane step.  Returns the number of instances finished by the
+// eigen-solver, or -1.
+extern "C" int64_t lane_host_run(const irlosc_params *params, int64_t B, const irlosc_io *io, double *tiles_out) {
+    KParams P;
+    if (build_kparams(*params, P) != IRLOSC_OK) return -1;
+    FRoles R;
+    int kd = 0;
+    bool hb = false;
+    if (!fused_roles(P, R, kd, hb)) { irlosc::fail(1, "not the DualUR5 topology"); return -1; }
+    static lane::TileSpec S;
+    if (!lane::build_tile_spec(P, R, kd, hb, S)) { irlosc::fail(1, "no tile layout"); return -1; }
+    KIo k;
+    memset(&k, 0, sizeof k);
+    if (resolve_m_layout(P, *io, k) != IRLOSC_OK) return -1;
+    k.J = io->J; k.j_layout = io->j_layout; k.ldj = io->ldj ? io->ldj : P.n;
+    k.j_stride = io->j_stride ? io->j_stride : (io->j_layout == IRLOSC_J_ROWS ? (int64_t)k.ldj * P.k : (int64_t)k.ldj * 6 * P.D);
+    k.dq = io->dq; k.bias = io->bias; k.ee_xyz = io->ee_xyz; k.ee_quat = io->ee_quat;
+    k.target_xyz = io->target_xyz; k.target_quat = io->target_quat; k.target_vel = io->target_vel;
+    k.max_vel = io->max_vel; k.ft_xmat = io->ft_xmat; k.ft_raw = io->ft_raw;
+    static lane::PackTable T;
+    if (lane::build_pack_table(P, k, S, T) != IRLOSC_OK) return -1;
+    const int64_t n_tiles = (B + lane::kTile - 1) / lane::kTile;
+    for (int64_t t = 0; t < n_tiles; ++t)
+        for (int l = 0; l < lane::kTile; ++l) {
+            const int64_t inst = std::min<int64_t>(t * lane::kTile + l, B - 1);
+            for (int e = 0; e < S.n_entries; ++e) tiles_out[(t * S.n_entries + e) * lane::kTile + l] = lane::pack_fetch(T, e, inst);
+        }
+    if (kd == 3 && hb) return run_lane<3, true>(P, R, S, tiles_out, io, B);
+    if (kd == 3 && !hb) return run_lane<3, false>(P, R, S, tiles_out, io, B);
+    if (kd == 6 && hb) return run_lane<6, true>(P, R, S, tiles_out, io, B);
+    return run_lane<6, false>(P, R, S, tiles_out, io, B);
+}
