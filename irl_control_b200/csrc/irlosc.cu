@@ -121,28 +121,30 @@ int32_t irlosc::resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k, 
     return IRLOSC_OK;
 }
 
-// Kernel selection (irlosc_set_kernel): 0 auto, 1 generic, 2 + v tiled-table variant v, 9 streaming.
+// Kernel selection for per-variable arrays (irlosc_set_kernel): 0 auto, 1 generic, 2 + v tree-table variant v,
+// 9 streaming.  (State held as batch-interleaved tiles goes to the lane kernel, irlosc_step_tiles.)
 //   auto, DualUR5 topology declared: 3-row arm devices (gain_test) -> tree-sparse 4-lane kernel when
-//   the layout is one it stages (tight packed / dense M, row-stacked J), 6-row arm devices -> streaming
+//   the layout is one it stages (tight packed / dense / qM, row-stacked J), 6-row arm devices -> streaming
 //   kernel; anything the tree kernel does not stage (strided views, full-6 J) -> streaming kernel;
-//   check_topology -> the kernels that read every entry.  No topology: dense kernels / generic.
+//   check_topology -> the tree kernel (it reads every entry) or generic.  No topology: generic.
 constexpr int kKernelStream = 9;
 
 static int32_t launch_step(irlosc_handle *h, int64_t B, const KIo &k, cudaStream_t st) {
     if (B == 0) return IRLOSC_OK;
     const bool stream_ok = stream_supported(h, k);
     if (k.m_layout == IRLOSC_M_QM) {
-        // MuJoCo's sparse qM: addressed by the streaming kernel's copy plan (auto / 9) and, on explicit request only
-        // (selector 2 + v, tight stride), by the tree-sparse kernel's qM instantiations
-        if (h->kernel_choice >= 2 && h->kernel_choice != kKernelStream) {
-            const int v = h->kernel_choice - 2;
-            if (!tiled_supported(h->kp, k, v))
-                return fail(IRLOSC_ERR_INVALID, "no tree-sparse kernel variant %d for IRLOSC_M_QM with this controller / stride", v);
+        // MuJoCo's sparse qM: the tree-sparse kernel's qM instantiations when it stages this layout (tight stride,
+        // row-stacked J) and the arm devices have 3 rows; otherwise the streaming kernel's copy plan
+        const int v = (h->kernel_choice >= 2 && h->kernel_choice != kKernelStream) ? h->kernel_choice - 2 : 0;
+        const bool tree_ok = h->kernel_choice != 1 && h->kernel_choice != kKernelStream && tiled_supported(h->kp, k, v);
+        if (tree_ok && (h->kernel_choice >= 2 || !stream_preferred(h))) {
             cudaError_t e = tiled_launch(h->kp, k, B, h->sm_count - h->sm_margin, st, &h->last_kernel, v);
             if (e != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "tiled kernel launch: %s", cudaGetErrorString(e));
             h->launches += 1;
             return IRLOSC_OK;
         }
+        if (h->kernel_choice >= 2 && h->kernel_choice != kKernelStream)
+            return fail(IRLOSC_ERR_INVALID, "no tree-sparse kernel variant %d for IRLOSC_M_QM with this controller / stride", v);
         if (!stream_ok || h->kernel_choice == 1)
             return fail(IRLOSC_ERR_INVALID, "IRLOSC_M_QM needs the declared DualUR5 topology (check_topology off) and "
                                             "kernel selector 0, 9 or 2 + v");

@@ -53,12 +53,6 @@ const FusedEntry *fused_table(int *count) {
         entry<6, false, 224, true>(0, "osc_step_fused<kd6,t224,smem>"),
         entry<6, true, 224, true>(0, "osc_step_fused<kd6,base,t224,smem>"),
         entry<3, false, 224, true>(0, "osc_step_fused<kd3,t224,smem>"),
-        entry<3, true, 256, false>(1, "osc_step_fused<kd3,base,t256,local>"),
-        entry<6, false, 256, false>(1, "osc_step_fused<kd6,t256,local>"),
-        entry<3, true, 384, false>(2, "osc_step_fused<kd3,base,t384,local>"),
-        entry<3, true, 192, true>(3, "osc_step_fused<kd3,base,t192,smem>"),
-        entry<3, true, 128, false>(4, "osc_step_fused<kd3,base,t128,local>"),
-        entry<3, true, 224, false>(6, "osc_step_fused<kd3,base,t224,local>"),
     };
     *count = (int)(sizeof t / sizeof t[0]);
     return t;

@@ -1,14 +1,9 @@
-// Kernel table and dispatch for the specialised DualUR5 OSC kernels.
-//
-//   kind 0  dense register-tiled kernels (osc_tiled.cuh: column/scratch, osc_rows.cuh: row/shuffle)
-//   kind 1  kinematic-tree-sparse kernel (osc_tree.cuh) - needs irlosc_params.has_topology and the
-//           DualUR5 tree; default whenever eligible
-// variant 0 of a shape is what irlosc_step dispatches to; the others are kept for A/B
-// measurements (irlosc_set_kernel(h, 2 + variant)).
+// Kernel table and dispatch of the record-staging DualUR5 kernel (osc_tree.cuh: kinematic-tree-sparse, 4 lanes per
+// instance, TMA-staged records) - needs irlosc_params.has_topology and the DualUR5 tree.  Without a topology the
+// generic kernel (osc_generic.cuh) is the dense fallback.  Variant 0 of a shape is what irlosc_step dispatches to;
+// the others are kept for A/B measurements (irlosc_set_kernel(h, 2 + variant)).
 #pragma once
 #include <cstdlib>
-#include "osc_tiled.cuh"
-#include "osc_rows.cuh"
 #include "osc_tree.cuh"
 
 namespace irlosc {
@@ -28,20 +23,6 @@ struct TiledEntry {
     int slot_fixed, priv; // tree only: bytes of the fixed slot part / per-warp scratch
     bool qm = false;      // tree only: M arrives as MuJoCo's sparse qM (IRLOSC_M_QM, tight stride 155)
 };
-
-template <int N, int K, int D, int G, bool PACKED, int MINB>
-inline TiledEntry tiled_entry(int variant, const char *name) {
-    return TiledEntry{0, N, K, D, PACKED, variant, MINB,
-                      (const void *)tiled::osc_step_tiled<N, K, D, G, PACKED, MINB>,
-                      sizeof(tiled::WarpSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name, 0, false, 0, 0, 0, 0};
-}
-
-template <int N, int K, int D, int G, bool PACKED, int MINB>
-inline TiledEntry rows_entry(int variant, const char *name) {
-    return TiledEntry{0, N, K, D, PACKED, variant, MINB,
-                      (const void *)rows::osc_step_rows<N, K, D, G, PACKED, MINB>,
-                      sizeof(rows::RowSmem<N, K, D, G, PACKED>) * tiled::kWarpsPerCta, name, 0, false, 0, 0, 0, 0};
-}
 
 constexpr size_t kTreeSmemLimit = 227 * 1024;
 constexpr int kTreeHeader = 64;
@@ -67,25 +48,12 @@ inline const TiledEntry *tiled_table(int *count) {
         tree_entry<6, false, false, 3, 2, 1>(0, "osc_step_tree<kd6,dense,w3,s2,g1>"),
         tree_entry<6, true, true, 4, 2, 1>(0, "osc_step_tree<kd6,base,packed,w4,s2,g1>"),
         tree_entry<6, true, false, 3, 2, 1>(0, "osc_step_tree<kd6,base,dense,w3,s2,g1>"),
-        tree_entry<3, true, true, 6, 3, 3>(3, "osc_step_tree<kd3,base,packed,w6,s3,g3>"),
-        tree_entry<3, true, true, 4, 4, 1>(4, "osc_step_tree<kd3,base,packed,w4,s4,g1>"),
-        // ---- tree-sparse on MuJoCo's sparse qM (IRLOSC_M_QM; explicit kernel selection only, not yet run on a GPU):
-        //      a slot is 27 KB instead of 38 KB, so a fourth slot and an eighth warp fit
+        // ---- tree-sparse on MuJoCo's sparse qM (IRLOSC_M_QM): a slot is 27 KB instead of 38 KB, so a fourth slot and
+        //      an eighth warp fit (round-1 driver run: 0.112 ms vs 0.143 ms packed at B = 65 536)
         tree_entry<3, true, true, 8, 4, 1, true>(0, "osc_step_tree<kd3,base,qM,w8,s4,g1>"),
         tree_entry<3, true, true, 7, 3, 1, true>(0, "osc_step_tree<kd3,base,qM,w7,s3,g1>"),
-        tree_entry<3, true, true, 7, 4, 1, true>(3, "osc_step_tree<kd3,base,qM,w7,s4,g1>"),
-        tree_entry<3, true, true, 8, 3, 1, true>(4, "osc_step_tree<kd3,base,qM,w8,s3,g1>"),
         tree_entry<6, false, true, 4, 2, 1, true>(0, "osc_step_tree<kd6,qM,w4,s2,g1>"),
         tree_entry<6, true, true, 4, 2, 1, true>(0, "osc_step_tree<kd6,base,qM,w4,s2,g1>"),
-        // ---- dense: default without topology (variant 1 when a topology is declared), all DualUR5 shapes;
-        //      variant 2 keeps the column/scratch kernel of the headline shape for A/B runs
-        rows_entry<25, 7, 3, 8, true, 2>(1, "osc_step_rows<n25,k7,D3,G8,packed>"),
-        rows_entry<25, 7, 3, 8, false, 2>(1, "osc_step_rows<n25,k7,D3,G8,dense>"),
-        tiled_entry<25, 7, 3, 8, true, 2>(2, "osc_step_tiled<n25,k7,D3,G8,packed>"),
-        tiled_entry<25, 12, 2, 16, true, 2>(1, "osc_step_tiled<n25,k12,D2,G16,packed>"),
-        tiled_entry<25, 12, 2, 16, false, 2>(1, "osc_step_tiled<n25,k12,D2,G16,dense>"),
-        tiled_entry<25, 13, 3, 16, true, 2>(1, "osc_step_tiled<n25,k13,D3,G16,packed>"),
-        tiled_entry<25, 13, 3, 16, false, 2>(1, "osc_step_tiled<n25,k13,D3,G16,dense>"),
     };
     *count = (int)(sizeof(table) / sizeof(table[0]));
     return table;
@@ -145,7 +113,8 @@ inline const TiledEntry *tiled_find(const KParams &P, const KIo &io, int variant
     bool has_base = false;
     const bool tree_ok = tree_roles(P, R, kd, has_base);
     if (roles_out) *roles_out = R;
-    const int want = tree_ok ? variant : variant + 1;     // dense variants are numbered from 1 in the table
+    if (!tree_ok) return nullptr;
+    const int want = variant;
     int cnt = 0;
     const TiledEntry *t = tiled_table(&cnt);
     for (int i = 0; i < cnt; ++i) {
@@ -192,8 +161,7 @@ inline cudaError_t tiled_launch(const KParams &P, const KIo &io, int64_t B, int 
         void *args[] = {(void *)&P, (void *)&io, (void *)&B, (void *)&R};
         return cudaLaunchKernel(e->fn, dim3(grid), dim3(e->warps * 32), args, smem, st);
     }
-    void *args[] = {(void *)&P, (void *)&io, (void *)&B};
-    return cudaLaunchKernel(e->fn, dim3(grid), dim3(tiled::kWarpsPerCta * 32), args, e->smem_per_cta, st);
+    return cudaErrorNotSupported;
 }
 
 }  // namespace irlosc

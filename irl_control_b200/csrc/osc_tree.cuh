@@ -42,7 +42,7 @@
 //
 // Reference restated: ir-lab/irl_control osc.py:41-68, 150-152, 156-181, 184-210.
 #pragma once
-#include "osc_rows.cuh"
+#include "osc_tma.cuh"
 
 namespace irlosc {
 namespace tree {

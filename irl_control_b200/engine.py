@@ -3,7 +3,9 @@
 Evaluates the reference's `OSC.generate` control law (osc.py:120-210) for B
 independent robot instances per call:
 
-    step(...)       state already in GPU memory (torch CUDA tensors, float64);
+    step_tiles(...) state in GPU memory in the native batch-interleaved tile layout
+                    (`pack_tiles` converts from per-variable tensors): the lane kernel
+    step(...)       state already in GPU memory as per-variable tensors (torch CUDA, float64);
                     asynchronous on the current torch stream, returns tensors
     step_host(...)  state in host memory (numpy arrays); host->device copies,
                     kernel and device->host copies are pipelined in chunks
@@ -246,8 +248,139 @@ class BatchedOSC:
             _native.check(self.lib.irlosc_step_host(self._handle, B, C.byref(io)))
         return out
 
+    # ------------------------------------------------------------------ batch-interleaved tiles (native layout)
+    @property
+    def tile_entries(self) -> int:
+        """E: doubles per instance in the tile layout (0: this controller has none)."""
+        return int(self.lib.irlosc_tile_entries(self._handle))
+
+    def tile_spec(self):
+        """[(array, i, j)] for every tile entry (`irlosc_tile_spec`, IRLOSC_ARR_* ids in `_native`)."""
+        E = self.tile_entries
+        buf = (_native.TileEntry * max(E, 1))()
+        self.lib.irlosc_tile_spec(self._handle, buf, E)
+        return [(buf[e].array, buf[e].i, buf[e].j) for e in range(E)]
+
+    def tiles_shape(self, B: int) -> tuple:
+        return ((B + _native.TILE - 1) // _native.TILE, self.tile_entries, _native.TILE)
+
+    def _io_inputs(self, state, B, on_device):
+        """irlosc_io with the input pointers of `state` (same checks as step / step_host)."""
+        import torch
+        state = self._accept_qM(state)
+        M = state["M"]
+        m_layout, j_layout = self._infer_layouts(state)
+        shapes = self._shapes(B, m_layout, j_layout)
+        if m_layout == _native.M_QM:
+            shapes["M"] = tuple(M.shape)
+
+        def ok_dev(name, t):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and t.device == M.device):
+                raise ValueError("state['%s'] must be a contiguous float64 CUDA tensor on %s" % (name, M.device))
+
+        def ok_host(name, a):
+            if not (isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]):
+                raise ValueError("state['%s'] must be a C-contiguous float64 numpy array" % name)
+        self._check(state, B, shapes, ok_dev if on_device else ok_host)
+        io = _native.Io()
+        io.m_layout, io.j_layout = m_layout, j_layout
+        if m_layout == _native.M_QM:
+            io.m_stride = int(M.shape[1])
+        for name in _FIELDS:
+            t = state.get(name)
+            setattr(io, name, (t.data_ptr() if on_device else t.ctypes.data) if t is not None else None)
+        return io
+
+    def pack_tiles(self, state: Dict, tiles=None):
+        """Per-variable CUDA tensors (the `step` fields, any M / J layout) -> tiles `[ceil(B/32), E, 32]` on the GPU
+        (`irlosc_pack_tiles`, asynchronous on the current stream)."""
+        import torch
+        B = int(state["dq"].shape[0])
+        dev = state["dq"].device
+        if tiles is None:
+            tiles = torch.empty(self.tiles_shape(B), dtype=torch.float64, device=dev)
+        io = self._io_inputs(state, B, True)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _native.check(self.lib.irlosc_pack_tiles(self._handle, B, C.byref(io), C.c_void_p(tiles.data_ptr()), C.c_void_p(stream)))
+        return tiles
+
+    def pack_tiles_host(self, state: Dict, tiles: Optional[np.ndarray] = None) -> np.ndarray:
+        """Same conversion between host numpy arrays (`irlosc_pack_tiles_host`; a data-layout helper)."""
+        B = int(state["dq"].shape[0])
+        if tiles is None:
+            tiles = np.empty(self.tiles_shape(B), dtype=np.float64)
+        io = self._io_inputs(state, B, False)
+        _native.check(self.lib.irlosc_pack_tiles_host(self._handle, B, C.byref(io), C.c_void_p(tiles.ctypes.data)))
+        return tiles
+
+    def step_tiles(self, tiles, B: int, out: Optional[Dict] = None, want_u_all: bool = False, want_status: bool = True,
+                   target_vel=None, gather: Optional[tuple] = None) -> Dict:
+        """One control step for B instances stored as batch-interleaved tiles on the GPU (`irlosc_step_tiles`): one
+        launch of the lane kernel, asynchronous on the current torch stream.  `gather` as in `step`."""
+        import torch
+        if not (tiles.is_cuda and tiles.dtype == torch.float64 and tiles.is_contiguous()):
+            raise ValueError("tiles must be a contiguous float64 CUDA tensor")
+        if tuple(tiles.shape) != self.tiles_shape(B):
+            raise ValueError("tiles has shape %s, expected %s" % (tuple(tiles.shape), self.tiles_shape(B)))
+        dev = tiles.device
+        out = {} if out is None else out
+        if "ctrl" not in out:
+            out["ctrl"] = torch.empty(B, self.n_ctrl, dtype=torch.float64, device=dev)
+        if want_u_all and "u_all" not in out:
+            out["u_all"] = torch.empty(B, self.n, dtype=torch.float64, device=dev)
+        if want_status and "status" not in out:
+            out["status"] = torch.empty(B, dtype=torch.uint8, device=dev)
+        io = _native.TilesIo()
+        io.tiles = tiles.data_ptr()
+        io.target_vel = target_vel.data_ptr() if target_vel is not None else None
+        io.ctrl = out["ctrl"].data_ptr()
+        io.u_all = out["u_all"].data_ptr() if "u_all" in out else None
+        io.status = out["status"].data_ptr() if "status" in out else None
+        if gather is not None:
+            ptrs, offset = gather[0], gather[1]
+            if len(gather) > 2 and gather[2]:
+                io.ctrl_multicast = int(gather[2])
+            if len(ptrs) > _native.MAX_PEERS:
+                raise ValueError("at most %d peers" % _native.MAX_PEERS)
+            io.n_gather, io.gather_offset = len(ptrs), int(offset)
+            for gi, ptr in enumerate(ptrs):
+                io.ctrl_gather[gi] = int(ptr)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _native.check(self.lib.irlosc_step_tiles(self._handle, B, C.byref(io), C.c_void_p(stream)))
+        return out
+
+    def step_tiles_host(self, tiles: np.ndarray, B: int, out: Optional[Dict] = None, want_u_all: bool = False,
+                        want_status: bool = True, target_vel: Optional[np.ndarray] = None) -> Dict:
+        """`step_tiles` with HOST numpy tiles (pinned memory makes the copies asynchronous); blocks until valid."""
+        if not (isinstance(tiles, np.ndarray) and tiles.dtype == np.float64 and tiles.flags["C_CONTIGUOUS"]):
+            raise ValueError("tiles must be a C-contiguous float64 numpy array")
+        if tuple(tiles.shape) != self.tiles_shape(B):
+            raise ValueError("tiles has shape %s, expected %s" % (tuple(tiles.shape), self.tiles_shape(B)))
+        out = {} if out is None else out
+        if "ctrl" not in out:
+            out["ctrl"] = np.empty((B, self.n_ctrl), dtype=np.float64)
+        if want_u_all and "u_all" not in out:
+            out["u_all"] = np.empty((B, self.n), dtype=np.float64)
+        if want_status and "status" not in out:
+            out["status"] = np.empty((B,), dtype=np.uint8)
+        io = _native.TilesIo()
+        io.tiles = tiles.ctypes.data
+        io.target_vel = target_vel.ctypes.data if target_vel is not None else None
+        io.ctrl = out["ctrl"].ctypes.data
+        io.u_all = out["u_all"].ctypes.data if "u_all" in out else None
+        io.status = out["status"].ctypes.data if "status" in out else None
+        if self._torch_device is not None:
+            import torch
+            with torch.cuda.device(self._torch_device):
+                _native.check(self.lib.irlosc_step_tiles_host(self._handle, B, C.byref(io)))
+        else:
+            _native.check(self.lib.irlosc_step_tiles_host(self._handle, B, C.byref(io)))
+        return out
+
     # ------------------------------------------------------------------ fused state provider
-    _FUSED_FIELDS = ("q", "dq", "target_xyz", "target_quat", "target_vel", "max_vel", "ft_raw")
+    _FUSED_FIELDS = (""q", "dq", "target_xyz", "target_quat", "target_vel", "max_vel", "ft_raw")
 
     def set_model(self, model: "_native.Model"):
         """Attach the rigid-body description (`rigid_model.reduce_model`) the fused step needs."""

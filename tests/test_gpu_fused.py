@@ -14,7 +14,8 @@ REL_TOL = 1e-6
 
 def _torch():
     import torch
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
     return torch
 
 

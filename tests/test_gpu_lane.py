@@ -1,0 +1,103 @@
+"""GPU: the lane kernel (`csrc/osc_lane.cuh`) on batch-interleaved tiles, through the C ABI
+(`irlosc_pack_tiles`, `irlosc_pack_tiles_host`, `irlosc_step_tiles`, `irlosc_step_tiles_host`), against the
+reference's golden outputs, the oracle and the streaming kernel (same per-instance arithmetic: bit-identical)."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_CASES, GOLDEN_CASES_F4, load_golden
+from test_gpu_parity import REL_TOL, _golden_state, _layout_from_dict, _rel_err, _torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("packed_M,full6_J", [(False, False), (True, True)])
+@pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4)
+def test_lane_kernel_matches_reference_golden(case, packed_M, full6_J):
+    torch = _torch()
+    from irl_control_b200 import _native
+    from irl_control_b200.engine import BatchedOSC
+    g, ld = load_golden(case)
+    layout = _layout_from_dict(ld, topology=True, check=False)
+    eng = BatchedOSC(layout, device=0)
+    st = _golden_state(g, layout, torch, packed_M, full6_J)
+    B = int(st["dq"].shape[0])
+    assert eng.tile_entries == len(eng.tile_spec()) > 0
+    tiles = eng.pack_tiles(st)
+    out = eng.step_tiles(tiles, B, want_u_all=True, target_vel=st.get("target_vel"))
+    torch.cuda.synchronize()
+    assert eng.last_kernel.startswith("osc_step_lane"), eng.last_kernel
+    ctrl, u_all, status = (out[k].cpu().numpy() for k in ("ctrl", "u_all", "status"))
+    bad = g["index_error"]
+    assert np.all((status[bad] & _native.ST_DX_RANGE) != 0) and np.all(np.isnan(ctrl[bad])) and np.all(np.isnan(u_all[bad]))
+    ok = ~bad
+    if ok.any():
+        assert np.array_equal((status[ok] & _native.ST_PINV) != 0, g["pinv"][ok])
+        assert not np.any(status[ok] & (_native.ST_M_NOT_PD | _native.ST_DX_RANGE | _native.ST_SPARSITY))
+        e_u = _rel_err(u_all[ok], g["u_all"][ok])
+        e_c = np.abs(ctrl[ok] - g["ctrl"][ok]).max(axis=1) / np.abs(g["u_all"][ok]).max(axis=1)
+        print("%s kernel=%s worst rel err u_all %.2e ctrl %.2e" % (case, eng.last_kernel, e_u.max(), e_c.max()))
+        assert e_u.max() < REL_TOL and e_c.max() < REL_TOL
+        vel = (np.asarray(g["target_vel"]) != 0).all(axis=-1).any(axis=-1)
+        assert np.array_equal((status[ok] & _native.ST_VEL_BRANCH) != 0, vel[ok])
+    # the host packer writes the same tiles; the host-buffer entry point returns the same results
+    host = {k: v.cpu().numpy() for k, v in st.items()}
+    th = eng.pack_tiles_host(host)
+    assert np.array_equal(th, tiles.cpu().numpy())
+    ho = eng.step_tiles_host(th, B, want_u_all=True, target_vel=host.get("target_vel"))
+    assert np.array_equal(ho["ctrl"], ctrl, equal_nan=True) and np.array_equal(ho["status"], status)
+    # the streaming kernel runs the same per-instance code on the same numbers
+    eng.set_kernel(9)
+    ref = eng.step(st, want_u_all=True)
+    assert torch.equal(ref["status"], out["status"])
+    assert np.array_equal(ref["u_all"].cpu().numpy(), u_all, equal_nan=True)
+
+
+@pytest.mark.parametrize("scenario,B", [("gain_test", 4096), ("admit_test", 8192), ("insertion", 16384), ("worst_case", 65536),
+                                        ("iros2022", 4097)])
+def test_lane_kernel_matches_oracle_on_baseline_configs(scenario, B):
+    """BASELINE.json configs 2-4 and the k = 13 worst case at their stated batch sizes (ragged last tile included);
+    the oracle checks a strided subset, every instance is compared with the streaming kernel bit for bit."""
+    torch = _torch()
+    from irl_control_b200 import _native
+    from irl_control_b200.engine import BatchedOSC
+    from irl_control_b200.synthetic import scenario_layout, synth_batch, kernel_inputs, oracle_inputs
+    from oracle import osc_numpy
+    layout = scenario_layout(scenario)
+    st = synth_batch(layout, B, seed=B + 3, device="cuda:0", insertion_schedule=(scenario == "insertion"))
+    eng = BatchedOSC(layout, device=0)
+    kin = kernel_inputs(st, layout, qM=True)
+    tiles = eng.pack_tiles(kin)
+    out = eng.step_tiles(tiles, B, want_u_all=True)
+    torch.cuda.synchronize()
+    u_all, status = out["u_all"].cpu().numpy(), out["status"].cpu().numpy()
+    assert np.isfinite(u_all).all() and not np.any(status & (_native.ST_M_NOT_PD | _native.ST_DX_RANGE))
+    idx = np.arange(0, B, max(1, B // 400))
+    ref = osc_numpy.osc_batch(layout.as_dict(), oracle_inputs(st, layout), idx=idx)
+    err = _rel_err(u_all[idx], ref["u_all"])
+    agree = ((status[idx] & _native.ST_PINV) != 0) == ref["pinv"]
+    near = np.abs(np.abs(ref["det"]) - 1e-4) < 1e-9
+    assert np.all(agree | near), "branch mismatch away from the det threshold"
+    print("%s B=%d kernel=%s: worst rel err %.2e, median %.2e, pinv share %.3f, eigen share %.5f" % (
+        scenario, B, eng.last_kernel, err[agree].max(), np.median(err), ref["pinv"].mean(), ((status & _native.ST_EIGEN) != 0).mean()))
+    assert err[agree].max() < REL_TOL
+    eng.set_kernel(9)
+    s2 = eng.step(kin, want_u_all=True)
+    assert torch.equal(s2["u_all"], out["u_all"]) and torch.equal(s2["status"], out["status"]) and torch.equal(s2["ctrl"], out["ctrl"])
+    cols = [j for dl in layout.devices for j in dl.actuator_trnids]
+    assert torch.equal(out["ctrl"], out["u_all"][:, cols])
+
+
+def test_lane_kernel_small_and_ragged_batches():
+    torch = _torch()
+    from irl_control_b200.engine import BatchedOSC
+    from irl_control_b200.synthetic import scenario_layout, synth_batch, kernel_inputs
+    layout = scenario_layout("gain_test")
+    eng = BatchedOSC(layout, device=0)
+    st = synth_batch(layout, 100, seed=5, device="cuda:0")
+    kin = kernel_inputs(st, layout, packed_M=True)
+    full = eng.step_tiles(eng.pack_tiles(kin), 100)["ctrl"].clone()
+    for B in (1, 31, 32, 33, 64, 99):
+        sub = {k: v[:B].contiguous() for k, v in kin.items()}
+        out = eng.step_tiles(eng.pack_tiles(sub), B)
+        assert out["ctrl"].shape == (B, layout.n_ctrl) and torch.equal(out["ctrl"], full[:B])
+    assert eng.step_tiles(torch.empty(eng.tiles_shape(0), dtype=torch.float64, device="cuda:0"), 0)["ctrl"].shape[0] == 0

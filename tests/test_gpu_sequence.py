@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 
 def test_sequence_on_gpu_matches_reference_loop_and_fused_step():
     import torch
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
     from irl_control_b200.engine import BatchedOSC
     from irl_control_b200.sequence import ActionSequence, default_ee_quat
     from irl_control_b200.synthetic import scenario_model

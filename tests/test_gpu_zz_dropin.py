@@ -14,5 +14,6 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("case", GOLDEN_CASES + GOLDEN_CASES_F4)
 def test_generate_on_the_gpu_reproduces_the_reference_goldens(case):
     import torch
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
     generate_on_golden(case)

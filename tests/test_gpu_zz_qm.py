@@ -33,10 +33,17 @@ def test_streaming_kernel_reads_sparse_qM(case, full6_J, pad):
     dense_state = _golden_state(g, layout, torch, False, full6_J)
     eng.set_kernel(9)
     dense = eng.step(dense_state, want_u_all=True)
-    eng.set_kernel(0)                                   # auto must route qM to the streaming kernel
-    out = eng.step(_with_qM(dense_state, layout, pad), want_u_all=True)
+    out = eng.step(_with_qM(dense_state, layout, pad), want_u_all=True)     # kernel 9 on qM: the same copy plan entries
     torch.cuda.synchronize()
     assert eng.last_kernel.startswith("osc_step_stream"), eng.last_kernel
+    # auto: 3-row arm devices with a tight qM and row-stacked J go to the tree-sparse kernel's qM instantiation,
+    # everything else to the streaming kernel
+    eng.set_kernel(0)
+    auto = eng.step(_with_qM(dense_state, layout, pad), want_u_all=True)
+    torch.cuda.synchronize()
+    kd3 = all(sum(d.ctrlr_dof) == 3 for d in layout.devices if d.name != "base")
+    want_tree = kd3 and not full6_J and pad == 0 and "target_vel" not in dense_state
+    assert ("osc_step_tree" in eng.last_kernel and "qM" in eng.last_kernel) or not want_tree, eng.last_kernel
     ok = ~np.array(g["index_error"])
     u, u_dense = out["u_all"].cpu().numpy(), dense["u_all"].cpu().numpy()
     assert np.array_equal(out["status"].cpu().numpy(), dense["status"].cpu().numpy())
@@ -46,6 +53,8 @@ def test_streaming_kernel_reads_sparse_qM(case, full6_J, pad):
         e_c = np.abs(out["ctrl"].cpu().numpy()[ok] - g["ctrl"][ok]).max(axis=1) / np.abs(g["u_all"][ok]).max(axis=1)
         assert e_c.max() < REL_TOL
         assert np.array_equal((out["status"].cpu().numpy()[ok] & _native.ST_PINV) != 0, g["pinv"][ok])
+        assert _rel_err(auto["u_all"].cpu().numpy()[ok], g["u_all"][ok]).max() < REL_TOL
+        assert np.array_equal((auto["status"].cpu().numpy()[ok] & _native.ST_PINV) != 0, g["pinv"][ok])
 
 
 def test_qM_full_batch_host_buffers_and_refusals():
@@ -61,16 +70,24 @@ def test_qM_full_batch_host_buffers_and_refusals():
     eng = BatchedOSC(layout, device=0)
     eng.set_kernel(9)
     a = eng.step(kernel_inputs(st, layout, packed_M=True), want_u_all=True)
-    eng.set_kernel(0)
     qin = kernel_inputs(st, layout, qM=True)
     assert tuple(qin["qM"].shape) == (B, 155)
     b = eng.step(qin, want_u_all=True)
     torch.cuda.synchronize()
     assert torch.equal(a["u_all"], b["u_all"]) and torch.equal(a["ctrl"], b["ctrl"]) and torch.equal(a["status"], b["status"])
+    # auto dispatch: the tree-sparse kernel on qM (default for this layout), bit-identical to its packed-M run
+    eng.set_kernel(0)
+    c = eng.step(qin, want_u_all=True)
+    assert "osc_step_tree" in eng.last_kernel and "qM" in eng.last_kernel, eng.last_kernel
+    d = eng.step(kernel_inputs(st, layout, packed_M=True), want_u_all=True)
+    assert "osc_step_tree" in eng.last_kernel and "packed" in eng.last_kernel, eng.last_kernel
+    assert torch.equal(c["u_all"], d["u_all"]) and torch.equal(c["ctrl"], d["ctrl"]) and torch.equal(c["status"], d["status"])
+    scale = a["u_all"].abs().amax(dim=1, keepdim=True)
+    assert ((c["u_all"] - a["u_all"]).abs() / scale).max().item() < REL_TOL
     n = 3000
     host = {k: v[:n].cpu().numpy() for k, v in qin.items()}
     h = eng.step_host(host, want_u_all=True)
-    assert np.array_equal(h["u_all"], b["u_all"][:n].cpu().numpy())
+    assert np.array_equal(h["u_all"], c["u_all"][:n].cpu().numpy())
     eng.set_kernel(1)                                 # the generic kernel cannot address qM
     with pytest.raises(_native.OscError):
         eng.step(qin)
