@@ -3,14 +3,20 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload gain_test] [--batch 65536]
 
-One "step" of the benchmark = one pass of the fused control-law kernel over a
-batch of B synthetic DualUR5 instances per GPU (each instance = one
-`OSC.generate`, osc.py:120-210).  `value` counts instances per second over
-all GPUs with the state resident in HBM; `e2e` is the same metric through
-`irlosc_step_host` (HOST buffers, copies inside the timed region).
-`--impl reference` times the CPU restatement of the reference (oracle/) on
-all host cores - the reference is pure Python and /root/reference does not
-exist on the GPU box, so this is `kind: "port"`.
+One "step" = one launch of the lane kernel (csrc/osc_lane.cuh) over a batch of B synthetic DualUR5 instances per
+GPU, each instance one `OSC.generate` (osc.py:120-210).  The state lives in HBM in the package's native batch layout,
+batch-interleaved tiles; successive steps read DIFFERENT input sets, so nothing is re-read
+from L2.
+
+    value      instances / s over all GPUs, state resident in HBM, result gather (N > 1) inside the timed region
+    e2e        the same metric through `BatchedOSC.step_tiles_host` -> `irlosc_step_tiles_host`: tiles in pinned HOST
+               memory, H2D + kernel + D2H inside the timed region (`e2e_arrays`: the per-variable-array entry point)
+    roofline   SURVEY 8d algorithmic bytes per step x B / kernel time (CUDA events) vs the measured HBM peak, plus the
+               same on the bytes the kernel actually moves
+    strong     fixed TOTAL batches (65 536 and 262 144) split over the N GPUs
+    configs    BASELINE.json configs 2-4 and the k = 13 worst case, each checked against the oracle and timed
+    cpu_baseline / --impl reference : the reference's own `OSC.generate` (unmodified sources staged by
+               oracle/stage_ref.py, stub simulator) on all host cores - or the numpy port when the sources are absent
 """
 import argparse
 import json
@@ -25,6 +31,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "DualUR5 OSC control-steps/sec"
 UNIT = "control-steps/s"
+N_INPUT_SETS = 3
 
 
 # ---------------------------------------------------------------- workload description
@@ -42,39 +49,15 @@ def algorithmic_bytes(layout, per_instance_max_vel=True):
     return 8 * words
 
 
-def side_legs():
-    """tools/side_legs.py in child processes (isolated from this one's CUDA context, bounded by a timeout): paths
-    written after the round's GPU budget was spent, each checked before it is timed.  Nothing from here enters
-    `value`, `e2e` or `roofline`."""
-    tool = os.path.join(ROOT, "tools", "side_legs.py")
-    runs = [("default", ["--legs", "qm,qm_admit,iros2022,sequence,coop"], {"IRLOSC_FIXUP_COOP": "0"}, 120),
-            ("fixup_coop", ["--legs", "coop"], {"IRLOSC_FIXUP_COOP": "1"}, 60),
-            ("qm_tree", ["--legs", "qm_tree,fp64_peak"], {}, 75)]
-    out = {}
-    for name, extra, env_add, limit in runs:
-        env = dict(os.environ, **env_add)
-        rec = {"legs": []}
-        try:
-            proc = subprocess.Popen([sys.executable, tool, "--steps", "10", "--warmup", "3"] + extra, env=env,
-                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
-            try:
-                so, se = proc.communicate(timeout=limit)
-            except subprocess.TimeoutExpired:
-                proc.kill()
-                so, se = proc.communicate()
-                rec["timeout_s"] = limit
-            for ln in so.splitlines():
-                try:
-                    rec["legs"].append(json.loads(ln))
-                except ValueError:
-                    pass
-            if proc.returncode not in (0, None):
-                rec["returncode"] = proc.returncode
-                rec["stderr_tail"] = se[-400:]
-        except Exception as exc:
-            rec["error"] = "%s: %s" % (type(exc).__name__, exc)
-        out[name] = rec
-    return out
+def run_config(workload, layout, B):
+    """Identical in both arms (the driver compares it)."""
+    tile_b = layout.tile_entries * 8
+    return {"workload": "%s layout (n=%d, k=%d, D=%d, admittance=%s), B=%d per GPU, fp64; state in batch-interleaved tiles "
+                        "(%d B per instance: tree non-zeros of M and J, dq, bias, poses, targets, max_vel), packed ctrl out"
+                        % (workload, layout.n, layout.k, layout.D, layout.admittance, B, tile_b),
+            "batch_per_gpu": B,
+            "l2_policy": "inputs larger than L2: %d distinct input sets of %.0f MB each, used in rotation (126 MB L2)"
+                         % (N_INPUT_SETS, tile_b * B / 1e6)}
 
 
 class ClockSampler:
@@ -90,7 +73,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -104,7 +87,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or \
+        rows = [r for (t, r) in self.rows if t0 - 0.02 <= t <= t1 + 0.05 and len(r) >= 7] or \
                [r for (_, r) in self.rows if len(r) >= 7]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
@@ -115,41 +98,111 @@ class ClockSampler:
                 "samples": len(rows), "power_w_max": max(float(r[2]) for r in rows)}
 
 
-# ---------------------------------------------------------------- CPU baseline (oracle port)
+# ---------------------------------------------------------------- CPU baseline (the reference, or its numpy port)
 def _cpu_worker(args):
+    """One pinned process: `per_core` instances through the reference's OSC.generate (kind "reference") or through
+    oracle/osc_numpy.py (kind "port").  Returns seconds of control-law work."""
+    core, kind, scenario, layout_dict, batch = args
     os.environ["OMP_NUM_THREADS"] = "1"
-    layout_dict, batch = args
+    try:
+        os.sched_setaffinity(0, {core})
+    except Exception:
+        pass
+    if kind == "reference":
+        from oracle import ref_harness
+        runner = getattr(_cpu_worker, "runner", None)
+        if runner is None:
+            runner = _cpu_worker.runner = ref_harness.scenario_runner(scenario)
+        spent, _calls, _f = ref_harness.time_reference_generate(runner, batch)
+        return spent
     from oracle import osc_numpy
     t0 = time.perf_counter()
     osc_numpy.osc_batch(layout_dict, batch)
     return time.perf_counter() - t0
 
 
-def cpu_baseline(layout, st_host, per_core=192):
-    """Times oracle/osc_numpy.py (statement-by-statement numpy port of OSC.generate) on all
-    host cores: one process per core, OMP_NUM_THREADS=1, `per_core` instances each."""
+def cpu_kind():
+    from oracle import ref_harness
+    return "reference" if ref_harness.reference_available() else "port"
+
+
+def host_cores():
+    try:
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return list(range(os.cpu_count() or 1))
+
+
+def cpu_baseline(scenario, layout, ob, per_core=96, repeats=5, pool=None):
+    """Whole-box rate of the CPU path: one pinned single-threaded process per host core, `per_core` instances each,
+    wall clock over the slowest worker, median of `repeats` rounds (after one warm-up round)."""
     import multiprocessing as mp
-    cores = os.cpu_count() or 1
-    total = st_host["M"].shape[0]
-    per_core = max(1, min(per_core, total // cores))
+    import numpy as np
+    cores = host_cores()
+    total = ob["M"].shape[0]
+    per_core = max(1, min(per_core, total // len(cores)))
+    kind = cpu_kind()
     jobs = []
-    for c in range(cores):
+    for c, core in enumerate(cores):
         sl = slice(c * per_core, (c + 1) * per_core)
-        jobs.append((layout.as_dict(), {k: v[sl] for k, v in st_host.items()}))
+        jobs.append((core, kind, scenario, layout.as_dict(), {k: v[sl] for k, v in ob.items()}))
     os.environ["OMP_NUM_THREADS"] = "1"
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(j[0], {k: v[:2] for k, v in j[1].items()}) for j in jobs])   # warm-up
-        t0 = time.perf_counter()
-        per = pool.map(_cpu_worker, jobs)
-        wall = time.perf_counter() - t0
-    n = per_core * cores
-    return {"value": n / wall, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d instances of the same workload (%d per core, one process per core, OMP_NUM_THREADS=1), "
-                      "oracle/osc_numpy.py; %.0f steps/s/core" % (n, per_core, per_core / (sum(per) / len(per)))}
+    own = pool is None
+    if own:
+        pool = mp.get_context("fork").Pool(len(cores))
+    try:
+        pool.map(_cpu_worker, [(j[0], j[1], j[2], j[3], {k: v[:2] for k, v in j[4].items()}) for j in jobs], chunksize=1)
+        rates, per = [], []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            secs = pool.map(_cpu_worker, jobs, chunksize=1)
+            wall = time.perf_counter() - t0
+            rates.append(per_core * len(cores) / wall)
+            per.append(per_core / (sum(secs) / len(secs)))
+    finally:
+        if own:
+            pool.close()
+    src = ("the UNMODIFIED reference OSC.generate (oracle/_ref or /root/reference, stub mujoco_py / transforms3d, fake simulator)"
+           if kind == "reference" else "oracle/osc_numpy.py (numpy port; reference sources not staged on this box)")
+    return {"value": float(np.median(rates)), "unit": UNIT, "cores": len(cores), "kind": kind,
+            "rounds": [round(r, 1) for r in rates], "steps_per_s_per_core": float(np.median(per)),
+            "sample": "%d instances of the same workload per round (%d per core, one pinned process per core, "
+                      "OMP_NUM_THREADS=1), median of %d rounds; %s" % (per_core * len(cores), per_core, repeats, src)}
 
 
-# ---------------------------------------------------------------- main
+# ---------------------------------------------------------------- helpers (GPU arm)
+def event_times(torch, fn, n):
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+    for i, (a, b) in enumerate(ev):
+        a.record()
+        fn(i)
+        b.record()
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ev]
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2]
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_for(kernel_name, workload, B):
+    """dram__bytes_read + dram__bytes_write of ONE launch from an `ncu --set full` capture (profiles/traffic.json), only
+    when it was captured for exactly this kernel instantiation, workload and batch."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.isfile(path):
+        return None
+    rec = json.load(open(path)).get("%s|%s|B%d" % (kernel_name, workload, B))
+    return rec.get("dram_bytes_per_launch") if rec else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -158,10 +211,6 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="gain_test")
     ap.add_argument("--batch", type=int, default=65536, help="instances per GPU")
-    ap.add_argument("--m-layout", default="packed", choices=["packed", "dense", "qM"],
-                    help="packed lower triangle (the SURVEY 8d record, default), dense n x n, or MuJoCo's sparse qM "
-                         "(IRLOSC_M_QM: 155 instead of 325 doubles; the roofline still counts the SURVEY record)")
-    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 generic, 2 tiled")
     ap.add_argument("--sm-margin", type=int, default=-1,
                     help="SMs left free for the gather when --gpus > 1 (-1: 0 for the fused gather, 8 for NCCL)")
     ap.add_argument("--gather-buffers", type=int, default=3, help="gathered output buffers in flight (>= 2)")
@@ -169,10 +218,9 @@ def main():
                     help="result gather for --gpus > 1: fused = multicast stores if the box has NVLS, else peer stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-fused", action="store_true", help="skip the fused state-provider measurement (SURVEY 8 f1)")
-    ap.add_argument("--no-side-legs", action="store_true",
-                    help="skip tools/side_legs.py (N = 1 only: checked side measurements of paths without a GPU run of "
-                         "their own yet, in a child process; use this flag under ncu)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline only: skip the strong-scaling, per-config, arrays-layout, fused-state and latency legs "
+                         "(use under ncu)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -185,25 +233,27 @@ def main():
 
     layout = scenario_layout(args.workload)
     B = args.batch
-    config = {"workload": "%s layout (n=%d, k=%d, D=%d, admittance=%s), B=%d per GPU, fp64, M %s, J rows [k][n], "
-                          "per-instance max_vel" % (args.workload, layout.n, layout.k, layout.D, layout.admittance,
-                                                    B, args.m_layout),
-              "batch_per_gpu": B, "l2_policy": "inputs larger than L2 (%.0f MB per step vs 126 MB)" % 0.0}
+    config = run_config(args.workload, layout, B)
 
     # ------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
         if rank != 0:
             return
-        st = synth_batch(layout, min(B, 8192), seed=0)
+        st = synth_batch(layout, 4096, seed=0)
         ob = oracle_inputs(st, layout)
+        import multiprocessing as mp
+        per_core = 64
+        pool = mp.get_context("fork").Pool(len(host_cores()))
         vals = []
-        for _ in range(args.warmup + args.steps):
-            vals.append(cpu_baseline(layout, ob, per_core=96))
+        try:
+            for _ in range(args.warmup + args.steps):       # one "step" = one round over per_core x cores instances
+                vals.append(cpu_baseline(args.workload, layout, ob, per_core=per_core, repeats=1, pool=pool))
+        finally:
+            pool.close()
         vals = vals[args.warmup:]
-        v = float(np.mean([x["value"] for x in vals]))
-        cb = dict(vals[-1], value=v)
-        n_inst = 96 * cb["cores"]
-        config["l2_policy"] = "n/a (CPU)"
+        v = float(np.median([x["value"] for x in vals]))
+        cb = dict(vals[-1], value=v, rounds=[round(x["value"], 1) for x in vals])
+        n_inst = per_core * cb["cores"]
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n_inst / v,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -222,21 +272,24 @@ def main():
         os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")     # 8 MB gather: a handful of channels saturates it
         dist.init_process_group("nccl", device_id=dev)
 
-    st = synth_batch(layout, B, seed=1000 * rank, device=dev)
-    kin = kernel_inputs(st, layout, packed_M=(args.m_layout == "packed"), qM=(args.m_layout == "qM"))
-    in_bytes = sum(v.numel() * v.element_size() for v in kin.values())
-    config["l2_policy"] = "inputs larger than L2 (%.0f MB read per step vs 126 MB L2)" % (in_bytes / 1e6)
     eng = BatchedOSC(layout, device=local_rank)
-    eng.set_kernel(args.kernel)
+    E = eng.tile_entries
+    assert E == layout.tile_entries and E > 0
+    # N_INPUT_SETS distinct batches per rank; tiles are the resident state, the qM arrays feed the arrays-layout legs
+    sts = [synth_batch(layout, B, seed=1000 * rank + i, device=dev) for i in range(N_INPUT_SETS)]
+    arrays = [kernel_inputs(s, layout, qM=True) for s in sts]
+    tiles = [eng.pack_tiles(a) for a in arrays]
+    torch.cuda.synchronize()
+    tile_bytes = E * 8
+
     # Result gather for N > 1 (the only exchange on this path), NBUF output buffers so that the gather
     # of step i overlaps the kernel of step i+1:
     #   fused : the step kernel stores its ctrl rows straight into every rank's gathered array through
-    #           peer-mapped symmetric memory (NVLink stores), followed by a symmetric-memory barrier
+    #           the NVSwitch multicast mapping (or peer-mapped pointers), followed by a symmetric-memory barrier
     #   nccl  : all_gather_into_tensor on NCCL's stream (fallback, or --gather nccl)
     NBUF = max(2, args.gather_buffers)
-    outs = [{"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)} for _ in range(NBUF)]
-    out = outs[0]
-    gathered = None
+    outs = [torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(NBUF)]
+    gathered, handles, gather_args, side = None, None, None, None
     pending = [None] * NBUF
     step_no = [0]
     gather_mode = "none"
@@ -249,32 +302,39 @@ def main():
                 handles = [symm_mem.rendezvous(t, dist.group.WORLD) for t in gathered]
                 mc_ptrs = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles]
                 if args.gather == "fused" and all(mc_ptrs):       # one multimem store per row through the switch
-                    gather_args = [([], rank * B, mc_ptrs[b]) for b in range(NBUF)]
+                    gather_args = [([], mc_ptrs[b]) for b in range(NBUF)]
                     gather_mode = "fused-multicast"
                 else:                                             # one store per row per peer
-                    gather_args = [([int(h.buffer_ptrs[r]) for r in range(world)], rank * B) for h in handles]
+                    gather_args = [([int(h.buffer_ptrs[r]) for r in range(world)], 0) for h in handles]
                     gather_mode = "fused-peer"
                 side = torch.cuda.Stream(device=dev)
             except Exception as exc:          # no symmetric memory on this box: NCCL gather
                 sys.stderr.write("fused gather unavailable (%s), using NCCL\n" % exc)
+                gathered = None
         if gather_mode == "nccl":
             gathered = [torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev) for _ in range(NBUF)]
-
     margin = args.sm_margin if args.sm_margin >= 0 else (8 if gather_mode == "nccl" else 0)
     if world > 1 and margin > 0:
         eng.set_sm_margin(margin)      # the NCCL gather kernel needs a few SMs to overlap the next step's kernel
 
-    def one_step():
-        b = step_no[0] % NBUF
-        step_no[0] += 1
-        if pending[b] is not None:          # the buffer's previous gather must be complete before it is overwritten
+    def wait_pending(b):
+        if pending[b] is not None:
             if gather_mode.startswith("fused"):
                 torch.cuda.current_stream().wait_event(pending[b])
             else:
                 pending[b].wait()
             pending[b] = None
+
+    def one_step(_i=None, nloc=B, t_list=tiles):
+        """One control step of this rank's shard of `nloc` instances (+ its share of the gather of world x nloc rows)."""
+        i = step_no[0]
+        b = i % NBUF
+        step_no[0] += 1
+        wait_pending(b)                     # the buffer's previous gather must be complete before it is overwritten
+        o = {"ctrl": outs[b][:nloc]}
         if gather_mode.startswith("fused"):
-            eng.step(kin, out=outs[b], want_status=False, gather=gather_args[b])
+            ptrs, mc = gather_args[b]
+            eng.step_tiles(t_list[i % N_INPUT_SETS], nloc, out=o, want_status=False, gather=(ptrs, rank * nloc, mc))
             done = torch.cuda.Event()
             done.record()
             with torch.cuda.stream(side):   # cross-GPU barrier off the critical path of the next kernel
@@ -284,133 +344,250 @@ def main():
                 fin.record()
             pending[b] = fin
         else:
-            eng.step(kin, out=outs[b], want_status=False)
+            eng.step_tiles(t_list[i % N_INPUT_SETS], nloc, out=o, want_status=False)
             if gather_mode == "nccl":
-                pending[b] = dist.all_gather_into_tensor(gathered[b], outs[b]["ctrl"], async_op=True)
+                pending[b] = dist.all_gather_into_tensor(gathered[b][:world * nloc], outs[b][:nloc], async_op=True)
 
     def drain():
         for b in range(NBUF):
-            if pending[b] is not None:
-                if gather_mode.startswith("fused"):
-                    torch.cuda.current_stream().wait_event(pending[b])
-                else:
-                    pending[b].wait()
-                pending[b] = None
+            wait_pending(b)
 
-    for _ in range(max(args.warmup, 3)):
-        one_step()
+    def timed_loop(n, **kw):
+        """n steps back to back between two events on the launching stream (gathers included); ms per step, max over ranks."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(n):
+            one_step(i, **kw)
+        drain()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / n
+
+    W = max(args.warmup, 3)
+    for i in range(W):
+        one_step(i)
     drain()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()          # all ranks enter the timed region together (after rank 0's sampler start-up)
     launches0 = eng.kernel_launches
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     t_wall0 = time.time()
-    ev[0].record()
-    for i in range(args.steps):
-        one_step()
-        ev[i + 1].record()
-    drain()
-    ev_end = torch.cuda.Event(enable_timing=True)
-    ev_end.record()
-    torch.cuda.synchronize()
-    t_wall1 = time.time()
-    if world > 1:
-        dist.barrier()
-    total_ms = ev[0].elapsed_time(ev_end)      # includes the last gather
+    ms_per_step = timed_loop(args.steps)
     launches = eng.kernel_launches - launches0
-    # kernel-only time for the roofline: events around the kernel alone, same stream
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in kev:
-        a.record()
-        eng.step(kin, out=out, want_status=False)
-        b.record()
-    torch.cuda.synchronize()
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kev) / len(kev)
-    kernel_name = eng.last_kernel
-    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-
-    tmax = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
-    ms_per_step = total_ms / args.steps
     value = world * B / (ms_per_step * 1e-3)
+    # the same loop for >= 1 s: what the rate is once clocks and power have settled
+    n_sus = int(min(40000, max(args.steps, 1.0 / (ms_per_step * 1e-3))))
+    sus_ms = timed_loop(n_sus)
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    sustained = {"steps": n_sus, "ms_per_step": sus_ms, "value": world * B / (sus_ms * 1e-3), "seconds": n_sus * sus_ms * 1e-3}
+
+    # kernel-only time for the roofline: events around the kernel alone, same stream, rotating inputs
+    out0 = {"ctrl": outs[0]}
+    ks = event_times(torch, lambda i: eng.step_tiles(tiles[i % N_INPUT_SETS], B, out=out0, want_status=False), max(args.steps, 10))
+    kernel_ms = sum(ks) / len(ks)
+    kernel_name = eng.last_kernel
+
+    # ------------------------------------------------------------ gather verification (N > 1)
+    gather_verified = None
+    if world > 1:
+        drain()
+        torch.cuda.synchronize()
+        dist.barrier()
+        step_no[0] = 0                                   # buffer 0, input set 0 on every rank
+        one_step(0)
+        drain()
+        torch.cuda.synchronize()
+        dist.barrier()
+        got = gathered[0]
+        ref = torch.empty(world * B, layout.n_ctrl, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(ref, outs[0])
+        same = bool(torch.equal(got, ref))
+        # rank 0 recomputes a foreign shard from scratch (rank 1's input set 0) and compares its gathered rows
+        if rank == 0:
+            st1 = synth_batch(layout, B, seed=1000 * 1 + 0, device=dev)
+            t1 = eng.pack_tiles(kernel_inputs(st1, layout, qM=True))
+            o1 = eng.step_tiles(t1, B, want_status=False)
+            torch.cuda.synchronize()
+            same = same and bool(torch.equal(o1["ctrl"], got[B:2 * B]))
+            del st1, t1, o1
+        flag = torch.tensor([1 if same else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        gather_verified = bool(flag.item() == 1)
+
+    # ------------------------------------------------------------ strong scaling: fixed TOTAL batch split over the ranks
+    strong = None
+    if not args.no_extras:
+        strong = []
+        for B_total in (65536, 262144):
+            nloc = B_total // world
+            if nloc * world != B_total or nloc < 32:
+                continue
+            if nloc > B and world > 1:
+                continue
+            saved_outs = None
+            if nloc <= B:
+                t_list = [t[:(nloc + 31) // 32] for t in tiles]          # a prefix of the resident tiles
+            else:                                                        # N = 1 at 262 144: a larger resident state
+                t_list = []
+                for i in range(N_INPUT_SETS):
+                    s_big = synth_batch(layout, nloc, seed=5000 + i, device=dev)
+                    t_list.append(eng.pack_tiles(kernel_inputs(s_big, layout, qM=True)))
+                    del s_big
+                saved_outs = list(outs)
+                for b in range(NBUF):
+                    outs[b] = torch.empty(nloc, layout.n_ctrl, dtype=torch.float64, device=dev)
+            for i in range(3):
+                one_step(i, nloc=nloc, t_list=t_list)
+            drain()
+            ms = timed_loop(max(args.steps, 20), nloc=nloc, t_list=t_list)
+            strong.append({"total_batch": B_total, "batch_per_gpu": nloc, "ms_per_step": ms, "value": B_total / (ms * 1e-3)})
+            if saved_outs is not None:
+                for b in range(NBUF):
+                    outs[b] = saved_outs[b]
+            del t_list
+        torch.cuda.empty_cache()
 
     # ------------------------------------------------------------ end to end (host buffers, copies timed)
-    e2e = None
+    e2e, e2e_arrays = None, None
     if not args.no_e2e:
+        def host_loop(call):
+            for _ in range(2):
+                call()
+            if world > 1:
+                dist.barrier()
+            reps = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                call()                                   # returns after the D2H copy completed
+            dt = (time.perf_counter() - t0) / reps
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item())
+        host_out = {"ctrl": pinned_empty((B, layout.n_ctrl))}
+        host_tiles = pinned_empty(eng.tiles_shape(B))
+        host_tiles[...] = tiles[0].cpu().numpy()
+        dt = host_loop(lambda: eng.step_tiles_host(host_tiles, B, out=host_out, want_status=False))
+        assert np.array_equal(host_out["ctrl"], eng.step_tiles(tiles[0], B, want_status=False)["ctrl"].cpu().numpy())
+        e2e = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(host_tiles.nbytes),
+               "d2h_bytes_per_step": int(host_out["ctrl"].nbytes), "ms_per_step": 1e3 * dt,
+               "api": "BatchedOSC.step_tiles_host -> irlosc_step_tiles_host (state tiles in pinned host memory, chunked "
+                      "H2D / lane kernel / D2H pipeline); a caller that assembles its batch writes tiles directly "
+                      "(irlosc_tile_spec), per-variable arrays go through e2e_arrays"}
+        del host_tiles
         host_in = {}
-        for k, v in kin.items():
+        for k, v in arrays[0].items():
             buf = pinned_empty(tuple(v.shape))
             buf[...] = v.cpu().numpy()
             host_in[k] = buf
-        host_out = {"ctrl": pinned_empty((B, layout.n_ctrl))}
-        h2d = sum(a.nbytes for a in host_in.values())
-        d2h = host_out["ctrl"].nbytes
-        for _ in range(2):
-            eng.step_host(host_in, out=host_out, want_status=False)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        reps = max(3, min(args.steps, 10))
-        for _ in range(reps):
-            eng.step_host(host_in, out=host_out, want_status=False)   # returns after D2H completed
-        dt = (time.perf_counter() - t0) / reps
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(tt.item()),
-               "api": "BatchedOSC.step_host -> irlosc_step_host (pinned host buffers, chunked H2D/kernel/D2H pipeline)"}
-        assert np.isfinite(host_out["ctrl"]).all()
+        dt = host_loop(lambda: eng.step_host(host_in, out=host_out, want_status=False))
+        e2e_arrays = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in.values())),
+                      "d2h_bytes_per_step": int(host_out["ctrl"].nbytes), "ms_per_step": 1e3 * dt, "kernel": eng.last_kernel,
+                      "api": "BatchedOSC.step_host -> irlosc_step_host (MuJoCo-style arrays in pinned host memory: sparse qM, "
+                             "J rows, dq, bias, poses, targets)"}
+        del host_in
 
-    # ------------------------------------------------------------ fused state provider
-    # Same control steps, but M / J / qfrc_bias / EE poses are computed on the GPU from (q, dq) inside
-    # the step kernel (irlosc_step_fused) instead of being read from HBM.  Its inputs (~0.6 KB per
-    # instance) fit in L2, so L2 is flushed between the individually timed steps.
-    fused = None
-    if not args.no_fused:
+    # ------------------------------------------------------------ other legs (every rank runs them; rank 0 reports)
+    extras = {}
+    if not args.no_extras:
+        extras = extra_legs(args, torch, np, eng, layout, sts, arrays, tiles, dev, world, dist, rank)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------ roofline + CPU baseline (rank 0)
+    peak, peak_src = hbm_peak()
+    abytes = algorithmic_bytes(layout)
+    moved = tile_bytes + 8 * layout.n_ctrl
+    achieved = abytes * B / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic_for(kernel_name, args.workload, B), "kernel": kernel_name, "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_step": abytes, "peak_source": peak_src,
+                "moved": {"bytes_per_step": moved, "achieved": moved * B / (kernel_ms * 1e-3) / 1e9,
+                          "frac": moved * B / (kernel_ms * 1e-3) / 1e9 / peak,
+                          "note": "what one launch reads and writes: the tile (tree non-zeros only) + packed ctrl"}}
+    cb = None
+    if world == 1 and not args.no_cpu_baseline:
+        sub = {k: v[:len(host_cores()) * 96] for k, v in sts[0].items()}
+        cb = cpu_baseline(args.workload, layout, oracle_inputs(sub, layout))
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
+            "sustained": sustained, "gather": gather_mode, "gather_verified": gather_verified, "strong": strong,
+            "e2e_arrays": e2e_arrays}
+    line.update(extras)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def extra_legs(args, torch, np, eng, layout, sts, arrays, tiles, dev, world, dist, rank):
+    """Measurements beside the headline: the per-variable-array kernels, the tile packer, the fused state provider
+    with its caller loop, BASELINE.json configs 2-4 + the worst case (checked against the oracle, N = 1 only), and the
+    B = 1 latency of the drop-in `OSC.generate`."""
+    from irl_control_b200.engine import BatchedOSC, pinned_empty
+    from irl_control_b200.synthetic import scenario_layout, synth_batch, kernel_inputs, oracle_inputs
+    B = args.batch
+    peak, _ = hbm_peak()
+    out = {"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)}
+    n = max(args.steps, 10)
+    res = {}
+
+    def allmax(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- per-variable arrays (MuJoCo's qM + J rows + ...): the record-staging tree kernel / streaming kernel, and the packer
+    eng.set_kernel(0)
+    for i in range(3):
+        eng.step(arrays[i % N_INPUT_SETS], out=out, want_status=False)
+    ms = allmax(median(event_times(torch, lambda i: eng.step(arrays[i % N_INPUT_SETS], out=out, want_status=False), n)))
+    in_b = sum(v.numel() * v.element_size() for v in arrays[0].values()) // B
+    res["arrays_layout"] = {"value": world * B / (ms * 1e-3), "ms_per_step": ms, "kernel": eng.last_kernel,
+                            "input_bytes_per_step": int(in_b), "roofline_frac": algorithmic_bytes(layout) * B / (ms * 1e-3) / 1e9 / peak,
+                            "api": "BatchedOSC.step -> irlosc_step (qM, J rows, dq, bias, poses, targets as separate arrays in HBM)"}
+    tb = torch.empty_like(tiles[0])
+    for i in range(3):
+        eng.pack_tiles(arrays[i % N_INPUT_SETS], tiles=tb)
+    ms = allmax(median(event_times(torch, lambda i: eng.pack_tiles(arrays[i % N_INPUT_SETS], tiles=tb), n)))
+    res["arrays_layout"]["pack_to_tiles_ms"] = ms
+    del tb
+
+    # ---- fused state provider (SURVEY 8 f1) and the caller loop inside the step (f2): q, dq in, torques out
+    try:
         from irl_control_b200.synthetic import fused_inputs, scenario_model
         _, model = scenario_model(args.workload)
         eng.set_model(model)
-        fin = fused_inputs(st, layout)
-        fout = {"ctrl": torch.empty(B, layout.n_ctrl, dtype=torch.float64, device=dev)}
+        fins = [fused_inputs(s, layout) for s in sts]
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-        for _ in range(max(args.warmup, 3)):
-            eng.step_fused(fin, out=fout, want_status=False)
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        l0 = eng.kernel_launches
-        fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, b in fev:
+        for i in range(3):
+            eng.step_fused(fins[i % N_INPUT_SETS], out=out, want_status=False)
+        ts = []
+        for i in range(n):
             flush.zero_()
-            a.record()
-            eng.step_fused(fin, out=fout, want_status=False)
-            b.record()
-        torch.cuda.synchronize()
-        f_ms = sum(a.elapsed_time(b) for a, b in fev) / len(fev)
-        f_launches = eng.kernel_launches - l0
-        ft = torch.tensor([f_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ft, op=dist.ReduceOp.MAX)
-        f_ms = float(ft.item())
-        f_in = sum(v.numel() * v.element_size() for v in fin.values())
-        fused = {"value": world * B / (f_ms * 1e-3), "unit": UNIT, "ms_per_step": f_ms, "kernel": eng.last_kernel,
-                 "gpu_launches": int(f_launches), "input_bytes_per_step": int(f_in // B),
-                 "l2_policy": "256 MB flush write between timed steps (inputs %.0f MB < L2)" % (f_in / 1e6),
-                 "api": "BatchedOSC.step_fused -> irlosc_step_fused (q, dq, targets in HBM)"}
-        # caller loop fused in: the insertion demo's WP / GRIP state machine per instance
+            ts += event_times(torch, lambda _i: eng.step_fused(fins[i % N_INPUT_SETS], out=out, want_status=False), 1)
+        ms = allmax(median(ts))
+        f_in = sum(v.numel() * v.element_size() for v in fins[0].values())
+        res["fused_state"] = {"value": world * B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "kernel": eng.last_kernel,
+                              "input_bytes_per_step": int(f_in // B),
+                              "l2_policy": "256 MB flush write between timed steps (inputs %.0f MB < L2)" % (f_in / 1e6),
+                              "parity": "against the package's own rigid-body model (dual_ur5.py); MuJoCo parity unpinned",
+                              "api": "BatchedOSC.step_fused -> irlosc_step_fused (q, dq, targets in HBM)"}
         try:
             from irl_control_b200.sequence import ActionSequence
-            # the reference's own 12-entry action list and object offsets (insertion_task.yaml), adapters placed
-            # at random per episode (insertion_task.py:341-369), waypoints from set_waypoint_targets (206-268)
             from irl_control_b200 import insertion
             from irl_control_b200.configs import action_config
             acfg = action_config("insertion_task.yaml")
@@ -418,28 +595,24 @@ def main():
             seq = ActionSequence(layout, acts, active_arm="ur5right")
             ia = seq.active_device
             placed = insertion.random_object_poses(B, "right", objs, rng=np.random.default_rng(7 + rank))
-            wp_xyz, wp_quat = insertion.waypoint_poses(acts, objs, placed, st["ee_xyz"][:, ia].cpu().numpy())
+            wp_xyz, wp_quat = insertion.waypoint_poses(acts, objs, placed, sts[0]["ee_xyz"][:, ia].cpu().numpy())
             sst = seq.new_state(B, wp_xyz, wp_quat, device=dev)
-            sin = {k: v for k, v in fin.items() if k not in ("target_xyz", "target_quat")}
+            sin = {k: v for k, v in fins[0].items() if k not in ("target_xyz", "target_quat")}
             for _ in range(3):
-                eng.step_sequence(sin, seq, sst, out=fout, want_status=False)
-            torch.cuda.synchronize()
-            sev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-            for a, b in sev:
+                eng.step_sequence(sin, seq, sst, out=out, want_status=False)
+            ts = []
+            for i in range(n):
                 flush.zero_()
-                a.record()
-                eng.step_sequence(sin, seq, sst, out=fout, want_status=False)
-                b.record()
-            torch.cuda.synchronize()
-            s_ms = sum(a.elapsed_time(b) for a, b in sev) / len(sev)
-            fused["sequence"] = {"value": B / (s_ms * 1e-3), "unit": "episode-steps/s per GPU", "ms_per_step": s_ms,
-                                 "api": "BatchedOSC.step_sequence -> irlosc_step_sequence (insertion_task.yaml: 12 actions, "
-                                        "randomised adapter poses per episode)"}
+                ts += event_times(torch, lambda _i: eng.step_sequence(sin, seq, sst, out=out, want_status=False), 1)
+            s_ms = allmax(median(ts))
+            res["fused_state"]["sequence"] = {"value": world * B / (s_ms * 1e-3), "unit": "episode-steps/s", "ms_per_step": s_ms,
+                                              "api": "BatchedOSC.step_sequence -> irlosc_step_sequence (insertion_task.yaml: 12 "
+                                                     "actions, randomised adapter poses per episode)"}
         except Exception as exc:      # the sequence step needs two arm devices in the layout
-            fused["sequence"] = {"unavailable": str(exc)}
+            res["fused_state"]["sequence"] = {"unavailable": str(exc)}
         if not args.no_e2e:
             host_in = {}
-            for k, v in fin.items():
+            for k, v in fins[0].items():
                 buf = pinned_empty(tuple(v.shape))
                 buf[...] = v.cpu().numpy()
                 host_in[k] = buf
@@ -448,60 +621,101 @@ def main():
                 eng.step_fused_host(host_in, out=host_out, want_status=False)
             if world > 1:
                 dist.barrier()
-            t0 = time.perf_counter()
             reps = max(3, min(args.steps, 10))
+            t0 = time.perf_counter()
             for _ in range(reps):
                 eng.step_fused_host(host_in, out=host_out, want_status=False)
-            dt = (time.perf_counter() - t0) / reps
-            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            assert np.isfinite(host_out["ctrl"]).all()
-            fused["e2e"] = {"value": world * B / float(tt.item()), "unit": UNIT,
-                            "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in.values())),
-                            "d2h_bytes_per_step": int(host_out["ctrl"].nbytes), "ms_per_step": 1e3 * float(tt.item()),
-                            "api": "BatchedOSC.step_fused_host -> irlosc_step_fused_host (pinned host buffers)"}
+            dt = allmax((time.perf_counter() - t0) / reps)
+            res["fused_state"]["e2e"] = {"value": world * B / dt, "unit": UNIT,
+                                         "h2d_bytes_per_step": int(sum(a.nbytes for a in host_in.values())),
+                                         "d2h_bytes_per_step": int(host_out["ctrl"].nbytes), "ms_per_step": 1e3 * dt,
+                                         "api": "BatchedOSC.step_fused_host -> irlosc_step_fused_host (pinned host buffers)"}
+        del flush
+    except Exception as exc:
+        res["fused_state"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    if world > 1 or rank != 0:
+        return res
 
-    # ------------------------------------------------------------ roofline + CPU baseline (rank 0)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    abytes = algorithmic_bytes(layout)
-    achieved = abytes * B / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tpath):
-        tj = json.load(open(tpath))
-        key = "%s_B%d_%s" % (args.workload, B, args.m_layout)
-        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": kernel_name, "kernel_ms": kernel_ms,
-                "algorithmic_bytes_per_step": abytes, "input_bytes_per_step": in_bytes // B, "peak_source": peak_src}
-    cb = None
-    if world == 1 and not args.no_cpu_baseline:
-        nsample = (os.cpu_count() or 1) * 192
-        sub = {k: v[:nsample] for k, v in st.items()}
-        cb = cpu_baseline(layout, oracle_inputs(sub, layout))
-    config["gather"] = gather_mode
-    side = None
-    if world == 1 and not args.no_side_legs:
-        side = side_legs()
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb, "fused_state": fused}
-    if side is not None:
-        line["side_legs"] = side
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    # ---- BASELINE.json configs 2-4 and the worst case: oracle check on a strided subset, then the kernel time
+    from oracle import osc_numpy
+    cfgs = []
+    for wl, Bc in (("gain_test", 4096), ("admit_test", 8192), ("insertion", 16384), ("worst_case", 65536)):
+        lay = scenario_layout(wl)
+        en = BatchedOSC(lay, device=dev.index)
+        ss = [synth_batch(lay, Bc, seed=77 + i, device=dev, insertion_schedule=(wl == "insertion")) for i in range(N_INPUT_SETS)]
+        tl = [en.pack_tiles(kernel_inputs(s, lay, qM=True)) for s in ss]
+        o = en.step_tiles(tl[0], Bc, want_u_all=True)
+        torch.cuda.synchronize()
+        idx = np.arange(0, Bc, max(1, Bc // 96))
+        ref = osc_numpy.osc_batch(lay.as_dict(), oracle_inputs(ss[0], lay), idx=idx)
+        got = o["u_all"].cpu().numpy()[idx]
+        err = float((np.abs(got - ref["u_all"]).max(axis=1) / np.abs(ref["u_all"]).max(axis=1)).max())
+        st_ = o["status"].cpu().numpy()
+        oc = {"ctrl": torch.empty(Bc, lay.n_ctrl, dtype=torch.float64, device=dev)}
+        ts = []
+        if tl[0].numel() * 8 * N_INPUT_SETS < (300 << 20):           # small inputs: flush L2 between steps instead
+            fl = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+            for i in range(n):
+                fl.zero_()
+                ts += event_times(torch, lambda _i: en.step_tiles(tl[i % N_INPUT_SETS], Bc, out=oc, want_status=False), 1)
+            policy = "256 MB flush write between timed steps"
+            del fl
+        else:
+            ts = event_times(torch, lambda i: en.step_tiles(tl[i % N_INPUT_SETS], Bc, out=oc, want_status=False), n)
+            policy = "inputs larger than L2 (rotating sets)"
+        ms = median(ts)
+        ab = algorithmic_bytes(lay)
+        mv = en.tile_entries * 8 + 8 * lay.n_ctrl
+        cfgs.append({"workload": wl, "B": Bc, "k": lay.k, "kernel": en.last_kernel, "ms": ms, "value": Bc / (ms * 1e-3),
+                     "roofline": {"frac": ab * Bc / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": ab,
+                                  "moved_bytes_per_step": mv, "moved_frac": mv * Bc / (ms * 1e-3) / 1e9 / peak},
+                     "max_rel_err_vs_oracle": err, "oracle_instances": int(len(idx)),
+                     "pinv_share": float(((st_ & 1) != 0).mean()), "warp_finished_share": float(((st_ & 4) != 0).mean()),
+                     "l2_policy": policy})
+        en.close()
+        del ss, tl, o, oc
+        torch.cuda.empty_cache()
+    res["configs"] = cfgs
+
+    # ---- B = 1: the drop-in OSC.generate (examples/gain_test.py:143-147 calls it every 1 ms) next to the CPU path
+    try:
+        import irl_control_b200 as pkg
+        from irl_control_b200.synthetic import build_scenario
+        app, osc, names, lay1 = build_scenario("gain_test")
+        targets = {nm: pkg.Target([0.3, 0.2, 0.6, 0.1, -0.3, 0.2]) for nm in names}
+        for _ in range(20):
+            osc.generate(targets)
+        ts = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            osc.generate(targets)
+            ts.append(time.perf_counter() - t0)
+        st1 = osc.gather_state(targets)
+        e1 = osc.engine_for(names)
+        t_call = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            e1.step_host(st1)
+            t_call.append(time.perf_counter() - t0)
+        st64 = synth_batch(lay1, 64, seed=3)
+        ob = oracle_inputs(st64, lay1)
+        t0 = time.perf_counter()
+        osc_numpy.osc_batch(lay1.as_dict(), ob)
+        port_us = 1e6 * (time.perf_counter() - t0) / 64
+        lat = {"generate_latency_us": 1e6 * median(ts), "generate_p90_us": 1e6 * sorted(ts)[int(0.9 * len(ts))],
+               "of_which_c_abi_step_host_us": 1e6 * median(t_call), "numpy_port_per_call_us": port_us,
+               "note": "B = 1 through Device / Robot / OSC.generate on the stand-in simulator: gather_state (Python) + "
+                       "irlosc_step_host (H2D, one kernel, D2H, stream sync); the reference's 1 kHz loop budget is 1000 us"}
+        if cpu_kind() == "reference":
+            from oracle import ref_harness
+            runner = ref_harness.scenario_runner("gain_test")
+            spent, calls, _ = ref_harness.time_reference_generate(runner, ob)
+            lat["reference_generate_per_call_us"] = 1e6 * spent / calls
+        res["latency_b1"] = lat
+    except Exception as exc:
+        res["latency_b1"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
+    return res
 
 
 if __name__ == "__main__":

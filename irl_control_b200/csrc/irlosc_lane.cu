@@ -40,59 +40,86 @@ struct LaneEntry {
     int kd;
     bool has_base;
     int threads;
+    bool staged;
     const void *fn;
     int fix_bytes;
     const char *name;
 };
 
-template <int KD, bool HB, int NT>
+template <int KD, bool HB, int NT, bool ST>
 LaneEntry lentry(const char *name) {
-    return LaneEntry{KD, HB, NT, (const void *)osc_step_lane<KD, HB, NT>, (int)((sizeof(fused::WarpFix<KD, HB>) + 15) & ~size_t(15)), name};
+    return LaneEntry{KD, HB, NT, ST, (const void *)osc_step_lane<KD, HB, NT, ST>, (int)((sizeof(fused::WarpFix<KD, HB>) + 15) & ~size_t(15)), name};
 }
 
-// A thread owns an instance and there is no staging memory, so the warps per SM are bounded by registers alone:
-// 65 536 / threads per thread.  More warps hide more latency, fewer registers spill more; the table keeps the
-// candidates that were measured (profiles/), lane_threads_for picks per batch.
+// A thread owns an instance, so the warps per SM are bounded by registers: 65 536 / threads per thread.  More warps
+// hide more latency, fewer registers spill more; the table keeps the candidates that were measured (profiles/).
+// "tma": groups staged through a per-warp shared-memory ring by TMA bulk copies; "ldg": direct coalesced loads.
 const LaneEntry *lane_table(int *count) {
     static const LaneEntry t[] = {
-        lentry<3, true, 256>("osc_step_lane<kd3,base,t256>"),   lentry<3, true, 320>("osc_step_lane<kd3,base,t320>"),
-        lentry<3, true, 384>("osc_step_lane<kd3,base,t384>"),   lentry<3, true, 448>("osc_step_lane<kd3,base,t448>"),
-        lentry<3, true, 512>("osc_step_lane<kd3,base,t512>"),
-        lentry<3, false, 256>("osc_step_lane<kd3,t256>"),       lentry<3, false, 384>("osc_step_lane<kd3,t384>"),
-        lentry<3, false, 448>("osc_step_lane<kd3,t448>"),
-        lentry<6, false, 256>("osc_step_lane<kd6,t256>"),       lentry<6, false, 320>("osc_step_lane<kd6,t320>"),
-        lentry<6, false, 384>("osc_step_lane<kd6,t384>"),       lentry<6, false, 448>("osc_step_lane<kd6,t448>"),
-        lentry<6, true, 256>("osc_step_lane<kd6,base,t256>"),   lentry<6, true, 320>("osc_step_lane<kd6,base,t320>"),
-        lentry<6, true, 384>("osc_step_lane<kd6,base,t384>"),   lentry<6, true, 448>("osc_step_lane<kd6,base,t448>"),
+        lentry<3, true, 224, true>("osc_step_lane<kd3,base,t224,tma>"),   lentry<3, true, 256, true>("osc_step_lane<kd3,base,t256,tma>"),
+        lentry<3, true, 320, true>("osc_step_lane<kd3,base,t320,tma>"),   lentry<3, true, 384, true>("osc_step_lane<kd3,base,t384,tma>"),
+        lentry<3, false, 224, true>("osc_step_lane<kd3,t224,tma>"),       lentry<3, false, 256, true>("osc_step_lane<kd3,t256,tma>"),
+        lentry<6, false, 224, true>("osc_step_lane<kd6,t224,tma>"),       lentry<6, false, 256, true>("osc_step_lane<kd6,t256,tma>"),
+        lentry<6, true, 224, true>("osc_step_lane<kd6,base,t224,tma>"),   lentry<6, true, 256, true>("osc_step_lane<kd6,base,t256,tma>"),
+        lentry<3, true, 224, false>("osc_step_lane<kd3,base,t224,ldg>"),  lentry<3, true, 256, false>("osc_step_lane<kd3,base,t256,ldg>"),
+        lentry<3, true, 384, false>("osc_step_lane<kd3,base,t384,ldg>"),
+        lentry<3, false, 256, false>("osc_step_lane<kd3,t256,ldg>"),
+        lentry<6, false, 256, false>("osc_step_lane<kd6,t256,ldg>"),
+        lentry<6, true, 256, false>("osc_step_lane<kd6,base,t256,ldg>"),
     };
     *count = (int)(sizeof t / sizeof t[0]);
     return t;
 }
+
+constexpr size_t kLaneSmem = 227 * 1024;
 
 int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
 }
 
-// default threads per CTA (one CTA per SM); IRLOSC_LANE_THREADS overrides for experiments
-int lane_threads_for(int kd, int64_t B, int sms) {
-    (void)B; (void)sms;
-    return kd == 3 ? 448 : 384;
+// Threads per CTA (one CTA per SM).  Measured (profiles/): 8 warps at the full 255 registers beat 10 - 14 warps with
+// spills in every configuration.  A warp owns a 32-instance tile, so a batch is ceil(tiles / (SMs x warps)) waves;
+// 7 warps are taken when that needs no more waves than 8 (B = 65 536 on 148 SMs: 1.73 waves of 8 or 1.98 of 7).
+// IRLOSC_LANE_THREADS overrides for experiments.
+int lane_threads_for(int64_t B, int sms) {
+    const int64_t tiles = (B + kTile - 1) / kTile;
+    const int64_t w8 = (tiles + (int64_t)sms * 8 - 1) / ((int64_t)sms * 8), w7 = (tiles + (int64_t)sms * 7 - 1) / ((int64_t)sms * 7);
+    return (w7 <= w8 && tiles > (int64_t)sms * 7) ? 224 : 256;
 }
 
 int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_tiles_io &io, cudaStream_t st) {
     const KParams &P = h->kp;
     int cnt = 0;
     const LaneEntry *t = lane_table(&cnt), *e = nullptr;
-    const int want = env_int("IRLOSC_LANE_THREADS", lane_threads_for(c.kd, B, h->sm_count));
-    for (int i = 0; i < cnt; ++i)
-        if (t[i].kd == c.kd && t[i].has_base == c.has_base && (e == nullptr || abs(t[i].threads - want) < abs(e->threads - want))) e = &t[i];
+    const int want = env_int("IRLOSC_LANE_THREADS", lane_threads_for(B, std::max(1, h->sm_count - h->sm_margin)));
+    // 3-row arm devices: groups staged by TMA bulk copies (measured -11 % vs direct loads); 6-row arm devices: direct
+    // loads (their groups are larger: the ring leaves room for fewer warps, measured +4 .. +14 %)
+    bool staged = env_int("IRLOSC_LANE_STAGED", c.kd == 3 ? 1 : 0) != 0;
+    int stage_bytes = 0;
+    for (int g = 0; g < kGroups; ++g) stage_bytes = std::max(stage_bytes, (c.spec.gbase[g + 1] - c.spec.gbase[g]) * kTile * 8);
+    int n_stages = 0, warp_bytes = 0;
+    for (int pass = 0; pass < 2 && !e; ++pass, staged = false) {
+        for (int i = 0; i < cnt; ++i)
+            if (t[i].kd == c.kd && t[i].has_base == c.has_base && t[i].staged == staged &&
+                (e == nullptr || abs(t[i].threads - want) < abs(e->threads - want))) e = &t[i];
+        if (!e) continue;
+        const int warps_ = e->threads / 32;
+        const int rest_bytes = ((32 * P.n_ctrl * 8 + 15) & ~15) + e->fix_bytes;
+        n_stages = 0;
+        if (e->staged) {      // ring depth: 3 preferred (two groups in flight while one is consumed), 2 if that is all that fits
+            n_stages = std::min(4, std::max(2, env_int("IRLOSC_LANE_STAGES", 3)));
+            while (n_stages > 2 && (size_t)warps_ * ((size_t)n_stages * stage_bytes + 64 + rest_bytes) > kLaneSmem) --n_stages;
+        }
+        warp_bytes = (e->staged ? n_stages * stage_bytes + 64 : 0) + rest_bytes;
+        if ((size_t)warps_ * warp_bytes > kLaneSmem) e = nullptr;      // the ring does not fit: direct loads
+    }
     if (!e) return fail(IRLOSC_ERR_INVALID, "no lane kernel for kd=%d base=%d", c.kd, (int)c.has_base);
     LaneArgs A;
     memset(&A, 0, sizeof A);
     A.tiles = io.tiles;
     A.n_entries = c.spec.n_entries;
-    A.pf = env_int("IRLOSC_LANE_PREFETCH", 0);
+    A.pf = env_int("IRLOSC_LANE_PREFETCH", 2);      // L2 prefetch two groups ahead (measured: -7 % at k = 7)
     for (int g = 0; g <= kGroups; ++g) A.gbase[g] = c.spec.gbase[g];
     A.target_vel = io.target_vel;
     A.u_all = io.u_all; A.ctrl = io.ctrl; A.status = io.status;
@@ -110,18 +137,18 @@ int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_
         G.ctrl_vec = G.ctrl_vec && al16(io.ctrl_gather[g]);
     }
     const int warps = e->threads / 32;
-    const int warp_bytes = ((32 * P.n_ctrl * 8 + 15) & ~15) + e->fix_bytes;
     const size_t smem = (size_t)warps * warp_bytes;
     static bool ready = false;
     if (!ready) {
         for (int i = 0; i < cnt; ++i)
-            CUDA_TRY(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            CUDA_TRY(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLaneSmem));
         ready = true;
     }
     const int sms = std::max(1, h->sm_count - h->sm_margin);
     const int64_t n_tiles = (B + kTile - 1) / kTile;
     const int grid = (int)std::min<int64_t>((n_tiles + warps - 1) / warps, (int64_t)sms);
-    void *args[] = {(void *)&P, (void *)&A, (void *)&B, (void *)&c.R, (void *)&G, (void *)&warp_bytes};
+    void *args[] = {(void *)&P, (void *)&A, (void *)&B, (void *)&c.R, (void *)&G, (void *)&warp_bytes, (void *)&stage_bytes,
+                    (void *)&n_stages};
     cudaError_t err = cudaLaunchKernel(e->fn, dim3(grid), dim3(e->threads), args, smem, st);
     if (err != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "lane kernel launch: %s", cudaGetErrorString(err));
     h->launches += 1;

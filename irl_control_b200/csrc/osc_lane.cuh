@@ -36,6 +36,7 @@
 #include "osc_fused_types.h"
 #include "osc_tail.cuh"
 #include "osc_stream.cuh"
+#include "osc_tma.cuh"
 #include "irlosc_build.h"
 
 namespace irlosc {
@@ -314,32 +315,76 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void *p, uint32_t bytes) 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
-template <int KD, bool HAS_BASE, int NT>
+// STAGED = false: lanes load their entries straight from HBM / L2 into registers (LDG, one coalesced 256-byte request
+//                 per entry), an optional bulk L2 prefetch runs A.pf groups ahead.
+// STAGED = true : a group of a tile is ONE contiguous block of HBM, so one elected lane brings it into the warp's
+//                 shared-memory ring with a single TMA bulk copy (cp.async.bulk + mbarrier complete_tx) NS - 1 groups
+//                 ahead of its use; the lanes then read conflict-free LDS.64 ([entry][lane]).  ncu on the LDG form:
+//                 47 % of the stall cycles are long_scoreboard (waiting for the loads of the group just started).
+template <int KD, bool HAS_BASE, int NT, bool STAGED>
 __global__ void __launch_bounds__(NT, 1)
 osc_step_lane(const __grid_constant__ KParams P, const __grid_constant__ LaneArgs A, const int64_t B,
-              const __grid_constant__ FRoles R, const __grid_constant__ stream::Gather G, const int warp_bytes) {
+              const __grid_constant__ FRoles R, const __grid_constant__ stream::Gather G, const int warp_bytes,
+              const int stage_bytes, const int n_stages) {
     extern __shared__ __align__(16) unsigned char lane_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = NT / 32;
     unsigned char *wbase = lane_smem + (size_t)warp * warp_bytes;
-    double *ctile = reinterpret_cast<double *>(wbase);                                   // [32][n_ctrl]
+    // per warp: [ring of n_stages x stage_bytes (STAGED)][mbarriers][packed ctrl tile][warp-finish scratch]
+    unsigned char *ring = wbase;
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(wbase + (STAGED ? (size_t)n_stages * stage_bytes : 0));
+    unsigned char *rest = reinterpret_cast<unsigned char *>(bars) + (STAGED ? 64 : 0);
+    double *ctile = reinterpret_cast<double *>(rest);                                   // [32][n_ctrl]
     fused::WarpFix<KD, HAS_BASE> &wfix =
-        *reinterpret_cast<fused::WarpFix<KD, HAS_BASE> *>(wbase + ((32 * P.n_ctrl * 8 + 15) & ~15));
+        *reinterpret_cast<fused::WarpFix<KD, HAS_BASE> *>(rest + ((32 * P.n_ctrl * 8 + 15) & ~15));
     const int64_t n_tiles = (B + kTile - 1) / kTile;
     const int64_t tile_doubles = (int64_t)A.n_entries * kTile;
     // warps of a CTA take neighbouring tiles, CTAs stride over the batch
-    for (int64_t tile = (int64_t)blockIdx.x * W + warp; tile < n_tiles; tile += (int64_t)gridDim.x * W) {
+    const int64_t gw = (int64_t)blockIdx.x * W + warp, gstride = (int64_t)gridDim.x * W;
+    const int64_t my_tiles = gw < n_tiles ? (n_tiles - gw + gstride - 1) / gstride : 0;
+    const int64_t total = my_tiles * kGroups;
+    int64_t seq = 0;                                     // groups consumed so far by this warp
+    auto issue = [&](int64_t q) {                        // one lane: bulk copy of group q of this warp's sequence
+        const int64_t tile = gw + (q / kGroups) * gstride;
+        const int g = (int)(q % kGroups);
+        const int s = (int)(q % n_stages);
+        const uint32_t bytes = (uint32_t)(A.gbase[g + 1] - A.gbase[g]) * kTile * 8u;
+        tiled::mbar_expect_tx(&bars[s], bytes);
+        tiled::bulk_g2s(ring + (size_t)s * stage_bytes, A.tiles + tile * tile_doubles + (size_t)A.gbase[g] * kTile, bytes, &bars[s]);
+    };
+    if (STAGED) {
+        if (lane == 0) {
+            for (int s = 0; s < n_stages; ++s) tiled::mbar_init(&bars[s], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            for (int64_t q = 0; q < n_stages - 1 && q < total; ++q) issue(q);
+        }
+        __syncwarp();
+    }
+    for (int64_t k = 0; k < my_tiles; ++k) {
+        const int64_t tile = gw + k * gstride;
         const double *tb = A.tiles + tile * tile_doubles;
         const double *tl = tb + lane;
         const int64_t inst = tile * kTile + lane;
         const bool valid = inst < B;
         const int64_t inst_c = valid ? inst : B - 1;
-        if (A.pf > 0 && lane == 0) bulk_prefetch_l2(tb, (uint32_t)((A.gbase[A.pf < kGroups ? A.pf : kGroups]) * kTile * 8));
+        if (!STAGED && A.pf > 0 && lane == 0) bulk_prefetch_l2(tb, (uint32_t)((A.gbase[A.pf < kGroups ? A.pf : kGroups]) * kTile * 8));
         auto group = [&](int g) {
-            if (A.pf > 0 && lane == 0 && g + A.pf < kGroups)
-                bulk_prefetch_l2(tb + (size_t)A.gbase[g + A.pf] * kTile,
-                                 (uint32_t)((A.gbase[g + A.pf + 1] - A.gbase[g + A.pf]) * kTile * 8));
-            const double *p = tl + (size_t)A.gbase[g] * kTile;
-            return [p](int e) { return LdStream{}(p + e * kTile); };
+            const double *p;
+            if (STAGED) {
+                __syncwarp();                            // every lane is done with the stage that is refilled now
+                const int64_t q = seq++;
+                if (lane == 0 && q + n_stages - 1 < total) {
+                    tiled::fence_proxy_async();
+                    issue(q + n_stages - 1);
+                }
+                tiled::mbar_wait(&bars[q % n_stages], (uint32_t)((q / n_stages) & 1));
+                p = reinterpret_cast<const double *>(ring + (size_t)(q % n_stages) * stage_bytes) + lane;
+            } else {
+                if (A.pf > 0 && lane == 0 && g + A.pf < kGroups)
+                    bulk_prefetch_l2(tb + (size_t)A.gbase[g + A.pf] * kTile,
+                                     (uint32_t)((A.gbase[g + A.pf + 1] - A.gbase[g + A.pf]) * kTile * 8));
+                p = tl + (size_t)A.gbase[g] * kTile;
+            }
+            return [p](int e) { return STAGED ? p[e * kTile] : LdStream{}(p + e * kTile); };
         };
         const JTile<KD, HAS_BASE, LdCached> ja{tl, {A.gbase[4], A.gbase[9]}, A.gbase[0], LdCached{}};
         LaneState<KD, HAS_BASE> T;

@@ -380,7 +380,7 @@ class BatchedOSC:
         return out
 
     # ------------------------------------------------------------------ fused state provider
-    _FUSED_FIELDS = (""q", "dq", "target_xyz", "target_quat", "target_vel", "max_vel", "ft_raw")
+    _FUSED_FIELDS = ("q", "dq", "target_xyz", "target_quat", "target_vel", "max_vel", "ft_raw")
 
     def set_model(self, model: "_native.Model"):
         """Attach the rigid-body description (`rigid_model.reduce_model`) the fused step needs."""

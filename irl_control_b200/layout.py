@@ -70,6 +70,20 @@ class OscLayout:
             at += len(d.actuator_trnids)
         return out
 
+    @property
+    def tile_entries(self) -> int:
+        """Doubles per instance in the batch-interleaved tile layout (csrc/osc_lane.cuh build_tile_spec;
+        `irlosc_tile_entries` is the authority, the GPU tests compare the two); 0 when the controller has none."""
+        arms = [d for d in self.devices if d.name != "base" and d.ee_joint in (6, 18)]
+        base = [d for d in self.devices if d.ee_joint == 0]
+        if self.joint_parent is None or len(arms) != 2 or len(arms) + len(base) != self.D or len(base) > 1:
+            return 0
+        kd = arms[0].n_rows
+        if arms[1].n_rows != kd or kd not in (3, 6) or (base and base[0].n_rows != 1):
+            return 0
+        dev_n = 31 if self.admittance else 16          # poses 14 + max_vel 2 [+ F/T frame 9 + raw wrench 6]
+        return 2 + (dev_n if base else 0) + 2 * (35 + 2 * 31 + 7 * kd + 6 + dev_n)
+
     def as_dict(self) -> Dict:
         return {
             "n": self.n, "use_g": self.use_g, "admittance": self.admittance,

@@ -121,9 +121,15 @@ class OSC:
             if dev.max_vel is not None:
                 st["max_vel"][0, d] = dev.max_vel
             if self.admittance is True:
-                R = dev.ft_frame_xmat()
-                st["ft_xmat"][0, d] = np.eye(3).reshape(-1) if R is None else np.asarray(R).reshape(-1)
-                st["ft_raw"][0, d] = dev.ft_raw()
+                if self.robot.is_using_sim():
+                    R = dev.ft_frame_xmat()
+                    st["ft_xmat"][0, d] = np.eye(3).reshape(-1) if R is None else np.asarray(R).reshape(-1)
+                    st["ft_raw"][0, d] = dev.ft_raw()
+                else:
+                    # polling-thread mode: the wrench of the SAME snapshot as the rest of the state (osc.py:179 reads
+                    # robot_state[name][FORCE / TORQUE]), already rotated into the world frame
+                    st["ft_xmat"][0, d] = np.eye(3).reshape(-1)
+                    st["ft_raw"][0, d] = np.concatenate([rs[nm][DeviceState.FORCE], rs[nm][DeviceState.TORQUE]])
         if np.any(tvel != 0.0):
             st["target_vel"] = tvel
         return st

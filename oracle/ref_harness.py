@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY - run the UNMODIFIED reference OSC against a fake sim.
 
 Imports `irl_control/{device,robot,osc,utils}.py` straight from
-/root/reference (read-only, never copied) after registering stub modules for
+/root/reference (or its verbatim, git-ignored copy oracle/_ref/ staged by oracle/stage_ref.py) after registering stub modules for
 the two third-party packages those files import and that do not exist in this
 image:
 
@@ -26,7 +26,17 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 import yaml
 
-REFERENCE_ROOT = os.environ.get("IRL_REFERENCE_ROOT", "/root/reference")
+def _reference_root() -> str:
+    """/root/reference (build container), else the verbatim copy staged by oracle/stage_ref.py (GPU box)."""
+    env = os.environ.get("IRL_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/irl_control/osc.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available() -> bool:
@@ -264,6 +274,48 @@ class ReferenceRunner:
         t.set_xyz(np.array(tgt_xyz, dtype=np.float64))
         t.set_quat(np.array(tgt_quat, dtype=np.float64))
         return self.osc.calc_error(t, self.robot.get_device(name))
+
+
+def scenario_runner(scenario: str, use_g: bool = True, nullspace: bool = True) -> "ReferenceRunner":
+    """The reference's own Device / Robot / OSC for a named scenario of irl_control_b200.synthetic.SCENARIOS, built from
+    the reference's YAML (start_body injected) on the fake simulator."""
+    from irl_control_b200.configs import SCENE_FREE_OBJECTS
+    from irl_control_b200.dual_ur5 import DualUR5Model
+    from irl_control_b200.synthetic import SCENARIOS
+    sc = SCENARIOS[scenario]
+    cfg = load_reference_yaml(sc["config"].replace("+start_body", ""), inject_start_body=True)
+    for dev in cfg["devices"]:                          # a scenario may stand for a user-edited YAML
+        dev.update(sc.get("config_patch", {}).get(dev["name"], {}))
+    model = DualUR5Model(n_free_objects=SCENE_FREE_OBJECTS[sc["scene"]])
+    return ReferenceRunner(model, cfg, sc["device_cfgs"], sc["targets"], "nullspace" if nullspace else None,
+                           use_g=use_g, admittance=sc["admittance"])
+
+
+def time_reference_generate(runner: "ReferenceRunner", batch: Dict[str, np.ndarray], repeat: int = 1):
+    """Seconds spent inside the UNMODIFIED `OSC.generate` (osc.py:120-210, state pulls of robot.py / device.py
+    included) over the instances of `batch` (oracle field names, see synthetic.oracle_inputs); loading an instance
+    into the fake simulator is not timed.  Returns (seconds, calls, last forces)."""
+    import time
+    B = batch["M"].shape[0]
+    spent, calls, forces = 0.0, 0, None
+    for _ in range(repeat):
+        for i in range(B):
+            st = {"M": batch["M"][i], "J6": batch["J"][i], "dq": batch["dq"][i], "bias": batch["bias"][i],
+                  "ee_xyz": batch["ee_xyz"][i], "ee_quat": batch["ee_quat"][i], "ft_xmat": batch["ft_xmat"][i],
+                  "ft_raw": batch["ft_raw"][i]}
+            runner.sim.load_instance(st, runner.target_names, runner.devices)
+            targets = {}
+            for d, name in enumerate(runner.target_names):
+                t = runner.Target()
+                t.set_xyz(np.array(batch["tgt_xyz"][i][d], dtype=np.float64))
+                t.set_quat(np.array(batch["tgt_quat"][i][d], dtype=np.float64))
+                targets[name] = t
+                runner.robot.get_device(name).max_vel = [float(batch["max_vel"][i][d][0]), float(batch["max_vel"][i][d][1])]
+            t0 = time.perf_counter()
+            _, forces = runner.osc.generate(targets)
+            spent += time.perf_counter() - t0
+            calls += 1
+    return spent, calls, forces
 
 
 # ---------------------------------------------------------------- the insertion demo's caller loop, unmodified

@@ -82,3 +82,51 @@ def generate_on_golden(case):
         worst = max(worst, np.abs(got - g["ctrl"][i]).max() / np.abs(g["u_all"][i]).max())
         assert [list(x) for x in idxs] == [list(robot.get_device(nm).ctrl_idxs) for nm in names]
     assert worst < 1e-6, worst
+
+
+def test_generate_from_the_polling_thread_cache(monkeypatch):
+    """`use_sim=False` (robot.py:103-123): `Robot.start()` runs in a thread, `generate` is served from the cached
+    snapshot - M, J, dq, EE poses and, with admittance, the ROTATED wrench of that same snapshot (osc.py:179) - and
+    returns what the live-simulator mode returns for the same state."""
+    import threading
+    import time
+    monkeypatch.setattr(pkg_osc, "BatchedOSC", _HostEngine)
+    g, ld = load_golden("admit_test_s1")
+    sc = SCENARIOS["admit_test"]
+    cfg = patched_config(sc)
+    model = DualUR5Model(n_free_objects=configs.SCENE_FREE_OBJECTS[sc["scene"]])
+    names = list(sc["targets"])
+    by_name = {c["name"]: c for c in cfg["controller_configs"]}
+    keys = ("M", "J6", "dq", "bias", "ee_xyz", "ee_quat", "ft_xmat", "ft_raw")
+    results = {}
+    for use_sim in (True, False):
+        sim = _Sim(model)
+        devices = [pkg.Device(d, model, sim, use_sim) for d in cfg["devices"]]
+        robot = pkg.Robot([devices[i] for i in cfg["robots"][0]["device_ids"]], "DualUR5", sim, use_sim)
+        osc = pkg.OSC(robot, sim, [(dev, dict(by_name[c])) for dev, c in sc["device_cfgs"]], dict(by_name["nullspace"]),
+                      admittance=True)
+        sim.load_instance({k: g[k][3] for k in keys}, names, devices)
+        targets = {}
+        for d, nm in enumerate(names):
+            t = pkg.Target(np.zeros(6), np.zeros(6))
+            t.set_xyz(g["target_xyz"][3][d])
+            t.set_quat(g["target_quat"][3][d])
+            targets[nm] = t
+        th = None
+        if not use_sim:
+            with pytest.raises(AssertionError):
+                osc.generate(targets)                           # not running yet (osc.py:129-130)
+            th = threading.Thread(target=robot.start, daemon=True)
+            th.start()
+            deadline = time.time() + 5.0
+            while time.time() < deadline and len(robot._cache) < 3:
+                time.sleep(0.005)
+            time.sleep(0.02)                                    # at least one full refresh of every variable
+            assert robot.is_running()
+        results[use_sim] = np.concatenate(osc.generate(targets)[1])
+        if th is not None:
+            robot.stop()
+            th.join(timeout=2.0)
+            assert not th.is_alive()
+    assert np.abs(results[True] - g["ctrl"][3]).max() < 1e-6 * np.abs(g["u_all"][3]).max()
+    assert np.allclose(results[False], results[True], rtol=0, atol=1e-9 * np.abs(results[True]).max())

@@ -34,8 +34,11 @@ def main():
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--threads", default="256,320,384,448,512")
     ap.add_argument("--prefetch", default="0,2")
+    ap.add_argument("--staged", default="1", help="comma-separated: 1 = TMA-staged ring, 0 = direct LDG")
+    ap.add_argument("--stages", default="3", help="comma-separated ring depths for the staged form")
     ap.add_argument("--nbuf", type=int, default=3)
     ap.add_argument("--others", default="tree_packed,tree_qm,stream_qm,fused,pack")
+    ap.add_argument("--sweep", default="", help="comma-separated batch sizes: time the default lane launch on prefixes of the tiles")
     args = ap.parse_args()
     import torch
     from irl_control_b200.engine import BatchedOSC
@@ -62,16 +65,35 @@ def main():
     ref = eng.step(kq[0], want_status=True)
     ref = {k: v.clone() for k, v in ref.items()}
     for th in [int(x) for x in args.threads.split(",") if x]:
-        for pf in [int(x) for x in args.prefetch.split(",") if x]:
-            os.environ["IRLOSC_LANE_THREADS"] = str(th)
-            os.environ["IRLOSC_LANE_PREFETCH"] = str(pf)
-            o = eng.step_tiles(tiles[0], B, want_status=True)
-            same = bool(torch.equal(o["ctrl"], ref["ctrl"]) and torch.equal(o["status"], ref["status"]))
-            med, mn = timeit(torch, lambda i: eng.step_tiles(tiles[i % args.nbuf], B, out=out, want_status=False), args.iters)
-            rec("lane", med, mn, threads=th, prefetch=pf, equal_to_stream=same, tile_bytes_per_instance=E * 8)
-    os.environ.pop("IRLOSC_LANE_THREADS", None)
-    os.environ.pop("IRLOSC_LANE_PREFETCH", None)
-    others = args.others.split(",")
+        for stg in [int(x) for x in args.staged.split(",") if x]:
+            variants = [("stages", int(x)) for x in args.stages.split(",") if x] if stg else \
+                       [("prefetch", int(x)) for x in args.prefetch.split(",") if x]
+            for key, val in variants:
+                os.environ["IRLOSC_LANE_THREADS"] = str(th)
+                os.environ["IRLOSC_LANE_STAGED"] = str(stg)
+                os.environ["IRLOSC_LANE_STAGES" if stg else "IRLOSC_LANE_PREFETCH"] = str(val)
+                o = eng.step_tiles(tiles[0], B, want_status=True)
+                same = bool(torch.equal(o["ctrl"], ref["ctrl"]) and torch.equal(o["status"], ref["status"]))
+                med, mn = timeit(torch, lambda i: eng.step_tiles(tiles[i % args.nbuf], B, out=out, want_status=False), args.iters)
+                rec("lane", med, mn, threads=th, staged=stg, **{key: val}, equal_to_stream=same, tile_bytes_per_instance=E * 8)
+    for k_ in ("IRLOSC_LANE_THREADS", "IRLOSC_LANE_PREFETCH", "IRLOSC_LANE_STAGED", "IRLOSC_LANE_STAGES"):
+        os.environ.pop(k_, None)
+    for Bs in [int(x) for x in args.sweep.split(",") if x]:
+        nt = (Bs + 31) // 32
+        sub = [t[:nt] for t in tiles]
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        ts = []
+        for i in range(args.iters + 3):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); eng.step_tiles(sub[i % args.nbuf], Bs, out={"ctrl": out["ctrl"][:Bs]}, want_status=False); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts = sorted(ts[3:])
+        r = dict(name="lane_sweep", scenario=args.scenario, B=Bs, ms=round(ts[len(ts) // 2], 5), ms_min=round(ts[0], 5),
+                 kernel=eng.last_kernel, steps_per_s=Bs / (ts[len(ts) // 2] * 1e-3), l2="flushed between steps")
+        print(json.dumps(r), flush=True)
+    others = [x for x in args.others.split(",") if x]
     scale = ref["ctrl"].abs().amax(dim=1, keepdim=True)
     if "tree_packed" in others:
         eng.set_kernel(0)
