@@ -218,6 +218,7 @@ def main():
                     help="result gather for --gpus > 1: fused = multicast stores if the box has NVLS, else peer stores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of one CUDA graph of K steps")
     ap.add_argument("--no-extras", action="store_true",
                     help="headline only: skip the strong-scaling, per-config, arrays-layout, fused-state and latency legs "
                          "(use under ncu)")
@@ -352,22 +353,60 @@ def main():
         for b in range(NBUF):
             wait_pending(b)
 
-    def timed_loop(n, **kw):
-        """n steps back to back between two events on the launching stream (gathers included); ms per step, max over ranks."""
+    launch_mode = ["eager"]
+
+    def capture(n, **kw):
+        """The n steps (kernel launches, side-stream barriers, buffer waits) as ONE CUDA graph: with a ~50 us kernel the
+        Python / driver cost of a step (event + barrier + launch calls) would otherwise set the pace."""
+        if args.no_graph:
+            return None
+        try:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            step_no[0] = 0
+            with torch.cuda.graph(g):
+                for i in range(n):
+                    one_step(i, **kw)
+                drain()
+            torch.cuda.synchronize()
+            return g
+        except Exception as exc:
+            sys.stderr.write("CUDA graph capture unavailable (%s: %s), timing eager launches\n" % (type(exc).__name__, exc))
+            for b in range(NBUF):
+                pending[b] = None
+            torch.cuda.synchronize()
+            return None
+
+    def timed_loop(n, repeat=1, **kw):
+        """`repeat` x n steps back to back between two events on the launching stream (gathers included); ms per step,
+        max over ranks."""
+        g = capture(n, **kw)
+        ok = torch.tensor([1 if g is not None else 0], device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # every rank replays, or none does
+        if int(ok.item()) == 0:
+            g = None
+        launch_mode[0] = "cuda graph of %d steps" % n if g is not None else "eager"
+        if g is not None:
+            g.replay()                                     # warm-up replay
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(n):
-            one_step(i, **kw)
-        drain()
+        for _ in range(repeat):
+            if g is not None:
+                g.replay()
+            else:
+                for i in range(n):
+                    one_step(i, **kw)
+                drain()
         b.record()
         torch.cuda.synchronize()
         t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / n
+        return float(t.item()) / (n * repeat)
 
     W = max(args.warmup, 3)
     for i in range(W):
@@ -377,22 +416,27 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    launches0 = eng.kernel_launches
     t_wall0 = time.time()
     ms_per_step = timed_loop(args.steps)
-    launches = eng.kernel_launches - launches0
+    launches = args.steps                  # one lane-kernel launch per step (the N > 1 barrier kernels are torch's)
+    headline_launch = launch_mode[0]
     value = world * B / (ms_per_step * 1e-3)
-    # the same loop for >= 1 s: what the rate is once clocks and power have settled
-    n_sus = int(min(40000, max(args.steps, 1.0 / (ms_per_step * 1e-3))))
-    sus_ms = timed_loop(n_sus)
+    # the same K steps repeated for >= 1 s: what the rate is once clocks and power have settled
+    rep = int(min(40000, max(1, 1.0 / (ms_per_step * 1e-3 * args.steps))))
+    sus_ms = timed_loop(args.steps, repeat=rep)
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    sustained = {"steps": n_sus, "ms_per_step": sus_ms, "value": world * B / (sus_ms * 1e-3), "seconds": n_sus * sus_ms * 1e-3}
+    sustained = {"steps": rep * args.steps, "ms_per_step": sus_ms, "value": world * B / (sus_ms * 1e-3),
+                 "seconds": rep * args.steps * sus_ms * 1e-3}
 
-    # kernel-only time for the roofline: events around the kernel alone, same stream, rotating inputs
+    # Kernel time for the roofline.  At N = 1 the timed region IS K launches of the kernel back to back, so its average
+    # launch duration is the region's time / K.  Events around single eager launches (which also see the ~5 us of
+    # launch + event overhead a graph hides) are reported beside it, and are the figure used when the region also
+    # contains the gather (N > 1).
     out0 = {"ctrl": outs[0]}
     ks = event_times(torch, lambda i: eng.step_tiles(tiles[i % N_INPUT_SETS], B, out=out0, want_status=False), max(args.steps, 10))
-    kernel_ms = sum(ks) / len(ks)
+    kernel_ms_isolated = sum(ks) / len(ks)
+    kernel_ms = ms_per_step if world == 1 else kernel_ms_isolated
     kernel_name = eng.last_kernel
 
     # ------------------------------------------------------------ gather verification (N > 1)
@@ -401,6 +445,8 @@ def main():
         drain()
         torch.cuda.synchronize()
         dist.barrier()
+        for b in range(NBUF):
+            pending[b] = None
         step_no[0] = 0                                   # buffer 0, input set 0 on every rank
         one_step(0)
         drain()
@@ -512,6 +558,9 @@ def main():
     achieved = abytes * B / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic_for(kernel_name, args.workload, B), "kernel": kernel_name, "kernel_ms": kernel_ms,
+                "kernel_ms_source": ("timed region / K (K back-to-back launches, nothing else on the stream)" if world == 1 else
+                                     "CUDA events around single eager launches (the timed region also holds the gather)"),
+                "kernel_ms_isolated_eager": kernel_ms_isolated,
                 "algorithmic_bytes_per_step": abytes, "peak_source": peak_src,
                 "moved": {"bytes_per_step": moved, "achieved": moved * B / (kernel_ms * 1e-3) / 1e9,
                           "frac": moved * B / (kernel_ms * 1e-3) / 1e9 / peak,
@@ -524,12 +573,83 @@ def main():
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
-            "sustained": sustained, "gather": gather_mode, "gather_verified": gather_verified, "strong": strong,
+            "sustained": sustained, "launch": headline_launch, "gather": gather_mode, "gather_verified": gather_verified,
+            "strong": strong,
             "e2e_arrays": e2e_arrays}
     line.update(extras)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def latency_b1(np, median, scenario="gain_test", calls=300):
+    """Wall time of one `OSC.generate(targets)` for one robot: this package's Device / Robot / OSC (state pull in Python,
+    then irlosc_step_host: H2D, one kernel, D2H, stream sync) and, when its sources are staged, the unmodified
+    reference's - same fake simulator class, same loaded instance, same targets."""
+    import irl_control_b200 as pkg
+    from irl_control_b200 import configs
+    from irl_control_b200.dual_ur5 import DualUR5Model
+    from irl_control_b200.synthetic import SCENARIOS, oracle_inputs, patched_config, scenario_layout, synth_batch
+    from oracle import osc_numpy, ref_harness
+
+    class Sim(ref_harness.FakeSim):
+        def full_mass_matrix(self):                      # what `_mj_fullM` yields (robot.py:69-70)
+            nv = self.model.nv
+            return np.asarray(self.data.qM, dtype=np.float64).reshape(nv, nv)
+
+    sc = SCENARIOS[scenario]
+    cfg = patched_config(sc)
+    lay = scenario_layout(scenario)
+    model = DualUR5Model(n_free_objects=configs.SCENE_FREE_OBJECTS[sc["scene"]])
+    sim = Sim(model)
+    devices = [pkg.Device(d, model, sim, True) for d in cfg["devices"]]
+    robot = pkg.Robot([devices[i] for i in cfg["robots"][0]["device_ids"]], "DualUR5", sim, True)
+    by_name = {c["name"]: c for c in cfg["controller_configs"]}
+    osc = pkg.OSC(robot, sim, [(dev, dict(by_name[c])) for dev, c in sc["device_cfgs"]], dict(by_name["nullspace"]),
+                  admittance=sc["admittance"])
+    names = list(sc["targets"])
+    st = synth_batch(lay, 64, seed=3)
+    ob = oracle_inputs(st, lay)
+    inst = {"M": ob["M"][5], "J6": ob["J"][5], "dq": ob["dq"][5], "bias": ob["bias"][5], "ee_xyz": ob["ee_xyz"][5],
+            "ee_quat": ob["ee_quat"][5], "ft_xmat": ob["ft_xmat"][5], "ft_raw": ob["ft_raw"][5]}
+    sim.load_instance(inst, names, devices)
+    targets = {}
+    for d, nm in enumerate(names):
+        t = pkg.Target(np.zeros(6), np.zeros(6))
+        t.set_xyz(ob["tgt_xyz"][5][d])
+        t.set_quat(ob["tgt_quat"][5][d])
+        targets[nm] = t
+    for _ in range(20):
+        idxs, forces = osc.generate(targets)
+    ref = osc_numpy.osc_batch(lay.as_dict(), {k: v[5:6] for k, v in ob.items()})
+    err = float(np.abs(np.concatenate(forces) - ref["ctrl"][0]).max() / np.abs(ref["u_all"][0]).max())
+    ts, tg, tc = [], [], []
+    for _ in range(calls):
+        t0 = time.perf_counter()
+        osc.generate(targets)
+        ts.append(time.perf_counter() - t0)
+    e1 = osc.engine_for(names)
+    for _ in range(calls):
+        t0 = time.perf_counter()
+        st1 = osc.gather_state(targets)
+        t1 = time.perf_counter()
+        e1.step_host(st1)
+        t2 = time.perf_counter()
+        tg.append(t1 - t0)
+        tc.append(t2 - t1)
+    t0 = time.perf_counter()
+    osc_numpy.osc_batch(lay.as_dict(), ob)
+    lat = {"generate_latency_us": 1e6 * median(ts), "generate_p90_us": 1e6 * sorted(ts)[int(0.9 * len(ts))],
+           "state_pull_python_us": 1e6 * median(tg), "c_abi_step_host_us": 1e6 * median(tc),
+           "numpy_port_per_call_us": 1e6 * (time.perf_counter() - t0) / 64, "max_rel_err_vs_oracle": err,
+           "kernel": e1.last_kernel,
+           "note": "B = 1 through Device / Robot / OSC.generate on a fake simulator: state pull (Python) + irlosc_step_host "
+                   "(H2D, one kernel, D2H, stream sync); the reference's 1 kHz loop budget is 1000 us"}
+    if cpu_kind() == "reference":
+        runner = ref_harness.scenario_runner(scenario)
+        spent, n_calls, _ = ref_harness.time_reference_generate(runner, {k: v[5:6] for k, v in ob.items()}, repeat=calls)
+        lat["reference_generate_per_call_us"] = 1e6 * spent / n_calls
+    return lat
 
 
 def extra_legs(args, torch, np, eng, layout, sts, arrays, tiles, dev, world, dist, rank):
@@ -678,41 +798,10 @@ def extra_legs(args, torch, np, eng, layout, sts, arrays, tiles, dev, world, dis
         torch.cuda.empty_cache()
     res["configs"] = cfgs
 
-    # ---- B = 1: the drop-in OSC.generate (examples/gain_test.py:143-147 calls it every 1 ms) next to the CPU path
+    # ---- B = 1: the drop-in OSC.generate (examples/gain_test.py:143-147 calls it every 1 ms) next to the reference's own,
+    #      both on the same stand-in simulator (oracle.ref_harness.FakeSim, cheap array accessors) and the same state
     try:
-        import irl_control_b200 as pkg
-        from irl_control_b200.synthetic import build_scenario
-        app, osc, names, lay1 = build_scenario("gain_test")
-        targets = {nm: pkg.Target([0.3, 0.2, 0.6, 0.1, -0.3, 0.2]) for nm in names}
-        for _ in range(20):
-            osc.generate(targets)
-        ts = []
-        for _ in range(200):
-            t0 = time.perf_counter()
-            osc.generate(targets)
-            ts.append(time.perf_counter() - t0)
-        st1 = osc.gather_state(targets)
-        e1 = osc.engine_for(names)
-        t_call = []
-        for _ in range(200):
-            t0 = time.perf_counter()
-            e1.step_host(st1)
-            t_call.append(time.perf_counter() - t0)
-        st64 = synth_batch(lay1, 64, seed=3)
-        ob = oracle_inputs(st64, lay1)
-        t0 = time.perf_counter()
-        osc_numpy.osc_batch(lay1.as_dict(), ob)
-        port_us = 1e6 * (time.perf_counter() - t0) / 64
-        lat = {"generate_latency_us": 1e6 * median(ts), "generate_p90_us": 1e6 * sorted(ts)[int(0.9 * len(ts))],
-               "of_which_c_abi_step_host_us": 1e6 * median(t_call), "numpy_port_per_call_us": port_us,
-               "note": "B = 1 through Device / Robot / OSC.generate on the stand-in simulator: gather_state (Python) + "
-                       "irlosc_step_host (H2D, one kernel, D2H, stream sync); the reference's 1 kHz loop budget is 1000 us"}
-        if cpu_kind() == "reference":
-            from oracle import ref_harness
-            runner = ref_harness.scenario_runner("gain_test")
-            spent, calls, _ = ref_harness.time_reference_generate(runner, ob)
-            lat["reference_generate_per_call_us"] = 1e6 * spent / calls
-        res["latency_b1"] = lat
+        res["latency_b1"] = latency_b1(np, median)
     except Exception as exc:
         res["latency_b1"] = {"unavailable": "%s: %s" % (type(exc).__name__, exc)}
     return res

@@ -15,8 +15,10 @@ the benchmark:
 This is input synthesis, not the control law: nothing here is on the timed
 path.  Tensors are torch float64 so the same code runs on the host (tests)
 and on the GPU (benchmark input generation).  Contacts, equality
-constraints, armature, damping and geom-derived inertias are not modelled;
-bodies without an <inertial> element are massless.
+constraints, armature and damping are not modelled.  Bodies without an <inertial> element
+take mass / centre of mass / inertia from their mesh geom at MuJoCo's default density, as MuJoCo's compiler does
+(`base_link_ur5right / _ur5left`, welded to the stand: tools/extract_dual_ur5.py, restated from MuJoCo 2.0 / 2.1's
+mesh algorithm - MuJoCo itself is absent, so this is unpinned); bodies with neither are massless.
 """
 from __future__ import annotations
 

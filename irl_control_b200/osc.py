@@ -89,16 +89,17 @@ class OSC:
 
     # ------------------------------------------------------------------
     def gather_state(self, targets: Dict[str, Target]) -> Dict[str, np.ndarray]:
-        """One robot's inputs as a batch of one, fields in target order (robot.py:125-136)."""
+        """One robot's inputs as a batch of one, fields in target order.  Pulls exactly the state variables the control
+        law reads (robot.py:125-136 pulls all of them: M, DQ, J, and per target device EE_XYZ, EE_QUAT [+ FORCE, TORQUE])
+        through the same `get_state` accessors, i.e. from the simulator or, in polling-thread mode, from the cache."""
         names = list(targets.keys())
-        rs = self.robot.get_all_states()
-        Js, _ = rs[RobotState.J]
-        n = self.robot.num_joints_total
+        robot = self.robot
+        Js, _ = robot.get_state(RobotState.J)
         D = len(names)
         st = {
-            "M": np.ascontiguousarray(rs[RobotState.M], dtype=np.float64)[None],
+            "M": np.ascontiguousarray(robot.get_state(RobotState.M), dtype=np.float64)[None],
             "J": np.ascontiguousarray(np.vstack([Js[nm] for nm in names]), dtype=np.float64)[None],
-            "dq": np.ascontiguousarray(rs[RobotState.DQ], dtype=np.float64)[None],
+            "dq": np.ascontiguousarray(robot.get_state(RobotState.DQ), dtype=np.float64)[None],
             "ee_xyz": np.zeros((1, D, 3)), "ee_quat": np.zeros((1, D, 4)),
             "target_xyz": np.zeros((1, D, 3)), "target_quat": np.zeros((1, D, 4)),
             "max_vel": np.zeros((1, D, 2)),
@@ -113,8 +114,8 @@ class OSC:
         for d, nm in enumerate(names):
             dev = self.robot.get_device(nm)
             tgt = targets[nm]
-            st["ee_xyz"][0, d] = rs[nm][DeviceState.EE_XYZ]
-            st["ee_quat"][0, d] = rs[nm][DeviceState.EE_QUAT]
+            st["ee_xyz"][0, d] = dev.get_state(DeviceState.EE_XYZ)
+            st["ee_quat"][0, d] = dev.get_state(DeviceState.EE_QUAT)
             st["target_xyz"][0, d] = tgt.get_xyz()
             st["target_quat"][0, d] = tgt.get_quat()
             tvel[0, d] = np.hstack([tgt.get_xyz_vel(), tgt.get_abg_vel()])
@@ -129,7 +130,7 @@ class OSC:
                     # polling-thread mode: the wrench of the SAME snapshot as the rest of the state (osc.py:179 reads
                     # robot_state[name][FORCE / TORQUE]), already rotated into the world frame
                     st["ft_xmat"][0, d] = np.eye(3).reshape(-1)
-                    st["ft_raw"][0, d] = np.concatenate([rs[nm][DeviceState.FORCE], rs[nm][DeviceState.TORQUE]])
+                    st["ft_raw"][0, d] = np.concatenate([dev.get_state(DeviceState.FORCE), dev.get_state(DeviceState.TORQUE)])
         if np.any(tvel != 0.0):
             st["target_vel"] = tvel
         return st

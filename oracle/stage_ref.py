@@ -18,10 +18,11 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.environ.get("IRL_REFERENCE_SRC", "/root/reference")
 DST = os.path.join(HERE, "_ref")
-# python sources, robot / action-sequence configs and the scene descriptions (no meshes, no images)
+# python sources, robot / action-sequence configs, the scene descriptions and one mesh (no other meshes, no images)
 PATTERNS = (("irl_control", (".py",)), ("irl_control/examples", (".py",)), ("irl_control/input_devices", (".py",)),
             ("irl_control/robot_configs", (".yaml",)), ("irl_control/action_sequence_configs", (".yaml",)),
-            ("irl_control/scenes", (".xml",)))
+            ("irl_control/scenes", (".xml",)),
+            ("irl_control/meshes/ur5", ("link0.stl",)))        # the one mesh whose volume enters the dynamics model
 
 
 def _files():

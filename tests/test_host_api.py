@@ -7,6 +7,7 @@ import pytest
 import irl_control_b200 as pkg
 from irl_control_b200.synthetic import SCENARIOS, build_scenario
 from irl_control_b200.dual_ur5 import DualUR5Model, dynamics, sample_joint_states
+from oracle.ref_harness import REFERENCE_ROOT as REF      # /root/reference, or its verbatim staged copy oracle/_ref
 
 
 def _app(cfg="default_xyz_abg.yaml+start_body", scene="gain_test_scene.xml"):
@@ -197,25 +198,25 @@ def test_bias_forces_satisfy_the_lagrangian_form():
 
 
 @pytest.mark.reference
-@pytest.mark.skipif(not os.path.isfile("/root/reference/irl_control/scenes/dual_ur5.xml"), reason="needs /root/reference")
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "irl_control/scenes/dual_ur5.xml")), reason="needs /root/reference")
 def test_model_table_is_what_the_extractor_reads_from_the_reference_scene():
     """`dual_ur5_model.py` (travels with the repo) == a fresh extraction from the reference's dual_ur5.xml."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "extract_dual_ur5.py"),
-                          "/root/reference/irl_control/scenes/dual_ur5.xml"], capture_output=True, text=True, check=True).stdout
+                          os.path.join(REF, "irl_control/scenes/dual_ur5.xml")], capture_output=True, text=True, check=True).stdout
     with open(os.path.join(root, "irl_control_b200", "dual_ur5_model.py")) as fh:
         assert out.strip() == fh.read().strip()
 
 
 @pytest.mark.reference
-@pytest.mark.skipif(not os.path.isdir("/root/reference/irl_control/robot_configs"), reason="needs /root/reference")
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "irl_control/robot_configs")), reason="needs /root/reference")
 def test_builtin_configs_equal_the_reference_yaml_files():
     """The Python copies in configs.py (they travel to the GPU box) carry the reference's YAML values."""
     import yaml
     from irl_control_b200 import configs
-    ref = "/root/reference/irl_control"
+    ref = os.path.join(REF, "irl_control")
     for name in ("default_xyz.yaml", "default_xyz_abg.yaml", "iros2022.yaml"):
         with open(os.path.join(ref, "robot_configs", name)) as fh:
             want = yaml.safe_load(fh)
@@ -227,7 +228,7 @@ def test_builtin_configs_equal_the_reference_yaml_files():
 
 
 @pytest.mark.reference
-@pytest.mark.skipif(not os.path.isfile("/root/reference/irl_control/osc.py"), reason="needs /root/reference")
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "irl_control/osc.py")), reason="needs /root/reference")
 @pytest.mark.parametrize("scenario", sorted(SCENARIOS))
 def test_host_classes_resolve_the_same_maps_as_the_reference_classes(scenario):
     """`Device` / `Robot` / `OSC` of this package next to the reference's own classes constructed on the same model

@@ -7,13 +7,86 @@ topology the reference gets from `load_model_from_path` (mujoco_app.py:17)
 must travel with the repo as plain data. Only what the OSC path needs is
 kept: the body tree, hinge joints, <inertial> elements, sites, actuators and
 sensors. Geoms, meshes, materials and equality constraints are dropped (no
-collision / rendering / constraint solving on this path).
+collision / rendering / constraint solving on this path) - except that a body
+WITHOUT an <inertial> element gets its mass, centre of mass and inertia from
+its mesh geoms at the default density of 1000 kg/m^3, as MuJoCo's compiler
+does (inertiafromgeom="auto"): base_link_ur5right / base_link_ur5left
+(dual_ur5.xml:63-64, 164-165) carry only the `link0` mesh and are welded to the
+rotating stand, so they contribute to M[stand][stand] and to qfrc_bias.
 
     python tools/extract_dual_ur5.py /root/reference/irl_control/scenes/dual_ur5.xml
 """
+import os
+import struct
 import sys
 import math
 import xml.etree.ElementTree as ET
+
+DEFAULT_DENSITY = 1000.0      # mjCGeom default density [kg / m^3]
+
+
+def read_stl(path):
+    """Triangles [(v0, v1, v2)] of a binary or ASCII STL."""
+    data = open(path, "rb").read()
+    n = struct.unpack_from("<I", data, 80)[0] if len(data) >= 84 else -1
+    if n >= 0 and len(data) == 84 + 50 * n:
+        tris = []
+        for i in range(n):
+            f = struct.unpack_from("<12f", data, 84 + 50 * i)
+            tris.append((f[3:6], f[6:9], f[9:12]))
+        return tris
+    verts = [tuple(float(x) for x in ln.split()[1:4]) for ln in data.decode("ascii", "replace").splitlines()
+             if ln.strip().startswith("vertex")]
+    return [tuple(verts[i:i + 3]) for i in range(0, len(verts) - 2, 3)]
+
+
+def mesh_inertial(tris, density=DEFAULT_DENSITY):
+    """(pos, quat_wxyz, mass, diaginertia) of a uniform-density mesh the way MuJoCo 2.0 / 2.1 (the engine behind
+    mujoco_py; `mjCMesh::Process`, later called inertia="legacy") computes it: the surface is cut into pyramids with
+    their apex at the area-weighted centroid of the faces, every pyramid counts with its ABSOLUTE volume, the centre of
+    mass and the second moments are the exact integrals over those pyramids, and the geom is given the principal
+    frame of that tensor.  MuJoCo itself is absent from this image: restated from its published algorithm, unpinned."""
+    import numpy as np
+    T = np.asarray(tris, dtype=np.float64)                       # [F][3][3]
+    cen = T.mean(axis=1)
+    area = 0.5 * np.linalg.norm(np.cross(T[:, 1] - T[:, 0], T[:, 2] - T[:, 0]), axis=1)
+    apex = (cen * area[:, None]).sum(0) / area.sum()
+    A = T - apex                                                  # vertices relative to the apex
+    vol = np.abs(np.einsum("fi,fi->f", A[:, 0], np.cross(A[:, 1], A[:, 2]))) / 6.0
+    com = apex + (vol[:, None] * (A.sum(axis=1) / 4.0)).sum(0) / vol.sum()
+    # second moments of a tetrahedron (apex at the origin o = 0, vertices a, b, c) about the origin:
+    #   int r r^T dV = V / 20 * (a a^T + b b^T + c c^T + s s^T),  s = a + b + c
+    C = np.zeros((3, 3))
+    for f in range(T.shape[0]):
+        P = T[f] - com
+        o = apex - com
+        pts = np.vstack([P, o[None]])
+        ssum = pts.sum(0)
+        C += vol[f] / 20.0 * (pts.T @ pts + np.outer(ssum, ssum))
+    I = np.trace(C) * np.eye(3) - C
+    w, V = np.linalg.eigh(I)
+    order = np.argsort(-w)                                        # MuJoCo orders the principal moments descending
+    w, V = w[order], V[:, order]
+    if np.linalg.det(V) < 0:
+        V[:, 2] = -V[:, 2]
+    # rotation matrix -> quaternion (w x y z)
+    tr = np.trace(V)
+    if tr > 0:
+        S = math.sqrt(tr + 1.0) * 2
+        q = [0.25 * S, (V[2, 1] - V[1, 2]) / S, (V[0, 2] - V[2, 0]) / S, (V[1, 0] - V[0, 1]) / S]
+    else:
+        i = int(np.argmax(np.diag(V)))
+        j, k = (i + 1) % 3, (i + 2) % 3
+        S = math.sqrt(1.0 + V[i, i] - V[j, j] - V[k, k]) * 2
+        q = [0.0] * 4
+        q[0] = (V[k, j] - V[j, k]) / S
+        q[1 + i] = 0.25 * S
+        q[1 + j] = (V[j, i] + V[i, j]) / S
+        q[1 + k] = (V[k, i] + V[i, k]) / S
+    if q[0] < 0:
+        q = [-x for x in q]
+    mass = density * vol.sum()
+    return ([float(x) for x in com], [float(x) for x in q], float(mass), [float(density * x) for x in w])
 
 
 def floats(s, n=None, default=None):
@@ -56,6 +129,9 @@ def frame_quat(el):
 def main(path):
     root = ET.parse(path).getroot()
     bodies = []
+    # mesh name -> file, resolved like the including scene does (<compiler meshdir="../meshes/"/>, gain_test_scene.xml:2)
+    meshdir = os.path.join(os.path.dirname(os.path.abspath(path)), "..", "meshes")
+    mesh_file = {m.get("name"): os.path.normpath(os.path.join(meshdir, m.get("file"))) for m in root.iter("mesh")}
 
     def walk(el, parent):
         name = el.get("name")
@@ -87,6 +163,14 @@ def main(path):
                     "pos": floats(ch.get("pos"), 3, [0.0, 0.0, 0.0]),
                     "quat": frame_quat(ch),
                 })
+        geoms = [g for g in el if g.tag == "geom"]
+        if rec["inertial"] is None and geoms:
+            # inertiafromgeom="auto": no <inertial> -> from the geoms (here always ONE mesh geom at the body origin)
+            assert len(geoms) == 1 and geoms[0].get("type") == "mesh" and geoms[0].get("mass") is None, name
+            assert floats(geoms[0].get("pos"), 3, [0.0, 0.0, 0.0]) == [0.0, 0.0, 0.0] and geoms[0].get("quat") is None
+            ipos, iquat, mass, diag = mesh_inertial(read_stl(mesh_file[geoms[0].get("mesh")]),
+                                                    float(geoms[0].get("density", DEFAULT_DENSITY)))
+            rec["inertial"] = {"pos": ipos, "quat": iquat, "mass": mass, "diaginertia": diag}
         bodies.append(rec)
         for ch in el:
             if ch.tag == "body":
@@ -107,7 +191,9 @@ def main(path):
     w("sensors 289-297). Frames are (pos, quat wxyz) relative to the parent body;")
     w("`euler=` attributes were converted with MuJoCo's default intrinsic xyz")
     w("sequence in radians. Geoms/meshes/equalities are intentionally absent: the")
-    w("OSC path never touches them.")
+    w("OSC path never touches them - except that bodies without an <inertial> element")
+    w("(base_link_ur5right / base_link_ur5left) carry the mass, centre of mass and")
+    w("principal inertia of their `link0` mesh at MuJoCo's default density of 1000 kg/m^3.")
     w('"""')
     w("")
     w("# (name, parent, pos, quat_wxyz, inertial|None, joints, sites)")
