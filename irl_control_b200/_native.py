@@ -177,7 +177,8 @@ _lib: Optional[C.CDLL] = None
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libirlosc.so")
+    # IRLOSC_LIB: an alternative build of the same library (A/B experiments of kernel variants only)
+    return os.environ.get("IRLOSC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libirlosc.so")
 
 
 def load() -> C.CDLL:

@@ -174,6 +174,14 @@ inline bool fused_roles(const KParams &P, FRoles &R, int &kd, bool &has_base) {
             if (R.joint_slot[j] >= 0) return false;
             R.joint_slot[j] = (int8_t)(P.dev[d].ctrl0 + c);
         }
+    auto owners = [&](int j) { unsigned m = 0; for (int d = 0; d < P.D; ++d) m |= ((P.dev[d].joint_mask >> j) & 1u) << d; return m; };
+    R.uniform_owner = 1;
+    for (int arm = 0; arm < 2; ++arm) {
+        const int jb = 1 + 12 * arm;
+        for (int i = 1; i < 6; ++i) if (owners(jb + i) != owners(jb)) R.uniform_owner = 0;
+        for (int half = 0; half < 2; ++half)
+            for (int r = 1; r < 3; ++r) if (owners(jb + 6 + 3 * half + r) != owners(jb + 6 + 3 * half)) R.uniform_owner = 0;
+    }
     return true;
 }
 

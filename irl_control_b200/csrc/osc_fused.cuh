@@ -356,6 +356,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
         double Hpre[6], FBpre[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) { Hpre[i] = 0.0; FBpre[i] = 0.0; }
+        const double cu_arm = coef_uv(P, R, vel_zero, jb);     // shared by the six arm joints when R.uniform_owner
         // joint angles / rates are fetched one joint ahead so that their latency hides behind a joint's work
         double q_nx = q[jb], dq_nx = dq[jb];
 #pragma unroll 1
@@ -368,7 +369,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
             dq_nx = dq[jb + i + 1];
             joint_down(jm, Bc, q_i, dq_i, Bn, s, r, Iw);
             body_wrench(jm.mass, r, Iw, Bn.v, Bn.a, h, fb);
-            const double cu = coef_uv(P, vel_zero, jb + i);
+            const double cu = R.uniform_owner ? cu_arm : coef_uv(P, R, vel_zero, jb + i);
             double x[6];
 #pragma unroll
             for (int e = 0; e < 6; ++e) x[e] = fma(cu, Hpre[e], gb * FBpre[e]);
@@ -434,6 +435,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
             const int gj = jb + 6 + 3 * half;
+            const double cu_grip = coef_uv(P, R, vel_zero, gj);  // shared by the half's three joints when R.uniform_owner
             const double qg0 = q[gj], qg1 = q[gj + 1], qg2 = q[gj + 2];
             const double dqg0 = dq[gj], dqg1 = dq[gj + 1], dqg2 = dq[gj + 2];
             double IAg[21], f[6], inv;
@@ -446,7 +448,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
                 double sb[6], rb[3], Iwb[6], hb[6], fbb[6];
                 joint_down(Mdl.grip[arm][half][1], B0, qg1, dqg1, B1, sb, rb, Iwb);
                 body_wrench(Mdl.grip[arm][half][1].mass, rb, Iwb, B1.v, B1.a, hb, fbb);
-                const double cu1 = coef_uv(P, vel_zero, gj + 1);
+                const double cu1 = R.uniform_owner ? cu_grip : coef_uv(P, R, vel_zero, gj + 1);
                 const double uv1 = dot6(sb, hb), b1 = dot6(sb, fbb);
                 put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj + 1, fma(cu1, uv1, gb * b1));
                 if (dbg && dbg->uv) { dbg->uv[gj + 1] = uv1; dbg->bias[gj + 1] = b1; }
@@ -457,7 +459,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
                 add_rigid(IAg, Mdl.grip[arm][half][1].mass, rb, Iwb);
                 m_ok = joint_up(IAg, sb, f, &inv) && m_ok;
             }
-            const double cu0 = coef_uv(P, vel_zero, gj);
+            const double cu0 = cu_grip;
             const double uv0 = dot6(sa, ha), b0 = dot6(sa, fba);
             put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj, fma(cu0, uv0, gb * b0));
             if (dbg && dbg->uv) { dbg->uv[gj] = uv0; dbg->bias[gj] = b0; }
@@ -472,7 +474,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
                 double sc[6], rc[3], Iwc[6], hc[6], fbc[6];
                 joint_down(Mdl.grip[arm][half][2], Bc, qg2, dqg2, B2, sc, rc, Iwc);
                 body_wrench(Mdl.grip[arm][half][2].mass, rc, Iwc, B2.v, B2.a, hc, fbc);
-                const double cu2 = coef_uv(P, vel_zero, gj + 2);
+                const double cu2 = R.uniform_owner ? cu_grip : coef_uv(P, R, vel_zero, gj + 2);
                 const double uv2 = dot6(sc, hc), b2 = dot6(sc, fbc);
                 put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj + 2, fma(cu2, uv2, gb * b2));
                 if (dbg && dbg->uv) { dbg->uv[gj + 2] = uv2; dbg->bias[gj + 2] = b2; }
@@ -506,7 +508,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
 #pragma unroll
             for (int e = 0; e < 6; ++e) Iw[e] = scr(o + 9 + e);
             // (M dq)_j and bias_j through the subtree sums: s . (X_total - X_prefix)
-            const double cu = coef_uv(P, vel_zero, jb + i);
+            const double cu = R.uniform_owner ? cu_arm : coef_uv(P, R, vel_zero, jb + i);
             double x[6];
 #pragma unroll
             for (int e = 0; e < 6; ++e) x[e] = fma(cu, Hpre[e], gb * FBpre[e]);
@@ -550,7 +552,7 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
     // ------------------------------------------------------------ stand joint couples the arms
     double f0[6], inv0;
     m_ok = joint_up(IA0, s0, f0, &inv0) && m_ok;
-    const double cu_st = coef_uv(P, vel_zero, 0);
+    const double cu_st = coef_uv(P, R, vel_zero, 0);
     const double uv_st = dot6(s0, Htot), b_st = dot6(s0, FBtot);
     const double base_st = fma(cu_st, uv_st, gb * b_st);
     if (dbg && dbg->uv) { dbg->uv[0] = uv_st; dbg->bias[0] = b_st; }

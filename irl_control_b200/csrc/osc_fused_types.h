@@ -28,6 +28,10 @@ struct KModel {
 struct FRoles {
     int dev_arm[2], dev_base, row_arm[2], row_base;
     int8_t joint_slot[IRLOSC_MAX_N];   // packed ctrl slot of joint j (osc.py:203-208), -1 = not returned
+    // 1 when, within each arm's six arm joints and within each gripper half's three joints, every joint belongs to the
+    // same set of target devices (true for every shipped configuration): the velocity-term coefficient of osc.py:174
+    // is then evaluated once per group instead of once per joint
+    int32_t uniform_owner;
 };
 struct FIo {
     const double *q, *dq, *target_xyz, *target_quat, *target_vel, *max_vel, *ft_raw;

@@ -266,7 +266,7 @@ IRLOSC_HD bool lane_instance(const KParams &P, const FRoles &R, const double *ta
         double ak[KT], j0r[KD], dxa[KD], c0, uv0;
         {
             auto rd = group(4 + 5 * arm);
-            m_ok = consume_rows<KD>(rd, P, vel_zero, gb, jb, S, ak, j0r, (double *)nullptr, dxa, (double (*)[KD]) nullptr,
+            m_ok = consume_rows<KD>(rd, P, R, vel_zero, gb, jb, S, ak, j0r, (double *)nullptr, dxa, (double (*)[KD]) nullptr,
                                     T.base_arm[arm], &c0, &uv0, dbg) && m_ok;
         }
         d0 += c0;
@@ -282,7 +282,7 @@ IRLOSC_HD bool lane_instance(const KParams &P, const FRoles &R, const double *ta
     }
     m_ok = m_ok && (d0 > 0.0);
     T.inv0 = fused::rcp64(d0);
-    T.base_st = fma(fused::coef_uv(P, vel_zero, 0), uv_st, gb * bias0);
+    T.base_st = fma(fused::coef_uv(P, R, vel_zero, 0), uv_st, gb * bias0);
     if (dbg && dbg->uv) dbg->uv[0] = uv_st;
     return fused::osc_tail<KD, HAS_BASE>(P, R, target_vel, vel_zero, 0, m_ok, T.akA, T.j0, T.dxr, T.g, ja, T.base_arm, T.base_st,
                                          T.inv0, T.u_all_row, T.ctrl_row, T.status, &T.force_pinv, dbg);
@@ -341,23 +341,35 @@ osc_step_lane(const __grid_constant__ KParams P, const __grid_constant__ LaneArg
     // warps of a CTA take neighbouring tiles, CTAs stride over the batch
     const int64_t gw = (int64_t)blockIdx.x * W + warp, gstride = (int64_t)gridDim.x * W;
     const int64_t my_tiles = gw < n_tiles ? (n_tiles - gw + gstride - 1) / gstride : 0;
-    const int64_t total = my_tiles * kGroups;
-    int64_t seq = 0;                                     // groups consumed so far by this warp
-    auto issue = [&](int64_t q) {                        // one lane: bulk copy of group q of this warp's sequence
-        const int64_t tile = gw + (q / kGroups) * gstride;
-        const int g = (int)(q % kGroups);
-        const int s = (int)(q % n_stages);
-        const uint32_t bytes = (uint32_t)(A.gbase[g + 1] - A.gbase[g]) * kTile * 8u;
-        tiled::mbar_expect_tx(&bars[s], bytes);
-        tiled::bulk_g2s(ring + (size_t)s * stage_bytes, A.tiles + tile * tile_doubles + (size_t)A.gbase[g] * kTile, bytes, &bars[s]);
+    // ---- ring state (warp-uniform, plain 32-bit counters: no divisions on the per-group path)
+    const uint32_t ring_u32 = tiled::smem_u32(ring), bars_u32 = tiled::smem_u32(bars);
+    int cs = 0;                                          // stage the next group is consumed from
+    uint32_t par = 0;                                    // bit s: parity of the next completion of stage s
+    int is = 0, ig = 0;                                  // stage / group of the next copy to issue
+    const double *itile = A.tiles + gw * tile_doubles;   // tile of the next copy to issue
+    int64_t ileft = my_tiles * kGroups;                  // copies still to issue
+    auto issue_next = [&]() {                            // lane 0 issues the bulk copy; every lane advances the counters
+        if (ileft > 0) {
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)(A.gbase[ig + 1] - A.gbase[ig]) * (kTile * 8u);
+                const uint32_t bar = bars_u32 + 8u * is;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(ring_u32 + (uint32_t)is * (uint32_t)stage_bytes), "l"(itile + (size_t)A.gbase[ig] * kTile), "r"(bytes),
+                               "r"(bar) : "memory");
+            }
+            --ileft;
+            if (++ig == kGroups) { ig = 0; itile += gstride * tile_doubles; }
+            if (++is == n_stages) is = 0;
+        }
     };
     if (STAGED) {
         if (lane == 0) {
             for (int s = 0; s < n_stages; ++s) tiled::mbar_init(&bars[s], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            for (int64_t q = 0; q < n_stages - 1 && q < total; ++q) issue(q);
         }
         __syncwarp();
+        for (int s = 0; s < n_stages - 1; ++s) issue_next();
     }
     for (int64_t k = 0; k < my_tiles; ++k) {
         const int64_t tile = gw + k * gstride;
@@ -371,13 +383,20 @@ osc_step_lane(const __grid_constant__ KParams P, const __grid_constant__ LaneArg
             const double *p;
             if (STAGED) {
                 __syncwarp();                            // every lane is done with the stage that is refilled now
-                const int64_t q = seq++;
-                if (lane == 0 && q + n_stages - 1 < total) {
-                    tiled::fence_proxy_async();
-                    issue(q + n_stages - 1);
-                }
-                tiled::mbar_wait(&bars[q % n_stages], (uint32_t)((q / n_stages) & 1));
-                p = reinterpret_cast<const double *>(ring + (size_t)(q % n_stages) * stage_bytes) + lane;
+                if (lane == 0) tiled::fence_proxy_async();
+                issue_next();
+                const uint32_t bar = bars_u32 + 8u * cs;
+                const uint32_t parity = (par >> cs) & 1u;
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "WAIT_%=:\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                    "@p bra DONE_%=;\n\t"
+                    "bra WAIT_%=;\n\t"
+                    "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+                p = reinterpret_cast<const double *>(ring + (size_t)cs * stage_bytes) + lane;
+                par ^= 1u << cs;
+                if (++cs == n_stages) cs = 0;
             } else {
                 if (A.pf > 0 && lane == 0 && g + A.pf < kGroups)
                     bulk_prefetch_l2(tb + (size_t)A.gbase[g + A.pf] * kTile,

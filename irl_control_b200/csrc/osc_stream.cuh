@@ -147,9 +147,11 @@ IRLOSC_HD bool consume_grip(const RD &rd, const KParams &P, const FRoles &R, uns
         uv2 = fma(rg2[i], S.dqC[i], uv2);
         S.uvC[i] = fma(rg0[i], q0, fma(rg1[i], q1, fma(rg2[i], q2, S.uvC[i])));
     }
-    fused::put_joint(R, u_all_row, ctrl_row, gj, fma(fused::coef_uv(P, vel_zero, gj), uv0, gb * rd(kBiasG)));
-    fused::put_joint(R, u_all_row, ctrl_row, gj + 1, fma(fused::coef_uv(P, vel_zero, gj + 1), uv1, gb * rd(kBiasG + 1)));
-    fused::put_joint(R, u_all_row, ctrl_row, gj + 2, fma(fused::coef_uv(P, vel_zero, gj + 2), uv2, gb * rd(kBiasG + 2)));
+    double cg[3];
+    fused::coef_uv_group<3>(P, R, vel_zero, gj, cg);
+    fused::put_joint(R, u_all_row, ctrl_row, gj, fma(cg[0], uv0, gb * rd(kBiasG)));
+    fused::put_joint(R, u_all_row, ctrl_row, gj + 1, fma(cg[1], uv1, gb * rd(kBiasG + 1)));
+    fused::put_joint(R, u_all_row, ctrl_row, gj + 2, fma(cg[2], uv2, gb * rd(kBiasG + 2)));
     if (dbg && dbg->uv) { dbg->uv[gj] = uv0; dbg->uv[gj + 1] = uv1; dbg->uv[gj + 2] = uv2; }
     {   // eliminate g1 (leaf): touches the C block, row g0 and pivot g0
         ok = ok && (d1 > 0.0);
@@ -191,7 +193,7 @@ IRLOSC_HD bool consume_grip(const RD &rd, const KParams &P, const FRoles &R, uns
 // Leaves: ak (the arm's block of A), j0r (stand column of the reduced rows), c0 (the arm's part of the
 // stand pivot), uv0 (its part of (M dq)_stand).
 template <int KD, class RD>
-IRLOSC_HD bool consume_rows(const RD &rd, const KParams &P, unsigned vel_zero, double gb, int jb, ArmState<KD> &S,
+IRLOSC_HD bool consume_rows(const RD &rd, const KParams &P, const FRoles &R, unsigned vel_zero, double gb, int jb, ArmState<KD> &S,
                             double *ak, double *j0r, double *jst, double *dxr, double (*jarm)[KD], double *base_arm,
                             double *c0, double *uv0, const Debug *dbg) {
     bool ok = true;
@@ -209,9 +211,11 @@ IRLOSC_HD bool consume_rows(const RD &rd, const KParams &P, unsigned vel_zero, d
         dxr[cr] = dx;
         if (jst != nullptr) jst[cr] = jr[cr][0];
     }
+    double ca[6];
+    fused::coef_uv_group<6>(P, R, vel_zero, jb, ca);
 #pragma unroll
     for (int i = 1; i < 7; ++i) {
-        base_arm[i - 1] = fma(fused::coef_uv(P, vel_zero, jb + i - 1), S.uvC[i], gb * rd(KD * 7 + i - 1));
+        base_arm[i - 1] = fma(ca[i - 1], S.uvC[i], gb * rd(KD * 7 + i - 1));
         if (dbg && dbg->uv) dbg->uv[jb + i - 1] = S.uvC[i];
     }
     *uv0 = S.uvC[0];
@@ -298,7 +302,7 @@ IRLOSC_HD bool stream_instance(const KParams &P, const FRoles &R, const Plan &pl
         double ak[KT], j0r[KD], jstr[KD], dxa[KD], c0, uv0;
         {
             auto rd = group(4 + 5 * arm);
-            m_ok = consume_rows<KD>(rd, P, vel_zero, gb, jb, S, ak, j0r, jstr, dxa, T.jarm[arm], T.base_arm[arm], &c0, &uv0, dbg) && m_ok;
+            m_ok = consume_rows<KD>(rd, P, R, vel_zero, gb, jb, S, ak, j0r, jstr, dxa, T.jarm[arm], T.base_arm[arm], &c0, &uv0, dbg) && m_ok;
         }
         d0 += c0;
         uv_st += uv0;
@@ -313,7 +317,7 @@ IRLOSC_HD bool stream_instance(const KParams &P, const FRoles &R, const Plan &pl
     }
     m_ok = m_ok && (d0 > 0.0);
     T.inv0 = fused::rcp64(d0);
-    T.base_st = fma(fused::coef_uv(P, vel_zero, 0), uv_st, gb * bias0);
+    T.base_st = fma(fused::coef_uv(P, R, vel_zero, 0), uv_st, gb * bias0);
     if (dbg && dbg->uv) dbg->uv[0] = uv_st;
     T.u_all_row = u_all_row;
     T.ctrl_row = ctrl_row;

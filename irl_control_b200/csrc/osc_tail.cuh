@@ -53,13 +53,28 @@ IRLOSC_HD double sqrt64(double d) {
 // Coefficient of (M dq)_j in u_j: the velocity term of the device that owns joint j when it took
 // the zero-target-velocity branch (osc.py:174, last device wins) plus the null-space term
 // (osc.py:195-200, collapsed form).
-IRLOSC_HD double coef_uv(const KParams &P, unsigned vel_zero, int j) {
+IRLOSC_HD double coef_uv(const KParams &P, const FRoles &, unsigned vel_zero, int j) {
+    // (a per-joint owner table in FRoles was measured SLOWER than these four mask tests: +10 % on the direct-load lane
+    //  kernel, profiles/r02_summary.md)
     double c = 0.0;
 #pragma unroll
     for (int d = 0; d < IRLOSC_MAX_DEVICES; ++d)
         if (d < P.D && ((vel_zero >> d) & 1u) && ((P.dev[d].joint_mask >> j) & 1u)) c = -1.0 * P.dev[d].kv;
     if (P.has_nullspace) c -= P.nullspace_kv;
     return c;
+}
+
+// The same for `count` consecutive joints of one group (an arm's six arm joints, a gripper half's three joints).
+template <int COUNT>
+IRLOSC_HD void coef_uv_group(const KParams &P, const FRoles &R, unsigned vel_zero, int j0, double *c) {
+    if (R.uniform_owner) {
+        const double c0 = coef_uv(P, R, vel_zero, j0);
+#pragma unroll
+        for (int i = 0; i < COUNT; ++i) c[i] = c0;
+    } else {
+#pragma unroll
+        for (int i = 0; i < COUNT; ++i) c[i] = coef_uv(P, R, vel_zero, j0 + i);
+    }
 }
 
 // Optional taps for the host test harness (all pointers may be null).
@@ -376,7 +391,7 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
             }
 #pragma unroll
             for (int i = 0; i < K; ++i) xa[i] = ya[i];
-            conv = (it >= 1) && (change < 1e-10);
+            conv = (it >= 1) && (change < 1e-8);      // eigenvector error d ~ change: the deflation error is d^2 lambda_2 / lambda_1
         }
         if (!conv) return false;
         // geff = P g
@@ -551,11 +566,17 @@ IRLOSC_HD bool osc_tail(const KParams &P, const FRoles &R, const double *target_
         }
 #pragma unroll
         for (int am = 0; am < 2; ++am) {
+            // all Jacobian entries of the arm first (they may be re-read from memory: one latency, not one per joint)
+            double jv[6][KD];
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+                for (int cr = 0; cr < KD; ++cr) jv[i][cr] = ja.arm(am, i, cr);
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
                 double jt = 0.0;
 #pragma unroll
-                for (int cr = 0; cr < KD; ++cr) jt = fma(ja.arm(am, i, cr), w[am * KD + cr], jt);
+                for (int cr = 0; cr < KD; ++cr) jt = fma(jv[i][cr], w[am * KD + cr], jt);
                 put_joint(R, u_all_row, ctrl_row, 1 + 12 * am + i, base_arm[am][i] - jt);
             }
         }

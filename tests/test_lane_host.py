@@ -86,3 +86,29 @@ def test_tile_layout_follows_the_exported_entry_table(case):
     kd = sum(layout.devices[0].ctrlr_dof) if layout.devices[0].name != "base" else sum(layout.devices[1].ctrlr_dof)
     n_j = sum(1 for arr, _, _ in spec if arr == 2)
     assert n_j == 2 * 7 * kd + (1 if any(d.name == "base" for d in layout.devices) else 0)
+
+
+def test_velocity_term_with_non_uniform_joint_ownership():
+    """`u_all[dev.joint_ids_all] = -kv * uv_all[...]` (osc.py:174) when a device's joint_ids_all is NOT a whole arm - no
+    shipped YAML does that, the kernels then evaluate the coefficient per joint instead of per group - against the
+    oracle, for the lane and the streaming step."""
+    import dataclasses
+    from irl_control_b200.synthetic import oracle_inputs, scenario_layout, synth_batch
+    from oracle import osc_numpy
+    layout = scenario_layout("gain_test")
+    devs = []
+    for d in layout.devices:
+        if d.name == "ur5right":
+            d = dataclasses.replace(d, joint_ids_all=tuple(j for j in d.joint_ids_all if j not in (3, 8, 12)))
+        devs.append(d)
+    layout = dataclasses.replace(layout, devices=tuple(devs))
+    st = synth_batch(layout, 96, seed=41)
+    state = {k: st[k].numpy() for k in ("M", "J", "dq", "bias", "ee_xyz", "ee_quat", "target_xyz", "target_quat", "max_vel")}
+    ref = osc_numpy.osc_batch(layout.as_dict(), oracle_inputs(st, layout))
+    scale = np.abs(ref["u_all"]).max(axis=1)
+    for run in (fused_host.run_lane, fused_host.run_stream):
+        out = run(layout, state)
+        assert (np.abs(out["u_all"] - ref["u_all"]).max(axis=1) / scale).max() < REL_TOL
+    # and it matters: with whole-arm ownership the excluded joints get the -kv (M dq) term
+    full = osc_numpy.osc_batch(scenario_layout("gain_test").as_dict(), oracle_inputs(st, layout))
+    assert np.abs(full["u_all"][:, [3, 8, 12]] - ref["u_all"][:, [3, 8, 12]]).max() > 1e-6
