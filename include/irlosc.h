@@ -16,7 +16,12 @@
  *
  * Threading: a handle is thread-compatible, not thread-safe (one caller at a
  * time per handle), matching the reference ("one caller thread runs
- * generate").  `irlosc_step` never synchronises with the host.
+ * generate").  The device-pointer steps (`irlosc_step`,
+ * `irlosc_step_tiles`, `irlosc_step_fused`, `irlosc_step_sequence`,
+ * `irlosc_step_waypoints`) are ONE kernel launch each, never synchronise with
+ * the host, never allocate, and keep no per-handle device state: steps issued
+ * on different streams may overlap freely.  The `*_host` forms own staging
+ * buffers and internal streams per handle and return when the outputs are valid.
  */
 #ifndef IRLOSC_H_
 #define IRLOSC_H_
@@ -42,7 +47,8 @@ extern "C" {
 /* per-instance status byte written by a step (bit field) */
 #define IRLOSC_ST_PINV 0x01         /* |det(J M^-1 J^T)| < 1e-4: pinv(rcond=1e-5) branch (osc.py:52-55) */
 #define IRLOSC_ST_M_NOT_PD 0x02     /* M had a non-positive pivot: outputs are NaN                      */
-#define IRLOSC_ST_EIGEN 0x04        /* task-space inverse went through the Jacobi eigen-solver          */
+#define IRLOSC_ST_EIGEN 0x04        /* task-space solve finished by the warp-cooperative Jacobi eigen-solver
+                                       (the thread's own inertia / deflation resolution could not decide it) */
 #define IRLOSC_ST_VEL_BRANCH 0x08   /* >=1 device took the non-zero target-velocity branch (osc.py:175-177) */
 #define IRLOSC_ST_DX_RANGE 0x10     /* that branch indexed dx out of range: the reference raises IndexError
                                        (robot.py:52-55 vs osc.py:150,176); outputs are NaN               */
@@ -57,7 +63,7 @@ extern "C" {
                                    ... down to its root, stored from dof_Madr[i] = sum of depth(r) for r < i
                                    (depth counts i itself).  Needs has_topology (joint_parent = dof_parentid of the
                                    robot's dofs, which must be the scene's first n dofs); nM = sum of depths (155
-                                   for the DualUR5), m_stride = the scene's nM.  Read by the streaming kernel only */
+                                   for the DualUR5), m_stride = the scene's nM */
 #define IRLOSC_J_ROWS 0         /* [B][k][ldj]   only the controlled rows, target order (osc.py:136-138) */
 #define IRLOSC_J_FULL6 1        /* [B][D][6][ldj] full [jacp;jacr] per target device (device.py:125-130);
                                    rows with ctrlr_dof == 0 are never read                              */
@@ -75,6 +81,13 @@ typedef struct irlosc_device_params {
     double max_vel[2];                    /* default when io.max_vel == NULL      (device.py:31)       */
     double kp, kv, ko;                    /* controller_configs entry             (osc.py:36)          */
     double k[3], d[3];                    /* stiffness / damping, xyz part        (osc.py:160-161)     */
+    /* What OSC.__init__ stored in the controller config (osc.py:35-39) - the reference computes these ONCE and reads
+     * them back every step, while kp / kv / ko are read fresh (osc.py:76,170): a caller that edits a gain after
+     * construction gets the stale vectors.  has_gain_vectors == 0: derived from kp / kv / ko above. */
+    int32_t has_gain_vectors;
+    int32_t reserved2_;
+    double task_space_gains[6];           /* [kp] * 3 + [ko] * 3 at construction  (osc.py:37)          */
+    double lamb[6];                       /* task_space_gains / kv at construction (osc.py:39)         */
     int32_t ee_joint;                     /* robot-local id of the deepest joint that moves the EE body,
                                              i.e. the last entry of Device.joint_ids (device.py:62-64);
                                              -1 = unknown (only read when has_topology)                 */
@@ -332,8 +345,7 @@ int32_t irlosc_set_model(irlosc_handle *h, const irlosc_model *model);
 
 /* Replaces: Robot.get_all_states + Device.get_all_states + OSC.generate (robot.py:125-136,
  * device.py:183-197, osc.py:120-210) for B instances given only joint positions / velocities and
- * targets.  Asynchronous on `cuda_stream`; launches the fused kernel and a fix-up kernel for the
- * instances that need the eigen-decomposition (pinv) branch. */
+ * targets.  Asynchronous on `cuda_stream`, one kernel. */
 int32_t irlosc_step_fused(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_device, void *cuda_stream);
 /* Same with HOST buffers, pipelined in chunks like irlosc_step_host. */
 int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irlosc_fused_io *io_host);
@@ -373,9 +385,9 @@ int32_t irlosc_calc_error(irlosc_handle *h, int64_t B, const double *ee_xyz, con
 int32_t irlosc_host_alloc(void **ptr, int64_t bytes);
 int32_t irlosc_host_free(void *ptr);
 
-/* Kernel selection: 0 = auto, 1 = generic (any n, k, layout), 2 + v = variant v of the 4-lane DualUR5
- * kernels (v = 0: tree-sparse), 9 = streaming thread-per-instance kernel; for the fused step 2 + v
- * selects its variant v.  Non-default choices exist for A/B measurements, see DESIGN.md. */
+/* Kernel selection of irlosc_step (per-variable arrays): 0 = auto, 1 = generic (any n, k, layout), 2 = the tree-sparse
+ * 4-lane record-staging kernel, 9 = streaming thread-per-instance kernel.  Non-default choices exist for A/B
+ * measurements, see DESIGN.md.  (irlosc_step_tiles always runs the lane kernel.) */
 int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which);
 /* Leave `sms` streaming multiprocessors free when launching the step kernel (default 0), so that a
  * collective running on another stream (the NCCL gather of ctrl) can overlap instead of queueing

@@ -52,6 +52,8 @@ class DeviceParams(C.Structure):
         ("max_vel", C.c_double * 2),
         ("kp", C.c_double), ("kv", C.c_double), ("ko", C.c_double),
         ("k", C.c_double * 3), ("d", C.c_double * 3),
+        ("has_gain_vectors", C.c_int32), ("reserved2_", C.c_int32),
+        ("task_space_gains", C.c_double * 6), ("lamb", C.c_double * 6),
         ("ee_joint", C.c_int32), ("reserved_", C.c_int32),
     ]
 

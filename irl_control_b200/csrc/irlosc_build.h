@@ -62,8 +62,8 @@ inline int32_t build_kparams(const irlosc_params &u, KParams &kp) {
         t.kv_over_ko = s.ko != 0.0 ? s.kv / s.ko : 0.0;
         if (!(s.kv != 0.0)) return fail(IRLOSC_ERR_INVALID, "device %d: kv must be non-zero", d);
         for (int i = 0; i < 6; ++i) {
-            t.gain[i] = (i < 3) ? s.kp : s.ko;
-            t.lamb[i] = t.gain[i] / s.kv;
+            t.gain[i] = s.has_gain_vectors ? s.task_space_gains[i] : ((i < 3) ? s.kp : s.ko);
+            t.lamb[i] = s.has_gain_vectors ? s.lamb[i] : t.gain[i] / s.kv;
             t.stiff[i] = (i < 3) ? s.k[i] : 1.0;
             t.damp[i] = (i < 3) ? s.d[i] : 1.0;
         }

@@ -32,6 +32,8 @@ class DeviceLayout:
     ko: float
     k: tuple
     d: tuple
+    gain_vectors: Optional[tuple] = None   # (task_space_gains[6], lamb[6]) as OSC.__init__ stored them (osc.py:35-39);
+                                           # None: derived from kp / kv / ko
     ee_joint: int = -1          # robot-local id of the last joint of Device.joint_ids (device.py:62-64)
     ee_body: str = ""           # Device.EE, the body whose pose / Jacobian the device reads (device.py:93-95,125)
 
@@ -94,6 +96,7 @@ class OscLayout:
                 "actuator_trnids": list(d.actuator_trnids), "ctrl_idxs": list(d.ctrl_idxs),
                 "dx_idx": list(d.dx_idx), "has_max_vel": d.has_max_vel, "max_vel": list(d.max_vel),
                 "kp": d.kp, "kv": d.kv, "ko": d.ko, "k": list(d.k), "d": list(d.d),
+                "gain_vectors": None if d.gain_vectors is None else [list(d.gain_vectors[0]), list(d.gain_vectors[1])],
                 "ee_joint": d.ee_joint,
             } for d in self.devices],
         }
@@ -134,6 +137,11 @@ class OscLayout:
             for j in range(3):
                 c.k[j] = float(d.k[j])
                 c.d[j] = float(d.d[j])
+            c.has_gain_vectors = int(d.gain_vectors is not None)
+            if d.gain_vectors is not None:
+                for j in range(6):
+                    c.task_space_gains[j] = float(d.gain_vectors[0][j])
+                    c.lamb[j] = float(d.gain_vectors[1][j])
             c.ee_joint = int(d.ee_joint)
         return p
 
@@ -192,6 +200,8 @@ def compile_layout(robot, device_configs: Dict[str, Dict], target_names: Sequenc
             max_vel=(float(mv[0]), float(mv[1])) if mv is not None else (0.0, 0.0),
             kp=float(cfg['kp']), kv=float(cfg['kv']), ko=float(cfg['ko']),
             k=tuple(float(x) for x in cfg['k']), d=tuple(float(x) for x in cfg['d']),
+            gain_vectors=((tuple(float(x) for x in cfg['task_space_gains']), tuple(float(x) for x in cfg['lamb']))
+                          if ('task_space_gains' in cfg and 'lamb' in cfg) else None),
             ee_joint=local.get(int(dev.joint_ids[-1]), -1) if len(dev.joint_ids) else -1,
             ee_body=str(getattr(dev, 'EE', '')),
         ))

@@ -8,7 +8,9 @@ NOT evaluated here: `generate` gathers one robot's state exactly as
 and unpacks the result.  `generate_batch` is the entry point the B200 path
 exists for: B independent robot instances per call, state resident in HBM.
 
-Differences from the reference that a caller can observe: none intended.
+Differences from the reference that a caller can observe: none intended.  In particular the gain vectors
+`task_space_gains` / `lamb` are the ones `__init__` stored in the (shared, mutable) config dict (osc.py:35-39): like
+the reference, a later edit of cfg['kp'] / ['kv'] / ['ko'] changes the saturation and the kv factors but not them.
 Quirks kept on purpose: per-device overwrite of the
 velocity term, `np.all(target_vel) == 0` branch rule, J_idxs in sub-device
 order (an out-of-range index there raises IndexError like numpy would).
@@ -53,7 +55,8 @@ class OSC:
         for name in names:
             dev = self.robot.sub_devices_dict[name]
             cfg = self.device_configs[name]
-            sig.append((dev.max_vel is None, cfg['kp'], cfg['kv'], cfg['ko'], tuple(cfg['k']), tuple(cfg['d'])))
+            sig.append((dev.max_vel is None, cfg['kp'], cfg['kv'], cfg['ko'], tuple(cfg['k']), tuple(cfg['d']),
+                        tuple(float(x) for x in cfg['task_space_gains']), tuple(float(x) for x in cfg['lamb'])))
         ns = None if self.nullspace_config is None else self.nullspace_config['kv']
         sig.append((ns, bool(self.use_g), self.admittance is True))
         return tuple(sig)

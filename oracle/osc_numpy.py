@@ -66,6 +66,8 @@ def task_space_inertia(J: np.ndarray, M: np.ndarray) -> Tuple[np.ndarray, np.nda
 
 def _gains(dev: Dict) -> Tuple[np.ndarray, np.ndarray]:
     """osc.py:36-39."""
+    if dev.get("gain_vectors") is not None:          # what OSC.__init__ stored (osc.py:37-39); kp / kv / ko may have changed since
+        return np.array(dev["gain_vectors"][0], dtype=np.float64), np.array(dev["gain_vectors"][1], dtype=np.float64)
     task_space_gains = np.array([dev["kp"]] * 3 + [dev["ko"]] * 3, dtype=np.float64)
     lamb = task_space_gains / dev["kv"]
     return task_space_gains, lamb

@@ -148,3 +148,36 @@ def test_max_vel_none_takes_the_unsaturated_gain_branch_like_the_reference(monke
         scale = max(np.abs(f).max() for f in rforces)
         for d in range(len(names)):
             assert np.abs(forces[d] - rforces[d]).max() < 1e-6 * scale, (cleared, names[d])
+
+
+def test_gains_edited_after_construction_behave_like_the_reference(monkeypatch):
+    """`OSC.__init__` stores `task_space_gains` and `lamb` in the config dict once (osc.py:35-39); `kp / kv / ko` are read
+    fresh every step (osc.py:76,170).  A caller that edits a gain afterwards therefore gets the NEW saturation / kv
+    factors with the OLD lamb - in the reference and here (also when a device has no velocity limit: old gains)."""
+    runner, osc, names, layout = _both("gain_test", monkeypatch)
+    ref_Target = ref_harness.import_reference()[3]
+    st = {k: v.numpy() for k, v in synth_batch(layout, 2, seed=23).items()}
+    for step, (edit, cleared) in enumerate(((dict(kp=320.0, kv=35.0), ()), (dict(ko=90.0, kv=12.0), ("ur5right",)))):
+        for o in (osc, runner.osc):
+            for nm in ("ur5right", "ur5left"):
+                for key, val in edit.items():
+                    o.device_configs[nm][key] = val
+        i = step
+        runner.run({k: v[i] for k, v in st.items()}, st["target_xyz"][i], st["target_quat"][i], max_vel=st["max_vel"][i])
+        mine, theirs = {}, {}
+        for d, nm in enumerate(names):
+            for cls, bag in ((pkg.Target, mine), (ref_Target, theirs)):
+                t = cls()
+                t.set_xyz(st["target_xyz"][i][d])
+                t.set_quat(st["target_quat"][i][d])
+                bag[nm] = t
+            mv = None if nm in cleared else [float(st["max_vel"][i][d][0]), float(st["max_vel"][i][d][1])]
+            osc.robot.get_device(nm).max_vel = mv
+            runner.robot.get_device(nm).max_vel = mv
+        ridx, rforces = runner.osc.generate(theirs)
+        idxs, forces = osc.generate(mine)
+        scale = max(np.abs(f).max() for f in rforces)
+        for d in range(len(names)):
+            assert np.abs(forces[d] - rforces[d]).max() < 1e-6 * scale, (step, names[d])
+    # the stored vectors are the ones of construction time, not of the edited gains
+    assert np.allclose(osc.device_configs["ur5right"]["lamb"], np.array([200.0] * 6) / 20.0)
