@@ -392,6 +392,10 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+            if gather_mode.startswith("fused"):
+                # a device-side barrier right before the start event: the host barrier leaves the ranks' streams
+                # hundreds of microseconds apart, which the first in-loop barrier would otherwise charge to the region
+                handles[0].barrier(channel=0)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(repeat):
@@ -541,6 +545,31 @@ def main():
                              "J rows, dq, bias, poses, targets)"}
         del host_in
 
+        # What the host side of the box can deliver: every rank copies 256 MB of pinned host memory to its GPU at the same
+        # time, nothing else running.  e2e is bounded by this, not by the kernels.
+        probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe_h, non_blocking=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(8):
+            probe_d.copy_(probe_h, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        gbs = torch.tensor([8 * probe_h.numel() / (a.elapsed_time(b) * 1e-3) / 1e9], dtype=torch.float64, device=dev)
+        lo_, sum_ = gbs.clone(), gbs.clone()
+        if world > 1:
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+            dist.all_reduce(sum_, op=dist.ReduceOp.SUM)
+        h2d_probe = {"h2d_gbs_per_rank_min": float(lo_.item()), "h2d_gbs_aggregate": float(sum_.item()),
+                     "e2e_h2d_gbs_aggregate": world * e2e["h2d_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9,
+                     "note": "plain pinned-memory cudaMemcpyAsync, all ranks concurrently; the aggregate is the ceiling of e2e"}
+        e2e["host_link"] = h2d_probe
+        del probe_h, probe_d
+
     # ------------------------------------------------------------ other legs (every rank runs them; rank 0 reports)
     extras = {}
     if not args.no_extras:
@@ -569,12 +598,21 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         sub = {k: v[:len(host_cores()) * 96] for k, v in sts[0].items()}
         cb = cpu_baseline(args.workload, layout, oracle_inputs(sub, layout))
+    gather_link = None
+    if world > 1:
+        # the all-gather delivers every other rank's rows into each GPU: NVLink ingress per GPU per step
+        bytes_in = (world - 1) * B * layout.n_ctrl * 8
+        gather_link = {"bytes_in_per_gpu_per_step": bytes_in, "achieved_gbs": bytes_in / (sustained["ms_per_step"] * 1e-3) / 1e9,
+                       "peak_gbs": 770.0, "peak_source": "measured peer-copy bandwidth per direction (B200_PROFILING.md)",
+                       "min_ms_per_step_at_peak": bytes_in / 770e9 * 1e3,
+                       "note": "when this exceeds the kernel time the step is NVLink-bound, not kernel-bound"}
+        gather_link["frac"] = gather_link["achieved_gbs"] / gather_link["peak_gbs"]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
             "sustained": sustained, "launch": headline_launch, "gather": gather_mode, "gather_verified": gather_verified,
-            "strong": strong,
+            "gather_link": gather_link, "strong": strong,
             "e2e_arrays": e2e_arrays}
     line.update(extras)
     print(json.dumps(line))

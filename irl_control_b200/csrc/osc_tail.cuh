@@ -257,6 +257,8 @@ enum TailHow : int {
 };
 
 constexpr int kBisectMax = 48;      // inertia evaluations while bracketing lambda_max
+constexpr int kPowerSteps = 3;      // power steps for the Rayleigh-quotient lower bound on lambda_max
+constexpr double kPowerMargin = 1.02;   // first upper-bound candidate: that far above the lower bound
 constexpr int kIterMax = 40;        // inverse / subspace iterations for the cut eigenvectors
 
 // The branch of osc.py:52-55 and its solution.  Returns false when the warp must finish the instance;
@@ -314,17 +316,37 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
         for (int it = 0; it < kBisectMax && !decided; ++it) {
             const int n = sys_count_below(S, sigma, &lost);
             if (lost) return false;
-            if (state == 0) {                           // cut-off from the upper bound
+            if (state == 0) {                           // cut-off from the upper bound ||A||_F
                 n_hi = n;
-                if (n == 0) { decided = true; break; }  // nothing can be cut
+                if (n == 0) { decided = true; break; }  // nothing can be cut (every k = 7 instance ends here)
+                // Something lies under the loosest cut-off: sharpen the lower bound with the Rayleigh quotient of a few
+                // power steps started from the column of the largest diagonal entry (within 1 % of lambda_max for 99 %
+                // of the DualUR5 instances; ||A||_F is 60 % above it at k = 12, 13) ...
+                double x[K], y[K];
+#pragma unroll
+                for (int i = 0; i < K; ++i) x[i] = (sys_entry(S, i, i) == dmax) ? 1.0 : 0.0;
+                sys_matvec(S, x, y);
+#pragma unroll 1
+                for (int p = 0; p < kPowerSteps; ++p) {
+                    double nn = 0.0, rho = 0.0;
+#pragma unroll
+                    for (int i = 0; i < K; ++i) nn = fma(y[i], y[i], nn);
+                    nn = rcp64(sqrt64(nn));
+#pragma unroll
+                    for (int i = 0; i < K; ++i) x[i] = y[i] * nn;
+                    sys_matvec(S, x, y);
+#pragma unroll
+                    for (int i = 0; i < K; ++i) rho = fma(x[i], y[i], rho);
+                    lo = fmax(lo, rho * (1.0 - 1e-12));  // a Rayleigh quotient never exceeds lambda_max (rounding margin)
+                }
                 sigma = kPinvRcond * lo;
                 state = 1;
             } else if (state == 1) {                    // cut-off from the lower bound
                 n_lo = n;
                 if (n_lo == n_hi) { decided = true; break; }
-                sigma = sqrt64(lo * hi);
+                sigma = lo * kPowerMargin;              // ... and try to confirm an upper bound just above it
                 state = 2;
-            } else if (state == 2) {                    // is lambda_max below the midpoint?
+            } else if (state == 2) {                    // is lambda_max below sigma?
                 moved_hi = (n == K);
                 if (moved_hi) hi = sigma; else lo = sigma;
                 sigma = kPinvRcond * (moved_hi ? hi : lo);
