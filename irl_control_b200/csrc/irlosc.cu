@@ -67,6 +67,8 @@ extern "C" int32_t irlosc_destroy(irlosc_handle *h) {
         if (h->stage[s].stream) cudaStreamDestroy(h->stage[s].stream);
         if (h->fstage[s].stream) cudaStreamDestroy(h->fstage[s].stream);
     }
+    if (h->small_host) cudaFreeHost(h->small_host);
+    if (h->small_dev) cudaFree(h->small_dev);
     lane_destroy(h);
     delete h;
     return IRLOSC_OK;
@@ -243,6 +245,60 @@ int32_t irlosc::ensure_cap(Staging &s, int slot, size_t bytes) {
     return IRLOSC_OK;
 }
 
+// Small batches (the drop-in OSC.generate calls this with B = 1 every millisecond, examples/gain_test.py:143-147): the
+// latency is the number of driver calls, so all inputs travel in ONE pinned staging block with one H2D copy, the
+// outputs come back in one D2H copy, one stream synchronisation.
+constexpr int64_t kSmallBatch = 64;
+struct HostIn { const double *src; size_t per; };
+
+static int32_t step_host_small(irlosc_handle *h, int64_t B, const KIo &hk, const HostIn *ins) {
+    const KParams &P = h->kp;
+    Staging &S = h->stage[0];
+    auto up = [](size_t b) { return (b + 255) & ~size_t(255); };
+    size_t in_off[12], at = 0;
+    for (int i = 0; i < 12; ++i) {
+        in_off[i] = at;
+        if (ins[i].src) at += up(ins[i].per * (size_t)B * sizeof(double));
+    }
+    const size_t in_bytes = at;
+    const size_t o_ctrl = at; at += up((size_t)B * P.n_ctrl * sizeof(double));
+    const size_t o_uall = at; if (hk.u_all) at += up((size_t)B * P.n * sizeof(double));
+    const size_t o_stat = at; if (hk.status) at += up((size_t)B);
+    const size_t total = at;
+    if (total > h->small_cap) {
+        if (h->small_host) { CUDA_TRY(cudaFreeHost(h->small_host)); h->small_host = nullptr; }
+        if (h->small_dev) { CUDA_TRY(cudaFree(h->small_dev)); h->small_dev = nullptr; }
+        h->small_cap = 0;
+        CUDA_TRY(cudaHostAlloc(&h->small_host, total, cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc(&h->small_dev, total));
+        h->small_cap = total;
+    }
+    unsigned char *hb = static_cast<unsigned char *>(h->small_host), *db = static_cast<unsigned char *>(h->small_dev);
+    KIo dk = hk;
+    const double *dptr[12];
+    for (int i = 0; i < 12; ++i) {
+        dptr[i] = nullptr;
+        if (!ins[i].src) continue;
+        memcpy(hb + in_off[i], ins[i].src, ins[i].per * (size_t)B * sizeof(double));
+        dptr[i] = reinterpret_cast<const double *>(db + in_off[i]);
+    }
+    CUDA_TRY(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, S.stream));
+    dk.M = dptr[0]; dk.J = dptr[1]; dk.dq = dptr[2]; dk.bias = dptr[3];
+    dk.ee_xyz = dptr[4]; dk.ee_quat = dptr[5]; dk.target_xyz = dptr[6]; dk.target_quat = dptr[7];
+    dk.target_vel = dptr[8]; dk.max_vel = dptr[9]; dk.ft_xmat = dptr[10]; dk.ft_raw = dptr[11];
+    dk.ctrl = reinterpret_cast<double *>(db + o_ctrl);
+    dk.u_all = hk.u_all ? reinterpret_cast<double *>(db + o_uall) : nullptr;
+    dk.status = hk.status ? db + o_stat : nullptr;
+    int32_t rc = launch_step(h, B, dk, S.stream);
+    if (rc != IRLOSC_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(hb + o_ctrl, db + o_ctrl, total - o_ctrl, cudaMemcpyDeviceToHost, S.stream));
+    CUDA_TRY(cudaStreamSynchronize(S.stream));
+    memcpy(hk.ctrl, hb + o_ctrl, (size_t)B * P.n_ctrl * sizeof(double));
+    if (hk.u_all) memcpy(hk.u_all, hb + o_uall, (size_t)B * P.n * sizeof(double));
+    if (hk.status) memcpy(hk.status, hb + o_stat, (size_t)B);
+    return IRLOSC_OK;
+}
+
 extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io *io) {
     if (!h) return fail(IRLOSC_ERR_INVALID, "handle is null");
     if (B < 0) return fail(IRLOSC_ERR_INVALID, "B is negative");
@@ -259,10 +315,11 @@ extern "C" int32_t irlosc_step_host(irlosc_handle *h, int64_t B, const irlosc_io
 
     // per-instance element counts of every array, in the slot order used below
     const size_t D = P.D, n = P.n;
-    struct In { const double *src; size_t per; } ins[12] = {
+    HostIn ins[12] = {
         {hk.M, (size_t)hk.m_stride}, {hk.J, (size_t)hk.j_stride}, {hk.dq, n}, {hk.bias, n},
         {hk.ee_xyz, 3 * D}, {hk.ee_quat, 4 * D}, {hk.target_xyz, 3 * D}, {hk.target_quat, 4 * D},
         {hk.target_vel, 6 * D}, {hk.max_vel, 2 * D}, {hk.ft_xmat, 9 * D}, {hk.ft_raw, 6 * D}};
+    if (B <= kSmallBatch) return step_host_small(h, B, hk, ins);
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(h->host_chunk, B));
     int turn = 0;
     for (int64_t b0 = 0; b0 < B; b0 += chunk, ++turn) {

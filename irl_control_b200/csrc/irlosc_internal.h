@@ -65,5 +65,7 @@ struct irlosc_handle {
     int fused_kd = 0;
     bool fused_base = false;
     irlosc::Staging fstage[irlosc::kPipeDepth];
+    void *small_host = nullptr, *small_dev = nullptr;   // one-block staging of irlosc_step_host for small batches
+    size_t small_cap = 0;
     void *lane_ctx = nullptr;     // tile layout + host pipeline of the tiled step (irlosc_lane.cu), created on first use
 };

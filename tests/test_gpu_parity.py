@@ -201,6 +201,12 @@ def test_step_host_equals_step_device():
     assert np.array_equal(host_out["ctrl"], dev_out["ctrl"].cpu().numpy())
     assert np.array_equal(host_out["u_all"], dev_out["u_all"].cpu().numpy())
     assert np.array_equal(host_out["status"], dev_out["status"].cpu().numpy())
+    # small batches take the one-block staging path (one H2D, one kernel, one D2H): B = 1 is the drop-in generate()
+    for nb in (1, 5, 64, 65):
+        sub = {k: v[:nb].copy() for k, v in host_in.items()}
+        small = eng.step_host(sub, want_u_all=True)
+        assert np.array_equal(small["ctrl"], host_out["ctrl"][:nb]) and np.array_equal(small["status"], host_out["status"][:nb])
+        assert np.array_equal(small["u_all"], host_out["u_all"][:nb])
 
 
 def test_empty_and_tiny_batches():
