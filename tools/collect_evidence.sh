@@ -26,4 +26,6 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:osc_
     python tools/lane_bench.py --scenario gain_test --threads 224 --staged 1 --stages 3 --others tree_qm --iters 5 > $OUT/${TAG}_ncu_tree.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:osc_step_fused -s 3 -c 1 -f -o $OUT/${TAG}_fused_gain_test \
     python tools/lane_bench.py --scenario gain_test --threads 224 --staged 1 --stages 3 --others fused --iters 5 > $OUT/${TAG}_ncu_fused.log 2>&1
-ls -la $OUT
+# summaries + traffic.json from the reports, then drop all but one report (gpurun brings back at most 64 MiB)
+python tools/evidence_to_profiles.py $TAG --on-box > $OUT/${TAG}_summarise.log 2>&1; tail -3 $OUT/${TAG}_summarise.log
+ls -la $OUT; du -sh $OUT

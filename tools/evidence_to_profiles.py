@@ -3,7 +3,9 @@
 summaries + hot source lines, the launch list, the bench lines, and profiles/traffic.json keyed the way bench.py looks
 it up ("<kernel name as irlosc_last_kernel prints it>|<workload>|B<batch>").
 
-    python tools/evidence_to_profiles.py r02
+    python tools/evidence_to_profiles.py r02 --on-box     # on the GPU box: summarise the .ncu-rep files next to them
+                                                          # (summaries + traffic.json) and delete the reports (64 MiB cap)
+    python tools/evidence_to_profiles.py r02              # here: copy the small files into profiles/
 """
 import csv
 import io
@@ -38,6 +40,10 @@ def printed_name(cxx):
 
 def main():
     tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    on_box = "--on-box" in sys.argv
+    global PROF
+    if on_box:
+        PROF = EV
     traffic_path = os.path.join(PROF, "traffic.json")
     traffic = {}
     for f in sorted(os.listdir(EV)):
@@ -67,7 +73,11 @@ def main():
                 traffic[key] = {"dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
                                 "gpu_time_us_under_ncu": float(m["gpu__time_duration.sum"]), "grid": grid, "block": block,
                                 "source": "profiles/%s_ncu_summary.txt (ncu --set full, one launch of this instantiation)" % base}
-        elif f.endswith((".json", ".csv", ".log")) and not f.endswith("_run.log"):
+            if on_box and "lane_gain_test" not in f:
+                os.remove(src)                       # keep one full report, the rest as summaries
+        elif on_box:
+            continue
+        elif f.endswith((".json", ".csv", ".log", ".txt")) and not f.endswith("_run.log"):
             if f.endswith("_launches.csv"):
                 keep = []
                 for ln in open(src, errors="replace"):
@@ -77,8 +87,12 @@ def main():
                     fh.write("".join(keep))
             elif f.endswith(".log") and "ncu_" in f:
                 continue
+            elif f == "traffic.json":
+                continue
             else:
                 shutil.copyfile(src, os.path.join(PROF, f))
+    if not on_box and os.path.isfile(os.path.join(EV, "traffic.json")):
+        traffic = json.load(open(os.path.join(EV, "traffic.json")))
     if traffic:
         with open(traffic_path, "w") as fh:
             json.dump(traffic, fh, indent=1, sort_keys=True)
