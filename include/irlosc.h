@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define IRLOSC_ABI_VERSION 7
+#define IRLOSC_ABI_VERSION 8
 #define IRLOSC_MAX_DEVICES 4   /* target devices per controller (DualUR5: base + 2 arms) */
 #define IRLOSC_MAX_N 32        /* robot DoF, Robot.num_joints_total (robot.py:32); DualUR5: 25 */
 #define IRLOSC_MAX_K 24        /* stacked task rows, sum of ctrlr_dof over targets; DualUR5: <= 13 */
@@ -387,8 +387,16 @@ int32_t irlosc_host_free(void *ptr);
 
 /* Kernel selection of irlosc_step (per-variable arrays): 0 = auto, 1 = generic (any n, k, layout), 2 = the tree-sparse
  * 4-lane record-staging kernel, 9 = streaming thread-per-instance kernel.  Non-default choices exist for A/B
- * measurements, see DESIGN.md.  (irlosc_step_tiles always runs the lane kernel.) */
+ * measurements, see DESIGN.md.  (irlosc_step_tiles has its own selector below.) */
 int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which);
+/* Kernel selection of irlosc_step_tiles / irlosc_step_tiles_host: IRLOSC_TILES_AUTO picks by layout and batch size
+ * (DESIGN.md), IRLOSC_TILES_LANE = one thread per instance (osc_step_lane), IRLOSC_TILES_PAIR = two lanes per
+ * instance, one per arm (osc_step_pair).  Both restate osc.py:120-210 on the same tiles; they differ in summation
+ * order only (results agree to rounding, the status flags exactly). */
+#define IRLOSC_TILES_AUTO 0
+#define IRLOSC_TILES_LANE 1
+#define IRLOSC_TILES_PAIR 2
+int32_t irlosc_set_tile_kernel(irlosc_handle *h, int32_t which);
 /* Leave `sms` streaming multiprocessors free when launching the step kernel (default 0), so that a
  * collective running on another stream (the NCCL gather of ctrl) can overlap instead of queueing
  * behind a grid that fills every SM. */

@@ -13,7 +13,7 @@ MAX_DEVICES = 4
 MAX_N = 32
 MAX_K = 24
 MAX_PEERS = 8
-ABI_VERSION = 7
+ABI_VERSION = 8
 MAX_ACTIONS = 16
 ACT_WP, ACT_GRIP = 0, 1
 
@@ -169,7 +169,7 @@ EXPORTS = [
     "irlosc_set_model", "irlosc_step_fused", "irlosc_step_fused_host", "irlosc_step_sequence", "irlosc_step_waypoints",
     "irlosc_last_error", "irlosc_abi_version", "irlosc_create", "irlosc_destroy",
     "irlosc_num_task_rows", "irlosc_num_ctrl", "irlosc_step", "irlosc_step_host",
-    "irlosc_calc_error", "irlosc_host_alloc", "irlosc_host_free", "irlosc_set_kernel", "irlosc_set_sm_margin",
+    "irlosc_calc_error", "irlosc_host_alloc", "irlosc_host_free", "irlosc_set_kernel", "irlosc_set_tile_kernel", "irlosc_set_sm_margin",
     "irlosc_kernel_launches", "irlosc_last_kernel",
     "irlosc_tile_entries", "irlosc_tile_spec", "irlosc_tiles_doubles", "irlosc_pack_tiles", "irlosc_pack_tiles_host",
     "irlosc_step_tiles", "irlosc_step_tiles_host",
@@ -230,6 +230,8 @@ def load() -> C.CDLL:
     lib.irlosc_host_free.argtypes = [C.c_void_p]
     lib.irlosc_set_kernel.restype = C.c_int32
     lib.irlosc_set_kernel.argtypes = [C.c_void_p, C.c_int32]
+    lib.irlosc_set_tile_kernel.restype = C.c_int32
+    lib.irlosc_set_tile_kernel.argtypes = [C.c_void_p, C.c_int32]
     lib.irlosc_set_sm_margin.restype = C.c_int32
     lib.irlosc_set_sm_margin.argtypes = [C.c_void_p, C.c_int32]
     lib.irlosc_kernel_launches.restype = C.c_int64

@@ -91,6 +91,13 @@ extern "C" int32_t irlosc_set_kernel(irlosc_handle *h, int32_t which) {
     return IRLOSC_OK;
 }
 
+extern "C" int32_t irlosc_set_tile_kernel(irlosc_handle *h, int32_t which) {
+    if (!h || which < IRLOSC_TILES_AUTO || which > IRLOSC_TILES_PAIR)
+        return fail(IRLOSC_ERR_INVALID, "tile kernel selector must be IRLOSC_TILES_AUTO, _LANE or _PAIR");
+    h->tile_kernel = which;
+    return IRLOSC_OK;
+}
+
 // ------------------------------------------------------------------ step (device pointers)
 int32_t irlosc::resolve_io(const irlosc_handle *h, const irlosc_io *io, KIo &k, bool need_outputs) {
     const KParams &P = h->kp;

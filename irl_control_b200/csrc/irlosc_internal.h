@@ -53,6 +53,7 @@ struct irlosc_handle {
     int device = 0;
     int sm_count = 0;
     int kernel_choice = 0;    // 0 auto, 1 generic, 2 + v specialised variant v
+    int tile_kernel = 0;      // IRLOSC_TILES_*
     int sm_margin = 0;        // SMs left free for overlapping collectives
     int64_t launches = 0;
     const char *last_kernel = "none";

@@ -10,6 +10,7 @@
 #include "irlosc_internal.h"
 #include "irlosc_build.h"
 #include "osc_lane.cuh"
+#include "osc_pair.cuh"
 
 using namespace irlosc;
 using namespace irlosc::lane;
@@ -23,6 +24,7 @@ struct LaneCtx {
     fused::FRoles R;
     TileSpec spec;
     Staging stage[kPipeDepth];    // host pipeline: 0 tiles, 1 target_vel, 2 ctrl, 3 u_all, 4 status
+    mutable int *sched = nullptr; // ticket counters of the pair kernel: [0] device entry point, [1 + s] host pipeline stage s
 };
 
 LaneCtx *ctx_of(irlosc_handle *h) {
@@ -73,6 +75,37 @@ const LaneEntry *lane_table(int *count) {
 
 constexpr size_t kLaneSmem = 227 * 1024;
 
+// Pair kernels (osc_pair.cuh): two lanes per instance.  Registers per thread = 65 536 / threads.
+struct PairEntry {
+    int kd;
+    bool has_base;
+    int threads;
+    const void *fn;
+    int fix_bytes;
+    const char *name;
+};
+template <int KD, bool HB, int NT>
+PairEntry pentry(const char *name) {
+    return PairEntry{KD, HB, NT, (const void *)pair::osc_step_pair<KD, HB, NT>, (int)((sizeof(fused::WarpFix<KD, HB>) + 15) & ~size_t(15)), name};
+}
+const PairEntry *pair_table(int *count) {
+    static const PairEntry t[] = {
+        pentry<3, true, 256>("osc_step_pair<kd3,base,t256>"),  pentry<3, true, 320>("osc_step_pair<kd3,base,t320>"),
+        pentry<3, true, 384>("osc_step_pair<kd3,base,t384>"),
+        pentry<3, true, 512>("osc_step_pair<kd3,base,t512>"),
+        pentry<3, false, 256>("osc_step_pair<kd3,t256>"),      pentry<3, false, 384>("osc_step_pair<kd3,t384>"),
+        pentry<3, false, 512>("osc_step_pair<kd3,t512>"),
+        pentry<6, false, 256>("osc_step_pair<kd6,t256>"),      pentry<6, false, 320>("osc_step_pair<kd6,t320>"),
+        pentry<6, false, 384>("osc_step_pair<kd6,t384>"),
+        pentry<6, false, 512>("osc_step_pair<kd6,t512>"),
+        pentry<6, true, 256>("osc_step_pair<kd6,base,t256>"),  pentry<6, true, 320>("osc_step_pair<kd6,base,t320>"),
+        pentry<6, true, 384>("osc_step_pair<kd6,base,t384>"),
+        pentry<6, true, 512>("osc_step_pair<kd6,base,t512>"),
+    };
+    *count = (int)(sizeof t / sizeof t[0]);
+    return t;
+}
+
 int env_int(const char *name, int dflt) {
     const char *e = getenv(name);
     return e ? atoi(e) : dflt;
@@ -88,7 +121,7 @@ int lane_threads_for(int64_t B, int sms) {
     return (w7 <= w8 && tiles > (int64_t)sms * 7) ? 224 : 256;
 }
 
-int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_tiles_io &io, cudaStream_t st) {
+int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_tiles_io &io, cudaStream_t st, int sched_slot = 0) {
     const KParams &P = h->kp;
     int cnt = 0;
     const LaneEntry *t = lane_table(&cnt), *e = nullptr;
@@ -136,6 +169,53 @@ int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_
         G.ctrl_gather[g] = io.ctrl_gather[g];
         G.ctrl_vec = G.ctrl_vec && al16(io.ctrl_gather[g]);
     }
+    const int sms = std::max(1, h->sm_count - h->sm_margin);
+    // Which kernel.  The pair kernel walks half the dependent chain per instance with half the state per thread:
+    // it wins whenever the batch is one wave of half tiles or less (latency of ONE half tile instead of one tile:
+    // B <= 16 x 8 warps x SMs), and for 6-row arm devices at every size (no spills; measured -13 % at B = 65 536,
+    // -27 % at 262 144).  3-row layouts above one wave: the TMA-staged lane kernel (measured 0.050 vs 0.060 ms).
+    // IRLOSC_PAIR (experiments) overrides: threads per CTA of the pair kernel, 0 = lane kernel.
+    const int64_t n_half = (B + pair::kHalf - 1) / pair::kHalf;
+    int pair_threads = 0;
+    if (h->tile_kernel == IRLOSC_TILES_PAIR || (h->tile_kernel == IRLOSC_TILES_AUTO && (c.kd > 3 || n_half <= (int64_t)sms * 8)))
+        pair_threads = 256;
+    if (h->tile_kernel == IRLOSC_TILES_AUTO) pair_threads = env_int("IRLOSC_PAIR", pair_threads);
+    if (pair_threads > 0) {
+        int pc = 0;
+        const PairEntry *pt = pair_table(&pc), *pe = nullptr;
+        for (int i = 0; i < pc; ++i)
+            if (pt[i].kd == c.kd && pt[i].has_base == c.has_base && (pe == nullptr || abs(pt[i].threads - pair_threads) < abs(pe->threads - pair_threads)))
+                pe = &pt[i];
+        if (!pe) return fail(IRLOSC_ERR_INVALID, "no pair kernel for kd=%d base=%d", c.kd, (int)c.has_base);
+        static bool pair_ready = false;
+        if (!pair_ready) {
+            for (int i = 0; i < pc; ++i)
+                CUDA_TRY(cudaFuncSetAttribute(pt[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLaneSmem));
+            pair_ready = true;
+        }
+        const int pw = pe->threads / 32;
+        // tickets pay when a warp has several half tiles to walk (IRLOSC_PAIR_TICKETS: experiments)
+        if (env_int("IRLOSC_PAIR_TICKETS", 1) != 0 && n_half > (int64_t)sms * pw) {
+            if (!c.sched) {
+                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+                CUDA_TRY(cudaStreamIsCapturing(st, &cap));
+                if (cap != cudaStreamCaptureStatusNone)
+                    return fail(IRLOSC_ERR_INVALID, "the first large step allocates its ticket counters: run one step before capturing a graph");
+                CUDA_TRY(cudaMalloc(&c.sched, (1 + kPipeDepth) * sizeof(int)));
+                CUDA_TRY(cudaMemset(c.sched, 0, (1 + kPipeDepth) * sizeof(int)));
+                CUDA_TRY(cudaDeviceSynchronize());      // once: the counters are zero before any stream uses them
+            }
+            A.sched = c.sched + sched_slot;
+        }
+        int pair_warp_bytes = ((pair::kHalf * P.n_ctrl * 8 + 15) & ~15) + pe->fix_bytes;
+        const int pgrid = (int)std::min<int64_t>((n_half + pw - 1) / pw, (int64_t)sms);
+        void *pargs[] = {(void *)&P, (void *)&A, (void *)&B, (void *)&c.R, (void *)&G, (void *)&pair_warp_bytes};
+        cudaError_t perr = cudaLaunchKernel(pe->fn, dim3(pgrid), dim3(pe->threads), pargs, (size_t)pw * pair_warp_bytes, st);
+        if (perr != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "pair kernel launch: %s", cudaGetErrorString(perr));
+        h->launches += 1;
+        h->last_kernel = pe->name;
+        return IRLOSC_OK;
+    }
     const int warps = e->threads / 32;
     const size_t smem = (size_t)warps * warp_bytes;
     static bool ready = false;
@@ -144,7 +224,6 @@ int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_
             CUDA_TRY(cudaFuncSetAttribute(t[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLaneSmem));
         ready = true;
     }
-    const int sms = std::max(1, h->sm_count - h->sm_margin);
     const int64_t n_tiles = (B + kTile - 1) / kTile;
     const int grid = (int)std::min<int64_t>((n_tiles + warps - 1) / warps, (int64_t)sms);
     void *args[] = {(void *)&P, (void *)&A, (void *)&B, (void *)&c.R, (void *)&G, (void *)&warp_bytes, (void *)&stage_bytes,
@@ -172,6 +251,7 @@ void irlosc::lane_destroy(irlosc_handle *h) {
             if (c->stage[s].buf[i]) cudaFree(c->stage[s].buf[i]);
         if (c->stage[s].stream) cudaStreamDestroy(c->stage[s].stream);
     }
+    if (c->sched) cudaFree(c->sched);
     delete c;
     h->lane_ctx = nullptr;
 }
@@ -297,7 +377,7 @@ extern "C" int32_t irlosc_step_tiles_host(irlosc_handle *h, int64_t B, const irl
         dk.ctrl = (double *)S.buf[2];
         dk.u_all = io->u_all ? (double *)S.buf[3] : nullptr;
         dk.status = io->status ? (uint8_t *)S.buf[4] : nullptr;
-        rc = launch_lane(h, *c, nb, dk, S.stream);
+        rc = launch_lane(h, *c, nb, dk, S.stream, 1 + turn % kPipeDepth);
         if (rc != IRLOSC_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(io->ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
                                  cudaMemcpyDeviceToHost, S.stream));

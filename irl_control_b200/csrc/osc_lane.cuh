@@ -298,6 +298,7 @@ struct LaneArgs {
     const double *target_vel;               // [B][D][6] plain array, optional
     double *u_all, *ctrl;
     uint8_t *status;
+    int *sched;                             // ticket counter of the launch (pair kernel), null = static assignment
 };
 
 struct LdStream {       // streaming load: read once, keep out of L1

@@ -82,11 +82,11 @@ struct ArmState {
     double c[28], uvC[7], dqC[7];
 };
 
-// osc.py:159-168,179-181 for one device from staged values.
+// osc.py:159-168,179-181 for one device from staged values: the unmasked six task components.
 template <class RD>
-IRLOSC_HD void device_signal_staged(const KParams &P, int d, const RD &rd, int e0, bool has_mvel, double *gpre) {
+IRLOSC_HD void device_u6_staged(const KParams &P, int d, const RD &rd, int e0, bool has_mvel, double *u6) {
     const KDevice &dv = P.dev[d];
-    double ee_p[3], ee_q[4], txyz[3], tquat[4], u6[6];
+    double ee_p[3], ee_q[4], txyz[3], tquat[4];
 #pragma unroll
     for (int i = 0; i < 3; ++i) { ee_p[i] = rd(e0 + kEeXyz + i); txyz[i] = rd(e0 + kTXyz + i); }
 #pragma unroll
@@ -105,6 +105,13 @@ IRLOSC_HD void device_signal_staged(const KParams &P, int d, const RD &rd, int e
 #pragma unroll
         for (int i = 0; i < 6; ++i) u6[i] += ft[i];
     }
+}
+// ... masked by the device's controlled DoF into its task rows of gpre.
+template <class RD>
+IRLOSC_HD void device_signal_staged(const KParams &P, int d, const RD &rd, int e0, bool has_mvel, double *gpre) {
+    const KDevice &dv = P.dev[d];
+    double u6[6];
+    device_u6_staged(P, d, rd, e0, has_mvel, u6);
     int r = dv.row0;
 #pragma unroll
     for (int i = 0; i < 6; ++i)

@@ -224,6 +224,39 @@ IRLOSC_HD void sys_solve(const TaskSys<KD, HB> &S, const double *r, double *w) {
     }
 }
 
+// y = (A - sigma I)^-1 x, sigma > 0, for the Rayleigh-quotient steps of the cut eigenvector.  The shifted blocks are
+// indefinite and factored without pivoting: a step may be inaccurate, the iteration corrects itself (and its result
+// is checked), non-finite values are the caller's to catch.
+template <int KD, bool HB>
+IRLOSC_HD void sys_solve_shifted(const TaskSys<KD, HB> &S, double sigma, const double *x, double *y) {
+    constexpr int KT = TaskSys<KD, HB>::KT;
+    double u[2 * KD];
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        double f[KT];
+        bool lost = false;
+        blk_factor<KD>(S.D[b], sigma, f, &lost);
+#pragma unroll
+        for (int i = 0; i < KD; ++i) { y[b * KD + i] = x[b * KD + i]; u[b * KD + i] = S.v[b * KD + i]; }
+        blk_solve<KD>(f, y + b * KD);
+        blk_solve<KD>(f, u + b * KD);
+    }
+    double gam = S.d0, t = 0.0, ub = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2 * KD; ++i) { gam = fma(S.v[i], u[i], gam); t = fma(S.v[i], y[i], t); }
+    if (HB) {
+        const double is = -rcp64(sigma);                    // the base's diagonal block is 0 - sigma
+        y[2 * KD] = x[2 * KD] * is;
+        ub = S.v[2 * KD] * is;
+        gam = fma(S.v[2 * KD], ub, gam);
+        t = fma(S.v[2 * KD], y[2 * KD], t);
+    }
+    t *= rcp64(gam);
+#pragma unroll
+    for (int i = 0; i < 2 * KD; ++i) y[i] = fma(-u[i], t, y[i]);
+    if (HB) y[2 * KD] = fma(-ub, t, y[2 * KD]);
+}
+
 // Number of eigenvalues of A below sigma (sigma > 0), by the inertia of the bordered matrix.
 template <int KD, bool HB>
 IRLOSC_HD int sys_count_below(const TaskSys<KD, HB> &S, double sigma, bool *lost) {
@@ -254,12 +287,22 @@ enum TailHow : int {
     kHowCut1 = 2,          // pinv removed one eigenvalue (deflation in the thread)
     kHowCut2 = 4,          // pinv removed two
     kHowWarp = 8,          // handed to the warp-cooperative eigen-solver
+    // ... and why (statistics of the host harness)
+    kWhyBlocks = 16,       // an arm block is not positive definite / lost a pivot
+    kWhyBaseZero = 32,     // base row with a zero stand entry
+    kWhyLost = 64,         // an inertia count lost a pivot to cancellation
+    kWhyUndecided = 128,   // the bracket of lambda_max did not settle the count
+    kWhyMany = 256,        // more than two eigenvalues under the cut-off
+    kWhyNoConv = 512,      // inverse iteration did not converge
+    kWhyResidual = 1024,   // residual test
 };
 
 constexpr int kBisectMax = 48;      // inertia evaluations while bracketing lambda_max
 constexpr int kPowerSteps = 3;      // power steps for the Rayleigh-quotient lower bound on lambda_max
 constexpr double kPowerMargin = 1.02;   // first upper-bound candidate: that far above the lower bound
 constexpr int kIterMax = 40;        // inverse / subspace iterations for the cut eigenvectors
+constexpr int kPlainIters = 8;      // ... of which plain ones before a single cut eigenvector switches to Rayleigh-quotient shifts
+constexpr int kRefineMax = 3;       // refinement steps of the task-space solution before the warp takes over
 
 // The branch of osc.py:52-55 and its solution.  Returns false when the warp must finish the instance;
 // *small_det then says whether the pinv branch is known to be the one taken.
@@ -272,7 +315,7 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
     bool lost = false;
     int nneg = blk_factor<KD>(S.D[0], 0.0, S.f[0], &lost);
     nneg += blk_factor<KD>(S.D[1], 0.0, S.f[1], &lost);
-    if (nneg != 0 || lost) return false;
+    if (nneg != 0 || lost) { *how |= kWhyBlocks; return false; }
 #pragma unroll
     for (int i = 0; i < 2 * KD; ++i) S.u[i] = S.v[i];
     blk_solve<KD>(S.f[0], S.u);
@@ -285,7 +328,7 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
     if (HB) {
         S.piv = rcp64(S.v[2 * KD]);
         detinv *= S.piv * S.piv;                        // det A = det D v_b^2 / d0
-        if (!(fabs(S.v[2 * KD]) > 0.0)) return false;
+        if (!(fabs(S.v[2 * KD]) > 0.0)) { *how |= kWhyBaseZero; return false; }
     } else {
         double gam = S.d0;
 #pragma unroll
@@ -307,15 +350,18 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
         }
     const double fro = sqrt64(fro2);
     int m = 0;
+    double hi_final = fro;
     if (small) {
         // bracket lambda_max until the count of eigenvalues under rcond * lambda_max is the same at both ends
         double hi = fro, lo = dmax, sigma = kPinvRcond * fro;
         int n_hi = -1, n_lo = -1, state = 0;
         bool moved_hi = false, decided = false;
+        int n_counts = 0;
 #pragma unroll 1
         for (int it = 0; it < kBisectMax && !decided; ++it) {
             const int n = sys_count_below(S, sigma, &lost);
-            if (lost) return false;
+            ++n_counts;
+            if (lost) { *how |= kWhyLost; return false; }
             if (state == 0) {                           // cut-off from the upper bound ||A||_F
                 n_hi = n;
                 if (n == 0) { decided = true; break; }  // nothing can be cut (every k = 7 instance ends here)
@@ -358,9 +404,11 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
                 state = 2;
             }
         }
-        if (!decided) return false;
+        *how |= (n_counts & 0xff) << 12;
+        if (!decided) { *how |= kWhyUndecided; return false; }
+        hi_final = hi;
         m = n_hi;
-        if (m > 2) return false;
+        if (m > 2) { *how |= kWhyMany; return false; }
     }
     double geff[K];
 #pragma unroll
@@ -370,14 +418,28 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
         // cut eigenvectors by inverse (subspace) iteration with the block solver
 #pragma unroll
         for (int i = 0; i < K; ++i) { xa[i] = 1.0; xb[i] = (i & 1) ? -1.0 : 1.0; }
-        bool conv = false;
+        bool conv = false, shifted = false;
+        double rho = 0.0;
+        int n_iter = 0;
 #pragma unroll 1
         for (int it = 0; it < kIterMax && !conv; ++it) {
             double ya[K], yb[K];
-            sys_solve(S, xa, ya);
+            if (m == 1 && it >= kPlainIters) {
+                // lambda_1 / lambda_2 is close to one (0.3 % of the cut instances): plain inverse iteration crawls.
+                // Shift by the Rayleigh quotient of the current vector (cubic convergence).
+                sys_matvec(S, xa, ya);
+                rho = 0.0;
+#pragma unroll
+                for (int i = 0; i < K; ++i) rho = fma(xa[i], ya[i], rho);
+                sys_solve_shifted(S, rho, xa, ya);
+                shifted = true;
+            } else {
+                sys_solve(S, xa, ya);
+            }
             double na = 0.0, dot = 0.0;
 #pragma unroll
             for (int i = 0; i < K; ++i) na = fma(ya[i], ya[i], na);
+            if (!(na > 0.0 && na < 1e300)) break;     // a shifted step broke down
             na = rcp64(sqrt64(na));
 #pragma unroll
             for (int i = 0; i < K; ++i) { ya[i] *= na; dot = fma(ya[i], xa[i], dot); }
@@ -414,8 +476,20 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
 #pragma unroll
             for (int i = 0; i < K; ++i) xa[i] = ya[i];
             conv = (it >= 1) && (change < 1e-8);      // eigenvector error d ~ change: the deflation error is d^2 lambda_2 / lambda_1
+            n_iter = it + 1;
         }
-        if (!conv) return false;
+        *how |= (n_iter & 0xff) << 20;
+        if (!conv) { *how |= kWhyNoConv; return false; }
+        if (shifted) {
+            // the shifted iteration converges to the eigenvector nearest its shifts: make sure that is the cut one
+            // (exactly one eigenvalue lies under the cut-off, and it is below rcond * hi)
+            double av[K];
+            sys_matvec(S, xa, av);
+            rho = 0.0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) rho = fma(xa[i], av[i], rho);
+            if (!(rho < kPinvRcond * hi_final)) { *how |= kWhyNoConv; return false; }
+        }
         // geff = P g
         double pa = 0.0, pb = 0.0;
 #pragma unroll
@@ -423,31 +497,46 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
 #pragma unroll
         for (int i = 0; i < K; ++i) { geff[i] = fma(-pa, xa[i], geff[i]); if (m == 2) geff[i] = fma(-pb, xb[i], geff[i]); }
     }
+    // onto the kept subspace (identity when nothing was cut)
+    auto keep = [&](double *z) {
+        if (m >= 1) {
+            double pa = 0.0, pb = 0.0;
+#pragma unroll
+            for (int i = 0; i < K; ++i) { pa = fma(xa[i], z[i], pa); if (m == 2) pb = fma(xb[i], z[i], pb); }
+#pragma unroll
+            for (int i = 0; i < K; ++i) { z[i] = fma(-pa, xa[i], z[i]); if (m == 2) z[i] = fma(-pb, xb[i], z[i]); }
+        }
+    };
     sys_solve(S, geff, w);
-    if (m >= 1) {
-        double pa = 0.0, pb = 0.0;
+    keep(w);
+    // ---- residual of the structured system on the kept subspace.  The block formulas lose digits when an arm's
+    // block is much worse conditioned than A itself (the stand joint supplies the direction the arm has lost):
+    // the residual is exact enough to repair that by iterative refinement.
+    double gmax = 0.0;
 #pragma unroll
-        for (int i = 0; i < K; ++i) { pa = fma(xa[i], w[i], pa); if (m == 2) pb = fma(xb[i], w[i], pb); }
+    for (int i = 0; i < K; ++i) gmax = fmax(gmax, fabs(gc[i]));
+    int passes = 0;
+#pragma unroll 1
+    for (;;) {
+        double r[K];
+        sys_matvec(S, w, r);
 #pragma unroll
-        for (int i = 0; i < K; ++i) { w[i] = fma(-pa, xa[i], w[i]); if (m == 2) w[i] = fma(-pb, xb[i], w[i]); }
+        for (int i = 0; i < K; ++i) r[i] -= geff[i];
+        keep(r);
+        double rmax = 0.0, wmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) { rmax = fmax(rmax, fabs(r[i])); wmax = fmax(wmax, fabs(w[i])); }
+        if (rmax <= 1e-10 * fma(fro, wmax, gmax)) break;
+        if (passes == kRefineMax || !(rmax == rmax)) { *how |= kWhyResidual; return false; }
+        ++passes;
+        double dw[K];
+        sys_solve(S, r, dw);
+        keep(dw);
+#pragma unroll
+        for (int i = 0; i < K; ++i) w[i] -= dw[i];
     }
-    // ---- residual of the structured system (on the kept subspace when something was cut)
-    double r[K];
-    sys_matvec(S, w, r);
-#pragma unroll
-    for (int i = 0; i < K; ++i) r[i] -= geff[i];
-    if (m >= 1) {
-        double pa = 0.0, pb = 0.0;
-#pragma unroll
-        for (int i = 0; i < K; ++i) { pa = fma(xa[i], r[i], pa); if (m == 2) pb = fma(xb[i], r[i], pb); }
-#pragma unroll
-        for (int i = 0; i < K; ++i) { r[i] = fma(-pa, xa[i], r[i]); if (m == 2) r[i] = fma(-pb, xb[i], r[i]); }
-    }
-    double rmax = 0.0, wmax = 0.0, gmax = 0.0;
-#pragma unroll
-    for (int i = 0; i < K; ++i) { rmax = fmax(rmax, fabs(r[i])); wmax = fmax(wmax, fabs(w[i])); gmax = fmax(gmax, fabs(gc[i])); }
-    if (!(rmax <= 1e-10 * fma(fro, wmax, gmax))) return false;
-    *how = m == 0 ? kHowInverse : m == 1 ? kHowCut1 : kHowCut2;
+    *how |= passes << 28;
+    *how = (*how & ~0xfff) | (m == 0 ? kHowInverse : m == 1 ? kHowCut1 : kHowCut2);
     return true;
 }
 

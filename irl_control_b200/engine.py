@@ -67,6 +67,12 @@ class BatchedOSC:
     def set_kernel(self, which: int):
         _native.check(self.lib.irlosc_set_kernel(self._handle, int(which)))
 
+    TILE_KERNELS = {"auto": 0, "lane": 1, "pair": 2}
+
+    def set_tile_kernel(self, which):
+        """Kernel of `step_tiles` / `step_tiles_host`: "auto", "lane" (a thread per instance) or "pair" (a lane per arm)."""
+        _native.check(self.lib.irlosc_set_tile_kernel(self._handle, self.TILE_KERNELS.get(which, which)))
+
     def set_sm_margin(self, sms: int):
         """Leave `sms` SMs free so a collective on another stream can overlap the step kernel."""
         _native.check(self.lib.irlosc_set_sm_margin(self._handle, int(sms)))

@@ -74,7 +74,7 @@ def run(layout, model, inp, debug=False):
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
     out["n_hard"] = int(rc)
-    out["how"] = how
+    out["how"], out["how_detail"] = how & 0xf, how
     out.update(dbg)
     return out
 
@@ -120,7 +120,7 @@ def run_stream(layout, state, debug=False, strides=None):
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
     out["n_hard"] = int(rc)
-    out["how"] = how
+    out["how"], out["how_detail"] = how & 0xf, how
     out["n_chunks"] = int(nch.value)
     out.update(dbg)
     return out
@@ -227,9 +227,11 @@ def run_lane(layout, state):
         lib.host_set_how(None)
     if rc < 0:
         raise RuntimeError(lib.fused_host_error().decode())
-    out["n_hard"], out["how"], out["tiles"] = int(rc), how, tiles
+    out["n_hard"], out["how"], out["how_detail"], out["tiles"] = int(rc), how & 0xf, how, tiles
     return out
 
 
-# TailHow bits of csrc/osc_tail.cuh (out["how"])
+# TailHow bits of csrc/osc_tail.cuh (out["how"]); out["how_detail"] keeps the statistics above them: why an instance
+# went to the warp (WHY_*), inertia counts (bits 12-19), eigenvector iterations (20-27), refinement steps (28-30)
 HOW_INVERSE, HOW_CUT1, HOW_CUT2, HOW_WARP = 1, 2, 4, 8
+WHY = {16: "blocks", 32: "base_zero", 64: "lost", 128: "undecided", 256: "many", 512: "no_convergence", 1024: "residual"}

@@ -60,8 +60,7 @@ def test_fused_step_matches_oracle(scenario, B):
     assert _rel(ctrl[idx], want).max() < REL_TOL
     assert np.isfinite(ctrl).all() and np.isfinite(u_all).all()
     assert np.abs(out["ee_xyz"].cpu().numpy() - st["ee_xyz"].cpu().numpy()).max() < 1e-12
-    if scenario != "gain_test" and B >= 2048:
-        assert len(hard) > 0
+    assert ((status & _native.ST_EIGEN) != 0).mean() < 2e-4        # the warp eigen-solver is the rare exception
     print("fused %s B=%d: max rel %.2e, eigen fix-ups %d" % (scenario, B, rel.max(), int((status & _native.ST_EIGEN != 0).sum())))
 
 

@@ -15,8 +15,8 @@ python -c "import __graft_entry__ as g; g.smoke()" > $OUT/${TAG}_smoke.log 2>&1;
 timeout 600 python bench.py > $OUT/${TAG}_bench_n1.json 2> $OUT/${TAG}_bench_n1.err; tail -2 $OUT/${TAG}_bench_n1.err
 timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/${TAG}_bench_reference_arm.json 2>> $OUT/${TAG}_bench_n1.err
 # 4. launch list of the same command (ncu per-launch times are cold-cache and serialised: compare SHARES)
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-    python bench.py --no-graph --no-cpu-baseline --steps 4 --warmup 3 > $OUT/${TAG}_launches_run.log 2>&1
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"osc_step|pack_tiles|calc_error" -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+    python bench.py --no-graph --no-cpu-baseline --no-extras --steps 4 --warmup 3 > $OUT/${TAG}_launches_run.log 2>&1
 # 5. one full capture of the default kernel per workload
 for wl in gain_test admit_test worst_case; do
     timeout 300 ncu --set full --clock-control none --import-source on -k regex:osc_step_lane -s 8 -c 1 -f -o $OUT/${TAG}_lane_$wl \

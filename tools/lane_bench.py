@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--staged", default="1", help="comma-separated: 1 = TMA-staged ring, 0 = direct LDG")
     ap.add_argument("--stages", default="3", help="comma-separated ring depths for the staged form")
     ap.add_argument("--nbuf", type=int, default=3)
+    ap.add_argument("--sweep-pair", type=int, default=0, help="CTA size of the pair kernel for the --sweep runs (0: default launch)")
+    ap.add_argument("--pair", default="", help="comma-separated CTA sizes of the pair kernel (two lanes per instance)")
     ap.add_argument("--others", default="tree_packed,tree_qm,stream_qm,fused,pack")
     ap.add_argument("--sweep", default="", help="comma-separated batch sizes: time the default lane launch on prefixes of the tiles")
     args = ap.parse_args()
@@ -78,6 +80,20 @@ def main():
                 rec("lane", med, mn, threads=th, staged=stg, **{key: val}, equal_to_stream=same, tile_bytes_per_instance=E * 8)
     for k_ in ("IRLOSC_LANE_THREADS", "IRLOSC_LANE_PREFETCH", "IRLOSC_LANE_STAGED", "IRLOSC_LANE_STAGES"):
         os.environ.pop(k_, None)
+    for th in [int(x) for x in args.pair.split(",") if x]:
+        for pf in [int(x) for x in args.prefetch.split(",") if x]:
+            os.environ["IRLOSC_PAIR"] = str(th)
+            os.environ["IRLOSC_LANE_PREFETCH"] = str(pf)
+            o = eng.step_tiles(tiles[0], B, want_status=True)
+            fin = torch.isfinite(ref["ctrl"])
+            err = float(((o["ctrl"] - ref["ctrl"]).abs()[fin].max() / ref["ctrl"].abs()[fin].max()).item())
+            same = bool(torch.equal(o["status"], ref["status"]) and torch.equal(torch.isfinite(o["ctrl"]), fin))
+            med, mn = timeit(torch, lambda i: eng.step_tiles(tiles[i % args.nbuf], B, out=out, want_status=False), args.iters)
+            rec("pair", med, mn, threads=th, prefetch=pf, status_equal=same, max_rel_err_vs_stream=err)
+    os.environ.pop("IRLOSC_PAIR", None)
+    os.environ.pop("IRLOSC_LANE_PREFETCH", None)
+    if args.sweep_pair:
+        os.environ["IRLOSC_PAIR"] = str(args.sweep_pair)
     for Bs in [int(x) for x in args.sweep.split(",") if x]:
         nt = (Bs + 31) // 32
         sub = [t[:nt] for t in tiles]
@@ -93,6 +109,7 @@ def main():
         r = dict(name="lane_sweep", scenario=args.scenario, B=Bs, ms=round(ts[len(ts) // 2], 5), ms_min=round(ts[0], 5),
                  kernel=eng.last_kernel, steps_per_s=Bs / (ts[len(ts) // 2] * 1e-3), l2="flushed between steps")
         print(json.dumps(r), flush=True)
+    os.environ.pop("IRLOSC_PAIR", None)
     others = [x for x in args.others.split(",") if x]
     scale = ref["ctrl"].abs().amax(dim=1, keepdim=True)
     if "tree_packed" in others:
