@@ -846,4 +846,11 @@ def extra_legs(args, torch, np, eng, layout, sts, arrays, tiles, dev, world, dis
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:                      # never leave a half-dead process behind on the GPU box
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)

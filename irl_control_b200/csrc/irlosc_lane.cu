@@ -59,12 +59,8 @@ LaneEntry lentry(const char *name) {
 const LaneEntry *lane_table(int *count) {
     static const LaneEntry t[] = {
         lentry<3, true, 224, true>("osc_step_lane<kd3,base,t224,tma>"),   lentry<3, true, 256, true>("osc_step_lane<kd3,base,t256,tma>"),
-        lentry<3, true, 320, true>("osc_step_lane<kd3,base,t320,tma>"),   lentry<3, true, 384, true>("osc_step_lane<kd3,base,t384,tma>"),
         lentry<3, false, 224, true>("osc_step_lane<kd3,t224,tma>"),       lentry<3, false, 256, true>("osc_step_lane<kd3,t256,tma>"),
-        lentry<6, false, 224, true>("osc_step_lane<kd6,t224,tma>"),       lentry<6, false, 256, true>("osc_step_lane<kd6,t256,tma>"),
-        lentry<6, true, 224, true>("osc_step_lane<kd6,base,t224,tma>"),   lentry<6, true, 256, true>("osc_step_lane<kd6,base,t256,tma>"),
         lentry<3, true, 224, false>("osc_step_lane<kd3,base,t224,ldg>"),  lentry<3, true, 256, false>("osc_step_lane<kd3,base,t256,ldg>"),
-        lentry<3, true, 384, false>("osc_step_lane<kd3,base,t384,ldg>"),
         lentry<3, false, 256, false>("osc_step_lane<kd3,t256,ldg>"),
         lentry<6, false, 256, false>("osc_step_lane<kd6,t256,ldg>"),
         lentry<6, true, 256, false>("osc_step_lane<kd6,base,t256,ldg>"),
@@ -89,18 +85,11 @@ PairEntry pentry(const char *name) {
     return PairEntry{KD, HB, NT, (const void *)pair::osc_step_pair<KD, HB, NT>, (int)((sizeof(fused::WarpFix<KD, HB>) + 15) & ~size_t(15)), name};
 }
 const PairEntry *pair_table(int *count) {
+    // 8 warps of 255 registers: measured against 10, 12 and 16 warps (204 / 168 / 128 registers, spills) at every batch
+    // size and layout, 8 won everywhere (profiles/r02_summary.md).
     static const PairEntry t[] = {
-        pentry<3, true, 256>("osc_step_pair<kd3,base,t256>"),  pentry<3, true, 320>("osc_step_pair<kd3,base,t320>"),
-        pentry<3, true, 384>("osc_step_pair<kd3,base,t384>"),
-        pentry<3, true, 512>("osc_step_pair<kd3,base,t512>"),
-        pentry<3, false, 256>("osc_step_pair<kd3,t256>"),      pentry<3, false, 384>("osc_step_pair<kd3,t384>"),
-        pentry<3, false, 512>("osc_step_pair<kd3,t512>"),
-        pentry<6, false, 256>("osc_step_pair<kd6,t256>"),      pentry<6, false, 320>("osc_step_pair<kd6,t320>"),
-        pentry<6, false, 384>("osc_step_pair<kd6,t384>"),
-        pentry<6, false, 512>("osc_step_pair<kd6,t512>"),
-        pentry<6, true, 256>("osc_step_pair<kd6,base,t256>"),  pentry<6, true, 320>("osc_step_pair<kd6,base,t320>"),
-        pentry<6, true, 384>("osc_step_pair<kd6,base,t384>"),
-        pentry<6, true, 512>("osc_step_pair<kd6,base,t512>"),
+        pentry<3, true, 256>("osc_step_pair<kd3,base,t256>"), pentry<3, false, 256>("osc_step_pair<kd3,t256>"),
+        pentry<6, true, 256>("osc_step_pair<kd6,base,t256>"), pentry<6, false, 256>("osc_step_pair<kd6,t256>"),
     };
     *count = (int)(sizeof t / sizeof t[0]);
     return t;
@@ -121,7 +110,10 @@ int lane_threads_for(int64_t B, int sms) {
     return (w7 <= w8 && tiles > (int64_t)sms * 7) ? 224 : 256;
 }
 
-int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_tiles_io &io, cudaStream_t st, int sched_slot = 0) {
+// B_whole: the batch the caller handed in (the host entry point launches it in chunks): the kernel choice follows it,
+// so that a batch gives the same bits whichever entry point it came through.
+int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_tiles_io &io, cudaStream_t st, int sched_slot = 0,
+                    int64_t B_whole = -1) {
     const KParams &P = h->kp;
     int cnt = 0;
     const LaneEntry *t = lane_table(&cnt), *e = nullptr;
@@ -176,8 +168,9 @@ int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_
     // -27 % at 262 144).  3-row layouts above one wave: the TMA-staged lane kernel (measured 0.050 vs 0.060 ms).
     // IRLOSC_PAIR (experiments) overrides: threads per CTA of the pair kernel, 0 = lane kernel.
     const int64_t n_half = (B + pair::kHalf - 1) / pair::kHalf;
+    const int64_t n_half_whole = ((B_whole < 0 ? B : B_whole) + pair::kHalf - 1) / pair::kHalf;
     int pair_threads = 0;
-    if (h->tile_kernel == IRLOSC_TILES_PAIR || (h->tile_kernel == IRLOSC_TILES_AUTO && (c.kd > 3 || n_half <= (int64_t)sms * 8)))
+    if (h->tile_kernel == IRLOSC_TILES_PAIR || (h->tile_kernel == IRLOSC_TILES_AUTO && (c.kd > 3 || n_half_whole <= (int64_t)sms * 8)))
         pair_threads = 256;
     if (h->tile_kernel == IRLOSC_TILES_AUTO) pair_threads = env_int("IRLOSC_PAIR", pair_threads);
     if (pair_threads > 0) {
@@ -377,7 +370,7 @@ extern "C" int32_t irlosc_step_tiles_host(irlosc_handle *h, int64_t B, const irl
         dk.ctrl = (double *)S.buf[2];
         dk.u_all = io->u_all ? (double *)S.buf[3] : nullptr;
         dk.status = io->status ? (uint8_t *)S.buf[4] : nullptr;
-        rc = launch_lane(h, *c, nb, dk, S.stream, 1 + turn % kPipeDepth);
+        rc = launch_lane(h, *c, nb, dk, S.stream, 1 + turn % kPipeDepth, B);
         if (rc != IRLOSC_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(io->ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
                                  cudaMemcpyDeviceToHost, S.stream));

@@ -114,35 +114,6 @@ __device__ __forceinline__ void pair_solve(const PairSys<KD, HB> &S, const doubl
     }
 }
 
-// y = (A - sigma I)^-1 x (osc_tail.cuh: sys_solve_shifted)
-template <int KD, bool HB>
-__device__ __forceinline__ void pair_solve_shifted(const PairSys<KD, HB> &S, double sigma, const double *x, double xb, double *y,
-                                                   double *yb) {
-    constexpr int KT = PairSys<KD, HB>::KT;
-    double f[KT], u[KD];
-    bool lost = false;
-    blk_factor<KD>(S.D, sigma, f, &lost);
-#pragma unroll
-    for (int i = 0; i < KD; ++i) { y[i] = x[i]; u[i] = S.v[i]; }
-    blk_solve<KD>(f, y);
-    blk_solve<KD>(f, u);
-    double gl = 0.0, tl = 0.0;
-#pragma unroll
-    for (int i = 0; i < KD; ++i) { gl = fma(S.v[i], u[i], gl); tl = fma(S.v[i], y[i], tl); }
-    double gam = S.d0 + S.duo.sum(gl), t = S.duo.sum(tl), ub = 0.0, ybv = 0.0;
-    if (HB) {
-        const double is = -rcp64(sigma);
-        ybv = xb * is;
-        ub = S.vb * is;
-        gam = fma(S.vb, ub, gam);
-        t = fma(S.vb, ybv, t);
-    }
-    t *= rcp64(gam);
-#pragma unroll
-    for (int i = 0; i < KD; ++i) y[i] = fma(-u[i], t, y[i]);
-    *yb = HB ? fma(-ub, t, ybv) : 0.0;
-}
-
 // Number of eigenvalues of A below sigma (osc_tail.cuh: sys_count_below); *lost is pair-uniform.
 template <int KD, bool HB>
 __device__ __forceinline__ int pair_count_below(const PairSys<KD, HB> &S, double sigma, bool *lost) {
@@ -231,7 +202,7 @@ __device__ bool pair_resolve(PairSys<KD, HB> &S, const double *gc, double gcb, d
         fro = sqrt64(fro2);
     }
     int m = 0;
-    double hi_final = fro;
+    double hi_final = fro, lo_final = 0.0;
     if (small) {
         double hi = fro, lo = dmax, sigma = kPinvRcond * fro;
         int n_hi = -1, n_lo = -1, state = 0;
@@ -282,6 +253,7 @@ __device__ bool pair_resolve(PairSys<KD, HB> &S, const double *gc, double gcb, d
         }
         if (!decided) return false;
         hi_final = hi;
+        lo_final = lo;
         m = n_hi;
         if (m > 2) return false;
     }
@@ -295,22 +267,14 @@ __device__ bool pair_resolve(PairSys<KD, HB> &S, const double *gc, double gcb, d
 #pragma unroll
         for (int i = 0; i < KD; ++i) { xa[i] = 1.0; xb[i] = ((row0 + i) & 1) ? -1.0 : 1.0; }
         if (HB) { xab = 1.0; xbb = ((2 * KD) & 1) ? -1.0 : 1.0; }
-        bool conv = false, shifted = false;
+        bool conv = false, sub = false;
 #pragma unroll 1
         for (int it = 0; it < kIterMax && !conv; ++it) {
             double ya[KD], yb[KD], yab, ybb = 0.0;
-            if (m == 1 && it >= kPlainIters) {           // Rayleigh-quotient shift (osc_tail.cuh)
-                pair_matvec(S, xa, xab, ya, &yab);
-                double rho = duo.sum(dot_own<KD>(xa, ya));
-                if (HB) rho = fma(xab, yab, rho);
-                pair_solve_shifted(S, rho, xa, xab, ya, &yab);
-                shifted = true;
-            } else {
-                pair_solve(S, xa, xab, ya, &yab);
-            }
+            if (m == 1 && it == kPlainIters) sub = true;      // second vector rides along, Rayleigh-Ritz at the end (osc_tail.cuh)
+            pair_solve(S, xa, xab, ya, &yab);
             double na = duo.sum(dot_own<KD>(ya, ya));
             if (HB) na = fma(yab, yab, na);
-            if (!(na > 0.0 && na < 1e300)) break;
             na = rcp64(sqrt64(na));
 #pragma unroll
             for (int i = 0; i < KD; ++i) ya[i] *= na;
@@ -318,7 +282,7 @@ __device__ bool pair_resolve(PairSys<KD, HB> &S, const double *gc, double gcb, d
             double dot = duo.sum(dot_own<KD>(ya, xa));
             if (HB) dot = fma(yab, xab, dot);
             double change = 0.0;
-            if (m == 2) {
+            if (m == 2 || sub) {
                 pair_solve(S, xb, xbb, yb, &ybb);
                 double pab = duo.sum(dot_own<KD>(ya, yb));
                 if (HB) pab = fma(yab, ybb, pab);
@@ -346,25 +310,41 @@ __device__ bool pair_resolve(PairSys<KD, HB> &S, const double *gc, double gcb, d
 #pragma unroll
                 for (int i = 0; i < KD; ++i) xb[i] = yb[i];
                 xbb = ybb;
-            } else {
-                const double sg = dot < 0.0 ? -1.0 : 1.0;
-#pragma unroll
-                for (int i = 0; i < KD; ++i) change = fmax(change, fabs(fma(sg, ya[i], -xa[i])));
-                if (HB) change = fmax(change, fabs(fma(sg, yab, -xab)));
             }
             change = duo.max(change);
+            if (m == 1) {
+                const double sg = dot < 0.0 ? -1.0 : 1.0;
+                double own = 0.0;
+#pragma unroll
+                for (int i = 0; i < KD; ++i) own = fmax(own, fabs(fma(sg, ya[i], -xa[i])));
+                if (HB) own = fmax(own, fabs(fma(sg, yab, -xab)));
+                own = duo.max(own);
+                if (!sub) change = own;
+                else if (own < 1e-8) { change = own; sub = false; }
+            }
 #pragma unroll
             for (int i = 0; i < KD; ++i) xa[i] = ya[i];
             xab = yab;
             conv = (it >= 1) && (change < 1e-8);
         }
         if (!conv) return false;
-        if (shifted) {                                   // is it the cut eigenvector the shifts converged to?
-            double av[KD], avb;
+        if (sub) {                                       // Rayleigh-Ritz on span{xa, xb}
+            double av[KD], bv[KD], avb, bvb;
             pair_matvec(S, xa, xab, av, &avb);
-            double rho = duo.sum(dot_own<KD>(xa, av));
-            if (HB) rho = fma(xab, avb, rho);
-            if (!(rho < kPinvRcond * hi_final)) return false;
+            pair_matvec(S, xb, xbb, bv, &bvb);
+            double haa = duo.sum(dot_own<KD>(xa, av)), hab = duo.sum(dot_own<KD>(xa, bv)), hbb = duo.sum(dot_own<KD>(xb, bv));
+            if (HB) { haa = fma(xab, avb, haa); hab = fma(xab, bvb, hab); hbb = fma(xbb, bvb, hbb); }
+            const double mid = 0.5 * (haa + hbb), half = 0.5 * (hbb - haa), rad = sqrt64(fma(half, half, hab * hab));
+            const double th1 = mid - rad, th2 = mid + rad;
+            double c1 = hab, s1 = th1 - haa;
+            const double c2 = th1 - hbb, s2 = hab;
+            if (fma(c2, c2, s2 * s2) > fma(c1, c1, s1 * s1)) { c1 = c2; s1 = s2; }
+            const double n2 = fma(c1, c1, s1 * s1);
+            if (!(n2 > 0.0) || !(th1 < kPinvRcond * hi_final) || !(th2 > kPinvRcond * lo_final)) return false;
+            const double nr = rcp64(sqrt64(n2));
+#pragma unroll
+            for (int i = 0; i < KD; ++i) xa[i] = (c1 * xa[i] + s1 * xb[i]) * nr;
+            if (HB) xab = (c1 * xab + s1 * xbb) * nr;
         }
         double pa = duo.sum(dot_own<KD>(xa, geff)), pb = 0.0;
         if (HB) pa = fma(xab, geb, pa);

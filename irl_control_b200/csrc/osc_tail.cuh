@@ -224,39 +224,6 @@ IRLOSC_HD void sys_solve(const TaskSys<KD, HB> &S, const double *r, double *w) {
     }
 }
 
-// y = (A - sigma I)^-1 x, sigma > 0, for the Rayleigh-quotient steps of the cut eigenvector.  The shifted blocks are
-// indefinite and factored without pivoting: a step may be inaccurate, the iteration corrects itself (and its result
-// is checked), non-finite values are the caller's to catch.
-template <int KD, bool HB>
-IRLOSC_HD void sys_solve_shifted(const TaskSys<KD, HB> &S, double sigma, const double *x, double *y) {
-    constexpr int KT = TaskSys<KD, HB>::KT;
-    double u[2 * KD];
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-        double f[KT];
-        bool lost = false;
-        blk_factor<KD>(S.D[b], sigma, f, &lost);
-#pragma unroll
-        for (int i = 0; i < KD; ++i) { y[b * KD + i] = x[b * KD + i]; u[b * KD + i] = S.v[b * KD + i]; }
-        blk_solve<KD>(f, y + b * KD);
-        blk_solve<KD>(f, u + b * KD);
-    }
-    double gam = S.d0, t = 0.0, ub = 0.0;
-#pragma unroll
-    for (int i = 0; i < 2 * KD; ++i) { gam = fma(S.v[i], u[i], gam); t = fma(S.v[i], y[i], t); }
-    if (HB) {
-        const double is = -rcp64(sigma);                    // the base's diagonal block is 0 - sigma
-        y[2 * KD] = x[2 * KD] * is;
-        ub = S.v[2 * KD] * is;
-        gam = fma(S.v[2 * KD], ub, gam);
-        t = fma(S.v[2 * KD], y[2 * KD], t);
-    }
-    t *= rcp64(gam);
-#pragma unroll
-    for (int i = 0; i < 2 * KD; ++i) y[i] = fma(-u[i], t, y[i]);
-    if (HB) y[2 * KD] = fma(-ub, t, y[2 * KD]);
-}
-
 // Number of eigenvalues of A below sigma (sigma > 0), by the inertia of the bordered matrix.
 template <int KD, bool HB>
 IRLOSC_HD int sys_count_below(const TaskSys<KD, HB> &S, double sigma, bool *lost) {
@@ -301,7 +268,7 @@ constexpr int kBisectMax = 48;      // inertia evaluations while bracketing lamb
 constexpr int kPowerSteps = 3;      // power steps for the Rayleigh-quotient lower bound on lambda_max
 constexpr double kPowerMargin = 1.02;   // first upper-bound candidate: that far above the lower bound
 constexpr int kIterMax = 40;        // inverse / subspace iterations for the cut eigenvectors
-constexpr int kPlainIters = 8;      // ... of which plain ones before a single cut eigenvector switches to Rayleigh-quotient shifts
+constexpr int kPlainIters = 8;      // ... of which plain ones before a single cut eigenvector takes a second vector along
 constexpr int kRefineMax = 3;       // refinement steps of the task-space solution before the warp takes over
 
 // The branch of osc.py:52-55 and its solution.  Returns false when the warp must finish the instance;
@@ -350,7 +317,7 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
         }
     const double fro = sqrt64(fro2);
     int m = 0;
-    double hi_final = fro;
+    double hi_final = fro, lo_final = 0.0;
     if (small) {
         // bracket lambda_max until the count of eigenvalues under rcond * lambda_max is the same at both ends
         double hi = fro, lo = dmax, sigma = kPinvRcond * fro;
@@ -407,6 +374,7 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
         *how |= (n_counts & 0xff) << 12;
         if (!decided) { *how |= kWhyUndecided; return false; }
         hi_final = hi;
+        lo_final = lo;
         m = n_hi;
         if (m > 2) { *how |= kWhyMany; return false; }
     }
@@ -418,33 +386,24 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
         // cut eigenvectors by inverse (subspace) iteration with the block solver
 #pragma unroll
         for (int i = 0; i < K; ++i) { xa[i] = 1.0; xb[i] = (i & 1) ? -1.0 : 1.0; }
-        bool conv = false, shifted = false;
-        double rho = 0.0;
+        bool conv = false, sub = false;
         int n_iter = 0;
 #pragma unroll 1
         for (int it = 0; it < kIterMax && !conv; ++it) {
             double ya[K], yb[K];
-            if (m == 1 && it >= kPlainIters) {
-                // lambda_1 / lambda_2 is close to one (0.3 % of the cut instances): plain inverse iteration crawls.
-                // Shift by the Rayleigh quotient of the current vector (cubic convergence).
-                sys_matvec(S, xa, ya);
-                rho = 0.0;
-#pragma unroll
-                for (int i = 0; i < K; ++i) rho = fma(xa[i], ya[i], rho);
-                sys_solve_shifted(S, rho, xa, ya);
-                shifted = true;
-            } else {
-                sys_solve(S, xa, ya);
-            }
+            // One eigenvalue to cut and no convergence yet: lambda_1 / lambda_2 is close to one (the two straddle the
+            // cut-off; 0.3 % of the cut instances) and plain inverse iteration crawls.  Iterate the span of the two
+            // smallest eigenvectors instead (rate lambda_2 / lambda_3) and separate them by Rayleigh-Ritz at the end.
+            if (m == 1 && it == kPlainIters) sub = true;
+            sys_solve(S, xa, ya);
             double na = 0.0, dot = 0.0;
 #pragma unroll
             for (int i = 0; i < K; ++i) na = fma(ya[i], ya[i], na);
-            if (!(na > 0.0 && na < 1e300)) break;     // a shifted step broke down
             na = rcp64(sqrt64(na));
 #pragma unroll
             for (int i = 0; i < K; ++i) { ya[i] *= na; dot = fma(ya[i], xa[i], dot); }
             double change = 0.0;
-            if (m == 2) {
+            if (m == 2 || sub) {
                 sys_solve(S, xb, yb);
                 double pab = 0.0, nb = 0.0;
 #pragma unroll
@@ -468,10 +427,14 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
                 }
 #pragma unroll
                 for (int i = 0; i < K; ++i) xb[i] = yb[i];
-            } else {
+            }
+            if (m == 1) {                           // the single vector on its own (also while the second one rides along)
                 const double sg = dot < 0.0 ? -1.0 : 1.0;
+                double own = 0.0;
 #pragma unroll
-                for (int i = 0; i < K; ++i) change = fmax(change, fabs(fma(sg, ya[i], -xa[i])));
+                for (int i = 0; i < K; ++i) own = fmax(own, fabs(fma(sg, ya[i], -xa[i])));
+                if (!sub) change = own;
+                else if (own < 1e-8) { change = own; sub = false; }      // it got there first: no Rayleigh-Ritz needed
             }
 #pragma unroll
             for (int i = 0; i < K; ++i) xa[i] = ya[i];
@@ -480,15 +443,25 @@ IRLOSC_HD bool sys_resolve(TaskSys<KD, HB> &S, const double *gc, double *w, bool
         }
         *how |= (n_iter & 0xff) << 20;
         if (!conv) { *how |= kWhyNoConv; return false; }
-        if (shifted) {
-            // the shifted iteration converges to the eigenvector nearest its shifts: make sure that is the cut one
-            // (exactly one eigenvalue lies under the cut-off, and it is below rcond * hi)
-            double av[K];
+        if (sub) {
+            // Rayleigh-Ritz on span{xa, xb}: the eigenvector of the smaller Ritz value is the one to cut
+            double av[K], bv[K];
             sys_matvec(S, xa, av);
-            rho = 0.0;
+            sys_matvec(S, xb, bv);
+            double haa = 0.0, hab = 0.0, hbb = 0.0;
 #pragma unroll
-            for (int i = 0; i < K; ++i) rho = fma(xa[i], av[i], rho);
-            if (!(rho < kPinvRcond * hi_final)) { *how |= kWhyNoConv; return false; }
+            for (int i = 0; i < K; ++i) { haa = fma(xa[i], av[i], haa); hab = fma(xa[i], bv[i], hab); hbb = fma(xb[i], bv[i], hbb); }
+            const double mid = 0.5 * (haa + hbb), half = 0.5 * (hbb - haa), rad = sqrt64(fma(half, half, hab * hab));
+            const double th1 = mid - rad, th2 = mid + rad;
+            double c1 = hab, s1 = th1 - haa;
+            const double c2 = th1 - hbb, s2 = hab;
+            if (fma(c2, c2, s2 * s2) > fma(c1, c1, s1 * s1)) { c1 = c2; s1 = s2; }
+            const double n2 = fma(c1, c1, s1 * s1);
+            // exactly one eigenvalue lies under the cut-off: below rcond * lo, the next one above rcond * hi
+            if (!(n2 > 0.0) || !(th1 < kPinvRcond * hi_final) || !(th2 > kPinvRcond * lo_final)) { *how |= kWhyNoConv; return false; }
+            const double nr = rcp64(sqrt64(n2));
+#pragma unroll
+            for (int i = 0; i < K; ++i) xa[i] = (c1 * xa[i] + s1 * xb[i]) * nr;
         }
         // geff = P g
         double pa = 0.0, pb = 0.0;

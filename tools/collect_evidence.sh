@@ -19,7 +19,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
     python bench.py --no-graph --no-cpu-baseline --no-extras --steps 4 --warmup 3 > $OUT/${TAG}_launches_run.log 2>&1
 # 5. one full capture of the default kernel per workload
 for wl in gain_test admit_test worst_case; do
-    timeout 300 ncu --set full --clock-control none --import-source on -k regex:osc_step_lane -s 8 -c 1 -f -o $OUT/${TAG}_lane_$wl \
+    timeout 300 ncu --set full --clock-control none --import-source on -k "regex:osc_step_(lane|pair)" -s 8 -c 1 -f -o $OUT/${TAG}_tiles_$wl \
         python bench.py --workload $wl --no-graph --no-extras --no-e2e --no-cpu-baseline --steps 3 --warmup 3 > $OUT/${TAG}_ncu_$wl.log 2>&1
 done
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:osc_step_tree -s 3 -c 1 -f -o $OUT/${TAG}_tree_gain_test \

@@ -35,6 +35,10 @@ def printed_name(cxx):
         hb = hb in ("1", "true")
         st = st in ("1", "true")
         return "osc_step_lane<kd%s%s,t%s,%s>" % (kd, ",base" if hb else "", nt, "tma" if st else "ldg")
+    m = re.search(r"osc_step_pair<\(?(?:int\))?(\d+), \(?(?:bool\))?(\d+|true|false), \(?(?:int\))?(\d+)>", cxx)
+    if m:
+        kd, hb, nt = m.groups()
+        return "osc_step_pair<kd%s%s,t%s>" % (kd, ",base" if hb in ("1", "true") else "", nt)
     return cxx
 
 
@@ -59,7 +63,7 @@ def main():
                 fh.write(summ + "\n" + lines)
             m = raw_metrics(src)
             wl = re.search(r"_(gain_test|admit_test|worst_case)$", base)
-            if wl and "osc_step_lane" in m.get("Kernel Name", ""):
+            if wl and ("osc_step_lane" in m.get("Kernel Name", "") or "osc_step_pair" in m.get("Kernel Name", "")):
                 rd = float(m["dram__bytes_read.sum"]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1}.get("Mbyte", 1e6)
                 # units of the raw page: read them from the second header row instead of guessing
                 raw = subprocess.check_output(["ncu", "-i", src, "--page", "raw", "--csv"], stderr=subprocess.DEVNULL).decode()
@@ -73,7 +77,7 @@ def main():
                 traffic[key] = {"dram_bytes_per_launch": int(rd + wr), "dram_bytes_read": int(rd), "dram_bytes_write": int(wr),
                                 "gpu_time_us_under_ncu": float(m["gpu__time_duration.sum"]), "grid": grid, "block": block,
                                 "source": "profiles/%s_ncu_summary.txt (ncu --set full, one launch of this instantiation)" % base}
-            if on_box and "lane_gain_test" not in f:
+            if on_box and "tiles_gain_test" not in f:
                 os.remove(src)                       # keep one full report, the rest as summaries
         elif on_box:
             continue
