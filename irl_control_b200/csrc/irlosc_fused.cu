@@ -9,6 +9,7 @@
 #include "irlosc_internal.h"
 #include "irlosc_build.h"
 #include "osc_fused.cuh"
+#include "osc_fused_pair.cuh"
 #include "osc_stream.cuh"
 #include <cstdlib>
 
@@ -67,6 +68,29 @@ const FusedEntry *fused_find(int kd, bool has_base, int variant = 0, int threads
     return nullptr;
 }
 
+// Two lanes per instance (osc_fused_pair.cuh), 8 warps x 255 registers like the tile pair kernel.
+struct FusedPairEntry {
+    int kd;
+    bool has_base;
+    int threads;
+    size_t smem;
+    const void *step;
+    const char *name;
+};
+template <int KD, bool HB, int NT>
+FusedPairEntry fpentry(const char *name) {
+    return FusedPairEntry{KD, HB, NT, (size_t)kScratchDoubles * NT * sizeof(double) + (size_t)(NT / 32) * sizeof(WarpFix<KD, HB>),
+                          (const void *)osc_step_fused_pair<KD, HB, NT>, name};
+}
+const FusedPairEntry *fused_pair_table(int *count) {
+    static const FusedPairEntry t[] = {
+        fpentry<3, true, 256>("osc_step_fused_pair<kd3,base,t256>"), fpentry<3, false, 256>("osc_step_fused_pair<kd3,t256>"),
+        fpentry<6, true, 256>("osc_step_fused_pair<kd6,base,t256>"), fpentry<6, false, 256>("osc_step_fused_pair<kd6,t256>"),
+    };
+    *count = (int)(sizeof t / sizeof t[0]);
+    return t;
+}
+
 // 8 or 7 warps per CTA for a batch of B (see fused_table)
 int fused_threads_for(int64_t B, int sms) {
     const int64_t tiles = (B + 31) / 32;
@@ -96,6 +120,34 @@ int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st,
     const int sms = std::max(1, h->sm_count - h->sm_margin);
     int want_threads = variant == 0 ? fused_threads_for(B, sms) : 0;
     if (const char *t = getenv("IRLOSC_FUSED_THREADS")) want_threads = atoi(t);                         // experiments only
+    if (!seq && variant == 0) {
+        // one wave of half tiles or less: the pair kernel's latency is one arm instead of two (measured -23 % at k = 7,
+        // -33 % at k = 12 for B <= 16 384); beyond that the thread-per-instance kernel is as fast or faster
+        int use_pair = (B + 15) / 16 <= (int64_t)sms * 8 ? 1 : 0;
+        if (const char *t = getenv("IRLOSC_FUSED_PAIR")) use_pair = atoi(t);                             // experiments only
+        if (use_pair) {
+            int pc = 0;
+            const FusedPairEntry *pt = fused_pair_table(&pc), *pe = nullptr;
+            for (int i = 0; i < pc; ++i)
+                if (pt[i].kd == h->fused_kd && pt[i].has_base == h->fused_base) pe = &pt[i];
+            if (!pe) return fail(IRLOSC_ERR_INVALID, "no fused pair kernel for kd=%d base=%d", h->fused_kd, (int)h->fused_base);
+            static bool ready = false;
+            if (!ready) {
+                for (int i = 0; i < pc; ++i)
+                    CUDA_TRY(cudaFuncSetAttribute(pt[i].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pt[i].smem));
+                ready = true;
+            }
+            const int pw = pe->threads / 32;
+            const int64_t n_half = (B + 15) / 16;
+            const int pgrid = (int)std::min<int64_t>((n_half + pw - 1) / pw, (int64_t)sms);
+            void *pargs[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr};
+            cudaError_t perr = cudaLaunchKernel(pe->step, dim3(pgrid), dim3(pe->threads), pargs, pe->smem, st);
+            if (perr != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fused pair kernel launch: %s", cudaGetErrorString(perr));
+            h->launches += 1;
+            h->last_kernel = pe->name;
+            return IRLOSC_OK;
+        }
+    }
     const FusedEntry *e = fused_find(h->fused_kd, h->fused_base, variant, want_threads);
     if (!e) e = fused_find(h->fused_kd, h->fused_base, variant);
     if (!e) return fail(IRLOSC_ERR_INVALID, "no fused kernel for kd=%d base=%d variant=%d", h->fused_kd, (int)h->fused_base, variant);

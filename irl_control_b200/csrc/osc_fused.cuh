@@ -269,6 +269,222 @@ IRLOSC_HD void device_signal_early(const KParams &P, const FIo &io, int64_t inst
         for (int i = 0; i < 4; ++i) io.ee_quat[(inst * D + d) * 4 + i] = ee_q[i];
 }
 
+// One arm of one instance: downward pass, EE pose and task signal, gripper halves, upward articulated sweep with the
+// arm's task rows.  Adds the arm's subtree momenta / bias wrenches to Hsum / FBsum and its articulated inertia at the
+// stand to IAsum; leaves the arm's block of A (ak_out), the stand column of the reduced and original task rows (j0a,
+// jsta), dx (dxa), the original Jacobian entries (jarm_a[joint][row]) and the joint terms (base_a) of ITS rows / joints,
+// and the device's task signal in g (task-row order).  Returns false when a pivot is not positive.
+template <int KD, bool SEQ>
+IRLOSC_HD bool fused_arm(const KParams &P, const KModel &Mdl, const FRoles &R, const FIo &io, int64_t inst, const Scratch &scr,
+                         int arm, unsigned vel_zero, double gb, const Body &S0, const double *s0, const double *q, const double *dq,
+                         double *g, double *ak_out, double *j0a, double *jsta, double *dxa, double (*jarm_a)[KD], double *base_a,
+                         double *Hsum, double *FBsum, double *IAsum, SeqResult &seq, const KSeq *Q, const Debug *dbg) {
+    constexpr int N = kN;
+    constexpr int KT = KD * (KD + 1) / 2;
+    const int D = P.D;
+    bool ok = true;
+    const int jb = 1 + 12 * arm;
+    const int dev = R.dev_arm[arm];
+    const int row_a = R.row_arm[arm];
+    // ---- downward pass over arm joints 1..6: FK, velocity, acceleration, momenta, prefix sums
+    Body Bc = S0;
+    double Hpre[6], FBpre[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { Hpre[i] = 0.0; FBpre[i] = 0.0; }
+    const double cu_arm = coef_uv(P, R, vel_zero, jb);     // shared by the six arm joints when R.uniform_owner
+    // joint angles / rates are fetched one joint ahead so that their latency hides behind a joint's work
+    double q_nx = q[jb], dq_nx = dq[jb];
+#pragma unroll 1
+    for (int i = 0; i < 6; ++i) {
+        const KJoint &jm = Mdl.arm[arm][i];
+        Body Bn;
+        double s[6], r[3], Iw[6], h[6], fb[6];
+        const double q_i = q_nx, dq_i = dq_nx;
+        q_nx = q[jb + i + 1];                  // i = 5: first gripper joint, still inside the row
+        dq_nx = dq[jb + i + 1];
+        joint_down(jm, Bc, q_i, dq_i, Bn, s, r, Iw);
+        body_wrench(jm.mass, r, Iw, Bn.v, Bn.a, h, fb);
+        const double cu = R.uniform_owner ? cu_arm : coef_uv(P, R, vel_zero, jb + i);
+        double x[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) x[e] = fma(cu, Hpre[e], gb * FBpre[e]);
+        const int o = i * kBodyScratch;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) scr(o + e) = s[e];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) scr(o + 6 + e) = r[e];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) scr(o + 9 + e) = Iw[e];
+        scr(o + 15) = dot6(s, x);
+        if (dbg && dbg->uv) { dbg->uv[jb + i] = -dot6(s, Hpre); dbg->bias[jb + i] = -dot6(s, FBpre); }
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { Hpre[e] += h[e]; FBpre[e] += fb[e]; }
+        Bc = Bn;
+    }
+    // Bc = arm link 6; Hpre / FBpre = sums over the arm links (grippers are added below)
+    // ---- EE pose, F/T frame, task signal and task forces (device.py:93-95,125-143; osc.py:156-181)
+    double ee_p[3];
+    {
+        const KFrame &F = Mdl.ee[dev];
+        double t[3], Re[9], Rf[9];
+        mat3_vec(Bc.R, F.pos, t);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) ee_p[i] = Bc.o[i] + t[i];
+        mat3_mul(Bc.R, F.R, Re);
+        double ee_q[4], mv0 = -1.0;
+        mat_to_quat(Re, ee_q);
+        if (SEQ && Q->mode == 1) {
+            // gain_test.py:138-158: target = wps[idx]; after generate, |EE_XYZ - target| < threshold -> next
+            // waypoint (wrapping).  The comparison uses the state this step is computed from.
+            int idx = io.wp_idx[inst * D + dev];
+            const double *wp = io.wps + (((size_t)inst * D + dev) * Q->W + idx) * 3;
+            double *tx = io.seq_tgt_xyz + (inst * D + dev) * 3;
+            double e2 = 0.0;
+            for (int i = 0; i < 3; ++i) { tx[i] = wp[i]; const double dlt = ee_p[i] - wp[i]; e2 = fma(dlt, dlt, e2); }
+            if (sqrt(e2) < Q->threshold) idx = (idx < Q->n_wp[dev] - 1) ? idx + 1 : 0;
+            io.wp_idx[inst * D + dev] = idx;
+        } else if (SEQ) {
+            if (dev == Q->active_dev) {
+                seq = seq_advance(*Q, P.dev[dev], io, inst, D, ee_p, ee_q);
+                mv0 = io.seq_mv0[inst];
+            } else if (seq.entered_wp) {
+                for (int i = 0; i < 3; ++i) io.seq_tgt_xyz[(inst * D + dev) * 3 + i] = ee_p[i];
+                for (int i = 0; i < 4; ++i) io.seq_tgt_quat[(inst * D + dev) * 4 + i] = Q->passive_quat[i];
+            }
+        }
+        const KFrame &T = Mdl.ft[dev];
+        if (P.admittance && T.has) mat3_mul(Bc.R, T.R, Rf);
+        device_signal_early(P, io, inst, dev, ee_p, ee_q, Rf, T.has != 0, mv0, g);
+#pragma unroll
+        for (int cr = 0; cr < KD; ++cr) {
+            double e0[6];
+            task_force(P.row_comp[row_a + cr], ee_p, e0);
+            dxa[cr] = dot6(e0, Bc.v);              // dx = J dq (osc.py:150)
+            jsta[cr] = dot6(e0, s0);                // J[r][stand]
+        }
+    }
+    // ---- gripper halves: leaves g1 -> g0 and g2, eliminated into link 6's articulated inertia
+    double IA[21];
+#pragma unroll
+    for (int e = 0; e < 21; ++e) IA[e] = 0.0;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int gj = jb + 6 + 3 * half;
+        const double cu_grip = coef_uv(P, R, vel_zero, gj);  // shared by the half's three joints when R.uniform_owner
+        const double qg0 = q[gj], qg1 = q[gj + 1], qg2 = q[gj + 2];
+        const double dqg0 = dq[gj], dqg1 = dq[gj + 1], dqg2 = dq[gj + 2];
+        double IAg[21], f[6], inv;
+        Body B0;
+        double sa[6], ra[3], Iwa[6], ha[6], fba[6];
+        joint_down(Mdl.grip[arm][half][0], Bc, qg0, dqg0, B0, sa, ra, Iwa);
+        body_wrench(Mdl.grip[arm][half][0].mass, ra, Iwa, B0.v, B0.a, ha, fba);
+        {
+            Body B1;
+            double sb[6], rb[3], Iwb[6], hb[6], fbb[6];
+            joint_down(Mdl.grip[arm][half][1], B0, qg1, dqg1, B1, sb, rb, Iwb);
+            body_wrench(Mdl.grip[arm][half][1].mass, rb, Iwb, B1.v, B1.a, hb, fbb);
+            const double cu1 = R.uniform_owner ? cu_grip : coef_uv(P, R, vel_zero, gj + 1);
+            const double uv1 = dot6(sb, hb), b1 = dot6(sb, fbb);
+            put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj + 1, fma(cu1, uv1, gb * b1));
+            if (dbg && dbg->uv) { dbg->uv[gj + 1] = uv1; dbg->bias[gj + 1] = b1; }
+#pragma unroll
+            for (int e = 0; e < 6; ++e) { ha[e] += hb[e]; fba[e] += fbb[e]; }     // subtree sums of g0
+#pragma unroll
+            for (int e = 0; e < 21; ++e) IAg[e] = 0.0;
+            add_rigid(IAg, Mdl.grip[arm][half][1].mass, rb, Iwb);
+            ok = joint_up(IAg, sb, f, &inv) && ok;
+        }
+        const double cu0 = cu_grip;
+        const double uv0 = dot6(sa, ha), b0 = dot6(sa, fba);
+        put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj, fma(cu0, uv0, gb * b0));
+        if (dbg && dbg->uv) { dbg->uv[gj] = uv0; dbg->bias[gj] = b0; }
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { Hpre[e] += ha[e]; FBpre[e] += fba[e]; }
+        add_rigid(IAg, Mdl.grip[arm][half][0].mass, ra, Iwa);
+        ok = joint_up(IAg, sa, f, &inv) && ok;
+#pragma unroll
+        for (int e = 0; e < 21; ++e) IA[e] += IAg[e];
+        {   // g2
+            Body B2;
+            double sc[6], rc[3], Iwc[6], hc[6], fbc[6];
+            joint_down(Mdl.grip[arm][half][2], Bc, qg2, dqg2, B2, sc, rc, Iwc);
+            body_wrench(Mdl.grip[arm][half][2].mass, rc, Iwc, B2.v, B2.a, hc, fbc);
+            const double cu2 = R.uniform_owner ? cu_grip : coef_uv(P, R, vel_zero, gj + 2);
+            const double uv2 = dot6(sc, hc), b2 = dot6(sc, fbc);
+            put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj + 2, fma(cu2, uv2, gb * b2));
+            if (dbg && dbg->uv) { dbg->uv[gj + 2] = uv2; dbg->bias[gj + 2] = b2; }
+#pragma unroll
+            for (int e = 0; e < 6; ++e) { Hpre[e] += hc[e]; FBpre[e] += fbc[e]; }
+#pragma unroll
+            for (int e = 0; e < 21; ++e) IAg[e] = 0.0;
+            add_rigid(IAg, Mdl.grip[arm][half][2].mass, rc, Iwc);
+            ok = joint_up(IAg, sc, f, &inv) && ok;
+#pragma unroll
+            for (int e = 0; e < 21; ++e) IA[e] += IAg[e];
+        }
+    }
+    // Hpre / FBpre now hold the sums over the whole arm subtree
+#pragma unroll
+    for (int e = 0; e < 6; ++e) { Hsum[e] += Hpre[e]; FBsum[e] += FBpre[e]; }
+    // ---- upward articulated sweep over arm joints 6..1 with the arm's task rows
+    double ak[KT], E[KD][6];
+#pragma unroll
+    for (int e = 0; e < KT; ++e) ak[e] = 0.0;
+#pragma unroll
+    for (int cr = 0; cr < KD; ++cr) task_force(P.row_comp[row_a + cr], ee_p, E[cr]);
+#pragma unroll 1
+    for (int i = 5; i >= 0; --i) {
+        const int o = i * kBodyScratch;
+        double s[6], r[3], Iw[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) s[e] = scr(o + e);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) r[e] = scr(o + 6 + e);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) Iw[e] = scr(o + 9 + e);
+        // (M dq)_j and bias_j through the subtree sums: s . (X_total - X_prefix)
+        const double cu = R.uniform_owner ? cu_arm : coef_uv(P, R, vel_zero, jb + i);
+        double x[6];
+#pragma unroll
+        for (int e = 0; e < 6; ++e) x[e] = fma(cu, Hpre[e], gb * FBpre[e]);
+        base_a[i] = dot6(s, x) - scr(o + 15);
+        if (dbg && dbg->uv) { dbg->uv[jb + i] += dot6(s, Hpre); dbg->bias[jb + i] += dot6(s, FBpre); }
+        {   // original J[r][joint] for J^T w: [jacp; jacr] column = [a x (p - c); a] = [s_ang x p + s_lin; s_ang]
+            double jp[3];
+            cross3(s, ee_p, jp);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) jp[e] += s[3 + e];
+#pragma unroll
+            for (int cr = 0; cr < KD; ++cr) {
+                const int comp = P.row_comp[row_a + cr];
+                jarm_a[i][cr] = comp == 0 ? jp[0] : comp == 1 ? jp[1] : comp == 2 ? jp[2] : comp == 3 ? s[0] : comp == 4 ? s[1] : s[2];
+            }
+        }
+        add_rigid(IA, Mdl.arm[arm][i].mass, r, Iw);
+        double f[6], inv;
+        ok = joint_up(IA, s, f, &inv) && ok;
+        double jk[KD];
+#pragma unroll
+        for (int cr = 0; cr < KD; ++cr) jk[cr] = dot6(s, E[cr]);
+#pragma unroll
+        for (int cr = 0; cr < KD; ++cr) {
+            const double tc = jk[cr] * inv;
+#pragma unroll
+            for (int c2 = cr; c2 < KD; ++c2) ak[c2 * (c2 + 1) / 2 + cr] = fma(jk[c2], tc, ak[c2 * (c2 + 1) / 2 + cr]);
+#pragma unroll
+            for (int e = 0; e < 6; ++e) E[cr][e] = fma(-tc, f[e], E[cr][e]);
+        }
+    }
+    // ---- what the stand joint needs from this arm
+#pragma unroll
+    for (int e = 0; e < 21; ++e) IAsum[e] += IA[e];
+#pragma unroll
+    for (int cr = 0; cr < KD; ++cr) j0a[cr] = dot6(s0, E[cr]);
+#pragma unroll
+    for (int e = 0; e < KT; ++e) ak_out[e] = ak[e];
+    return ok;
+}
+
 // Returns true when the task-space solve must be finished by the warp (state_warp_finish on T rewrites the
 // chain joints).
 template <int KD, bool HAS_BASE, bool SEQ = false>
@@ -348,205 +564,8 @@ IRLOSC_HD bool fused_instance(const KParams &P, const KModel &Mdl, const FRoles 
             const int act_arm = (R.dev_arm[0] == Q->active_dev) ? 0 : 1;
             arm = it == 0 ? act_arm : 1 - act_arm;
         }
-        const int jb = 1 + 12 * arm;
-        const int dev = R.dev_arm[arm];
-        const int row_a = R.row_arm[arm];
-        // ---- downward pass over arm joints 1..6: FK, velocity, acceleration, momenta, prefix sums
-        Body Bc = S0;
-        double Hpre[6], FBpre[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { Hpre[i] = 0.0; FBpre[i] = 0.0; }
-        const double cu_arm = coef_uv(P, R, vel_zero, jb);     // shared by the six arm joints when R.uniform_owner
-        // joint angles / rates are fetched one joint ahead so that their latency hides behind a joint's work
-        double q_nx = q[jb], dq_nx = dq[jb];
-#pragma unroll 1
-        for (int i = 0; i < 6; ++i) {
-            const KJoint &jm = Mdl.arm[arm][i];
-            Body Bn;
-            double s[6], r[3], Iw[6], h[6], fb[6];
-            const double q_i = q_nx, dq_i = dq_nx;
-            q_nx = q[jb + i + 1];                  // i = 5: first gripper joint, still inside the row
-            dq_nx = dq[jb + i + 1];
-            joint_down(jm, Bc, q_i, dq_i, Bn, s, r, Iw);
-            body_wrench(jm.mass, r, Iw, Bn.v, Bn.a, h, fb);
-            const double cu = R.uniform_owner ? cu_arm : coef_uv(P, R, vel_zero, jb + i);
-            double x[6];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) x[e] = fma(cu, Hpre[e], gb * FBpre[e]);
-            const int o = i * kBodyScratch;
-#pragma unroll
-            for (int e = 0; e < 6; ++e) scr(o + e) = s[e];
-#pragma unroll
-            for (int e = 0; e < 3; ++e) scr(o + 6 + e) = r[e];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) scr(o + 9 + e) = Iw[e];
-            scr(o + 15) = dot6(s, x);
-            if (dbg && dbg->uv) { dbg->uv[jb + i] = -dot6(s, Hpre); dbg->bias[jb + i] = -dot6(s, FBpre); }
-#pragma unroll
-            for (int e = 0; e < 6; ++e) { Hpre[e] += h[e]; FBpre[e] += fb[e]; }
-            Bc = Bn;
-        }
-        // Bc = arm link 6; Hpre / FBpre = sums over the arm links (grippers are added below)
-        // ---- EE pose, F/T frame, task signal and task forces (device.py:93-95,125-143; osc.py:156-181)
-        double ee_p[3];
-        {
-            const KFrame &F = Mdl.ee[dev];
-            double t[3], Re[9], Rf[9];
-            mat3_vec(Bc.R, F.pos, t);
-#pragma unroll
-            for (int i = 0; i < 3; ++i) ee_p[i] = Bc.o[i] + t[i];
-            mat3_mul(Bc.R, F.R, Re);
-            double ee_q[4], mv0 = -1.0;
-            mat_to_quat(Re, ee_q);
-            if (SEQ && Q->mode == 1) {
-                // gain_test.py:138-158: target = wps[idx]; after generate, |EE_XYZ - target| < threshold -> next
-                // waypoint (wrapping).  The comparison uses the state this step is computed from.
-                int idx = io.wp_idx[inst * D + dev];
-                const double *wp = io.wps + (((size_t)inst * D + dev) * Q->W + idx) * 3;
-                double *tx = io.seq_tgt_xyz + (inst * D + dev) * 3;
-                double e2 = 0.0;
-                for (int i = 0; i < 3; ++i) { tx[i] = wp[i]; const double dlt = ee_p[i] - wp[i]; e2 = fma(dlt, dlt, e2); }
-                if (sqrt(e2) < Q->threshold) idx = (idx < Q->n_wp[dev] - 1) ? idx + 1 : 0;
-                io.wp_idx[inst * D + dev] = idx;
-            } else if (SEQ) {
-                if (dev == Q->active_dev) {
-                    seq = seq_advance(*Q, P.dev[dev], io, inst, D, ee_p, ee_q);
-                    mv0 = io.seq_mv0[inst];
-                } else if (seq.entered_wp) {
-                    for (int i = 0; i < 3; ++i) io.seq_tgt_xyz[(inst * D + dev) * 3 + i] = ee_p[i];
-                    for (int i = 0; i < 4; ++i) io.seq_tgt_quat[(inst * D + dev) * 4 + i] = Q->passive_quat[i];
-                }
-            }
-            const KFrame &T = Mdl.ft[dev];
-            if (P.admittance && T.has) mat3_mul(Bc.R, T.R, Rf);
-            device_signal_early(P, io, inst, dev, ee_p, ee_q, Rf, T.has != 0, mv0, g);
-#pragma unroll
-            for (int cr = 0; cr < KD; ++cr) {
-                double e0[6];
-                task_force(P.row_comp[row_a + cr], ee_p, e0);
-                dxr[row_a + cr] = dot6(e0, Bc.v);              // dx = J dq (osc.py:150)
-                jst[row_a + cr] = dot6(e0, s0);                // J[r][stand]
-            }
-        }
-        // ---- gripper halves: leaves g1 -> g0 and g2, eliminated into link 6's articulated inertia
-        double IA[21];
-#pragma unroll
-        for (int e = 0; e < 21; ++e) IA[e] = 0.0;
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-            const int gj = jb + 6 + 3 * half;
-            const double cu_grip = coef_uv(P, R, vel_zero, gj);  // shared by the half's three joints when R.uniform_owner
-            const double qg0 = q[gj], qg1 = q[gj + 1], qg2 = q[gj + 2];
-            const double dqg0 = dq[gj], dqg1 = dq[gj + 1], dqg2 = dq[gj + 2];
-            double IAg[21], f[6], inv;
-            Body B0;
-            double sa[6], ra[3], Iwa[6], ha[6], fba[6];
-            joint_down(Mdl.grip[arm][half][0], Bc, qg0, dqg0, B0, sa, ra, Iwa);
-            body_wrench(Mdl.grip[arm][half][0].mass, ra, Iwa, B0.v, B0.a, ha, fba);
-            {
-                Body B1;
-                double sb[6], rb[3], Iwb[6], hb[6], fbb[6];
-                joint_down(Mdl.grip[arm][half][1], B0, qg1, dqg1, B1, sb, rb, Iwb);
-                body_wrench(Mdl.grip[arm][half][1].mass, rb, Iwb, B1.v, B1.a, hb, fbb);
-                const double cu1 = R.uniform_owner ? cu_grip : coef_uv(P, R, vel_zero, gj + 1);
-                const double uv1 = dot6(sb, hb), b1 = dot6(sb, fbb);
-                put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj + 1, fma(cu1, uv1, gb * b1));
-                if (dbg && dbg->uv) { dbg->uv[gj + 1] = uv1; dbg->bias[gj + 1] = b1; }
-#pragma unroll
-                for (int e = 0; e < 6; ++e) { ha[e] += hb[e]; fba[e] += fbb[e]; }     // subtree sums of g0
-#pragma unroll
-                for (int e = 0; e < 21; ++e) IAg[e] = 0.0;
-                add_rigid(IAg, Mdl.grip[arm][half][1].mass, rb, Iwb);
-                m_ok = joint_up(IAg, sb, f, &inv) && m_ok;
-            }
-            const double cu0 = cu_grip;
-            const double uv0 = dot6(sa, ha), b0 = dot6(sa, fba);
-            put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj, fma(cu0, uv0, gb * b0));
-            if (dbg && dbg->uv) { dbg->uv[gj] = uv0; dbg->bias[gj] = b0; }
-#pragma unroll
-            for (int e = 0; e < 6; ++e) { Hpre[e] += ha[e]; FBpre[e] += fba[e]; }
-            add_rigid(IAg, Mdl.grip[arm][half][0].mass, ra, Iwa);
-            m_ok = joint_up(IAg, sa, f, &inv) && m_ok;
-#pragma unroll
-            for (int e = 0; e < 21; ++e) IA[e] += IAg[e];
-            {   // g2
-                Body B2;
-                double sc[6], rc[3], Iwc[6], hc[6], fbc[6];
-                joint_down(Mdl.grip[arm][half][2], Bc, qg2, dqg2, B2, sc, rc, Iwc);
-                body_wrench(Mdl.grip[arm][half][2].mass, rc, Iwc, B2.v, B2.a, hc, fbc);
-                const double cu2 = R.uniform_owner ? cu_grip : coef_uv(P, R, vel_zero, gj + 2);
-                const double uv2 = dot6(sc, hc), b2 = dot6(sc, fbc);
-                put_joint(R, io.u_all ? io.u_all + inst * N : nullptr, io.ctrl + inst * P.n_ctrl, gj + 2, fma(cu2, uv2, gb * b2));
-                if (dbg && dbg->uv) { dbg->uv[gj + 2] = uv2; dbg->bias[gj + 2] = b2; }
-#pragma unroll
-                for (int e = 0; e < 6; ++e) { Hpre[e] += hc[e]; FBpre[e] += fbc[e]; }
-#pragma unroll
-                for (int e = 0; e < 21; ++e) IAg[e] = 0.0;
-                add_rigid(IAg, Mdl.grip[arm][half][2].mass, rc, Iwc);
-                m_ok = joint_up(IAg, sc, f, &inv) && m_ok;
-#pragma unroll
-                for (int e = 0; e < 21; ++e) IA[e] += IAg[e];
-            }
-        }
-        // Hpre / FBpre now hold the sums over the whole arm subtree
-#pragma unroll
-        for (int e = 0; e < 6; ++e) { Htot[e] += Hpre[e]; FBtot[e] += FBpre[e]; }
-        // ---- upward articulated sweep over arm joints 6..1 with the arm's task rows
-        double ak[KT], E[KD][6];
-#pragma unroll
-        for (int e = 0; e < KT; ++e) ak[e] = 0.0;
-#pragma unroll
-        for (int cr = 0; cr < KD; ++cr) task_force(P.row_comp[row_a + cr], ee_p, E[cr]);
-#pragma unroll 1
-        for (int i = 5; i >= 0; --i) {
-            const int o = i * kBodyScratch;
-            double s[6], r[3], Iw[6];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) s[e] = scr(o + e);
-#pragma unroll
-            for (int e = 0; e < 3; ++e) r[e] = scr(o + 6 + e);
-#pragma unroll
-            for (int e = 0; e < 6; ++e) Iw[e] = scr(o + 9 + e);
-            // (M dq)_j and bias_j through the subtree sums: s . (X_total - X_prefix)
-            const double cu = R.uniform_owner ? cu_arm : coef_uv(P, R, vel_zero, jb + i);
-            double x[6];
-#pragma unroll
-            for (int e = 0; e < 6; ++e) x[e] = fma(cu, Hpre[e], gb * FBpre[e]);
-            base_arm[arm][i] = dot6(s, x) - scr(o + 15);
-            if (dbg && dbg->uv) { dbg->uv[jb + i] += dot6(s, Hpre); dbg->bias[jb + i] += dot6(s, FBpre); }
-            {   // original J[r][joint] for J^T w: [jacp; jacr] column = [a x (p - c); a] = [s_ang x p + s_lin; s_ang]
-                double jp[3];
-                cross3(s, ee_p, jp);
-#pragma unroll
-                for (int e = 0; e < 3; ++e) jp[e] += s[3 + e];
-#pragma unroll
-                for (int cr = 0; cr < KD; ++cr) {
-                    const int comp = P.row_comp[row_a + cr];
-                    jarm[arm][i][cr] = comp == 0 ? jp[0] : comp == 1 ? jp[1] : comp == 2 ? jp[2] : comp == 3 ? s[0] : comp == 4 ? s[1] : s[2];
-                }
-            }
-            add_rigid(IA, Mdl.arm[arm][i].mass, r, Iw);
-            double f[6], inv;
-            m_ok = joint_up(IA, s, f, &inv) && m_ok;
-            double jk[KD];
-#pragma unroll
-            for (int cr = 0; cr < KD; ++cr) jk[cr] = dot6(s, E[cr]);
-#pragma unroll
-            for (int cr = 0; cr < KD; ++cr) {
-                const double tc = jk[cr] * inv;
-#pragma unroll
-                for (int c2 = cr; c2 < KD; ++c2) ak[c2 * (c2 + 1) / 2 + cr] = fma(jk[c2], tc, ak[c2 * (c2 + 1) / 2 + cr]);
-#pragma unroll
-                for (int e = 0; e < 6; ++e) E[cr][e] = fma(-tc, f[e], E[cr][e]);
-            }
-        }
-        // ---- what the stand joint needs from this arm
-#pragma unroll
-        for (int e = 0; e < 21; ++e) IA0[e] += IA[e];
-#pragma unroll
-        for (int cr = 0; cr < KD; ++cr) j0[row_a + cr] = dot6(s0, E[cr]);
-#pragma unroll
-        for (int e = 0; e < KT; ++e) akA[arm][e] = ak[e];
+        m_ok = fused_arm<KD, SEQ>(P, Mdl, R, io, inst, scr, arm, vel_zero, gb, S0, s0, q, dq, g, akA[arm], j0 + R.row_arm[arm],
+                                  jst + R.row_arm[arm], dxr + R.row_arm[arm], jarm[arm], base_arm[arm], Htot, FBtot, IA0, seq, Q, dbg) && m_ok;
     }
 
     // ------------------------------------------------------------ stand joint couples the arms

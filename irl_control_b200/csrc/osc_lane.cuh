@@ -428,7 +428,7 @@ osc_step_lane(const __grid_constant__ KParams P, const __grid_constant__ LaneArg
 
 // arrays of irlosc_io -> tiles.  A CTA per tile; a warp writes one entry of the tile per iteration (one coalesced
 // 256-byte row), reading it from the 32 instances' records.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)      // (static: this header is part of two translation units)
 pack_tiles_kernel(const __grid_constant__ PackTable T, double *tiles, const int64_t B) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, W = blockDim.x >> 5;
     const int64_t n_tiles = (B + kTile - 1) / kTile;

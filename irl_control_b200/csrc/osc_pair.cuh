@@ -405,6 +405,162 @@ __device__ bool pair_resolve(PairSys<KD, HB> &S, const double *gc, double gcb, d
     return true;
 }
 
+// What follows the elimination, for the two lanes of an instance (all 32 lanes of the warp call this together: the
+// warp-cooperative finish is inside).  The lane brings S (its block D, its rows of v, vb, d0, inv0), its rows of the
+// task signal gc and of dx = J dq, the base row's gcb / dxb (both lanes), its arm's joint terms base_arm, the stand's
+// base_st; ja(cr, i) returns J[row cr of the lane's arm][i = 0: stand, 1..6: the arm's joints].
+template <int KD, bool HAS_BASE, class JA>
+__device__ __forceinline__ void pair_tail(const KParams &P, const FRoles &R, PairSys<KD, HAS_BASE> &S, double *gc, double gcb,
+                                          const double *dxa, double dxb, const double *base_arm, double base_st, bool m_ok,
+                                          const JA &ja, const double *target_vel, unsigned vel_zero, int flags, double *u_all_row,
+                                          double *ctrl_row, uint8_t *status, bool valid, fused::WarpFix<KD, HAS_BASE> &wfix, int lane) {
+    using RC = fused::Rec<KD, HAS_BASE>;
+    constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
+    const Duo duo = S.duo;
+    const int arm = duo.arm, jb = 1 + 12 * arm, D = P.D;
+    const double jb0 = S.vb;
+    // ---- velocity-tracking term (osc.py:175-177) and the null-space part of g
+    if (target_vel != nullptr && ((~vel_zero) & ((1u << D) - 1u)) != 0u) {
+        double dxf[K];                                   // dx in task-row order (N3: dx_idx may point anywhere)
+#pragma unroll
+        for (int cr = 0; cr < KD; ++cr) {
+            const double o = duo.other(dxa[cr]);
+            dxf[R.row_arm[arm] + cr] = dxa[cr];
+            dxf[R.row_arm[arm ^ 1] + cr] = o;
+        }
+        if (HAS_BASE) dxf[R.row_base] = dxb;
+#pragma unroll 1
+        for (int d = 0; d < D; ++d) {
+            if ((vel_zero >> d) & 1u) continue;
+            const KDevice &dv = P.dev[d];
+            flags |= IRLOSC_ST_VEL_BRANCH;
+            const bool mine = d == R.dev_arm[arm], base = HAS_BASE && d == R.dev_base;
+            int r = 0;
+            for (int i = 0; i < 6; ++i)
+                if (dv.dof[i]) {
+                    const int src = dv.dx_idx[r];
+                    if (src >= K) flags |= IRLOSC_ST_DX_RANGE;
+                    else {
+                        const double add = dv.kv * (dxf[src] - target_vel[d * 6 + i]) * dv.damp[i];
+                        if (mine) {
+#pragma unroll
+                            for (int s = 0; s < KD; ++s)
+                                if (r == s) gc[s] += add;
+                        }
+                        if (base) gcb += add;
+                    }
+                    ++r;
+                }
+        }
+    }
+    {
+        const double kvn = P.has_nullspace ? P.nullspace_kv : 0.0;
+#pragma unroll
+        for (int r = 0; r < KD; ++r) gc[r] = fma(-kvn, dxa[r], gc[r]);
+        if (HAS_BASE) gcb = fma(-kvn, dxb, gcb);
+    }
+    if (!m_ok) flags |= IRLOSC_ST_M_NOT_PD;
+    const bool poison = (flags & (IRLOSC_ST_M_NOT_PD | IRLOSC_ST_DX_RANGE)) != 0;
+    double w[KD], wb = 0.0;
+    bool small_det = false, solved = true;
+    if (!poison) solved = pair_resolve(S, gc, gcb, w, &wb, &small_det);
+    if (solved && small_det) flags |= IRLOSC_ST_PINV;
+    const bool hard = !poison && !solved;
+    // ---- joint-space assembly + packing
+    if (!hard && !poison) {
+        double jv[7][KD];
+#pragma unroll
+        for (int i = 0; i < 7; ++i)
+#pragma unroll
+            for (int cr = 0; cr < KD; ++cr) jv[i][cr] = ja(cr, i);
+        {
+            double jt = 0.0;
+#pragma unroll
+            for (int cr = 0; cr < KD; ++cr) jt = fma(jv[0][cr], w[cr], jt);
+            jt = duo.sum(jt);
+            if (HAS_BASE) jt = fma(jb0, wb, jt);
+            if (arm == 0) fused::put_joint(R, u_all_row, ctrl_row, 0, base_st - jt);
+        }
+#pragma unroll
+        for (int i = 1; i < 7; ++i) {
+            double jt = 0.0;
+#pragma unroll
+            for (int cr = 0; cr < KD; ++cr) jt = fma(jv[i][cr], w[cr], jt);
+            fused::put_joint(R, u_all_row, ctrl_row, jb + i - 1, base_arm[i - 1] - jt);
+        }
+    }
+    if (poison) {
+        __syncwarp(duo.mask);                            // the partner's gripper outputs are in place
+        if (arm == 0) {
+            const double qnan = nan("");
+            if (u_all_row)
+                for (int j = 0; j < kN; ++j) u_all_row[j] = qnan;
+            for (int c = 0; c < P.n_ctrl; ++c) ctrl_row[c] = qnan;
+        }
+    }
+        if (status && arm == 0) *status = (uint8_t)flags;
+    // ---- instances left to the warp: record (canonical rows), Jacobi eigen-solver, owner finishes
+    unsigned todo = __ballot_sync(0xffffffffu, hard && valid && arm == 0);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        if ((lane & ~1) == src) {
+            double *rec = wfix.rec;
+            double vo[KD];
+#pragma unroll
+            for (int i = 0; i < KD; ++i) vo[i] = duo.other(S.v[i]);
+            const int r0 = arm * KD, o0 = (arm ^ 1) * KD;
+#pragma unroll
+            for (int i = 0; i < KD; ++i) {
+                const double vi = S.v[i] * S.inv0;
+#pragma unroll
+                for (int j = 0; j < KD; ++j) {
+                    rec[RC::A + (r0 + i) * K + r0 + j] = fma(vi, S.v[j], S.D[i >= j ? ltri(i, j) : ltri(j, i)]);
+                    rec[RC::A + (r0 + i) * K + o0 + j] = vi * vo[j];
+                }
+                if (HAS_BASE) {
+                    rec[RC::A + (r0 + i) * K + 2 * KD] = vi * jb0;
+                    rec[RC::A + (2 * KD) * K + r0 + i] = vi * jb0;
+                }
+                rec[RC::G + r0 + i] = gc[i];
+                rec[RC::JST + r0 + i] = ja(i, 0);
+            }
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                rec[RC::BASE + 1 + 6 * arm + i] = base_arm[i];
+#pragma unroll
+                for (int cr = 0; cr < KD; ++cr)
+                    rec[RC::JARM + (arm * 6 + i) * KD + cr] = ja(cr, i + 1);
+            }
+            if (arm == 0) {
+                if (HAS_BASE) {
+                    rec[RC::A + (2 * KD) * K + 2 * KD] = (jb0 * S.inv0) * jb0;
+                    rec[RC::G + 2 * KD] = gcb;
+                    rec[RC::JST + 2 * KD] = jb0;
+                }
+                rec[RC::BASE] = base_st;
+                rec[RC::ABAD] = small_det ? 0.0 : 1.0;
+                wfix.flags = 0;
+            }
+        }
+        __syncwarp();
+        tiled::eigen_solve<K, K>(reinterpret_cast<double (*)[K]>(wfix.rec + RC::A), wfix.Vs, wfix.rec + RC::G, wfix.w, wfix.cbuf,
+                                 wfix.sbuf, wfix.rec[RC::ABAD] == 0.0, lane, &wfix.flags);
+        __syncwarp();
+        if (lane == src) {
+            fused::fixup_finish<KD, HAS_BASE>(R, u_all_row, ctrl_row, wfix.rec, wfix.w, 0, 1);
+            if (status) *status = (uint8_t)(*status | wfix.flags);
+        }
+        __syncwarp();
+    }
+}
+
+// Original Jacobian entries of the lane's arm, re-read from the tile (L2).
+struct lane_jrow_t {
+    const double *p;
+    __device__ __forceinline__ double operator()(int cr, int i) const { return lane::LdCached{}(p + (size_t)(cr * 7 + i) * kTile); }
+};
+
 // ---------------------------------------------------------------- kernel
 // Packed ctrl rows of `n_valid` consecutive instances starting at inst0 (a multiple of 16): local array, peer-mapped
 // gathered arrays or the NVSwitch multicast mapping (stream::write_ctrl_tile for a half tile).
@@ -439,8 +595,6 @@ __global__ void __launch_bounds__(NT, 1)
 osc_step_pair(const __grid_constant__ KParams P, const __grid_constant__ LaneArgs A, const int64_t B,
               const __grid_constant__ FRoles R, const __grid_constant__ stream::Gather G, const int warp_bytes) {
     using namespace stream;
-    using RC = fused::Rec<KD, HAS_BASE>;
-    constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
     constexpr int W = NT / 32;
     static_assert(W % 2 == 0, "the two halves of a tile go to neighbouring warps of a CTA");
     extern __shared__ __align__(16) unsigned char pair_smem[];
@@ -567,142 +721,9 @@ osc_step_pair(const __grid_constant__ KParams P, const __grid_constant__ LaneArg
         S.inv0 = rcp64(d0);
         S.vb = jb0;
         const double base_st = fma(fused::coef_uv(P, R, vel_zero, 0), uv_st, gb * bias0);
-        // ---- velocity-tracking term (osc.py:175-177) and the null-space part of g
-        if (target_vel != nullptr && ((~vel_zero) & ((1u << D) - 1u)) != 0u) {
-            double dxf[K];                                   // dx in task-row order (N3: dx_idx may point anywhere)
-#pragma unroll
-            for (int cr = 0; cr < KD; ++cr) {
-                const double o = duo.other(dxa[cr]);
-                dxf[R.row_arm[arm] + cr] = dxa[cr];
-                dxf[R.row_arm[arm ^ 1] + cr] = o;
-            }
-            if (HAS_BASE) dxf[R.row_base] = dxb;
-#pragma unroll 1
-            for (int d = 0; d < D; ++d) {
-                if ((vel_zero >> d) & 1u) continue;
-                const KDevice &dv = P.dev[d];
-                flags |= IRLOSC_ST_VEL_BRANCH;
-                const bool mine = d == R.dev_arm[arm], base = HAS_BASE && d == R.dev_base;
-                int r = 0;
-                for (int i = 0; i < 6; ++i)
-                    if (dv.dof[i]) {
-                        const int src = dv.dx_idx[r];
-                        if (src >= K) flags |= IRLOSC_ST_DX_RANGE;
-                        else {
-                            const double add = dv.kv * (dxf[src] - target_vel[d * 6 + i]) * dv.damp[i];
-                            if (mine) {
-#pragma unroll
-                                for (int s = 0; s < KD; ++s)
-                                    if (r == s) gc[s] += add;
-                            }
-                            if (base) gcb += add;
-                        }
-                        ++r;
-                    }
-            }
-        }
-        {
-            const double kvn = P.has_nullspace ? P.nullspace_kv : 0.0;
-#pragma unroll
-            for (int r = 0; r < KD; ++r) gc[r] = fma(-kvn, dxa[r], gc[r]);
-            if (HAS_BASE) gcb = fma(-kvn, dxb, gcb);
-        }
-        if (!m_ok) flags |= IRLOSC_ST_M_NOT_PD;
-        const bool poison = (flags & (IRLOSC_ST_M_NOT_PD | IRLOSC_ST_DX_RANGE)) != 0;
-        double w[KD], wb = 0.0;
-        bool small_det = false, solved = true;
-        if (!poison) solved = pair_resolve(S, gc, gcb, w, &wb, &small_det);
-        if (solved && small_det) flags |= IRLOSC_ST_PINV;
-        const bool hard = !poison && !solved;
-        // ---- joint-space assembly + packing
-        const double *jrow = tl + (size_t)A.gbase[4 + 5 * arm] * kTile;       // the arm's task rows: [cr][stand, joints 1..6]
-        if (!hard && !poison) {
-            double jv[7][KD];
-#pragma unroll
-            for (int i = 0; i < 7; ++i)
-#pragma unroll
-                for (int cr = 0; cr < KD; ++cr) jv[i][cr] = lane::LdCached{}(jrow + (size_t)(cr * 7 + i) * kTile);
-            {
-                double jt = 0.0;
-#pragma unroll
-                for (int cr = 0; cr < KD; ++cr) jt = fma(jv[0][cr], w[cr], jt);
-                jt = duo.sum(jt);
-                if (HAS_BASE) jt = fma(jb0, wb, jt);
-                if (arm == 0) fused::put_joint(R, u_all_row, ctrl_row, 0, base_st - jt);
-            }
-#pragma unroll
-            for (int i = 1; i < 7; ++i) {
-                double jt = 0.0;
-#pragma unroll
-                for (int cr = 0; cr < KD; ++cr) jt = fma(jv[i][cr], w[cr], jt);
-                fused::put_joint(R, u_all_row, ctrl_row, jb + i - 1, base_arm[i - 1] - jt);
-            }
-        }
-        if (poison) {
-            __syncwarp(duo.mask);                            // the partner's gripper outputs are in place
-            if (arm == 0) {
-                const double qnan = nan("");
-                if (u_all_row)
-                    for (int j = 0; j < kN; ++j) u_all_row[j] = qnan;
-                for (int c = 0; c < P.n_ctrl; ++c) ctrl_row[c] = qnan;
-            }
-        }
-        uint8_t *status = (A.status && valid) ? A.status + inst : nullptr;
-        if (status && arm == 0) *status = (uint8_t)flags;
-        // ---- instances left to the warp: record (canonical rows), Jacobi eigen-solver, owner finishes
-        unsigned todo = __ballot_sync(0xffffffffu, hard && valid && arm == 0);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            if ((lane & ~1) == src) {
-                double *rec = wfix.rec;
-                double vo[KD];
-#pragma unroll
-                for (int i = 0; i < KD; ++i) vo[i] = duo.other(S.v[i]);
-                const int r0 = arm * KD, o0 = (arm ^ 1) * KD;
-#pragma unroll
-                for (int i = 0; i < KD; ++i) {
-                    const double vi = S.v[i] * S.inv0;
-#pragma unroll
-                    for (int j = 0; j < KD; ++j) {
-                        rec[RC::A + (r0 + i) * K + r0 + j] = fma(vi, S.v[j], S.D[i >= j ? ltri(i, j) : ltri(j, i)]);
-                        rec[RC::A + (r0 + i) * K + o0 + j] = vi * vo[j];
-                    }
-                    if (HAS_BASE) {
-                        rec[RC::A + (r0 + i) * K + 2 * KD] = vi * jb0;
-                        rec[RC::A + (2 * KD) * K + r0 + i] = vi * jb0;
-                    }
-                    rec[RC::G + r0 + i] = gc[i];
-                    rec[RC::JST + r0 + i] = lane::LdCached{}(jrow + (size_t)(i * 7) * kTile);
-                }
-#pragma unroll
-                for (int i = 0; i < 6; ++i) {
-                    rec[RC::BASE + 1 + 6 * arm + i] = base_arm[i];
-#pragma unroll
-                    for (int cr = 0; cr < KD; ++cr)
-                        rec[RC::JARM + (arm * 6 + i) * KD + cr] = lane::LdCached{}(jrow + (size_t)(cr * 7 + i + 1) * kTile);
-                }
-                if (arm == 0) {
-                    if (HAS_BASE) {
-                        rec[RC::A + (2 * KD) * K + 2 * KD] = (jb0 * S.inv0) * jb0;
-                        rec[RC::G + 2 * KD] = gcb;
-                        rec[RC::JST + 2 * KD] = jb0;
-                    }
-                    rec[RC::BASE] = base_st;
-                    rec[RC::ABAD] = small_det ? 0.0 : 1.0;
-                    wfix.flags = 0;
-                }
-            }
-            __syncwarp();
-            tiled::eigen_solve<K, K>(reinterpret_cast<double (*)[K]>(wfix.rec + RC::A), wfix.Vs, wfix.rec + RC::G, wfix.w, wfix.cbuf,
-                                     wfix.sbuf, wfix.rec[RC::ABAD] == 0.0, lane, &wfix.flags);
-            __syncwarp();
-            if (lane == src) {
-                fused::fixup_finish<KD, HAS_BASE>(R, u_all_row, ctrl_row, wfix.rec, wfix.w, 0, 1);
-                if (status) *status = (uint8_t)(*status | wfix.flags);
-            }
-            __syncwarp();
-        }
+        const lane_jrow_t jrow{tl + (size_t)A.gbase[4 + 5 * arm] * kTile};       // the arm's task rows: [cr][stand, joints 1..6]
+        pair_tail<KD, HAS_BASE>(P, R, S, gc, gcb, dxa, dxb, base_arm, base_st, m_ok, jrow, target_vel, vel_zero, flags, u_all_row,
+                                ctrl_row, (A.status && valid) ? A.status + inst : nullptr, valid, wfix, lane);
         __syncwarp();
         {
             const int64_t left = B - ht * kHalf;
