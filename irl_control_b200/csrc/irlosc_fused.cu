@@ -115,7 +115,8 @@ int32_t check_fio(const irlosc_handle *h, const irlosc_fused_io *io, FIo &k) {
     return IRLOSC_OK;
 }
 
-int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st, const KSeq *seq = nullptr) {
+// B_whole: the batch the caller handed in (the host entry point launches chunks of it); the kernel choice follows it.
+int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st, const KSeq *seq = nullptr, int64_t B_whole = -1) {
     const int variant = (h->kernel_choice >= 2 && h->kernel_choice < 9) ? h->kernel_choice - 2 : 0;
     const int sms = std::max(1, h->sm_count - h->sm_margin);
     int want_threads = variant == 0 ? fused_threads_for(B, sms) : 0;
@@ -123,7 +124,7 @@ int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st,
     if (!seq && variant == 0) {
         // one wave of half tiles or less: the pair kernel's latency is one arm instead of two (measured -23 % at k = 7,
         // -33 % at k = 12 for B <= 16 384); beyond that the thread-per-instance kernel is as fast or faster
-        int use_pair = (B + 15) / 16 <= (int64_t)sms * 8 ? 1 : 0;
+        int use_pair = ((B_whole < 0 ? B : B_whole) + 15) / 16 <= (int64_t)sms * 8 ? 1 : 0;
         if (const char *t = getenv("IRLOSC_FUSED_PAIR")) use_pair = atoi(t);                             // experiments only
         if (use_pair) {
             int pc = 0;
@@ -408,7 +409,7 @@ extern "C" int32_t irlosc_step_fused_host(irlosc_handle *h, int64_t B, const irl
         dk.status = hk.status ? (uint8_t *)S.buf[10] : nullptr;
         dk.ee_xyz = hk.ee_xyz ? (double *)S.buf[11] : nullptr;
         dk.ee_quat = hk.ee_quat ? (double *)S.buf[12] : nullptr;
-        result = launch_fused(h, nb, dk, S.stream);
+        result = launch_fused(h, nb, dk, S.stream, nullptr, B);
         if (result != IRLOSC_OK) break;
         CUDA_TRY(cudaMemcpyAsync(hk.ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
                                  cudaMemcpyDeviceToHost, S.stream));

@@ -47,14 +47,16 @@ def test_sequence_on_gpu_matches_reference_loop_and_fused_step():
             mv2[:, seq.active_device, 0] = st["max_vel0"]
             ref = eng.step_fused({"q": qd[t].contiguous(), "dq": dqd[t].contiguous(), "max_vel": mv2,
                                   "target_xyz": st["target_xyz"], "target_quat": st["target_quat"]}, want_u_all=True)
-            # (another template instantiation, and the active arm is processed first: equal up to rounding)
+            # (another kernel - the plain step of a small batch runs a lane per arm - and the active arm is processed
+            #  first: equal up to rounding amplified by the conditioning of the task-space matrix)
             scale = ref["u_all"].abs().amax(dim=1, keepdim=True)
-            assert ((out["u_all"] - ref["u_all"]).abs() / scale).max().item() < 1e-9
+            worst = ((out["u_all"] - ref["u_all"]).abs() / scale).max().item()
+            assert worst < 1e-6, worst
             gf = torch.tensor([p["gripper_force"] for p in seq.params] + [0.0], dtype=torch.float64, device=dev)[st["action"].long()]
             want = ref["ctrl"].clone()
             sel = gf != 0
             want[sel, seq.gripper_slot] = gf[sel]
-            assert ((out["ctrl"] - want).abs() / scale).max().item() < 1e-9
+            assert ((out["ctrl"] - want).abs() / scale).max().item() < 1e-6
             assert torch.equal(out["ctrl"][sel, seq.gripper_slot], gf[sel])
             recs.append({k: st[k][:n_chk].cpu().numpy().copy() for k in ("action", "err", "max_vel0", "target_xyz", "target_quat")})
         d = layout.as_dict()["devices"][ia]
@@ -108,7 +110,7 @@ def test_waypoint_cycling_on_gpu_matches_the_gain_test_loop():
         ref = eng.step_fused({"q": qd[t].contiguous(), "dq": dqd[t].contiguous(), "max_vel": mv,
                               "target_xyz": st["target_xyz"], "target_quat": st["target_quat"]}, want_u_all=True)
         scale = ref["u_all"].abs().amax(dim=1, keepdim=True)
-        assert ((out["u_all"] - ref["u_all"]).abs() / scale).max().item() < 1e-9
+        assert ((out["u_all"] - ref["u_all"]).abs() / scale).max().item() < 1e-6      # two kernels: equal up to rounding
         got.append((st["target_xyz"][:n_chk].cpu().numpy().copy(), before))
     for i in range(n_chk):
         for d in (0, 1):
