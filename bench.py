@@ -377,9 +377,13 @@ def main():
             torch.cuda.synchronize()
             return None
 
-    def timed_loop(n, repeat=1, **kw):
+    region_log = []
+
+    def timed_loop(n, repeat=1, regions=1, **kw):
         """`repeat` x n steps back to back between two events on the launching stream (gathers included); ms per step,
-        max over ranks."""
+        max over ranks.  regions > 1: that measurement taken `regions` times (each one bracketed by barrier + synchronize
+        on both sides), the median is returned and every region is logged - a 1 ms region on several GPUs is at the mercy
+        of how far apart the ranks' streams happen to be when it starts."""
         g = capture(n, **kw)
         ok = torch.tensor([1 if g is not None else 0], device=dev)
         if world > 1:
@@ -389,28 +393,33 @@ def main():
         launch_mode[0] = "cuda graph of %d steps" % n if g is not None else "eager"
         if g is not None:
             g.replay()                                     # warm-up replay
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            if gather_mode.startswith("fused"):
-                # a device-side barrier right before the start event: the host barrier leaves the ranks' streams
-                # hundreds of microseconds apart, which the first in-loop barrier would otherwise charge to the region
-                handles[0].barrier(channel=0)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(repeat):
-            if g is not None:
-                g.replay()
-            else:
-                for i in range(n):
-                    one_step(i, **kw)
-                drain()
-        b.record()
-        torch.cuda.synchronize()
-        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()) / (n * repeat)
+        times = []
+        for _ in range(regions):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+                if gather_mode.startswith("fused"):
+                    # a device-side barrier right before the start event: the host barrier leaves the ranks' streams
+                    # hundreds of microseconds apart, which the first in-loop barrier would otherwise charge to the region
+                    handles[0].barrier(channel=0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(repeat):
+                if g is not None:
+                    g.replay()
+                else:
+                    for i in range(n):
+                        one_step(i, **kw)
+                    drain()
+            b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()) / (n * repeat))
+        if regions > 1:
+            region_log[:] = times
+        return sorted(times)[len(times) // 2]
 
     W = max(args.warmup, 3)
     for i in range(W):
@@ -421,7 +430,8 @@ def main():
         sampler.start()
         time.sleep(0.25)
     t_wall0 = time.time()
-    ms_per_step = timed_loop(args.steps)
+    ms_per_step = timed_loop(args.steps, regions=5)
+    headline_regions = list(region_log)
     launches = args.steps                  # one lane-kernel launch per step (the N > 1 barrier kernels are torch's)
     headline_launch = launch_mode[0]
     value = world * B / (ms_per_step * 1e-3)
@@ -611,7 +621,10 @@ def main():
             "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cb,
-            "sustained": sustained, "launch": headline_launch, "gather": gather_mode, "gather_verified": gather_verified,
+            "sustained": sustained,
+            "timed_regions": {"count": len(headline_regions), "ms_per_step": [round(x, 6) for x in headline_regions],
+                              "reported": "median; each region is exactly K steps between barrier + synchronize"},
+            "launch": headline_launch, "gather": gather_mode, "gather_verified": gather_verified,
             "gather_link": gather_link, "strong": strong,
             "e2e_arrays": e2e_arrays}
     line.update(extras)

@@ -19,9 +19,11 @@
  * generate").  The device-pointer steps (`irlosc_step`,
  * `irlosc_step_tiles`, `irlosc_step_fused`, `irlosc_step_sequence`,
  * `irlosc_step_waypoints`) are ONE kernel launch each, never synchronise with
- * the host, never allocate, and keep no per-handle device state: steps issued
- * on different streams may overlap freely.  The `*_host` forms own staging
- * buffers and internal streams per handle and return when the outputs are valid.
+ * the host and never allocate; steps issued on different streams may overlap
+ * freely.  (The only per-handle device state is 16 ticket counters of the pair
+ * kernel, allocated by the first tile call of a handle and keyed by stream; a
+ * launch rewinds its own counter.)  The `*_host` forms own staging buffers and
+ * internal streams per handle and return when the outputs are valid.
  */
 #ifndef IRLOSC_H_
 #define IRLOSC_H_
@@ -369,7 +371,8 @@ int64_t irlosc_tiles_doubles(const irlosc_handle *h, int64_t B);
 int32_t irlosc_pack_tiles(irlosc_handle *h, int64_t B, const irlosc_io *io_device, double *tiles_device, void *cuda_stream);
 int32_t irlosc_pack_tiles_host(irlosc_handle *h, int64_t B, const irlosc_io *io_host, double *tiles_host);
 /* Replaces: OSC.generate (osc.py:120-210) for B instances stored as tiles in device memory: ONE kernel, the
- * lane kernel (csrc/osc_lane.cuh).  Asynchronous on `cuda_stream`, never synchronises with the host. */
+ * tile kernels (csrc/osc_lane.cuh, csrc/osc_pair.cuh; irlosc_set_tile_kernel).  Asynchronous on `cuda_stream`, never
+ * synchronises with the host. */
 int32_t irlosc_step_tiles(irlosc_handle *h, int64_t B, const irlosc_tiles_io *io_device, void *cuda_stream);
 /* Same with HOST buffers (pinned via irlosc_host_alloc): tiles go host -> device in chunks, ctrl / u_all / status
  * come back, pipelined over internal streams; returns when the outputs are valid. */

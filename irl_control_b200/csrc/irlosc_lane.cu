@@ -24,7 +24,12 @@ struct LaneCtx {
     fused::FRoles R;
     TileSpec spec;
     Staging stage[kPipeDepth];    // host pipeline: 0 tiles, 1 target_vel, 2 ctrl, 3 u_all, 4 status
-    mutable int *sched = nullptr; // ticket counters of the pair kernel: [0] device entry point, [1 + s] host pipeline stage s
+    // ticket counters of the pair kernel, one per stream that steps of this handle are issued on (a launch rewinds its
+    // counter itself; launches on one stream run in order, launches on different streams must not share one)
+    static constexpr int kSchedSlots = 16;
+    int *sched = nullptr;
+    cudaStream_t sched_stream[kSchedSlots] = {};
+    int sched_used = 0;
 };
 
 LaneCtx *ctx_of(irlosc_handle *h) {
@@ -32,6 +37,14 @@ LaneCtx *ctx_of(irlosc_handle *h) {
         LaneCtx *c = new (std::nothrow) LaneCtx();
         if (!c) return nullptr;
         c->ok = fused_roles(h->kp, c->R, c->kd, c->has_base) && build_tile_spec(h->kp, c->R, c->kd, c->has_base, c->spec);
+        if (c->ok) {     // 64 bytes of device memory, here so that no step ever allocates; without them: static assignment
+            if (cudaMalloc(&c->sched, LaneCtx::kSchedSlots * sizeof(int)) != cudaSuccess ||
+                cudaMemset(c->sched, 0, LaneCtx::kSchedSlots * sizeof(int)) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+                cudaGetLastError();
+                if (c->sched) cudaFree(c->sched);
+                c->sched = nullptr;
+            }
+        }
         h->lane_ctx = c;
     }
     return static_cast<LaneCtx *>(h->lane_ctx);
@@ -112,8 +125,7 @@ int lane_threads_for(int64_t B, int sms) {
 
 // B_whole: the batch the caller handed in (the host entry point launches it in chunks): the kernel choice follows it,
 // so that a batch gives the same bits whichever entry point it came through.
-int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_tiles_io &io, cudaStream_t st, int sched_slot = 0,
-                    int64_t B_whole = -1) {
+int32_t launch_lane(irlosc_handle *h, LaneCtx &c, int64_t B, const irlosc_tiles_io &io, cudaStream_t st, int64_t B_whole = -1) {
     const KParams &P = h->kp;
     int cnt = 0;
     const LaneEntry *t = lane_table(&cnt), *e = nullptr;
@@ -188,17 +200,15 @@ int32_t launch_lane(irlosc_handle *h, const LaneCtx &c, int64_t B, const irlosc_
         }
         const int pw = pe->threads / 32;
         // tickets pay when a warp has several half tiles to walk (IRLOSC_PAIR_TICKETS: experiments)
-        if (env_int("IRLOSC_PAIR_TICKETS", 1) != 0 && n_half > (int64_t)sms * pw) {
-            if (!c.sched) {
-                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-                CUDA_TRY(cudaStreamIsCapturing(st, &cap));
-                if (cap != cudaStreamCaptureStatusNone)
-                    return fail(IRLOSC_ERR_INVALID, "the first large step allocates its ticket counters: run one step before capturing a graph");
-                CUDA_TRY(cudaMalloc(&c.sched, (1 + kPipeDepth) * sizeof(int)));
-                CUDA_TRY(cudaMemset(c.sched, 0, (1 + kPipeDepth) * sizeof(int)));
-                CUDA_TRY(cudaDeviceSynchronize());      // once: the counters are zero before any stream uses them
+        if (env_int("IRLOSC_PAIR_TICKETS", 1) != 0 && n_half > (int64_t)sms * pw && c.sched) {
+            int slot = -1;
+            for (int i = 0; i < c.sched_used && slot < 0; ++i)
+                if (c.sched_stream[i] == st) slot = i;
+            if (slot < 0 && c.sched_used < LaneCtx::kSchedSlots) {
+                slot = c.sched_used++;
+                c.sched_stream[slot] = st;
             }
-            A.sched = c.sched + sched_slot;
+            if (slot >= 0) A.sched = c.sched + slot;     // more streams than counters: this launch assigns statically
         }
         int pair_warp_bytes = ((pair::kHalf * P.n_ctrl * 8 + 15) & ~15) + pe->fix_bytes;
         const int pgrid = (int)std::min<int64_t>((n_half + pw - 1) / pw, (int64_t)sms);
@@ -370,7 +380,7 @@ extern "C" int32_t irlosc_step_tiles_host(irlosc_handle *h, int64_t B, const irl
         dk.ctrl = (double *)S.buf[2];
         dk.u_all = io->u_all ? (double *)S.buf[3] : nullptr;
         dk.status = io->status ? (uint8_t *)S.buf[4] : nullptr;
-        rc = launch_lane(h, *c, nb, dk, S.stream, 1 + turn % kPipeDepth, B);
+        rc = launch_lane(h, *c, nb, dk, S.stream, B);
         if (rc != IRLOSC_OK) return rc;
         CUDA_TRY(cudaMemcpyAsync(io->ctrl + (size_t)b0 * P.n_ctrl, dk.ctrl, (size_t)nb * P.n_ctrl * sizeof(double),
                                  cudaMemcpyDeviceToHost, S.stream));
