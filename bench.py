@@ -811,7 +811,8 @@ def extra_legs(args, torch, np, eng, layout, sts, arrays, tiles, dev, world, dis
     # ---- BASELINE.json configs 2-4 and the worst case: oracle check on a strided subset, then the kernel time
     from oracle import osc_numpy
     cfgs = []
-    for wl, Bc in (("gain_test", 4096), ("admit_test", 8192), ("insertion", 16384), ("worst_case", 65536)):
+    for wl, Bc in (("gain_test", 4096), ("admit_test", 8192), ("insertion", 16384), ("worst_case", 65536), ("admit_test", 65536),
+                   ("iros2022", 65536)):
         lay = scenario_layout(wl)
         en = BatchedOSC(lay, device=dev.index)
         ss = [synth_batch(lay, Bc, seed=77 + i, device=dev, insertion_schedule=(wl == "insertion")) for i in range(N_INPUT_SETS)]

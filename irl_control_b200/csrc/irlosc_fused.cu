@@ -138,11 +138,13 @@ int32_t launch_fused(irlosc_handle *h, int64_t B, const FIo &k, cudaStream_t st,
                     CUDA_TRY(cudaFuncSetAttribute(pt[i].step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pt[i].smem));
                 ready = true;
             }
-            const int pw = pe->threads / 32;
             const int64_t n_half = (B + 15) / 16;
+            // spread a small batch over the SMs: CTAs of 1 .. 8 warps (see launch_lane)
+            const int pw = (int)std::max<int64_t>(1, std::min<int64_t>(pe->threads / 32, (n_half + sms - 1) / sms));
             const int pgrid = (int)std::min<int64_t>((n_half + pw - 1) / pw, (int64_t)sms);
+            const size_t psmem = pe->smem / (pe->threads / 32) * pw;
             void *pargs[] = {(void *)&h->kp, (void *)&h->km, (void *)&k, (void *)&B, (void *)&h->fr};
-            cudaError_t perr = cudaLaunchKernel(pe->step, dim3(pgrid), dim3(pe->threads), pargs, pe->smem, st);
+            cudaError_t perr = cudaLaunchKernel(pe->step, dim3(pgrid), dim3(pw * 32), pargs, psmem, st);
             if (perr != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "fused pair kernel launch: %s", cudaGetErrorString(perr));
             h->launches += 1;
             h->last_kernel = pe->name;

@@ -198,7 +198,14 @@ int32_t launch_lane(irlosc_handle *h, LaneCtx &c, int64_t B, const irlosc_tiles_
                 CUDA_TRY(cudaFuncSetAttribute(pt[i].fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLaneSmem));
             pair_ready = true;
         }
-        const int pw = pe->threads / 32;
+        // One wave or less: spread the half tiles over the SMs as CTAs of 1 .. 8 warps (a warp alone on its
+        // scheduler walks its chain faster than two sharing one) instead of filling a few SMs with 8 warps each.
+        int pw = pe->threads / 32;
+        if (env_int("IRLOSC_PAIR_SPREAD", 1) != 0) {
+            const int64_t per_sm = (n_half + sms - 1) / sms;
+            if (per_sm < pw) pw = (int)std::max<int64_t>(1, per_sm);
+        }
+        const int pthreads = pw * 32;
         // tickets pay when a warp has several half tiles to walk (IRLOSC_PAIR_TICKETS: experiments)
         if (env_int("IRLOSC_PAIR_TICKETS", 1) != 0 && n_half > (int64_t)sms * pw && c.sched) {
             int slot = -1;
@@ -213,7 +220,7 @@ int32_t launch_lane(irlosc_handle *h, LaneCtx &c, int64_t B, const irlosc_tiles_
         int pair_warp_bytes = ((pair::kHalf * P.n_ctrl * 8 + 15) & ~15) + pe->fix_bytes;
         const int pgrid = (int)std::min<int64_t>((n_half + pw - 1) / pw, (int64_t)sms);
         void *pargs[] = {(void *)&P, (void *)&A, (void *)&B, (void *)&c.R, (void *)&G, (void *)&pair_warp_bytes};
-        cudaError_t perr = cudaLaunchKernel(pe->fn, dim3(pgrid), dim3(pe->threads), pargs, (size_t)pw * pair_warp_bytes, st);
+        cudaError_t perr = cudaLaunchKernel(pe->fn, dim3(pgrid), dim3(pthreads), pargs, (size_t)pw * pair_warp_bytes, st);
         if (perr != cudaSuccess) return fail(IRLOSC_ERR_CUDA, "pair kernel launch: %s", cudaGetErrorString(perr));
         h->launches += 1;
         h->last_kernel = pe->name;

@@ -31,10 +31,10 @@ osc_step_fused_pair(const __grid_constant__ KParams P, const __grid_constant__ K
                     const int64_t B, const __grid_constant__ FRoles R) {
     constexpr int K = 2 * KD + (HAS_BASE ? 1 : 0);
     constexpr int N = kN;
-    constexpr int W = NT / 32;
+    const int W = blockDim.x >> 5;                       // <= NT / 32
     extern __shared__ __align__(16) double fused_pair_smem[];
-    const Scratch scr{fused_pair_smem + threadIdx.x, NT};
-    WarpFix<KD, HAS_BASE> &wfix = reinterpret_cast<WarpFix<KD, HAS_BASE> *>(fused_pair_smem + kScratchDoubles * NT)[threadIdx.x >> 5];
+    const Scratch scr{fused_pair_smem + threadIdx.x, (int)blockDim.x};
+    WarpFix<KD, HAS_BASE> &wfix = reinterpret_cast<WarpFix<KD, HAS_BASE> *>(fused_pair_smem + kScratchDoubles * blockDim.x)[threadIdx.x >> 5];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int arm = lane & 1, li = lane >> 1;
     const int D = P.D;

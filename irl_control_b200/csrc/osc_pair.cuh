@@ -595,8 +595,7 @@ __global__ void __launch_bounds__(NT, 1)
 osc_step_pair(const __grid_constant__ KParams P, const __grid_constant__ LaneArgs A, const int64_t B,
               const __grid_constant__ FRoles R, const __grid_constant__ stream::Gather G, const int warp_bytes) {
     using namespace stream;
-    constexpr int W = NT / 32;
-    static_assert(W % 2 == 0, "the two halves of a tile go to neighbouring warps of a CTA");
+    const int W = blockDim.x >> 5;                       // <= NT / 32: small batches are launched as more, smaller CTAs
     extern __shared__ __align__(16) unsigned char pair_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int arm = lane & 1, li = lane >> 1;
