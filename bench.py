@@ -3,7 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload gain_test] [--batch 65536]
 
-One "step" = one launch of the lane kernel (csrc/osc_lane.cuh) over a batch of B synthetic DualUR5 instances per
+One "step" = one launch of a tile kernel (csrc/osc_lane.cuh: a thread per instance, the headline workload; or
+csrc/osc_pair.cuh: a lane per arm, 6-row layouts and small batches) over a batch of B synthetic DualUR5 instances per
 GPU, each instance one `OSC.generate` (osc.py:120-210).  The state lives in HBM in the package's native batch layout,
 batch-interleaved tiles; successive steps read DIFFERENT input sets, so nothing is re-read
 from L2.
@@ -14,7 +15,8 @@ from L2.
     roofline   SURVEY 8d algorithmic bytes per step x B / kernel time (CUDA events) vs the measured HBM peak, plus the
                same on the bytes the kernel actually moves
     strong     fixed TOTAL batches (65 536 and 262 144) split over the N GPUs
-    configs    BASELINE.json configs 2-4 and the k = 13 worst case, each checked against the oracle and timed
+    configs    BASELINE.json configs 2-4, the k = 13 worst case, admit_test and iros2022 at B = 65 536, each checked against
+               the oracle and timed
     cpu_baseline / --impl reference : the reference's own `OSC.generate` (unmodified sources staged by
                oracle/stage_ref.py, stub simulator) on all host cores - or the numpy port when the sources are absent
 """
@@ -540,7 +542,7 @@ def main():
         e2e = {"value": world * B / dt, "unit": UNIT, "h2d_bytes_per_step": int(host_tiles.nbytes),
                "d2h_bytes_per_step": int(host_out["ctrl"].nbytes), "ms_per_step": 1e3 * dt,
                "api": "BatchedOSC.step_tiles_host -> irlosc_step_tiles_host (state tiles in pinned host memory, chunked "
-                      "H2D / lane kernel / D2H pipeline); a caller that assembles its batch writes tiles directly "
+                      "H2D / tile kernel / D2H pipeline); a caller that assembles its batch writes tiles directly "
                       "(irlosc_tile_spec), per-variable arrays go through e2e_arrays"}
         del host_tiles
         host_in = {}
