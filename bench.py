@@ -16,7 +16,7 @@ from L2.
                same on the bytes the kernel actually moves
     strong     fixed TOTAL batches (65 536 and 262 144) split over the N GPUs
     configs    BASELINE.json configs 2-4, the k = 13 worst case, admit_test and iros2022 at B = 65 536, each checked against
-               the oracle and timed
+               the oracle and timed; batch_sweep: B = 256 ... 262 144 for gain_test and k = 13 (config 5 at one GPU)
     cpu_baseline / --impl reference : the reference's own `OSC.generate` (unmodified sources staged by
                oracle/stage_ref.py, stub simulator) on all host cores - or the numpy port when the sources are absent
 """
@@ -337,7 +337,7 @@ def main():
         o = {"ctrl": outs[b][:nloc]}
         if gather_mode.startswith("fused"):
             ptrs, mc = gather_args[b]
-            eng.step_tiles(t_list[i % N_INPUT_SETS], nloc, out=o, want_status=False, gather=(ptrs, rank * nloc, mc))
+            eng.step_tiles(t_list[i % len(t_list)], nloc, out=o, want_status=False, gather=(ptrs, rank * nloc, mc))
             done = torch.cuda.Event()
             done.record()
             with torch.cuda.stream(side):   # cross-GPU barrier off the critical path of the next kernel
@@ -347,7 +347,7 @@ def main():
                 fin.record()
             pending[b] = fin
         else:
-            eng.step_tiles(t_list[i % N_INPUT_SETS], nloc, out=o, want_status=False)
+            eng.step_tiles(t_list[i % len(t_list)], nloc, out=o, want_status=False)
             if gather_mode == "nccl":
                 pending[b] = dist.all_gather_into_tensor(gathered[b][:world * nloc], outs[b][:nloc], async_op=True)
 
@@ -496,7 +496,12 @@ def main():
                 continue
             saved_outs = None
             if nloc <= B:
-                t_list = [t[:(nloc + 31) // 32] for t in tiles]          # a prefix of the resident tiles
+                # distinct slices of the resident tiles, enough of them that a replay of the K-step graph reads more than
+                # the L2 holds (a third of a wave of 8 192 instances is 20 MB: three rotating prefixes would stay in L2)
+                nt = (nloc + 31) // 32
+                slice_bytes = nt * eng.tile_entries * 32 * 8
+                n_off = int(max(1, min((B // 32) // nt, -(-(320 << 20) // (slice_bytes * N_INPUT_SETS)))))
+                t_list = [t[j * nt:(j + 1) * nt] for j in range(n_off) for t in tiles]
             else:                                                        # N = 1 at 262 144: a larger resident state
                 t_list = []
                 for i in range(N_INPUT_SETS):
@@ -510,7 +515,8 @@ def main():
                 one_step(i, nloc=nloc, t_list=t_list)
             drain()
             ms = timed_loop(max(args.steps, 20), nloc=nloc, t_list=t_list)
-            strong.append({"total_batch": B_total, "batch_per_gpu": nloc, "ms_per_step": ms, "value": B_total / (ms * 1e-3)})
+            strong.append({"total_batch": B_total, "batch_per_gpu": nloc, "ms_per_step": ms, "value": B_total / (ms * 1e-3),
+                           "distinct_input_mb": round(len(t_list) * t_list[0].numel() * 8 / 2**20, 1)})
             if saved_outs is not None:
                 for b in range(NBUF):
                     outs[b] = saved_outs[b]
@@ -812,20 +818,21 @@ def extra_legs(args, torch, np, eng, layout, sts, arrays, tiles, dev, world, dis
 
     # ---- BASELINE.json configs 2-4 and the worst case: oracle check on a strided subset, then the kernel time
     from oracle import osc_numpy
-    cfgs = []
-    for wl, Bc in (("gain_test", 4096), ("admit_test", 8192), ("insertion", 16384), ("worst_case", 65536), ("admit_test", 65536),
-                   ("iros2022", 65536)):
+    def time_config(wl, Bc, check=True):
         lay = scenario_layout(wl)
         en = BatchedOSC(lay, device=dev.index)
         ss = [synth_batch(lay, Bc, seed=77 + i, device=dev, insertion_schedule=(wl == "insertion")) for i in range(N_INPUT_SETS)]
         tl = [en.pack_tiles(kernel_inputs(s, lay, qM=True)) for s in ss]
         o = en.step_tiles(tl[0], Bc, want_u_all=True)
         torch.cuda.synchronize()
-        idx = np.arange(0, Bc, max(1, Bc // 96))
-        ref = osc_numpy.osc_batch(lay.as_dict(), oracle_inputs(ss[0], lay), idx=idx)
-        got = o["u_all"].cpu().numpy()[idx]
-        err = float((np.abs(got - ref["u_all"]).max(axis=1) / np.abs(ref["u_all"]).max(axis=1)).max())
         st_ = o["status"].cpu().numpy()
+        r = {"workload": wl, "B": Bc, "k": lay.k}
+        if check:
+            idx = np.arange(0, Bc, max(1, Bc // 96))
+            ref = osc_numpy.osc_batch(lay.as_dict(), oracle_inputs(ss[0], lay), idx=idx)
+            got = o["u_all"].cpu().numpy()[idx]
+            r["max_rel_err_vs_oracle"] = float((np.abs(got - ref["u_all"]).max(axis=1) / np.abs(ref["u_all"]).max(axis=1)).max())
+            r["oracle_instances"] = int(len(idx))
         oc = {"ctrl": torch.empty(Bc, lay.n_ctrl, dtype=torch.float64, device=dev)}
         ts = []
         if tl[0].numel() * 8 * N_INPUT_SETS < (300 << 20):           # small inputs: flush L2 between steps instead
@@ -841,16 +848,24 @@ def extra_legs(args, torch, np, eng, layout, sts, arrays, tiles, dev, world, dis
         ms = median(ts)
         ab = algorithmic_bytes(lay)
         mv = en.tile_entries * 8 + 8 * lay.n_ctrl
-        cfgs.append({"workload": wl, "B": Bc, "k": lay.k, "kernel": en.last_kernel, "ms": ms, "value": Bc / (ms * 1e-3),
-                     "roofline": {"frac": ab * Bc / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": ab,
-                                  "moved_bytes_per_step": mv, "moved_frac": mv * Bc / (ms * 1e-3) / 1e9 / peak},
-                     "max_rel_err_vs_oracle": err, "oracle_instances": int(len(idx)),
-                     "pinv_share": float(((st_ & 1) != 0).mean()), "warp_finished_share": float(((st_ & 4) != 0).mean()),
-                     "l2_policy": policy})
+        r.update({"kernel": en.last_kernel, "ms": ms, "value": Bc / (ms * 1e-3),
+                  "roofline": {"frac": ab * Bc / (ms * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_step": ab,
+                               "moved_bytes_per_step": mv, "moved_frac": mv * Bc / (ms * 1e-3) / 1e9 / peak},
+                  "pinv_share": float(((st_ & 1) != 0).mean()), "warp_finished_share": float(((st_ & 4) != 0).mean()),
+                  "l2_policy": policy})
         en.close()
         del ss, tl, o, oc
         torch.cuda.empty_cache()
-    res["configs"] = cfgs
+        return r
+
+    res["configs"] = [time_config(wl, Bc) for wl, Bc in (("gain_test", 4096), ("admit_test", 8192), ("insertion", 16384),
+                                                         ("worst_case", 65536), ("admit_test", 65536), ("iros2022", 65536))]
+    # SURVEY 8d config 5 at one GPU: the batch sweep of the headline layout and of the k = 13 worst case (each step is
+    # timed by its own events; the N > 1 points of config 5 are the weak headline and `strong`)
+    res["batch_sweep"] = {wl: [{k_: v for k_, v in time_config(wl, Bs, check=False).items()
+                                if k_ in ("B", "kernel", "ms", "value", "roofline", "l2_policy")}
+                               for Bs in (256, 1024, 4096, 16384, 65536, 262144)] for wl in ("gain_test", "worst_case")}
+
 
     # ---- B = 1: the drop-in OSC.generate (examples/gain_test.py:143-147 calls it every 1 ms) next to the reference's own,
     #      both on the same stand-in simulator (oracle.ref_harness.FakeSim, cheap array accessors) and the same state
