@@ -151,6 +151,38 @@ def test_rank_deficient_task_rows_go_through_the_warp_eigen_solver(scenario, til
     assert err.max() < REL_TOL
 
 
+@pytest.mark.parametrize("scenario", ["gain_test", "admit_test"])
+def test_pinned_tile_kernel_gives_the_same_bits_at_every_batch_size(scenario):
+    """`IRLOSC_TILES_AUTO` serves small and large batches with different kernels (equal to rounding); a caller that
+    needs bit-identical results across batch sizes - or across GPU counts of a strong-scaling run - pins one."""
+    torch = _torch()
+    from irl_control_b200.engine import BatchedOSC
+    from irl_control_b200.synthetic import scenario_layout, synth_batch, kernel_inputs
+    layout = scenario_layout(scenario)
+    eng = BatchedOSC(layout, device=0)
+    B = 40000                                   # above one wave of half tiles: auto picks per batch size
+    st = synth_batch(layout, B, seed=3, device="cuda:0")
+    tiles = eng.pack_tiles(kernel_inputs(st, layout, qM=True))
+    small = 4096
+    names = {}
+    for tile_kernel in ("lane", "pair"):
+        eng.set_tile_kernel(tile_kernel)
+        big = eng.step_tiles(tiles, B)["ctrl"].clone()
+        names[tile_kernel] = eng.last_kernel
+        part = eng.step_tiles(tiles[:small // 32].contiguous(), small)["ctrl"]
+        assert eng.last_kernel.startswith(TILE_KERNEL_NAME[tile_kernel])
+        assert torch.equal(part, big[:small]), tile_kernel
+    eng.set_tile_kernel("auto")
+    a_big = eng.step_tiles(tiles, B)["ctrl"].clone()
+    k_big = eng.last_kernel
+    a_small = eng.step_tiles(tiles[:small // 32].contiguous(), small)["ctrl"]
+    k_small = eng.last_kernel
+    scale = a_big[:small].abs().amax(dim=1, keepdim=True)
+    assert ((a_small - a_big[:small]).abs() / scale).max().item() < REL_TOL
+    print("%s: auto picks %s at B = %d and %s at B = %d" % (scenario, k_big, B, k_small, small))
+    assert k_small.startswith("osc_step_pair")
+
+
 def test_lane_kernel_small_and_ragged_batches():
     torch = _torch()
     from irl_control_b200.engine import BatchedOSC
